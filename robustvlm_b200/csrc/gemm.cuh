@@ -1,0 +1,248 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] * B[N,K]^T     (16-bit operands, fp32 accumulation in TMEM)
+//
+// This is the contraction engine under every linear layer of the CLIP ViT
+// forward and input-gradient backward (open_clip VisionTransformer, SURVEY.md
+// Appendix A; reference call sites train/adversarial_training_clip.py:253-257,
+// train/pgd_train.py:32,38).  The reference runs these as cuBLAS SGEMMs through
+// torch.nn.Linear; here they are TMA -> shared memory (128B swizzle) ->
+// tcgen05.mma -> TMEM -> fused epilogue.
+//
+// Roles (256 threads, 1 CTA / SM, persistent over output tiles):
+//   warp 0 lane 0 : TMA producer   (kStages-deep smem ring, full/empty mbarriers)
+//   warp 1 lane 0 : MMA issuer     (tcgen05.mma, double-buffered TMEM accumulator)
+//   warp 2        : TMEM allocator
+//   warps 4..7    : epilogue       (tcgen05.ld -> registers -> Epi functor -> HBM)
+//
+// Tile: BLOCK_M = 128 (UMMA M, one TMEM lane per row), BLOCK_N = BN (UMMA N),
+// BLOCK_K = 64 elements (= one 128-byte swizzle row).
+//
+// Operand majors: the default is K-major for both (activations [M,K] row-major,
+// weights [N,K] row-major).  B_MN / A_MN select MN-major operands (B given as
+// [K,N] row-major, A given as [K,M] row-major) so transposed products (wgrad,
+// attention backward) need no data transposition.
+#pragma once
+#include "ptx.cuh"
+
+namespace rvlm {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kBBytes = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
+};
+
+// The epilogue functor interface:
+//   __device__ void operator()(int row, int col0, const float (&acc)[32]) const
+// is called once per (row, 32-column chunk) with row < M and col0 < N already
+// guaranteed (N is required to be a multiple of 32 by the host wrappers).
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              int M, int N, int K, int fmt, Epi epi) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+        uint8_t* sa = smem_a + stage * S::kABytes;
+        uint8_t* sb = smem_b + stage * S::kBBytes;
+        if constexpr (!A_MN) {
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * GEMM_BM);
+        } else {
+#pragma unroll
+          for (int j = 0; j < GEMM_BM / 64; ++j)
+            tma_load_2d(sa + j * 8192, &tmA, &full_bar[stage], m_blk * GEMM_BM + j * 64,
+                        kb * GEMM_BK);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(sb + j * 8192, &tmB, &full_bar[stage], n_blk * BN + j * 64, kb * GEMM_BK);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc_f16((uint32_t)fmt, GEMM_BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
+        const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          // K-major: advance 16 elements = 32 B inside the swizzle row.
+          // MN-major: advance 16 K-rows = 2 x 1024 B groups.
+          const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, 8192, 1024)
+                                      : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, 8192, 1024)
+                                      : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_f16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (row < M) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          epi(row, col0, v);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side: tensor-map construction + launch
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+// 2-D tensor map over a row-major [rows, cols] 16-bit matrix with row pitch
+// `ld` elements; box = [box_rows, 64 cols], 128B swizzle, zero OOB fill.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols = 64);
+// 3-D variant: [d2, d1, d0] with strides (s2, s1, 1) elements, box [1, box1, box0].
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t s1, uint64_t s2, uint32_t box0, uint32_t box1);
+
+int sm_count();
+
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int fmt,
+                  const Epi& epi, cudaStream_t stream, int max_ctas = 0) {
+  if (N % 32 != 0 || M <= 0 || K <= 0) return -22;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
+  else       rc = make_tmap_2d(&tmA, A, K, M, lda, GEMM_BK);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_2d(&tmB, B, N, K, ldb, BN);
+  else       rc = make_tmap_2d(&tmB, B, K, N, ldb, GEMM_BK);
+  if (rc) return rc;
+  auto kern = gemm16_kernel<BN, A_MN, B_MN, Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GemmSmem<BN>::kTotal);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    attr_set = true;
+  }
+  const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
+  int grid = sm_count();
+  if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+  if (num_tiles < grid) grid = num_tiles;
+  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+}  // namespace rvlm

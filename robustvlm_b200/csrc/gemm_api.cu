@@ -1,0 +1,64 @@
+// C-ABI entry points for the tcgen05 GEMM family (include/rvlm.h §1).
+#include "gemm.cuh"
+#include "epilogues.cuh"
+#include "../../include/rvlm.h"
+
+using namespace rvlm;
+
+namespace {
+
+template <class Epi>
+int dispatch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int fmt,
+             int flags, const Epi& epi, cudaStream_t st) {
+  const bool bmn = flags & RVLM_GEMM_B_MN, amn = flags & RVLM_GEMM_A_MN,
+             bn128 = flags & RVLM_GEMM_BN128;
+  if (fmt != 0 && fmt != 1) return RVLM_ERR_INVAL;
+  if (!amn && !bmn) {
+    return bn128 ? launch_gemm16<128, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, st)
+                 : launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, st);
+  }
+  if (!amn && bmn) {
+    return bn128 ? launch_gemm16<128, false, true>(A, lda, B, ldb, M, N, K, fmt, epi, st)
+                 : launch_gemm16<256, false, true>(A, lda, B, ldb, M, N, K, fmt, epi, st);
+  }
+  if (amn && !bmn) return launch_gemm16<128, true, false>(A, lda, B, ldb, M, N, K, fmt, epi, st);
+  return launch_gemm16<128, true, true>(A, lda, B, ldb, M, N, K, fmt, epi, st);
+}
+
+}  // namespace
+
+extern "C" int rvlm_gemm16_out16(const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                                 const float* bias, int M, int N, int K, int fmt, int flags,
+                                 void* stream) {
+  if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 7)) return RVLM_ERR_ALIGN;
+  EpiStore16 epi{reinterpret_cast<uint16_t*>(C), ldc, bias, fmt};
+  return dispatch(A, lda, B, ldb, M, N, K, fmt, flags, epi, (cudaStream_t)stream);
+}
+
+extern "C" int rvlm_gemm16_out32(const void* A, int lda, const void* B, int ldb, float* C, int ldc,
+                                 const float* bias, const float* resid, int ldr, int M, int N,
+                                 int K, int fmt, int flags, void* stream) {
+  if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 3)) return RVLM_ERR_ALIGN;
+  if (resid && ((reinterpret_cast<uintptr_t>(resid) & 15) || (ldr & 3))) return RVLM_ERR_ALIGN;
+  EpiStore32 epi{C, ldc, bias, resid, ldr};
+  return dispatch(A, lda, B, ldb, M, N, K, fmt, flags, epi, (cudaStream_t)stream);
+}
+
+extern "C" int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* H, void* Act,
+                                int ld, const float* bias, int M, int N, int K, int fmt,
+                                void* stream) {
+  if ((reinterpret_cast<uintptr_t>(Act) & 15) || (reinterpret_cast<uintptr_t>(H) & 15) || (ld & 7))
+    return RVLM_ERR_ALIGN;
+  EpiGelu epi{reinterpret_cast<uint16_t*>(H), reinterpret_cast<uint16_t*>(Act), ld, bias, fmt};
+  return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, (cudaStream_t)stream);
+}
+
+extern "C" int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int ldb, void* out,
+                                    const void* H, int ld, int M, int N, int K, int fmt, int fmt_h,
+                                    void* stream) {
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(H) & 15) || (ld & 7))
+    return RVLM_ERR_ALIGN;
+  EpiGeluBwd epi{reinterpret_cast<uint16_t*>(out), ld, reinterpret_cast<const uint16_t*>(H), fmt_h,
+                 fmt};
+  return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, (cudaStream_t)stream);
+}

@@ -1,0 +1,75 @@
+// Host-side helpers shared by all kernels: driver entry point for tensor-map
+// encoding (resolved at run time so the library links without libcuda and can be
+// dlopen'ed on a machine with no GPU), SM count, error strings.
+#include "gemm.cuh"
+#include "../../include/rvlm.h"
+
+namespace rvlm {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return RVLM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15)) return RVLM_ERR_ALIGN;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : RVLM_ERR_TMAP;
+}
+
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t s1, uint64_t s2, uint32_t box0, uint32_t box1) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return RVLM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((s1 * 2) & 15) || ((s2 * 2) & 15))
+    return RVLM_ERR_ALIGN;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 2, s2 * 2};
+  cuuint32_t box[3] = {box0, box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : RVLM_ERR_TMAP;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  return n;
+}
+
+}  // namespace rvlm
+
+extern "C" const char* rvlm_strerror(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case RVLM_ERR_INVAL: return "invalid argument";
+    case RVLM_ERR_ALIGN: return "pointer or pitch not 16-byte aligned";
+    case RVLM_ERR_DRIVER: return "cuTensorMapEncodeTiled entry point unavailable";
+    case RVLM_ERR_TMAP: return "tensor map encode failed";
+    case RVLM_ERR_NOMEM: return "workspace too small";
+    case RVLM_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return code <= -1000 ? "CUDA runtime error (code = -1000 - cudaError_t)" : "unknown";
+  }
+}
+
+extern "C" int rvlm_abi_version(void) { return RVLM_ABI_VERSION; }

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the adversarial-perturbation hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one complete inner attack call -- `pgd()` with 10 iterations, ell_inf,
+eps = 4/255, stepsize 1/255, FARE (l2-embedding) loss, ViT-L/14, 256 synthetic
+224x224x3 images per GPU (BASELINE.json configs[1]; weak scaling: every rank attacks its
+own 256 images, the inner loop needs no collective -- SURVEY.md §8e).
+value   = images attacked per second over all ranks, inputs resident in HBM
+e2e     = the same through the reference-facing call `robustvlm_b200.attacks.pgd` with
+          pinned HOST inputs: H2D of the batch and D2H of the adversarial images inside
+          the timed region.
+roofline = achieved tensor throughput of the dominant kernel (the tcgen05 GEMM):
+          algorithmic 2*M*N*K per launch / CUDA-event time of that launch, summed over
+          every GEMM launch of the timed steps, against the measured bf16 peak.
+--impl reference times the reference's own CPU PyTorch path for the same metric (the
+CPU oracle restatement of train/pgd_train.py::pgd around the restated open_clip ViT --
+/root/reference itself cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+EPS, STEPSIZE, ITERS = 4 / 255, 1 / 255, 10
+FWD_GF = {"ViT-L-14": 162.03, "ViT-B-32": 8.82}      # BASELINE.md §2, GFLOP / image
+BWD_GF = {"ViT-L-14": 168.52, "ViT-B-32": 8.91}
+METRIC = "adversarial images/sec (ViT-L/14, 10-step PGD linf)"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4)
+                          if len(s) >= 6 and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def synth(B, seed, device="cpu"):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, 224, 224, generator=g)
+    d0 = (torch.rand(B, 3, 224, 224, generator=g) * 2 - 1) * EPS
+    return x.to(device), d0.to(device)
+
+
+# ------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU baseline arm: the oracle port of the reference's pgd() around the restated ViT."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import attacks as oa
+    from oracle import vit as ovit
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    name = args.model
+    model = ovit.ClipVisionModel(ovit.build(name, seed=1)).eval()
+    model_orig = ovit.ClipVisionModel(ovit.build(name, seed=2)).eval()
+    Bs = 2
+    x, d0 = synth(Bs, seed=0)
+    with torch.no_grad():
+        e_orig = model_orig(x, output_normalize=False)
+    wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+
+    def one(n_it):
+        t0 = time.perf_counter()
+        oa.pgd(model, wrap, x, None, "linf", EPS, n_it, STEPSIZE, False, perturbation=d0.clone(),
+               mode="max")
+        return time.perf_counter() - t0
+
+    t1 = one(1)                                   # probe (also warms the thread pool)
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    n_it = int(max(1, min(ITERS, budget // max(t1, 1e-3))))
+    for _ in range(args.warmup):
+        one(n_it)
+    times = [one(n_it) for _ in range(args.steps)]
+    per_call = sum(times) / len(times) / n_it * ITERS      # seconds for a 10-iteration call
+    val = Bs / per_call
+    sample = (f"{Bs} images x {n_it} of {ITERS} PGD iterations per step, scaled to {ITERS}; "
+              f"{name} fp32, torch {torch.__version__}, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s", "n_gpus": 0,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_call * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, Bs),
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B):
+    return {"workload": f"{args.model} FARE(l2) {ITERS}-step PGD linf eps=4/255 step=1/255, "
+                        f"{B} synthetic 224x224x3 images per GPU, random-init weights",
+            "per_gpu_batch": B, "chunk": args.chunk, "parallelism": f"dp{args.gpus}",
+            "l2_flush": "inputs larger than L2 (154 MB images + ~40 GB activations per step)"}
+
+
+def cpu_baseline_sample(model_name, seconds=20.0):
+    """Bounded CPU sample of the same workload (oracle port), rank 0, N = 1 only."""
+    import torch
+    from oracle import attacks as oa
+    from oracle import vit as ovit
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    model = ovit.ClipVisionModel(ovit.build(model_name, seed=1)).eval()
+    model_orig = ovit.ClipVisionModel(ovit.build(model_name, seed=2)).eval()
+    Bs = 2
+    x, d0 = synth(Bs, seed=0)
+    with torch.no_grad():
+        e_orig = model_orig(x, output_normalize=False)
+    wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+    t0 = time.perf_counter()
+    oa.pgd(model, wrap, x, None, "linf", EPS, 1, STEPSIZE, False, perturbation=d0.clone(),
+           mode="max")
+    t1 = time.perf_counter() - t0
+    n_it = int(max(1, min(ITERS, seconds // max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    oa.pgd(model, wrap, x, None, "linf", EPS, n_it, STEPSIZE, False, perturbation=d0.clone(),
+           mode="max")
+    t = (time.perf_counter() - t0) / n_it * ITERS
+    return {"value": Bs / t, "unit": "img/s", "cores": cores, "kind": "port",
+            "sample": f"{Bs} images x {n_it} of {ITERS} PGD iterations (scaled), {model_name} fp32 "
+                      f"oracle port of train/pgd_train.py::pgd, {cores} threads"}
+
+
+# ------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from robustvlm_b200 import _native as nat
+    from robustvlm_b200 import attacks, model as rmodel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    vt = rmodel.VisionTransformer(args.model, seed=1).to(dev)
+    vt_orig = rmodel.VisionTransformer(args.model, seed=2).to(dev)
+    m = rmodel.ClipVisionModel(vt, None, None).eval()
+    m_orig = rmodel.ClipVisionModel(vt_orig, None, None).eval()
+    x_h, d0_h = synth(B, seed=100 + rank)
+    x_h, d0_h = x_h.pin_memory(), d0_h.pin_memory()
+    x, d0 = x_h.to(dev), d0_h.to(dev)
+    chunk = min(args.chunk, B)
+    with torch.no_grad():
+        e_orig = torch.cat([m_orig(x[i:i + chunk], output_normalize=False)
+                            for i in range(0, B, chunk)])
+    vt_orig._engine = None           # release the frozen tower's workspace
+    torch.cuda.empty_cache()
+    wrap = rmodel.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+
+    def step_resident():
+        return attacks.pgd(m, wrap, x, None, "linf", EPS, ITERS, STEPSIZE, False,
+                           perturbation=d0, mode="max", chunk=chunk)
+
+    out_h = torch.empty_like(x_h).pin_memory()
+
+    def step_e2e():
+        xd = x_h.to(dev, non_blocking=True)
+        dd = d0_h.to(dev, non_blocking=True)
+        adv = attacks.pgd(m, wrap, xd, None, "linf", EPS, ITERS, STEPSIZE, False,
+                          perturbation=dd, mode="max", chunk=chunk)
+        out_h.copy_(adv, non_blocking=True)
+        return adv
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        if profile:
+            nat.lib().rvlm_profile_gemm(1)
+        nat.lib().rvlm_launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        fn_l = nat.lib().rvlm_launch_count
+        fn_l.restype = nat.ctypes.c_longlong
+        launches = int(fn_l())
+        prof = None
+        if profile:
+            from ctypes import byref, c_double, c_longlong
+            tms, tfl, nl = c_double(), c_double(), c_longlong()
+            nat.check(nat.lib().rvlm_profile_gemm_collect(byref(tms), byref(tfl), byref(nl)))
+            nat.lib().rvlm_profile_gemm(0)
+            prof = (tms.value, tfl.value, nl.value)
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, prof, (sampler.summary() if sampler else None)
+
+    for _ in range(args.warmup):
+        step_resident()
+    ms, launches, prof, clocks = timed(step_resident, args.steps, profile=True)
+    for _ in range(min(args.warmup, 1)):
+        step_e2e()
+    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+
+    n_img = B * world * args.steps
+    value = n_img / (ms / 1e3)
+    e2e = n_img / (ms_e2e / 1e3)
+    if rank == 0:
+        peak_tf, _, which = read_peaks()
+        gemm_ms, gemm_fl, gemm_n = prof
+        achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+        algo_tf = (FWD_GF[args.model] + BWD_GF[args.model]) * ITERS * B * args.steps / 1e3
+        line = {
+            "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 fwd operands / bf16 bwd operands, f32 accumulate + residual stream",
+            "data": "synthetic", "config": workload_config(args, B),
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(2 * x_h.numel() * 4),
+                    "d2h_bytes_per_step": int(x_h.numel() * 4)},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                         "traffic": None, "peak_source": f"{which} bf16_tflops_sustained",
+                         "kernel": "gemm16_kernel (tcgen05)", "launches": gemm_n,
+                         "gemm_ms_per_step": gemm_ms / args.steps,
+                         "gemm_share_of_step": gemm_ms / ms if ms else None,
+                         "whole_step_algorithmic_tflops": algo_tf / (ms / 1e3)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(args.model)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="ViT-L-14")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--chunk", type=int, default=256, help="engine micro-batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

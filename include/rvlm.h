@@ -47,6 +47,14 @@ extern "C" {
 int rvlm_abi_version(void);
 const char* rvlm_strerror(int code);
 
+/* Accounting for the benchmark: number of kernels this library has launched, and an
+ * optional mode that brackets every tcgen05 GEMM launch with CUDA events on its stream
+ * (collect() synchronises and returns the summed device time and algorithmic FLOPs). */
+long long rvlm_launch_count(void);
+void rvlm_launch_count_reset(void);
+int rvlm_profile_gemm(int enable);
+int rvlm_profile_gemm_collect(double* total_ms, double* total_flops, long long* launches);
+
 /* ------------------------------------------------------------------------ *
  * 1. tcgen05 GEMM (the contraction under every nn.Linear / Conv2d-as-GEMM of
  *    the open_clip VisionTransformer the reference wraps,
@@ -76,6 +84,183 @@ int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* H, vo
 /* out = (A*B^T) .* QuickGELU'(H) ; 16-bit [M,N] pitch ld; H in fmt_h, A/B/out in fmt */
 int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int ldb, void* out, const void* H,
                          int ld, int M, int N, int K, int fmt, int fmt_h, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * 2. Perturbation updates.  Tensors are contiguous fp32 [B, n] (n % 4 == 0).
+ *    `workspace` (ell_2 variants): rvlm_update_workspace_bytes(B) bytes.
+ * ------------------------------------------------------------------------ */
+size_t rvlm_update_workspace_bytes(int B);
+
+/* One PGD iteration's update given the loss gradient (train/pgd_train.py:37-59 with
+ * normalize_grad / project_perturbation of vlm_eval/attacks/utils.py:8-26):
+ * NaN scrub, sign, momentum, +-stepsize, clamp(+-eps), delta = clamp(x+delta,0,1)-x.
+ * In place on delta and velocity.  Bit-exact w.r.t. the reference's fp32 sequence. */
+int rvlm_pgd_update_linf(float* delta, float* velocity, const float* grad, const float* x, int B,
+                         long long n, float stepsize, float eps, int maximize, float momentum,
+                         void* stream);
+/* ell_2 variant (F.normalize with eps 1e-12, torch.renorm with maxnorm eps). */
+int rvlm_pgd_update_l2(float* delta, float* velocity, const float* grad, const float* x, int B,
+                       long long n, float stepsize, float eps, int maximize, float momentum,
+                       float* workspace, void* stream);
+
+/* One APGD proposal step (train/apgd_train.py:205-254 == autoattack/autopgd_base.py:328-350).
+ * In place: x_adv_old <- x_adv; x_adv <- new iterate.  step_size is per sample [B];
+ * a = 1.0 on the first iteration, 0.75 afterwards. */
+int rvlm_apgd_step_linf(float* x_adv, float* x_adv_old, const float* x, const float* grad,
+                        const float* step_size, int B, long long n, float eps, float a,
+                        void* stream);
+int rvlm_apgd_step_l2(float* x_adv, float* x_adv_old, const float* x, const float* grad,
+                      const float* step_size, int B, long long n, float eps, float a,
+                      float* workspace, void* stream);
+
+/* APGD bookkeeping after the model evaluation of iteration `iter`
+ * (train/apgd_train.py:301-355 == autoattack/autopgd_base.py:388-446), all on device:
+ *   acc &= pred; x_best_adv[!pred] = x_adv; best-loss tracking (x_best, grad_best,
+ *   loss_best, loss_steps[iter]); and, when k_check > 0 (a check-point of the
+ *   data-independent schedule), the oscillation / no-improvement test with
+ *   k_thr = (float)(k_check * rho): halve step_size and restart from x_best/grad_best.
+ * flags[B] is scratch. */
+int rvlm_apgd_bookkeep(float* x_adv, float* grad, float* x_best, float* grad_best,
+                       float* x_best_adv, const float* loss_indiv, const int* pred,
+                       float* loss_steps, float* loss_best, float* loss_best_last,
+                       float* reduced_last, float* step_size, int* acc, int* flags, int B,
+                       long long n, int n_iter, int iter, int k_check, float k_thr, void* stream);
+
+/* out = a + b (x_adv = x + delta, train/pgd_train.py:68) */
+int rvlm_add_f32(float* out, const float* a, const float* b, long long n, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * 3. ViT building blocks (exported for unit tests and for callers that compose
+ *    their own pipelines).  Residual stream fp32 [M, W]; 16-bit operands in fmt.
+ * ------------------------------------------------------------------------ */
+/* y = LayerNorm(x) (eps 1e-5, affine); y16 and/or y32 may be NULL; stats [M,2] = (mean, rstd) */
+int rvlm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16,
+                       float* y32, float* stats, int M, int W, int fmt, void* stream);
+/* dx = dres + LayerNorm'(dy); dres/dx32/dx16 may be NULL; dx32 may alias dres.
+ * drop_T > 0: rows with row % drop_T == 0 are skipped and the rest compacted. */
+int rvlm_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma,
+                       const float* dres, float* dx32, void* dx16, int M, int W, int fmt,
+                       int drop_T, void* stream);
+/* Multi-head attention core, head dim 64, no mask: softmax(q k^T / 8) v.
+ *   qkv16 [B*T, 3W] (q | k | v per token; head h at columns 64h..64h+63), W = 64 H
+ *   o16 [B*T, W]; lse [B, H, T] (log-sum-exp of the scaled scores)
+ * tcgen05 kernels (production) and CUDA-core kernels (on-device checker). */
+int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H, int fmt,
+                  void* stream);
+int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse,
+                  void* dqkv16, int B, int T, int H, int fmt, int fmt_g, void* stream);
+int rvlm_attn_fwd_simt(const void* qkv16, void* o16, float* lse, int B, int T, int H, int fmt,
+                       void* stream);
+int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void* do16, const float* lse,
+                       void* dqkv16, int B, int T, int H, int fmt, int fmt_g, void* stream);
+
+/* ------------------------------------------------------------------------ *
+ * 4. The fused engine.  Replaces, for a CLIP vision tower in open_clip
+ *    `VisionTransformer` layout (state-dict keys in the field names below):
+ *      ClipVisionModel.forward            train/adversarial_training_clip.py:253-257
+ *      loss + torch.autograd.grad(loss,x) train/pgd_train.py:32-38, train/apgd_train.py:181-185
+ *      the whole pgd() loop               train/pgd_train.py:29-68
+ * ------------------------------------------------------------------------ */
+typedef void* rvlm_vit_handle;
+
+#define RVLM_VIT_ATTN_SIMT 1 /* flags: use the CUDA-core attention (debug / checker) */
+
+typedef struct {
+  int image, patch, width, layers, heads, mlp, out_dim;
+  float mean[3], std[3]; /* Normalize() inside the model (:116,254) */
+  int fmt_fwd;           /* 16-bit format of forward operands  (RVLM_FMT_F16 recommended) */
+  int fmt_bwd;           /* 16-bit format of gradient operands (RVLM_FMT_BF16 recommended) */
+  int flags;
+} rvlm_vit_config;
+
+/* Device fp32 pointers, open_clip VisionTransformer.state_dict() layout. Per-layer
+ * entries are host arrays of `layers` device pointers. */
+typedef struct {
+  const float* conv1_weight;         /* [W, 3, p, p] */
+  const float* class_embedding;      /* [W] */
+  const float* positional_embedding; /* [T, W] */
+  const float* ln_pre_weight;
+  const float* ln_pre_bias;
+  const float* ln_post_weight;
+  const float* ln_post_bias;
+  const float* proj;                         /* [W, out_dim] */
+  const float* const* ln_1_weight;           /* transformer.resblocks.{i}.ln_1.weight */
+  const float* const* ln_1_bias;
+  const float* const* attn_in_proj_weight;   /* [3W, W] */
+  const float* const* attn_in_proj_bias;     /* [3W] */
+  const float* const* attn_out_proj_weight;  /* [W, W] */
+  const float* const* attn_out_proj_bias;
+  const float* const* ln_2_weight;
+  const float* const* ln_2_bias;
+  const float* const* mlp_c_fc_weight;       /* [mlp, W] */
+  const float* const* mlp_c_fc_bias;
+  const float* const* mlp_c_proj_weight;     /* [W, mlp] */
+  const float* const* mlp_c_proj_bias;
+} rvlm_vit_weights;
+
+/* The attack loss on the embedding (ComputeLossWrapper / compute_loss,
+ * train/adversarial_training_clip.py:260-274,495-528) or on zero-shot logits
+ * (ClassificationModel, CLIP_eval/clip_robustbench.py:50-69 + CE,
+ * autoattack/autopgd_base.py:244). */
+#define RVLM_LOSS_L2 1 /* sum_d (emb - emb_orig)^2            (FARE)  */
+#define RVLM_LOSS_CE 2 /* CE(emb @ (logit_scale * text), y)   (TeCoA) */
+typedef struct {
+  int mode;
+  int output_normalize;     /* F.normalize(emb, dim=-1) before the loss */
+  int pred_on_logits;       /* pred = argmax(class logits)==y (1) or argmax(emb)==y (0) */
+  const float* emb_orig;    /* [B, out_dim]        (RVLM_LOSS_L2) */
+  const float* text;        /* [out_dim, n_classes] (RVLM_LOSS_CE) */
+  int n_classes;
+  float logit_scale;
+  const long long* targets; /* [B] int64, may be NULL for RVLM_LOSS_L2 */
+} rvlm_loss_config;
+
+#define RVLM_NORM_LINF 0
+#define RVLM_NORM_L2 2
+
+/* Converts the fp32 weights into the engine's own 16-bit operand copies (allocates
+ * device memory once, here; no allocation in any later call). */
+int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weights* weights, void* stream,
+                    rvlm_vit_handle* out);
+/* Re-read the weights (after an optimiser step of the outer training loop). */
+int rvlm_vit_update_weights(rvlm_vit_handle h, const rvlm_vit_weights* weights, void* stream);
+int rvlm_vit_destroy(rvlm_vit_handle h);
+/* Caller-owned scratch for a batch of B images; with_backward = 1 also holds the
+ * per-layer activations the input-gradient backward needs. */
+size_t rvlm_vit_workspace_bytes(rvlm_vit_handle h, int B, int with_backward);
+
+/* emb_out[B, out_dim] = model(x + delta) (delta may be NULL); x, delta: [B,3,H,W] in [0,1].
+ * keep_for_backward = 1 leaves the activations in the workspace (which must then be sized
+ * with_backward = 1) for a following rvlm_vit_backward_input on the same workspace. */
+int rvlm_vit_forward(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, const float* x,
+                     const float* delta, int B, int output_normalize, int keep_for_backward,
+                     float* emb_out, void* stream);
+/* grad_out[B,3,H,W] = (d emb / d x)^T d_emb for the forward just run with
+ * keep_for_backward = 1 (the vector-Jacobian product torch.autograd.grad(loss, x) needs for
+ * an arbitrary loss on the embedding; d_emb: [B, out_dim] w.r.t. the returned, possibly
+ * normalised, embedding).  Same per-sample positive-rescaling caveat as below when
+ * fmt_bwd is fp16. */
+int rvlm_vit_backward_input(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, int B,
+                            const float* d_emb, int output_normalize, float* grad_out,
+                            void* stream);
+/* Per-sample loss, pred flag, embedding / logits, and d(sum_b loss_b)/d(x+delta) as
+ * grad_out[B,3,H,W].  The gradient of each sample may be rescaled by a positive
+ * per-sample constant (every consumer on this path applies sign() or an ell_2
+ * normalisation per sample).  Outputs other than grad_out may be NULL. */
+int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, const float* x,
+                       const float* delta, int B, const rvlm_loss_config* loss, float* grad_out,
+                       float* loss_out, int* pred_out, float* emb_out, float* logits_out,
+                       int want_grad, void* stream);
+/* The whole pgd() call: x_adv_out = x + delta_final.  delta0 = initial perturbation
+ * (may be NULL = zeros).  loss_trace (may be NULL): [iterations, B] per-sample loss at
+ * each iteration's forward.  No host synchronisation inside. */
+int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, const float* x,
+                 const float* delta0, int B, const rvlm_loss_config* loss, int norm, float eps,
+                 float stepsize, int iterations, int maximize, float momentum, float* x_adv_out,
+                 float* loss_trace, void* stream);
+/* Test hook: pointer of an internal workspace buffer (see vit_engine.cu). */
+int rvlm_vit_debug_buffer(rvlm_vit_handle h, void* workspace, int B, int with_backward, int which,
+                          int layer, void** ptr_out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,342 @@
+"""Attack-side call surface of the reference, on CUDA kernels.
+
+  pgd                  train/pgd_train.py:5-68            (same signature)
+  apgd_train           train/apgd_train.py:125-373        (same signature)
+  APGDAttack           autoattack/autopgd_base.py:89-582  (same ctor / perturb / attack_single_run)
+  project_perturbation, normalize_grad   vlm_eval/attacks/utils.py:8-26
+
+Two execution paths behind each entry point, both on the GPU and both ending in the
+hand-written update kernels (there is no CPU / eager fallback -- CPU tensors raise):
+
+  fused    `forward` is a robustvlm_b200 ClipVisionModel around our VisionTransformer
+           and the loss is a ComputeLossWrapper with loss in {l2, ce} (the FARE / TeCoA
+           configurations): the whole model evaluation + loss + input gradient runs in
+           the C engine; for pgd the complete loop is one C call (rvlm_pgd_run) with
+           the delta-update fused into the last backward kernel.
+  generic  any differentiable `forward` / `loss_fn`: torch.autograd supplies the
+           gradient (through the engine's VJP when the tower is ours), the update,
+           projection, APGD step and bookkeeping run in the C kernels.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import _native as nat
+from ._native import c_float, c_int, c_int64
+from .engine import NORM_L2, NORM_LINF, LossSpec
+from .model import ClassificationModel, ClipVisionModel, ComputeLossWrapper, VisionTransformer
+
+LINF_NAMES = ("inf", "linf", "Linf")   # vlm_eval/attacks/utils.py:9
+L2_NAMES = (2, 2.0, "l2", "L2", "2")   # vlm_eval/attacks/utils.py:12
+
+
+def _norm_id(norm):
+    if norm in LINF_NAMES:
+        return NORM_LINF
+    if norm in L2_NAMES:
+        return NORM_L2
+    raise NotImplementedError(f"Norm {norm} not supported")
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise nat.RvlmError(f"{what} must be a CUDA tensor: robustvlm_b200 has no CPU path")
+
+
+def _flat_n(t):
+    return math.prod(t.shape[1:])
+
+
+def _upd_ws(B, device):
+    fn = nat.lib().rvlm_update_workspace_bytes
+    fn.restype = nat.c_size_t
+    return torch.empty(int(fn(c_int(B))), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------
+# primitives (kept for API parity; both are thin wrappers over the update kernels' math)
+# ----------------------------------------------------------------------------------------
+def project_perturbation(perturbation, eps, norm):
+    if _norm_id(norm) == NORM_LINF:
+        return torch.clamp(perturbation, -eps, eps)
+    return torch.renorm(perturbation, p=2, dim=0, maxnorm=eps)
+
+
+def normalize_grad(grad, p):
+    if _norm_id(p) == NORM_LINF:
+        return grad.sign()
+    return torch.nn.functional.normalize(grad.view(grad.shape[0], -1), p=2, dim=1).view_as(grad)
+
+
+def _fusable(forward, loss_fn):
+    return (isinstance(forward, ClipVisionModel) and isinstance(forward.model, VisionTransformer)
+            and isinstance(loss_fn, ComputeLossWrapper) and loss_fn.loss_str in ("l2", "ce"))
+
+
+def _loss_spec(loss_fn: ComputeLossWrapper, targets, output_normalize, pred_on_logits=False):
+    return LossSpec(loss_fn.loss_str, output_normalize, emb_orig=loss_fn.embedding_orig,
+                    text=loss_fn.embedding_text_labels_norm, logit_scale=loss_fn.logit_scale,
+                    targets=targets, pred_on_logits=pred_on_logits)
+
+
+# ----------------------------------------------------------------------------------------
+# PGD
+# ----------------------------------------------------------------------------------------
+def pgd(forward, loss_fn, data_clean, targets, norm, eps, iterations, stepsize, output_normalize,
+        perturbation=None, mode="min", momentum=0.9, verbose=False, chunk=None):
+    """Minimize or maximize the given loss (train/pgd_train.py:5-68); returns
+    data_clean + perturbation (detached)."""
+    _need_cuda(data_clean, "data_clean")
+    assert torch.max(data_clean) < 1.0 + 1e-6 and torch.min(data_clean) > -1e-6   # :24
+    if mode not in ("min", "max"):
+        raise ValueError(f"Unknown mode: {mode}")                                  # :54
+    nid = _norm_id(norm)
+    x = data_clean.detach().float().contiguous()
+    if _fusable(forward, loss_fn) and not verbose:
+        eng = forward.engine()
+        spec = _loss_spec(loss_fn, targets, output_normalize)
+        d0 = perturbation.detach().float().contiguous() if perturbation is not None else None
+        return eng.pgd_run(x, spec, norm=nid, eps=float(eps), stepsize=float(stepsize),
+                           iterations=int(iterations), maximize=(mode == "max"),
+                           momentum=float(momentum), delta0=d0, chunk=chunk)
+    # ---- generic path: autograd gradient + CUDA update kernels
+    B, n = x.shape[0], _flat_n(x)
+    delta = (torch.zeros_like(x) if perturbation is None
+             else perturbation.detach().float().clone().contiguous())
+    velocity = torch.zeros_like(x)                                                 # :28
+    ws = _upd_ws(B, x.device) if nid == NORM_L2 else None
+    for i in range(iterations):
+        delta.requires_grad_(True)
+        with torch.enable_grad():
+            out = forward(x + delta, output_normalize=output_normalize)            # :32
+            loss = loss_fn(out, targets)                                           # :33
+            if verbose:
+                print(f"[{i}] {loss.item():.5f}")
+        grad = torch.autograd.grad(loss, delta)[0].detach().float().contiguous()   # :38
+        delta = delta.detach()
+        if nid == NORM_LINF:
+            nat.call("rvlm_pgd_update_linf", nat.ptr(delta), nat.ptr(velocity), nat.ptr(grad),
+                     nat.ptr(x), c_int(B), c_int64(n), c_float(stepsize), c_float(eps),
+                     c_int(int(mode == "max")), c_float(momentum), nat.stream_ptr())
+        else:
+            nat.call("rvlm_pgd_update_l2", nat.ptr(delta), nat.ptr(velocity), nat.ptr(grad),
+                     nat.ptr(x), c_int(B), c_int64(n), c_float(stepsize), c_float(eps),
+                     c_int(int(mode == "max")), c_float(momentum), nat.ptr(ws), nat.stream_ptr())
+    out = torch.empty_like(x)
+    nat.call("rvlm_add_f32", nat.ptr(out), nat.ptr(x), nat.ptr(delta), c_int64(x.numel()),
+             nat.stream_ptr())
+    return out                                                                     # :68
+
+
+# ----------------------------------------------------------------------------------------
+# APGD core (device resident; the check-point schedule is data independent, so the host
+# never reads a device value inside the loop)
+# ----------------------------------------------------------------------------------------
+def apgd_schedule(n_iter):
+    """(k0, n_iter_min, size_decr): train/apgd_train.py:151-154 == autopgd_base.py:151-153"""
+    return (max(int(0.22 * n_iter), 1), max(int(0.06 * n_iter), 1), max(int(0.03 * n_iter), 1))
+
+
+def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_last_grad):
+    """fwd_bwd(x_adv, need_grad) -> (loss_indiv[B] f32, pred[B] int32, grad | None).
+    Returns (x_best, acc(bool), loss_best, x_best_adv)."""
+    B, n, dev = x.shape[0], _flat_n(x), x.device
+    x_adv = x_start.clamp(0.0, 1.0).contiguous()
+    x_best, x_best_adv = x_adv.clone(), x_adv.clone()
+    loss, pred, grad = fwd_bwd(x_adv, True)
+    grad = grad.contiguous()
+    grad_best = grad.clone()
+    acc = pred.to(torch.int32).clone()
+    loss_best = loss.clone()
+    loss_best_last = loss.clone()
+    reduced_last = torch.ones_like(loss)
+    step_size = torch.full((B,), float(alpha * eps), device=dev, dtype=torch.float32)
+    x_adv_old = x_adv.clone()
+    loss_steps = torch.zeros(n_iter, B, device=dev, dtype=torch.float32)
+    flags = torch.zeros(B, device=dev, dtype=torch.int32)
+    ws = _upd_ws(B, dev) if norm == "L2" else None
+    k, k_min, k_decr = apgd_schedule(n_iter)
+    counter3 = 0
+    for i in range(n_iter):
+        a = 0.75 if i > 0 else 1.0
+        if norm == "Linf":
+            nat.call("rvlm_apgd_step_linf", nat.ptr(x_adv), nat.ptr(x_adv_old), nat.ptr(x),
+                     nat.ptr(grad), nat.ptr(step_size), c_int(B), c_int64(n), c_float(eps),
+                     c_float(a), nat.stream_ptr())
+        else:
+            nat.call("rvlm_apgd_step_l2", nat.ptr(x_adv), nat.ptr(x_adv_old), nat.ptr(x),
+                     nat.ptr(grad), nat.ptr(step_size), c_int(B), c_int64(n), c_float(eps),
+                     c_float(a), nat.ptr(ws), nat.stream_ptr())
+        need_grad = not (skip_last_grad and i == n_iter - 1)
+        loss, pred, g_new = fwd_bwd(x_adv, need_grad)
+        if g_new is not None:
+            grad.copy_(g_new)
+        counter3 += 1
+        is_ck = counter3 == k
+        nat.call("rvlm_apgd_bookkeep", nat.ptr(x_adv), nat.ptr(grad), nat.ptr(x_best),
+                 nat.ptr(grad_best), nat.ptr(x_best_adv), nat.ptr(loss.contiguous()),
+                 nat.ptr(pred.to(torch.int32).contiguous()), nat.ptr(loss_steps),
+                 nat.ptr(loss_best), nat.ptr(loss_best_last), nat.ptr(reduced_last),
+                 nat.ptr(step_size), nat.ptr(acc), nat.ptr(flags), c_int(B), c_int64(n),
+                 c_int(n_iter), c_int(i), c_int(k if is_ck else 0), c_float(float(k * thr_decr)),
+                 nat.stream_ptr())
+        if is_ck:
+            counter3 = 0
+            k = max(k - k_decr, k_min)
+    return x_best, acc.bool(), loss_best, x_best_adv
+
+
+def _autograd_fwd_bwd(model_call, loss_call, y):
+    def fwd_bwd(x_adv, need_grad):
+        xa = x_adv.detach().clone().requires_grad_(need_grad)
+        with torch.enable_grad():
+            logits = model_call(xa)
+            loss_indiv = loss_call(logits, y)
+            g = (torch.autograd.grad(loss_indiv.sum(), [xa])[0].detach().float()
+                 if need_grad else None)
+        pred = (logits.detach().max(1)[1] == y).to(torch.int32)
+        return loss_indiv.detach().float(), pred, g
+    return fwd_bwd
+
+
+def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss_fn=None, verbose=False,
+               is_train=True, initial_stepsize=None):
+    """Training-time APGD (train/apgd_train.py:125-373); returns x_best_adv."""
+    assert not model.training                                                      # :127
+    norm = norm.replace("linf", "Linf").replace("l2", "L2")                        # :128
+    if use_rs:
+        raise NotImplementedError                                                  # :135
+    if norm not in ("Linf", "L2"):
+        raise NotImplementedError(f"norm {norm}: only Linf / L2 are built (SURVEY.md §8a)")
+    _need_cuda(x, "x")
+    x = x.detach().float().contiguous()
+    alpha = 2.0 if not initial_stepsize else initial_stepsize / eps                # :158,168
+    if _fusable(model, loss_fn):
+        eng = model.engine()
+        spec = _loss_spec(loss_fn, y, True)     # apgd_train always normalises (:181,288)
+
+        def fwd_bwd(x_adv, need_grad):
+            r = eng.loss_grad(x_adv, spec, want_grad=need_grad)
+            return r["loss"], r["pred"].to(torch.int32), r["grad"]
+    else:
+        fwd_bwd = _autograd_fwd_bwd(lambda xa: model(xa, output_normalize=True), loss_fn, y)
+    _, _, _, x_best_adv = _apgd_core(fwd_bwd, x, x.clone(), norm, float(eps), n_iter, alpha, 0.75,
+                                     skip_last_grad=True)
+    return x_best_adv                                                              # :373
+
+
+def dlr_loss(x, y):
+    """autoattack/autopgd_base.py:195-201"""
+    x_sorted, ind_sorted = x.sort(dim=1)
+    ind = (ind_sorted[:, -1] == y).float()
+    u = torch.arange(x.shape[0], device=x.device)
+    return -(x[u, y] - x_sorted[:, -2] * ind - x_sorted[:, -1] * (1.0 - ind)) / (
+        x_sorted[:, -1] - x_sorted[:, -3] + 1e-12)
+
+
+class APGDAttack:
+    """AutoPGD (autoattack/autopgd_base.py:89-582): ell_inf / ell_2, CE / DLR, restarts over
+    the still-robust points."""
+
+    def __init__(self, predict, n_iter=100, norm="Linf", n_restarts=1, eps=None, seed=0, loss="ce",
+                 eot_iter=1, rho=0.75, topk=None, verbose=False, device=None, use_largereps=False,
+                 is_tf_model=False, logger=None, alpha=None, use_rs=True):
+        assert norm in ("Linf", "L2", "L1") and eps is not None                    # :146-147
+        if norm == "L1" or use_largereps or is_tf_model:
+            raise NotImplementedError("only Linf / L2, PyTorch models (SURVEY.md §8a)")
+        self.model, self.n_iter, self.eps, self.norm = predict, n_iter, eps, norm
+        self.n_restarts, self.seed, self.loss, self.eot_iter = n_restarts, seed, loss, eot_iter
+        self.thr_decr, self.topk, self.verbose, self.device = rho, topk, verbose, device
+        self.use_rs, self.use_largereps, self.alpha, self.logger = use_rs, False, alpha, logger
+        self.n_iter_orig, self.eps_orig, self.y_target = n_iter, eps, None
+
+    def normalize(self, x):
+        """:180-193"""
+        if self.norm == "Linf":
+            t = x.abs().view(x.shape[0], -1).max(1)[0]
+        else:
+            t = (x ** 2).view(x.shape[0], -1).sum(-1).sqrt()
+        return x / (t.view(-1, *([1] * (x.dim() - 1))) + 1e-12)
+
+    def _fwd_bwd(self, y):
+        m = self.model
+        if (self.loss == "ce" and self.eot_iter == 1 and isinstance(m, ClassificationModel)
+                and isinstance(m.visual.model, VisionTransformer)):
+            eng = m.visual.engine()
+            spec = LossSpec("ce", True, text=m.text_embedding, logit_scale=m.logit_scale_value,
+                            targets=y, pred_on_logits=True)
+
+            def fused(x_adv, need_grad):
+                r = eng.loss_grad(x_adv, spec, want_grad=need_grad)
+                return r["loss"], r["pred"].to(torch.int32), r["grad"]
+            return fused
+        if self.loss == "ce":
+            crit = torch.nn.CrossEntropyLoss(reduction="none")                     # :244
+        elif self.loss == "dlr":
+            crit = dlr_loss
+        else:
+            raise ValueError("unknowkn loss")
+        base = _autograd_fwd_bwd(m, crit, y)
+        if self.eot_iter == 1:
+            return base
+
+        def eot(x_adv, need_grad):                                                 # :267-286
+            acc_g, out = None, None
+            for _ in range(self.eot_iter):
+                out = base(x_adv, need_grad)
+                if need_grad:
+                    acc_g = out[2] if acc_g is None else acc_g + out[2]
+            return out[0], out[1], (acc_g / float(self.eot_iter) if need_grad else None)
+        return eot
+
+    def attack_single_run(self, x, y, x_init=None):
+        """:205-451 -> (x_best, acc, loss_best, x_best_adv)"""
+        _need_cuda(x, "x")
+        x = x.detach().float().contiguous()
+        if self.use_rs:                                                            # :210-218
+            if self.norm == "Linf":
+                t = 2 * torch.rand(x.shape).to(x.device).detach() - 1               # CPU RNG
+            else:
+                t = torch.randn(x.shape).to(x.device).detach()
+            x_adv = x + self.eps * torch.ones_like(x).detach() * self.normalize(t)
+        else:
+            x_adv = x.clone()
+        if x_init is not None:
+            x_adv = x_init.clone()
+        alpha = 2.0 if self.alpha is None else self.alpha                          # :295-299
+        return _apgd_core(self._fwd_bwd(y), x, x_adv, self.norm, float(self.eps), self.n_iter,
+                          alpha, self.thr_decr, skip_last_grad=False)
+
+    def perturb(self, x, y=None, best_loss=False, x_init=None):
+        """:453-548"""
+        assert self.loss in ("ce", "dlr")
+        _need_cuda(x, "x")
+        if self.device is None:
+            self.device = x.device
+        x = x.detach().clone().float().to(self.device)
+        with torch.no_grad():
+            y_pred = self.model(x).max(1)[1]                                       # :469
+        y = y_pred.detach().clone().long() if y is None else y.detach().clone().long().to(self.device)
+        adv = x.clone()
+        acc = y_pred == y                                                          # :480
+        if best_loss:
+            adv_best = x.detach().clone()
+            loss_best = torch.full((x.shape[0],), -float("inf"), device=self.device)
+            for _ in range(self.n_restarts):
+                best_curr, _, loss_curr, _ = self.attack_single_run(x, y)
+                m = loss_curr > loss_best
+                adv_best[m] = best_curr[m]
+                loss_best[m] = loss_curr[m]
+            return adv_best
+        torch.random.manual_seed(self.seed)                                        # :505
+        for _ in range(self.n_restarts):                                           # :508
+            idx = acc.nonzero().flatten()          # the one host sync per restart (as :509)
+            if idx.numel() == 0:
+                continue
+            _, acc_curr, _, adv_curr = self.attack_single_run(x[idx].clone(), y[idx].clone())
+            fooled = (acc_curr == 0).nonzero().flatten()
+            acc[idx[fooled]] = False                                               # :521-525
+            adv[idx[fooled]] = adv_curr[fooled].clone()
+        return adv

@@ -1,0 +1,538 @@
+// tcgen05 multi-head attention for the CLIP ViT (head dim 64, T <= 272 tokens, no
+// mask): forward and the input-gradient backward (nn.MultiheadAttention inside
+// open_clip's ResidualAttentionBlock; reached from
+// train/pgd_train.py:32,38 through ClipVisionModel.forward).
+//
+// One skeleton, three modes.  Per work item (image b, head h) a persistent CTA runs,
+// for each 128-row tile:
+//
+//   FWD  : S = Q_i K^T            -> P = softmax rows (fp32, exp2)      -> O_i  = P V
+//   DQ   : S = Q_i K^T            -> P = exp(S/8 - lse_i)
+//          dP = dO_i V^T          -> dS = P (dP - D_i) / 8              -> dQ_i = dS K
+//   DKV  : S^T = K_j Q^T          -> P^T = exp(S^T/8 - lse)             -> dV_j = P^T dO
+//          dP^T = V_j dO^T        -> dS^T = P^T (dP^T - D) / 8          -> dK_j = dS^T Q
+//
+// "mma1" is a [128 x kvp] product of two K-major operands (kvp = T rounded up to 16,
+// the full token range is one UMMA N extent, 256 + 16 for T = 257); its fp32 result
+// lives in TMEM, one row per thread of the four worker warps, so the row softmax needs
+// no cross-thread reduction.  The 16-bit P / dS tile is written by those threads
+// straight into 128B-swizzled shared memory as the K-major A operand of "mma2", whose
+// B operand (V, K, dO or Q: [tokens, 64] row-major) is consumed MN-major, so nothing is
+// ever transposed in memory.  TMA loads everything (3-D tensor maps over [B, T, cols] so
+// rows beyond T are zero-filled per image).
+//
+// Warp roles: warps 0-3 = row workers (TMEM lane == tile row), warp 4 = TMEM allocator
+// and, lane 0, the TMA + MMA issuer.
+#include "gemm.cuh"
+#include "../../include/rvlm.h"
+
+namespace rvlm {
+
+constexpr int AT_THREADS = 160;
+enum { AT_FWD = 0, AT_DQ = 1, AT_DKV = 2 };
+constexpr uint32_t AT_TMEM_S = 0, AT_TMEM_ACC = 320, AT_TMEM_ACC2 = 384;
+
+struct AttnParams {
+  int B, T, H, W;
+  int kvp, nblk, ntile, nbox, boxrows;
+  int fmt, fmt_g;
+  const uint16_t* o;     // [B*T, W]   (DQ / DKV: forward output, for D = rowsum(dO * O))
+  const uint16_t* d_o;   // [B*T, W]
+  const float* lse;      // [B, H, T]  (DQ / DKV)
+  uint16_t* o_out;       // FWD
+  float* lse_out;        // FWD
+  uint16_t* dqkv;        // [B*T, 3W]  (DQ / DKV)
+};
+
+__host__ __device__ constexpr uint32_t idesc_ab(uint32_t afmt, uint32_t bfmt, uint32_t M,
+                                                uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (a_mn << 15) | (b_mn << 16) |
+         ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[128 x kvp] = A[128 x 64] * B[kvp x 64]^T, both K-major
+__device__ __forceinline__ void issue_mma1(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr,
+                                           int kvp, uint32_t afmt, uint32_t bfmt) {
+  const int n0 = kvp > 256 ? 256 : kvp;
+  const uint32_t id0 = idesc_ab(afmt, bfmt, 128, n0, 0, 0);
+  const uint32_t id1 = idesc_ab(afmt, bfmt, 128, kvp - n0, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+    umma_f16(tmem_d, ad, make_smem_desc_sw128(b_addr + k * 32, 16, 1024), id0, k > 0);
+    if (kvp > 256)
+      umma_f16(tmem_d + 256, ad, make_smem_desc_sw128(b_addr + 256 * 128 + k * 32, 16, 1024), id1,
+               k > 0);
+  }
+}
+
+// D[128 x 64] = A[128 x kvp] (K-major, 64-wide 16 KB blocks) * B[kvp x 64] (MN-major)
+__device__ __forceinline__ void issue_mma2(uint32_t tmem_d, uint32_t p_addr, uint32_t b_addr,
+                                           int kvp, uint32_t afmt, uint32_t bfmt) {
+  const uint32_t id = idesc_ab(afmt, bfmt, 128, 64, 0, 1);
+  const int steps = kvp >> 4;
+  for (int s = 0; s < steps; ++s) {
+    const uint64_t ad =
+        make_smem_desc_sw128(p_addr + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024);
+    const uint64_t bd = make_smem_desc_sw128(b_addr + s * 2048, 8192, 1024);
+    umma_f16(tmem_d, ad, bd, id, s > 0);
+  }
+}
+
+// byte offset of 8 consecutive 16-bit elements (row r, columns c0..c0+7, c0 % 8 == 0) in
+// the K-major 128B-swizzled block layout
+__device__ __forceinline__ uint32_t p_off(int r, int c0) {
+  return (uint32_t)((c0 >> 6) * 16384 + r * 128 + ((((c0 & 63) >> 3) ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ float dot_rows16(const uint16_t* a, int fa, const uint16_t* b, int fb) {
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 ua = reinterpret_cast<const uint4*>(a)[j];
+    const uint4 ub = reinterpret_cast<const uint4*>(b)[j];
+    const uint32_t* pa = &ua.x;
+    const uint32_t* pb = &ub.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack2(pa[i], fa), y = unpack2(pb[i], fb);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  return acc;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
+               const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x boxrows
+               const __grid_constant__ CUtensorMap tmDoTile, // dO,  box 64 x 128
+               const __grid_constant__ CUtensorMap tmDoFull, // dO,  box 64 x boxrows
+               AttnParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int kvp = P.kvp, T = P.T, W = P.W;
+  const int full_bytes = kvp * 128;
+  uint8_t* s_full0 = smem;
+  uint8_t* s_full1 = s_full0 + full_bytes;
+  uint8_t* s_tile0 = s_full1 + full_bytes;  // [2][16384]
+  uint8_t* s_tile1 = s_tile0 + 2 * 16384;   // [2][16384]
+  uint8_t* s_p = s_tile1 + 2 * 16384;       // [nblk][16384]
+  float* s_lse = reinterpret_cast<float*>(s_p + P.nblk * 16384);  // [kvp] (DKV)
+  float* s_dvec = s_lse + kvp;                                    // [kvp] (DKV)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dvec + kvp);
+  uint64_t* bar_full = bars + 0;     // full0 + full1 landed
+  uint64_t* bar_tile = bars + 1;     // [2]
+  uint64_t* bar_s = bars + 3;        // mma1 result ready
+  uint64_t* bar_p = bars + 4;        // P / dS written (128 arrivals)
+  uint64_t* bar_acc = bars + 5;      // mma2 result(s) ready
+  uint64_t* bar_acc_free = bars + 6; // accumulators drained (128 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(&bar_tile[0], 1);
+    mbar_init(&bar_tile[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = P.B * P.H;
+  const uint32_t f = (uint32_t)P.fmt, fg = (uint32_t)P.fmt_g;
+  // column offsets (elements) of q / k / v inside a qkv row
+  const int colQ = 0, colK = W, colV = 2 * W;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issuer =====================
+      uint32_t g = 0;  // global tile counter
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int b = item / P.H, h = item % P.H;
+        if (it > 0) mbar_wait(bar_acc, (g - 1) & 1, 10);  // every MMA of the previous item retired
+        mbar_arrive_expect_tx(bar_full, 2 * full_bytes);
+        for (int i = 0; i < P.nbox; ++i) {
+          const int r0 = i * P.boxrows;
+          if (MODE == AT_DKV) {
+            tma_load_3d(s_full0 + r0 * 128, &tmFull, bar_full, colQ + h * 64, r0, b);
+            tma_load_3d(s_full1 + r0 * 128, &tmDoFull, bar_full, h * 64, r0, b);
+          } else {
+            tma_load_3d(s_full0 + r0 * 128, &tmFull, bar_full, colK + h * 64, r0, b);
+            tma_load_3d(s_full1 + r0 * 128, &tmFull, bar_full, colV + h * 64, r0, b);
+          }
+        }
+        auto load_tile = [&](int j, uint32_t gg) {
+          const int buf = gg & 1;
+          mbar_arrive_expect_tx(&bar_tile[buf], MODE == AT_FWD ? 16384 : 32768);
+          if (MODE == AT_DKV) {
+            tma_load_3d(s_tile0 + buf * 16384, &tmTile, &bar_tile[buf], colK + h * 64, j * 128, b);
+            tma_load_3d(s_tile1 + buf * 16384, &tmTile, &bar_tile[buf], colV + h * 64, j * 128, b);
+          } else {
+            tma_load_3d(s_tile0 + buf * 16384, &tmTile, &bar_tile[buf], colQ + h * 64, j * 128, b);
+            if (MODE == AT_DQ)
+              tma_load_3d(s_tile1 + buf * 16384, &tmDoTile, &bar_tile[buf], h * 64, j * 128, b);
+          }
+        };
+        load_tile(0, g);
+        mbar_wait(bar_full, it & 1, 11);
+        for (int j = 0; j < P.ntile; ++j, ++g) {
+          const int buf = g & 1;
+          if (j + 1 < P.ntile) load_tile(j + 1, g + 1);
+          mbar_wait(&bar_tile[buf], (g >> 1) & 1, 12);
+          tc_fence_after();
+          const uint32_t t0 = smem_u32(s_tile0 + buf * 16384);
+          const uint32_t t1 = smem_u32(s_tile1 + buf * 16384);
+          const uint32_t f0 = smem_u32(s_full0), f1 = smem_u32(s_full1), pa = smem_u32(s_p);
+          if (MODE == AT_FWD) {
+            issue_mma1(tmem + AT_TMEM_S, t0, f0, kvp, f, f);          // S = Q K^T
+            umma_commit(bar_s);
+            mbar_wait(bar_p, g & 1, 13);
+            tc_fence_after();
+            if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 14);
+            tc_fence_after();
+            issue_mma2(tmem + AT_TMEM_ACC, pa, f1, kvp, f, f);        // O = P V
+            umma_commit(bar_acc);
+          } else if (MODE == AT_DQ) {
+            issue_mma1(tmem + AT_TMEM_S, t0, f0, kvp, f, f);          // S = Q K^T
+            umma_commit(bar_s);
+            mbar_wait(bar_p, (2 * g) & 1, 13);
+            tc_fence_after();
+            issue_mma1(tmem + AT_TMEM_S, t1, f1, kvp, fg, f);         // dP = dO V^T
+            umma_commit(bar_s);
+            mbar_wait(bar_p, (2 * g + 1) & 1, 15);
+            tc_fence_after();
+            if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 14);
+            tc_fence_after();
+            issue_mma2(tmem + AT_TMEM_ACC, pa, f0, kvp, fg, f);       // dQ = dS K
+            umma_commit(bar_acc);
+          } else {
+            issue_mma1(tmem + AT_TMEM_S, t0, f0, kvp, f, f);          // S^T = K Q^T
+            umma_commit(bar_s);
+            mbar_wait(bar_p, (2 * g) & 1, 13);
+            tc_fence_after();
+            if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 14);
+            tc_fence_after();
+            issue_mma2(tmem + AT_TMEM_ACC, pa, f1, kvp, f, fg);       // dV = P^T dO
+            issue_mma1(tmem + AT_TMEM_S, t1, f1, kvp, f, fg);         // dP^T = V dO^T
+            umma_commit(bar_s);                                       // (also: dV retired)
+            mbar_wait(bar_p, (2 * g + 1) & 1, 15);
+            tc_fence_after();
+            issue_mma2(tmem + AT_TMEM_ACC2, pa, f0, kvp, fg, f);      // dK = dS^T Q
+            umma_commit(bar_acc);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== row workers =====================
+    const int r = threadIdx.x;  // tile row == TMEM lane
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const float c2 = 0.125f * 1.4426950408889634f;  // scale * log2(e)
+    const int n32 = kvp >> 5, rem16 = (kvp & 31) >> 4;
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int b = item / P.H, h = item % P.H;
+      if (MODE == AT_DKV) {
+        // per-token lse and D = rowsum(dO * O) for all q of this (b, h)
+        for (int q = r; q < kvp; q += 128) {
+          float L = INFINITY, Dv = 0.f;
+          if (q < T) {
+            L = P.lse[((size_t)b * P.H + h) * T + q] * 1.4426950408889634f;
+            const size_t ro = ((size_t)b * T + q) * W + h * 64;
+            Dv = dot_rows16(P.o + ro, P.fmt, P.d_o + ro, P.fmt_g);
+          }
+          s_lse[q] = L;
+          s_dvec[q] = Dv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      for (int j = 0; j < P.ntile; ++j, ++g) {
+        const int row = j * 128 + r;        // q row (FWD/DQ) or kv row (DKV) inside the image
+        const bool valid = row < T;
+        const bool warp_valid = (j * 128 + warp * 32) < T;
+        const size_t grow = (size_t)b * T + row;
+        if (MODE == AT_FWD) {
+          mbar_wait(bar_s, g & 1, 20);
+          tc_fence_after();
+          float mx = -INFINITY, sum = 0.f;
+          if (warp_valid) {
+            for (int c = 0; c < n32 + rem16; ++c) {
+              uint32_t v[32];
+              const int nv = c < n32 ? 32 : 16;
+              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
+              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nv && c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float mc = mx * c2;
+            for (int c = 0; c < n32 + rem16; ++c) {
+              uint32_t v[32];
+              const int nv = c < n32 ? 32 : 16;
+              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
+              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+              tmem_ld_wait();
+              float p[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                p[i] = (i < nv && c * 32 + i < T) ? exp2f(__uint_as_float(v[i]) * c2 - mc) : 0.f;
+                sum += p[i];
+              }
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                if (q8 * 8 < nv) {
+                  uint4 u;
+                  u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
+                  u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
+                  u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
+                  u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
+                  *reinterpret_cast<uint4*>(s_p + p_off(r, c * 32 + q8 * 8)) = u;
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_p);
+          mbar_wait(bar_acc, g & 1, 21);
+          tc_fence_after();
+          if (warp_valid) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(tmem + lane_off + AT_TMEM_ACC, v0);
+            tmem_ld32(tmem + lane_off + AT_TMEM_ACC + 32, v1);
+            tmem_ld_wait();
+            if (valid) {
+              const float inv = 1.f / sum;
+              uint4* dst = reinterpret_cast<uint4*>(P.o_out + grow * W + h * 64);
+#pragma unroll
+              for (int q8 = 0; q8 < 8; ++q8) {
+                const uint32_t* s = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+                uint4 u;
+                u.x = pack2(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv, P.fmt);
+                u.y = pack2(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv, P.fmt);
+                u.z = pack2(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv, P.fmt);
+                u.w = pack2(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv, P.fmt);
+                dst[q8] = u;
+              }
+              P.lse_out[((size_t)b * P.H + h) * T + row] = mx * 0.125f + logf(sum);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_acc_free);
+        } else {
+          // ---------------- backward modes ----------------
+          float Lr = 0.f, Dr = 0.f;  // DQ: this row's lse (log2 units) and D
+          if (MODE == AT_DQ && valid) {
+            Lr = P.lse[((size_t)b * P.H + h) * T + row] * 1.4426950408889634f;
+            Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt, P.d_o + grow * W + h * 64, P.fmt_g);
+          }
+          // pass 1: P = exp(S/8 - lse)
+          mbar_wait(bar_s, (2 * g) & 1, 22);
+          tc_fence_after();
+          if (warp_valid) {
+            for (int c = 0; c < n32 + rem16; ++c) {
+              uint32_t v[32];
+              const int nv = c < n32 ? 32 : 16;
+              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
+              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+              tmem_ld_wait();
+              float p[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (i < nv) {
+                  const float L = (MODE == AT_DQ) ? Lr : s_lse[c * 32 + i];
+                  const bool colv = (MODE == AT_DQ) ? (c * 32 + i < T) : true;
+                  p[i] = (colv && valid) ? exp2f(__uint_as_float(v[i]) * c2 - L) : 0.f;
+                } else {
+                  p[i] = 0.f;
+                }
+              }
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                if (q8 * 8 < nv) {
+                  uint4 u;
+                  u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
+                  u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
+                  u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
+                  u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
+                  *reinterpret_cast<uint4*>(s_p + p_off(r, c * 32 + q8 * 8)) = u;
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_p);
+          // pass 2: dS = P (dP - D) / 8, in place over P
+          mbar_wait(bar_s, (2 * g + 1) & 1, 23);
+          tc_fence_after();
+          if (warp_valid) {
+            for (int c = 0; c < n32 + rem16; ++c) {
+              uint32_t v[32];
+              const int nv = c < n32 ? 32 : 16;
+              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
+              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+              tmem_ld_wait();
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                if (q8 * 8 < nv) {
+                  uint4* sp = reinterpret_cast<uint4*>(s_p + p_off(r, c * 32 + q8 * 8));
+                  const uint4 pu = *sp;
+                  const uint32_t* pw = &pu.x;
+                  float d[8];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 pp = unpack2(pw[i], P.fmt);
+                    const int col = c * 32 + q8 * 8 + 2 * i;
+                    const float D0 = (MODE == AT_DQ) ? Dr : s_dvec[col];
+                    const float D1 = (MODE == AT_DQ) ? Dr : s_dvec[col + 1];
+                    d[2 * i] = pp.x * (__uint_as_float(v[q8 * 8 + 2 * i]) - D0) * 0.125f;
+                    d[2 * i + 1] = pp.y * (__uint_as_float(v[q8 * 8 + 2 * i + 1]) - D1) * 0.125f;
+                  }
+                  uint4 u;
+                  u.x = pack2(d[0], d[1], P.fmt_g);
+                  u.y = pack2(d[2], d[3], P.fmt_g);
+                  u.z = pack2(d[4], d[5], P.fmt_g);
+                  u.w = pack2(d[6], d[7], P.fmt_g);
+                  *sp = u;
+                }
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_p);
+          // epilogue
+          mbar_wait(bar_acc, g & 1, 24);
+          tc_fence_after();
+          if (warp_valid) {
+            const int nacc = (MODE == AT_DKV) ? 2 : 1;
+            for (int a = 0; a < nacc; ++a) {
+              uint32_t v0[32], v1[32];
+              const uint32_t col = (a == 0) ? AT_TMEM_ACC : AT_TMEM_ACC2;
+              tmem_ld32(tmem + lane_off + col, v0);
+              tmem_ld32(tmem + lane_off + col + 32, v1);
+              tmem_ld_wait();
+              if (valid) {
+                // DQ: dQ at column 0; DKV: a == 0 -> dV (2W), a == 1 -> dK (W)
+                const int cofs = (MODE == AT_DQ) ? 0 : (a == 0 ? 2 * W : W);
+                uint4* dst = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + cofs + h * 64);
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) {
+                  const uint32_t* s = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+                  uint4 u;
+                  u.x = pack2(__uint_as_float(s[0]), __uint_as_float(s[1]), P.fmt_g);
+                  u.y = pack2(__uint_as_float(s[2]), __uint_as_float(s[3]), P.fmt_g);
+                  u.z = pack2(__uint_as_float(s[4]), __uint_as_float(s[5]), P.fmt_g);
+                  u.w = pack2(__uint_as_float(s[6]), __uint_as_float(s[7]), P.fmt_g);
+                  dst[q8] = u;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar_acc_free);
+        }
+      }
+      if (MODE == AT_DKV) asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+struct AttnPlan {
+  AttnParams P;
+  size_t smem;
+  CUtensorMap tmTile, tmFull, tmDoTile, tmDoFull;
+};
+
+static int make_plan(AttnPlan& pl, const void* qkv, const void* d_o, int B, int T, int H, int fmt,
+                     int fmt_g) {
+  if (B <= 0 || T <= 0 || T > 272 || H <= 0) return RVLM_ERR_UNSUPPORTED;
+  AttnParams& P = pl.P;
+  P.B = B; P.T = T; P.H = H; P.W = H * 64;
+  P.kvp = (T + 15) / 16 * 16;
+  P.nblk = (P.kvp + 63) / 64;
+  P.ntile = (T + 127) / 128;
+  P.nbox = P.kvp > 256 ? 2 : 1;
+  P.boxrows = P.kvp / P.nbox;
+  P.fmt = fmt; P.fmt_g = fmt_g;
+  pl.smem = (size_t)2 * P.kvp * 128 + 4 * 16384 + (size_t)P.nblk * 16384 + (size_t)2 * P.kvp * 4 +
+            128 + 1024;
+  const uint64_t W3 = 3ull * P.W;
+  int rc = make_tmap_3d(&pl.tmTile, qkv, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&pl.tmFull, qkv, W3, T, B, W3, (uint64_t)T * W3, 64, P.boxrows);
+  if (rc) return rc;
+  const void* dptr = d_o ? d_o : qkv;  // unused maps still need a valid encoding
+  const uint64_t Wd = d_o ? (uint64_t)P.W : W3;
+  rc = make_tmap_3d(&pl.tmDoTile, dptr, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);
+  if (rc) return rc;
+  return make_tmap_3d(&pl.tmDoFull, dptr, Wd, T, B, Wd, (uint64_t)T * Wd, 64, P.boxrows);
+}
+
+template <int MODE>
+static int launch_attn(const AttnPlan& pl, cudaStream_t st) {
+  auto kern = attn_tc_kernel<MODE>;
+  static size_t set = 0;
+  if (pl.smem > set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pl.smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    set = pl.smem;
+  }
+  int grid = sm_count();
+  if (pl.P.B * pl.P.H < grid) grid = pl.P.B * pl.P.H;
+  kern<<<grid, AT_THREADS, pl.smem, st>>>(pl.tmTile, pl.tmFull, pl.tmDoTile, pl.tmDoFull, pl.P);
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+}  // namespace rvlm
+
+using namespace rvlm;
+
+extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H,
+                             int fmt, void* stream) {
+  AttnPlan pl{};
+  int rc = make_plan(pl, qkv16, nullptr, B, T, H, fmt, fmt);
+  if (rc) return rc;
+  pl.P.o_out = reinterpret_cast<uint16_t*>(o16);
+  pl.P.lse_out = lse;
+  return launch_attn<AT_FWD>(pl, (cudaStream_t)stream);
+}
+
+extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16,
+                             const float* lse, void* dqkv16, int B, int T, int H, int fmt,
+                             int fmt_g, void* stream) {
+  AttnPlan pl{};
+  int rc = make_plan(pl, qkv16, do16, B, T, H, fmt, fmt_g);
+  if (rc) return rc;
+  pl.P.o = reinterpret_cast<const uint16_t*>(o16);
+  pl.P.d_o = reinterpret_cast<const uint16_t*>(do16);
+  pl.P.lse = lse;
+  pl.P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
+  rc = launch_attn<AT_DQ>(pl, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_attn<AT_DKV>(pl, (cudaStream_t)stream);
+}

@@ -1,0 +1,154 @@
+// Internal (non-ABI) declarations shared between the engine and its kernels.
+#pragma once
+#include "ptx.cuh"
+
+namespace rvlm {
+
+// ---- head.cu -------------------------------------------------------------
+struct HeadArgs {
+  const float* xL;        // [B*T, W]
+  int T, W, D, C;
+  const float* ln_g;
+  const float* ln_b;
+  const float* proj;      // [W, D]
+  int mode;               // 0 none, 1 l2 (FARE), 2 ce (TeCoA / zero-shot classifier),
+                          // 3 external d(loss)/d(emb) passed in emb_orig
+  int normalize;          // F.normalize(emb) before the loss / output
+  int pred_on_logits;     // 1: pred from class logits, 0: from the embedding
+  const float* emb_orig;  // [B, D]      (mode 1)
+  const float* text;      // [D, C]      (mode 2)
+  float logit_scale;
+  const long long* y;     // [B]         (may be null -> pred = 0)
+  float* emb_out;         // [B, D]      (may be null)
+  float* logits_out;      // [B, C]      (may be null)
+  float* loss;            // [B]         (may be null)
+  int* pred;              // [B]         (may be null)
+  float* dx32;            // [B*T, W]    (may be null -> no backward)
+  uint16_t* dx16;         // [B*T, W]    (may be null)
+  int fmt_g;
+  float grad_scale;       // multiplies d loss_b / d emb
+  int grad_unit;          // 1: rescale each sample's CLS-row gradient to unit max-abs
+};
+int launch_head(const HeadArgs& A, int B, cudaStream_t st);
+
+// ---- patch.cu ------------------------------------------------------------
+struct PatchGeom {
+  int image, patch, grid, np, kp;  // np = grid*grid patches / image, kp = 3*patch*patch
+  float mean[3], inv_std[3];
+};
+// NCHW fp32 image batch <-> patch-major [B*np, kp] fp32
+int launch_patchify(const float* img, float* pm, int B, const PatchGeom& g, cudaStream_t st);
+int launch_unpatchify(const float* pm, float* img, int B, const PatchGeom& g, cudaStream_t st);
+// A16[r, k] = 16-bit((x[r,k] + delta[r,k] - mean_c) / std_c); delta may be null
+int launch_patch_operand(const float* xp, const float* dp, uint16_t* a16, int lda, long long rows,
+                         const PatchGeom& g, int fmt, cudaStream_t st);
+// tok[b, 0, :] = cls + pos[0]
+int launch_cls_rows(float* tok, const float* cls, const float* pos, int B, int T, int W,
+                    cudaStream_t st);
+// out = x + delta (patch-major) written as NCHW image
+int launch_unpatchify_add(const float* xp, const float* dp, float* img, int B, const PatchGeom& g,
+                          cudaStream_t st);
+
+// GEMM epilogue: patch-embedding forward.  Row r = b*np + p  ->  token row b*T + 1 + p.
+struct EpiPatchFwd {
+  float* tok;        // [B*T, W]
+  const float* pos;  // [T, W]
+  int np, T, W;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
+    const int b = row / np, p = row - b * np;
+    float4* d = reinterpret_cast<float4*>(tok + ((size_t)b * T + 1 + p) * W + col0);
+    const float4* ps = reinterpret_cast<const float4*>(pos + (size_t)(1 + p) * W + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 q = __ldg(ps + j);
+      float4 o;
+      o.x = acc[4 * j + 0] + q.x; o.y = acc[4 * j + 1] + q.y;
+      o.z = acc[4 * j + 2] + q.z; o.w = acc[4 * j + 3] + q.w;
+      d[j] = o;
+    }
+  }
+};
+
+// GEMM epilogue: patch-embedding dgrad -> input gradient in patch-major layout,
+// G[r, k] = acc / std_c  (chain rule through Normalize, train/adversarial_training_clip.py:254)
+struct EpiPatchGrad {
+  float* G;  // [rows, kp]
+  int kp, pp;  // pp = patch*patch
+  float inv_std[3];
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
+    float* g = G + (size_t)row * kp + col0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = col0 + 4 * j;
+      if (k < kp) {  // kp % 4 == 0
+        float4 o;
+        o.x = acc[4 * j + 0] * inv_std[(k + 0) / pp];
+        o.y = acc[4 * j + 1] * inv_std[(k + 1) / pp];
+        o.z = acc[4 * j + 2] * inv_std[(k + 2) / pp];
+        o.w = acc[4 * j + 3] * inv_std[(k + 3) / pp];
+        reinterpret_cast<float4*>(g)[j] = o;
+      }
+    }
+  }
+};
+
+// GEMM epilogue: patch-embedding dgrad with the ell_inf PGD update fused in
+// (train/pgd_train.py:37-59): NaN scrub, sign, momentum, +-stepsize, clamp(+-eps),
+// delta = clamp(x+delta,0,1)-x, and the next iteration's normalised 16-bit GEMM operand,
+// so no separate elementwise kernel runs per PGD step.  sign(acc / std) == sign(acc).
+struct EpiPatchPgdLinf {
+  const float* xp;   // [rows, kp]
+  float* dp;         // [rows, kp] delta (in place)
+  float* vp;         // [rows, kp] velocity (in place)
+  uint16_t* a16;     // [rows, lda] next forward operand
+  int kp, pp, lda, fmt;
+  float stepsize, eps, dir, momentum;
+  float mean[3], inv_std[3];
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
+    const size_t off = (size_t)row * kp + col0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = col0 + 4 * j;
+      if (k >= kp) break;
+      const float4 x4 = *reinterpret_cast<const float4*>(xp + off + 4 * j);
+      float4 d4 = *reinterpret_cast<float4*>(dp + off + 4 * j);
+      float4 v4 = *reinterpret_cast<float4*>(vp + off + 4 * j);
+      const float* xx = &x4.x;
+      float* dd = &d4.x;
+      float* vv = &v4.x;
+      float nx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float g = acc[4 * j + i];
+        if (g != g) g = 0.f;
+        const float gs = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+        const float m = __fadd_rn(__fmul_rn(momentum, vv[i]), gs);
+        const float vn = (m > 0.f) ? 1.f : ((m < 0.f) ? -1.f : 0.f);
+        float dn = __fadd_rn(dd[i], __fmul_rn(__fmul_rn(stepsize, vn), dir));
+        dn = fminf(fmaxf(dn, -eps), eps);
+        const float xa = fminf(fmaxf(__fadd_rn(xx[i], dn), 0.f), 1.f);
+        dd[i] = __fsub_rn(xa, xx[i]);
+        vv[i] = vn;
+        const int c = (k + i) / pp;
+        nx[i] = (__fadd_rn(xx[i], dd[i]) - mean[c]) * inv_std[c];
+      }
+      *reinterpret_cast<float4*>(dp + off + 4 * j) = d4;
+      *reinterpret_cast<float4*>(vp + off + 4 * j) = v4;
+      uint2 pk;
+      pk.x = pack2(nx[0], nx[1], fmt);
+      pk.y = pack2(nx[2], nx[3], fmt);
+      *reinterpret_cast<uint2*>(a16 + (size_t)row * lda + k) = pk;
+    }
+  }
+};
+
+// ---- misc elementwise (convert.cu) ----------------------------------------
+int launch_convert16(const float* src, uint16_t* dst, long long n, int fmt, cudaStream_t st);
+// dst[c, r] (pitch ldd) = 16-bit(src[r, c]) for src [R, C] row-major
+int launch_transpose_convert16(const float* src, uint16_t* dst, int R, int C, int ldd, int fmt,
+                               cudaStream_t st);
+// dst[r, c] (pitch ldd >= C) = 16-bit(src[r, c]); pad columns untouched
+int launch_convert16_pitched(const float* src, uint16_t* dst, int R, int C, int ldd, int fmt,
+                             cudaStream_t st);
+
+}  // namespace rvlm

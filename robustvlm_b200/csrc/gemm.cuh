@@ -216,6 +216,16 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 
 int sm_count();
 
+// launch accounting (bench.py's gpu_launches) and optional per-launch CUDA-event timing
+// of the GEMM kernel (bench.py's roofline.achieved)
+void count_launch(int n = 1);
+struct GemmProfScope {
+  cudaStream_t st;
+  int slot;
+  GemmProfScope(cudaStream_t s, double flops);
+  ~GemmProfScope();
+};
+
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int fmt,
                   const Epi& epi, cudaStream_t stream, int max_ctas = 0) {
@@ -240,8 +250,13 @@ int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   int grid = sm_count();
   if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
   if (num_tiles < grid) grid = num_tiles;
-  kern<<<grid, GEMM_THREADS, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  {
+    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K);
+    kern<<<grid, GEMM_THREADS, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
+    e = cudaGetLastError();
+  }
+  count_launch();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 

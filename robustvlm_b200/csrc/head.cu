@@ -1,0 +1,231 @@
+// Embedding head + attack loss, forward and backward in one launch.
+//
+//   pooled = ln_post(x_L[:, 0]);  emb = pooled @ proj;  optional F.normalize(emb)
+//       (open_clip VisionTransformer tail + ClipVisionModel.forward,
+//        train/adversarial_training_clip.py:253-257)
+//   FARE   : loss_b = sum_d (emb - emb_orig)^2                     (:509-521)
+//   TeCoA  : loss_b = CE(emb @ (logit_scale * T), y)               (:500-504,523-528)
+//            (also the zero-shot classifier of the evaluation APGD,
+//             CLIP_eval/clip_robustbench.py:50-69, with normalisation on)
+//   pred_b = [argmax(out_b) == y_b], out = class logits or the embedding itself
+//            (apgd_train's quirk, train/apgd_train.py:191,301)
+// and the gradient of loss_b w.r.t. the CLS row of the last residual stream, written
+// into row b*T of the [B*T, W] gradient buffers (all other rows are zero: only the
+// CLS token reaches the loss).
+//
+// Tiny work (B rows): one CTA per sample, fp32 SIMT.
+#include "engine_internal.cuh"
+#include "../../include/rvlm.h"
+
+namespace rvlm {
+
+void count_launch(int n);
+constexpr int HEAD_THREADS = 256;
+
+__device__ __forceinline__ float blk_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+  return t;
+}
+__device__ __forceinline__ float blk_max(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffff, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = -INFINITY;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t = fmaxf(t, red[i]);
+  return t;
+}
+// first index attaining the maximum (torch.max semantics)
+__device__ __forceinline__ int blk_argmax(const float* v, int n, float* red, int* redi) {
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float x = v[i];
+    if (x > best || (x == best && i < bi)) { best = x; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffff, best, o);
+    const int oi = __shfl_xor_sync(0xffffffff, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = best; redi[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  float fb = -INFINITY;
+  int fi = 0x7fffffff;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i)
+    if (red[i] > fb || (red[i] == fb && redi[i] < fi)) { fb = red[i]; fi = redi[i]; }
+  return fi;
+}
+
+__global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
+  extern __shared__ float sm[];
+  const int W = A.W, D = A.D, C = A.C;
+  float* xh = sm;               // [W] normalised row
+  float* pooled = xh + W;       // [W]
+  float* e = pooled + W;        // [D] embedding (normalised if requested)
+  float* de = e + D;            // [D]
+  float* lg = de + D;           // [C] logits / dlogits
+  __shared__ float red[32];
+  __shared__ int redi[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* xr = A.xL + (size_t)b * A.T * W;
+
+  // ---- ln_post
+  float s = 0.f;
+  for (int i = tid; i < W; i += HEAD_THREADS) { xh[i] = xr[i]; s += xh[i]; }
+  const float mean = blk_sum(s, red) / W;
+  float q = 0.f;
+  for (int i = tid; i < W; i += HEAD_THREADS) { const float d = xh[i] - mean; q += d * d; }
+  const float rstd = 1.f / sqrtf(blk_sum(q, red) / W + 1e-5f);
+  for (int i = tid; i < W; i += HEAD_THREADS) {
+    xh[i] = (xh[i] - mean) * rstd;
+    pooled[i] = xh[i] * A.ln_g[i] + A.ln_b[i];
+  }
+  __syncthreads();
+  // ---- projection
+  for (int d = tid; d < D; d += HEAD_THREADS) {
+    float acc = 0.f;
+    for (int w = 0; w < W; ++w) acc += pooled[w] * __ldg(A.proj + (size_t)w * D + d);
+    e[d] = acc;
+  }
+  __syncthreads();
+  float nrm = 1.f;
+  if (A.normalize) {
+    float ss = 0.f;
+    for (int d = tid; d < D; d += HEAD_THREADS) ss += e[d] * e[d];
+    nrm = fmaxf(sqrtf(blk_sum(ss, red)), 1e-12f);
+    for (int d = tid; d < D; d += HEAD_THREADS) e[d] = e[d] / nrm;
+    __syncthreads();
+  }
+  if (A.emb_out)
+    for (int d = tid; d < D; d += HEAD_THREADS) A.emb_out[(size_t)b * D + d] = e[d];
+
+  const long long yb = A.y ? A.y[b] : -1;
+  float loss = 0.f;
+  int pred = 0;
+  if (A.mode == 1) {
+    float ss = 0.f;
+    for (int d = tid; d < D; d += HEAD_THREADS) {
+      const float df = e[d] - A.emb_orig[(size_t)b * D + d];
+      ss += df * df;
+      de[d] = 2.f * df;
+    }
+    loss = blk_sum(ss, red);
+  } else if (A.mode == 3) {
+    // upstream gradient w.r.t. the (normalised) embedding supplied by the caller
+    for (int d = tid; d < D; d += HEAD_THREADS) de[d] = A.emb_orig[(size_t)b * D + d];
+  } else if (A.mode == 2) {
+    for (int c = tid; c < C; c += HEAD_THREADS) {
+      float acc = 0.f;
+      for (int d = 0; d < D; ++d) acc += e[d] * __ldg(A.text + (size_t)d * C + c);
+      lg[c] = acc * A.logit_scale;
+    }
+    __syncthreads();
+    if (A.logits_out)
+      for (int c = tid; c < C; c += HEAD_THREADS) A.logits_out[(size_t)b * C + c] = lg[c];
+    if (A.pred_on_logits) pred = (blk_argmax(lg, C, red, redi) == (int)yb) ? 1 : 0;
+    float mx = -INFINITY;
+    for (int c = tid; c < C; c += HEAD_THREADS) mx = fmaxf(mx, lg[c]);
+    mx = blk_max(mx, red);
+    float se = 0.f;
+    for (int c = tid; c < C; c += HEAD_THREADS) se += expf(lg[c] - mx);
+    se = blk_sum(se, red);
+    const float lz = mx + logf(se);
+    loss = (yb >= 0 && yb < C) ? lz - lg[yb] : 0.f;
+    __syncthreads();
+    for (int c = tid; c < C; c += HEAD_THREADS)
+      lg[c] = expf(lg[c] - lz) - ((long long)c == yb ? 1.f : 0.f);
+    __syncthreads();
+    // d e = logit_scale * text @ dlogits
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int d = warp; d < D; d += HEAD_THREADS / 32) {
+      float acc = 0.f;
+      for (int c = lane; c < C; c += 32) acc += __ldg(A.text + (size_t)d * C + c) * lg[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+      if (lane == 0) de[d] = acc * A.logit_scale;
+    }
+  }
+  __syncthreads();
+  if ((A.mode == 1 || A.mode == 2) && !(A.mode == 2 && A.pred_on_logits))
+    pred = (blk_argmax(e, D, red, redi) == (int)yb) ? 1 : 0;
+  if (tid == 0) {
+    if (A.loss) A.loss[b] = loss;
+    if (A.pred) A.pred[b] = pred;
+  }
+  if (A.mode == 0 || !A.dx32) return;
+
+  // ---- backward: normalise
+  if (A.normalize) {
+    float dot = 0.f;
+    for (int d = tid; d < D; d += HEAD_THREADS) dot += e[d] * de[d];
+    dot = blk_sum(dot, red);
+    for (int d = tid; d < D; d += HEAD_THREADS) de[d] = (de[d] - e[d] * dot) / nrm;
+  }
+  __syncthreads();
+  // ---- d pooled = proj @ d emb  (reuse `pooled` as g = dpooled * gamma)
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int w = warp; w < W; w += HEAD_THREADS / 32) {
+      float acc = 0.f;
+      for (int d = lane; d < D; d += 32) acc += __ldg(A.proj + (size_t)w * D + d) * de[d];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+      if (lane == 0) pooled[w] = acc * A.ln_g[w] * A.grad_scale;
+    }
+  }
+  __syncthreads();
+  // ---- ln_post backward
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = tid; i < W; i += HEAD_THREADS) { s1 += pooled[i]; s2 += pooled[i] * xh[i]; }
+  const float c1 = blk_sum(s1, red) / W;
+  const float c2 = blk_sum(s2, red) / W;
+  float mxabs = 0.f;
+  for (int i = tid; i < W; i += HEAD_THREADS) {
+    const float v = rstd * (pooled[i] - c1 - xh[i] * c2);
+    pooled[i] = v;
+    mxabs = fmaxf(mxabs, fabsf(v));
+  }
+  float unit = 1.f;
+  if (A.grad_unit) {
+    mxabs = blk_max(mxabs, red);
+    unit = (mxabs > 0.f && mxabs < INFINITY) ? 1.f / mxabs : 1.f;
+  }
+  __syncthreads();
+  float* d32 = A.dx32 + (size_t)b * A.T * W;
+  uint16_t* d16 = A.dx16 ? A.dx16 + (size_t)b * A.T * W : nullptr;
+  for (int i = tid; i < W; i += HEAD_THREADS) {
+    const float v = pooled[i] * unit;
+    d32[i] = v;
+    if (d16) {
+      if (A.fmt_g) { __nv_bfloat16 h = __float2bfloat16_rn(v); d16[i] = *reinterpret_cast<uint16_t*>(&h); }
+      else { __half h = __float2half_rn(v); d16[i] = *reinterpret_cast<uint16_t*>(&h); }
+    }
+  }
+}
+
+int launch_head(const HeadArgs& A, int B, cudaStream_t st) {
+  const size_t smem = (size_t)(2 * A.W + 2 * A.D + (A.C > 0 ? A.C : 1)) * sizeof(float);
+  static size_t set = 0;
+  if (smem > set && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    set = smem;
+  }
+  head_kernel<<<B, HEAD_THREADS, smem, st>>>(A);
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+}  // namespace rvlm

@@ -2,6 +2,8 @@
 // encoding (resolved at run time so the library links without libcuda and can be
 // dlopen'ed on a machine with no GPU), SM count, error strings.
 #include "gemm.cuh"
+#include <atomic>
+#include <vector>
 #include "../../include/rvlm.h"
 
 namespace rvlm {
@@ -48,6 +50,29 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   return r == CUDA_SUCCESS ? 0 : RVLM_ERR_TMAP;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct ProfRec { cudaEvent_t e0, e1; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+
+GemmProfScope::GemmProfScope(cudaStream_t s, double flops) : st(s), slot(-1) {
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof.size()) {
+    ProfRec r{};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    g_prof.push_back(r);
+  }
+  slot = (int)g_prof_used++;
+  g_prof[slot].flops = flops;
+  cudaEventRecord(g_prof[slot].e0, st);
+}
+GemmProfScope::~GemmProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
 int sm_count() {
   static int n = 0;
   if (n) return n;
@@ -73,3 +98,31 @@ extern "C" const char* rvlm_strerror(int code) {
 }
 
 extern "C" int rvlm_abi_version(void) { return RVLM_ABI_VERSION; }
+
+extern "C" long long rvlm_launch_count(void) { return rvlm::g_launches.load(); }
+extern "C" void rvlm_launch_count_reset(void) { rvlm::g_launches.store(0); }
+
+extern "C" int rvlm_profile_gemm(int enable) {
+  rvlm::g_prof_on = enable != 0;
+  rvlm::g_prof_used = 0;
+  return 0;
+}
+
+extern "C" int rvlm_profile_gemm_collect(double* total_ms, double* total_flops,
+                                         long long* launches) {
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < rvlm::g_prof_used; ++i) {
+    cudaError_t e = cudaEventSynchronize(rvlm::g_prof[i].e1);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    float t = 0.f;
+    e = cudaEventElapsedTime(&t, rvlm::g_prof[i].e0, rvlm::g_prof[i].e1);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    ms += t;
+    fl += rvlm::g_prof[i].flops;
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (long long)rvlm::g_prof_used;
+  rvlm::g_prof_used = 0;
+  return 0;
+}

@@ -1,0 +1,542 @@
+// The fused CLIP-ViT attack engine: forward, input-gradient backward and the whole
+// PGD inner loop of the reference (train/pgd_train.py:29-68 around
+// ClipVisionModel.forward, train/adversarial_training_clip.py:253-257) as a stream
+// of hand-written sm_100a kernels with no host synchronisation.
+//
+// Data layout in HBM (M = B*T token rows, W = width):
+//   residual stream x_l, x_mid_l       fp32  [M, W]      (kept per layer for the backward)
+//   GEMM operands / activations        16-bit [M, *]     (fmt_fwd forward, fmt_bwd gradients)
+//   attack state x, delta, velocity    fp32  [B*np, 3*p*p]  patch-major for the whole loop
+//   weights                            16-bit, [N, K] row-major (K-major UMMA operands):
+//                                      forward copies in fmt_fwd, transposed dgrad copies
+//                                      in fmt_bwd
+// Backward is dgrad-only (torch.autograd.grad(loss, perturbation), train/pgd_train.py:38).
+#include "gemm.cuh"
+#include "epilogues.cuh"
+#include "engine_internal.cuh"
+#include "../../include/rvlm.h"
+
+#include <vector>
+#include <new>
+
+using namespace rvlm;
+
+extern "C" int rvlm_attn_fwd_simt(const void*, void*, float*, int, int, int, int, void*);
+extern "C" int rvlm_attn_bwd_simt(const void*, const void*, const void*, const float*, void*, int,
+                                  int, int, int, int, void*);
+extern "C" int rvlm_attn_fwd(const void*, void*, float*, int, int, int, int, void*);
+extern "C" int rvlm_attn_bwd(const void*, const void*, const void*, const float*, void*, int, int,
+                             int, int, int, void*);
+extern "C" int rvlm_layernorm_fwd(const float*, const float*, const float*, void*, float*, float*,
+                                  int, int, int, void*);
+extern "C" int rvlm_layernorm_bwd(const float*, const float*, const float*, const float*,
+                                  const float*, float*, void*, int, int, int, int, void*);
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct LayerDev {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *bfc, *bpr;
+  uint16_t *wqkv, *wo, *wfc, *wpr;      // forward operands [N, K], fmt_fwd
+  uint16_t *wqkvT, *woT, *wfcT, *wprT;  // dgrad operands   [K_fwd, N_fwd] = [N', K'], fmt_bwd
+};
+
+struct Engine {
+  rvlm_vit_config cfg;
+  int T, np, kp, kld, kp32, W, D, L, H, F;
+  PatchGeom geom;
+  uint8_t* slab = nullptr;
+  size_t slab_bytes = 0;
+  float *cls, *pos, *lnpre_g, *lnpre_b, *lnpost_g, *lnpost_b, *proj;
+  uint16_t *conv_w, *conv_wT;
+  std::vector<LayerDev> layers;
+  int attn_simt = 0;
+};
+
+// ---- workspace carving --------------------------------------------------------
+struct Ws {
+  // attack state (patch-major)
+  float *xp, *dp, *vp, *gp;
+  uint16_t* a16;
+  // forward
+  float *tok32, *stats_pre;
+  float *x32;     // [(L+1)] or [2] x [M, W]
+  float *xm32;    // [L] or [1]
+  float *stats1, *stats2;  // [L] x [M, 2]
+  uint16_t *qkv16, *o16, *h16;  // [L] or [1]
+  float* lse;     // [L] x [B, H, T]
+  uint16_t *y16, *act16;
+  // backward
+  float *dx32, *dz32;
+  uint16_t *dx16, *dh16, *do16, *dqkv16, *dtok16;
+  // head
+  float *emb, *loss;
+  int* pred;
+  float* upd;     // update-kernel reduction workspace
+  size_t total;
+  int stash;
+  size_t M;
+};
+
+template <class Tp>
+Tp* take(uint8_t*& p, size_t& used, size_t n_elems) {
+  const size_t bytes = align_up(n_elems * sizeof(Tp), 1024);
+  Tp* r = reinterpret_cast<Tp*>(p);
+  if (p) p += bytes;
+  used += bytes;
+  return r;
+}
+
+Ws carve(const Engine& E, uint8_t* base, int B, int stash) {
+  Ws w{};
+  uint8_t* p = base;
+  size_t used = 0;
+  const size_t M = (size_t)B * E.T, W = E.W, F = E.F, L = E.L;
+  const size_t R = (size_t)B * E.np;
+  const size_t nl = stash ? L : 1;
+  w.M = M;
+  w.stash = stash;
+  w.xp = take<float>(p, used, R * E.kp);
+  w.dp = take<float>(p, used, R * E.kp);
+  w.vp = take<float>(p, used, R * E.kp);
+  w.gp = take<float>(p, used, R * E.kp);
+  w.a16 = take<uint16_t>(p, used, R * E.kld);
+  w.tok32 = take<float>(p, used, M * W);
+  w.stats_pre = take<float>(p, used, M * 2);
+  w.x32 = take<float>(p, used, (stash ? L + 1 : 2) * M * W);
+  w.xm32 = take<float>(p, used, nl * M * W);
+  w.stats1 = take<float>(p, used, nl * M * 2);
+  w.stats2 = take<float>(p, used, nl * M * 2);
+  w.qkv16 = take<uint16_t>(p, used, nl * M * 3 * W);
+  w.o16 = take<uint16_t>(p, used, nl * M * W);
+  w.h16 = take<uint16_t>(p, used, nl * M * F);
+  w.lse = take<float>(p, used, nl * (size_t)B * E.H * E.T);
+  w.y16 = take<uint16_t>(p, used, M * W);
+  w.act16 = take<uint16_t>(p, used, M * F);
+  w.emb = take<float>(p, used, (size_t)B * E.D);
+  w.loss = take<float>(p, used, B);
+  w.pred = take<int>(p, used, B);
+  w.upd = take<float>(p, used, (size_t)B * 32 * 3);
+  if (stash) {
+    w.dx32 = take<float>(p, used, M * W);
+    w.dz32 = take<float>(p, used, M * W);
+    w.dx16 = take<uint16_t>(p, used, M * W);
+    w.dh16 = take<uint16_t>(p, used, M * F);
+    w.do16 = take<uint16_t>(p, used, M * W);
+    w.dqkv16 = take<uint16_t>(p, used, M * 3 * W);
+    w.dtok16 = take<uint16_t>(p, used, R * W);
+  }
+  w.total = used;
+  return w;
+}
+
+#define RV(call)                 \
+  do {                           \
+    int _rc = (call);            \
+    if (_rc) return _rc;         \
+  } while (0)
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e - 1000; }
+
+// ---- forward --------------------------------------------------------------------
+// Precondition: w.a16 holds the normalised 16-bit patch operand of the batch.
+int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
+  const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
+  const int ff = E.cfg.fmt_fwd;
+  const size_t MW = (size_t)M * W;
+  void* stv = (void*)st;
+  RV(launch_cls_rows(w.tok32, E.cls, E.pos, B, E.T, W, st));
+  {
+    EpiPatchFwd epi{w.tok32, E.pos, E.np, E.T, W};
+    RV((launch_gemm16<256, false, false>(w.a16, E.kld, E.conv_w, E.kld, R, W, E.kp, ff, epi, st)));
+  }
+  RV(rvlm_layernorm_fwd(w.tok32, E.lnpre_g, E.lnpre_b, nullptr, w.x32, w.stats_pre, M, W, ff, stv));
+  for (int l = 0; l < E.L; ++l) {
+    const LayerDev& Lw = E.layers[l];
+    const size_t s = w.stash ? (size_t)l : 0;
+    float* x_in = w.stash ? w.x32 + (size_t)l * MW : w.x32 + (size_t)(l & 1) * MW;
+    float* x_out = w.stash ? w.x32 + (size_t)(l + 1) * MW : w.x32 + (size_t)((l + 1) & 1) * MW;
+    float* xm = w.xm32 + s * MW;
+    uint16_t* qkv = w.qkv16 + s * MW * 3;
+    uint16_t* o = w.o16 + s * MW;
+    uint16_t* h = w.h16 + s * (size_t)M * F;
+    float* lse = w.lse + s * (size_t)B * E.H * E.T;
+    float* st1 = w.stats1 + s * (size_t)M * 2;
+    float* st2 = w.stats2 + s * (size_t)M * 2;
+    RV(rvlm_layernorm_fwd(x_in, Lw.ln1_g, Lw.ln1_b, w.y16, nullptr, st1, M, W, ff, stv));
+    {
+      EpiStore16 epi{qkv, 3 * W, Lw.bqkv, ff};
+      RV((launch_gemm16<256, false, false>(w.y16, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
+    }
+    if (E.attn_simt) RV(rvlm_attn_fwd_simt(qkv, o, lse, B, E.T, E.H, ff, stv));
+    else RV(rvlm_attn_fwd(qkv, o, lse, B, E.T, E.H, ff, stv));
+    {
+      EpiStore32 epi{xm, W, Lw.bo, x_in, W};
+      RV((launch_gemm16<256, false, false>(o, W, Lw.wo, W, M, W, W, ff, epi, st)));
+    }
+    RV(rvlm_layernorm_fwd(xm, Lw.ln2_g, Lw.ln2_b, w.y16, nullptr, st2, M, W, ff, stv));
+    {
+      EpiGelu epi{w.stash ? h : nullptr, w.act16, F, Lw.bfc, ff};
+      RV((launch_gemm16<256, false, false>(w.y16, W, Lw.wfc, W, M, F, W, ff, epi, st)));
+    }
+    {
+      EpiStore32 epi{x_out, W, Lw.bpr, xm, W};
+      RV((launch_gemm16<256, false, false>(w.act16, F, Lw.wpr, F, M, W, F, ff, epi, st)));
+    }
+  }
+  return 0;
+}
+
+const float* final_x(const Engine& E, const Ws& w, int B) {
+  const size_t MW = (size_t)B * E.T * E.W;
+  return w.stash ? w.x32 + (size_t)E.L * MW : w.x32 + (size_t)(E.L & 1) * MW;
+}
+
+int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, int normalize,
+             float* emb_out, float* logits_out, bool backward, cudaStream_t st) {
+  HeadArgs A{};
+  A.xL = final_x(E, w, B);
+  A.T = E.T; A.W = E.W; A.D = E.D;
+  A.ln_g = E.lnpost_g; A.ln_b = E.lnpost_b; A.proj = E.proj;
+  A.mode = lc ? lc->mode : 0;
+  A.normalize = lc ? lc->output_normalize : normalize;
+  A.C = (lc && lc->mode == 2) ? lc->n_classes : 0;
+  A.pred_on_logits = lc ? lc->pred_on_logits : 0;
+  A.emb_orig = lc ? lc->emb_orig : nullptr;
+  A.text = lc ? lc->text : nullptr;
+  A.logit_scale = lc ? lc->logit_scale : 1.f;
+  A.y = lc ? (const long long*)lc->targets : nullptr;
+  A.emb_out = emb_out ? emb_out : w.emb;
+  A.logits_out = logits_out;
+  A.loss = w.loss;
+  A.pred = w.pred;
+  A.fmt_g = E.cfg.fmt_bwd;
+  A.grad_scale = 1.f;
+  A.grad_unit = (E.cfg.fmt_bwd == RVLM_FMT_F16) ? 1 : 0;
+  if (backward) {
+    const size_t MW = (size_t)B * E.T * E.W;
+    cudaError_t e = cudaMemsetAsync(w.dx32, 0, MW * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = cudaMemsetAsync(w.dx16, 0, MW * sizeof(uint16_t), st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    A.dx32 = w.dx32;
+    A.dx16 = w.dx16;
+  }
+  return launch_head(A, B, st);
+}
+
+// ---- backward (dgrad only) down to the token gradient of the patch rows -----------
+int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
+  const int M = B * E.T, W = E.W, F = E.F;
+  const int ff = E.cfg.fmt_fwd, fg = E.cfg.fmt_bwd;
+  const size_t MW = (size_t)M * W;
+  void* stv = (void*)st;
+  for (int l = E.L - 1; l >= 0; --l) {
+    const LayerDev& Lw = E.layers[l];
+    const float* x_in = w.x32 + (size_t)l * MW;
+    const float* xm = w.xm32 + (size_t)l * MW;
+    const uint16_t* qkv = w.qkv16 + (size_t)l * MW * 3;
+    const uint16_t* o = w.o16 + (size_t)l * MW;
+    const uint16_t* h = w.h16 + (size_t)l * M * F;
+    const float* lse = w.lse + (size_t)l * B * E.H * E.T;
+    const float* st1 = w.stats1 + (size_t)l * M * 2;
+    const float* st2 = w.stats2 + (size_t)l * M * 2;
+    {  // d act -> d h (through QuickGELU)
+      EpiGeluBwd epi{w.dh16, F, h, ff, fg};
+      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
+    }
+    {  // d ln_2 output
+      EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
+      RV((launch_gemm16<256, false, false>(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
+    }
+    RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+    {  // d attention output
+      EpiStore16 epi{w.do16, W, nullptr, fg};
+      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
+    }
+    if (E.attn_simt) RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, ff, fg, stv));
+    else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, ff, fg, stv));
+    {  // d ln_1 output
+      EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
+      RV((launch_gemm16<256, false, false>(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
+                                           st)));
+    }
+    RV(rvlm_layernorm_bwd(w.dz32, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+  }
+  // ln_pre backward, compacted to patch rows (the CLS row's input is a constant)
+  RV(rvlm_layernorm_bwd(w.dx32, w.tok32, w.stats_pre, E.lnpre_g, nullptr, nullptr, w.dtok16, M, W,
+                        fg, E.T, stv));
+  return 0;
+}
+
+int run_patch_grad(const Engine& E, const Ws& w, int B, cudaStream_t st) {
+  EpiPatchGrad epi{w.gp, E.kp, E.cfg.patch * E.cfg.patch,
+                   {E.geom.inv_std[0], E.geom.inv_std[1], E.geom.inv_std[2]}};
+  return launch_gemm16<256, false, false>(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
+                                          E.cfg.fmt_bwd, epi, st);
+}
+
+int run_patch_pgd_linf(const Engine& E, const Ws& w, int B, float stepsize, float eps,
+                       int maximize, float momentum, cudaStream_t st) {
+  EpiPatchPgdLinf epi{w.xp, w.dp, w.vp, w.a16, E.kp, E.cfg.patch * E.cfg.patch, E.kld,
+                      E.cfg.fmt_fwd, stepsize, eps, maximize ? 1.f : -1.f, momentum,
+                      {E.geom.mean[0], E.geom.mean[1], E.geom.mean[2]},
+                      {E.geom.inv_std[0], E.geom.inv_std[1], E.geom.inv_std[2]}};
+  return launch_gemm16<256, false, false>(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
+                                          E.cfg.fmt_bwd, epi, st);
+}
+
+int load_weights(Engine& E, const rvlm_vit_weights* wt, cudaStream_t st) {
+  const int W = E.W, F = E.F, D = E.D, ff = E.cfg.fmt_fwd, fg = E.cfg.fmt_bwd;
+  auto cp = [&](float* dst, const float* src, size_t n) {
+    return cuda_rc(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  };
+  RV(cp(E.cls, wt->class_embedding, W));
+  RV(cp(E.pos, wt->positional_embedding, (size_t)E.T * W));
+  RV(cp(E.lnpre_g, wt->ln_pre_weight, W));
+  RV(cp(E.lnpre_b, wt->ln_pre_bias, W));
+  RV(cp(E.lnpost_g, wt->ln_post_weight, W));
+  RV(cp(E.lnpost_b, wt->ln_post_bias, W));
+  RV(cp(E.proj, wt->proj, (size_t)W * D));
+  // conv1.weight [W, 3, p, p] == [W, kp] row-major
+  RV(launch_convert16_pitched(wt->conv1_weight, E.conv_w, W, E.kp, E.kld, ff, st));
+  RV(launch_transpose_convert16(wt->conv1_weight, E.conv_wT, W, E.kp, W, fg, st));
+  for (int l = 0; l < E.L; ++l) {
+    LayerDev& Lw = E.layers[l];
+    RV(cp(Lw.ln1_g, wt->ln_1_weight[l], W));
+    RV(cp(Lw.ln1_b, wt->ln_1_bias[l], W));
+    RV(cp(Lw.ln2_g, wt->ln_2_weight[l], W));
+    RV(cp(Lw.ln2_b, wt->ln_2_bias[l], W));
+    RV(cp(Lw.bqkv, wt->attn_in_proj_bias[l], 3 * (size_t)W));
+    RV(cp(Lw.bo, wt->attn_out_proj_bias[l], W));
+    RV(cp(Lw.bfc, wt->mlp_c_fc_bias[l], F));
+    RV(cp(Lw.bpr, wt->mlp_c_proj_bias[l], W));
+    RV(launch_convert16(wt->attn_in_proj_weight[l], Lw.wqkv, (long long)3 * W * W, ff, st));
+    RV(launch_convert16(wt->attn_out_proj_weight[l], Lw.wo, (long long)W * W, ff, st));
+    RV(launch_convert16(wt->mlp_c_fc_weight[l], Lw.wfc, (long long)F * W, ff, st));
+    RV(launch_convert16(wt->mlp_c_proj_weight[l], Lw.wpr, (long long)W * F, ff, st));
+    RV(launch_transpose_convert16(wt->attn_in_proj_weight[l], Lw.wqkvT, 3 * W, W, 3 * W, fg, st));
+    RV(launch_transpose_convert16(wt->attn_out_proj_weight[l], Lw.woT, W, W, W, fg, st));
+    RV(launch_transpose_convert16(wt->mlp_c_fc_weight[l], Lw.wfcT, F, W, F, fg, st));
+    RV(launch_transpose_convert16(wt->mlp_c_proj_weight[l], Lw.wprT, W, F, W, fg, st));
+  }
+  return 0;
+}
+
+int prep_state(const Engine& E, const Ws& w, int B, const float* x_img, const float* delta_img,
+               bool zero_velocity, cudaStream_t st) {
+  RV(launch_patchify(x_img, w.xp, B, E.geom, st));
+  const size_t n = (size_t)B * E.np * E.kp;
+  if (delta_img) RV(launch_patchify(delta_img, w.dp, B, E.geom, st));
+  else RV(cuda_rc(cudaMemsetAsync(w.dp, 0, n * sizeof(float), st)));
+  if (zero_velocity) RV(cuda_rc(cudaMemsetAsync(w.vp, 0, n * sizeof(float), st)));
+  RV(launch_patch_operand(w.xp, delta_img ? w.dp : nullptr, w.a16, E.kld, (long long)B * E.np,
+                          E.geom, E.cfg.fmt_fwd, st));
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI
+// =============================================================================
+extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weights* weights,
+                               void* stream, rvlm_vit_handle* out) {
+  if (!cfg || !weights || !out) return RVLM_ERR_INVAL;
+  if (cfg->width % 128 || cfg->width != cfg->heads * 64 || cfg->mlp % 32 || cfg->image % cfg->patch)
+    return RVLM_ERR_UNSUPPORTED;
+  if (cfg->width != 128 && cfg->width != 256 && cfg->width != 768 && cfg->width != 1024)
+    return RVLM_ERR_UNSUPPORTED;
+  Engine* E = new (std::nothrow) Engine();
+  if (!E) return RVLM_ERR_NOMEM;
+  E->cfg = *cfg;
+  E->W = cfg->width; E->D = cfg->out_dim; E->L = cfg->layers; E->H = cfg->heads; E->F = cfg->mlp;
+  const int g = cfg->image / cfg->patch;
+  E->np = g * g;
+  E->T = E->np + 1;
+  E->kp = 3 * cfg->patch * cfg->patch;
+  E->kld = (int)align_up(E->kp, 8);
+  E->kp32 = (int)align_up(E->kp, 32);
+  E->geom.image = cfg->image; E->geom.patch = cfg->patch; E->geom.grid = g;
+  E->geom.np = E->np; E->geom.kp = E->kp;
+  for (int c = 0; c < 3; ++c) { E->geom.mean[c] = cfg->mean[c]; E->geom.inv_std[c] = 1.f / cfg->std[c]; }
+  if (E->T > 272 || (E->kp & 3)) { delete E; return RVLM_ERR_UNSUPPORTED; }
+  E->attn_simt = (cfg->flags & RVLM_VIT_ATTN_SIMT) ? 1 : 0;
+  // size the slab
+  const size_t W = E->W, F = E->F, D = E->D, L = E->L;
+  size_t used = 0;
+  uint8_t* p = nullptr;
+  auto plan = [&](uint8_t* base) {
+    p = base; used = 0;
+    E->cls = take<float>(p, used, W); E->pos = take<float>(p, used, (size_t)E->T * W);
+    E->lnpre_g = take<float>(p, used, W); E->lnpre_b = take<float>(p, used, W);
+    E->lnpost_g = take<float>(p, used, W); E->lnpost_b = take<float>(p, used, W);
+    E->proj = take<float>(p, used, W * D);
+    E->conv_w = take<uint16_t>(p, used, W * E->kld);
+    E->conv_wT = take<uint16_t>(p, used, (size_t)E->kp32 * W);
+    E->layers.resize(L);
+    for (size_t l = 0; l < L; ++l) {
+      LayerDev& Lw = E->layers[l];
+      Lw.ln1_g = take<float>(p, used, W); Lw.ln1_b = take<float>(p, used, W);
+      Lw.ln2_g = take<float>(p, used, W); Lw.ln2_b = take<float>(p, used, W);
+      Lw.bqkv = take<float>(p, used, 3 * W); Lw.bo = take<float>(p, used, W);
+      Lw.bfc = take<float>(p, used, F); Lw.bpr = take<float>(p, used, W);
+      Lw.wqkv = take<uint16_t>(p, used, 3 * W * W); Lw.wo = take<uint16_t>(p, used, W * W);
+      Lw.wfc = take<uint16_t>(p, used, F * W); Lw.wpr = take<uint16_t>(p, used, W * F);
+      Lw.wqkvT = take<uint16_t>(p, used, 3 * W * W); Lw.woT = take<uint16_t>(p, used, W * W);
+      Lw.wfcT = take<uint16_t>(p, used, F * W); Lw.wprT = take<uint16_t>(p, used, W * F);
+    }
+  };
+  plan(nullptr);
+  E->slab_bytes = used;
+  cudaError_t e = cudaMalloc(&E->slab, E->slab_bytes);
+  if (e != cudaSuccess) { delete E; return cuda_rc(e); }
+  plan(E->slab);
+  cudaStream_t st = (cudaStream_t)stream;
+  e = cudaMemsetAsync(E->slab, 0, E->slab_bytes, st);
+  if (e != cudaSuccess) { cudaFree(E->slab); delete E; return cuda_rc(e); }
+  int rc = load_weights(*E, weights, st);
+  if (rc) { cudaFree(E->slab); delete E; return rc; }
+  *out = E;
+  return 0;
+}
+
+extern "C" int rvlm_vit_update_weights(rvlm_vit_handle h, const rvlm_vit_weights* weights,
+                                       void* stream) {
+  if (!h || !weights) return RVLM_ERR_INVAL;
+  return load_weights(*reinterpret_cast<Engine*>(h), weights, (cudaStream_t)stream);
+}
+
+extern "C" int rvlm_vit_destroy(rvlm_vit_handle h) {
+  if (!h) return 0;
+  Engine* E = reinterpret_cast<Engine*>(h);
+  cudaFree(E->slab);
+  delete E;
+  return 0;
+}
+
+extern "C" size_t rvlm_vit_workspace_bytes(rvlm_vit_handle h, int B, int with_backward) {
+  if (!h || B <= 0) return 0;
+  return carve(*reinterpret_cast<Engine*>(h), nullptr, B, with_backward).total;
+}
+
+extern "C" int rvlm_vit_forward(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                                const float* x, const float* delta, int B, int output_normalize,
+                                int keep_for_backward, float* emb_out, void* stream) {
+  if (!h || !workspace || !x || !emb_out || B <= 0) return RVLM_ERR_INVAL;
+  const Engine& E = *reinterpret_cast<Engine*>(h);
+  Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, keep_for_backward ? 1 : 0);
+  if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  RV(prep_state(E, w, B, x, delta, false, st));
+  RV(run_forward(E, w, B, st));
+  return run_head(E, w, B, nullptr, output_normalize, emb_out, nullptr, false, st);
+}
+
+extern "C" int rvlm_vit_backward_input(rvlm_vit_handle h, void* workspace,
+                                       size_t workspace_bytes, int B, const float* d_emb,
+                                       int output_normalize, float* grad_out, void* stream) {
+  if (!h || !workspace || !d_emb || !grad_out || B <= 0) return RVLM_ERR_INVAL;
+  const Engine& E = *reinterpret_cast<Engine*>(h);
+  Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 1);
+  if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  rvlm_loss_config lc{};
+  lc.mode = 3;
+  lc.output_normalize = output_normalize;
+  lc.emb_orig = d_emb;
+  RV(run_head(E, w, B, &lc, 0, nullptr, nullptr, true, st));
+  RV(run_backward(E, w, B, st));
+  RV(run_patch_grad(E, w, B, st));
+  return launch_unpatchify(w.gp, grad_out, B, E.geom, st);
+}
+
+extern "C" int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                                  const float* x, const float* delta, int B,
+                                  const rvlm_loss_config* loss, float* grad_out, float* loss_out,
+                                  int* pred_out, float* emb_out, float* logits_out, int want_grad,
+                                  void* stream) {
+  if (!h || !workspace || !x || !loss || B <= 0) return RVLM_ERR_INVAL;
+  if (loss->mode != 1 && loss->mode != 2) return RVLM_ERR_INVAL;
+  const Engine& E = *reinterpret_cast<Engine*>(h);
+  Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 1);
+  if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  RV(prep_state(E, w, B, x, delta, false, st));
+  RV(run_forward(E, w, B, st));
+  RV(run_head(E, w, B, loss, 0, emb_out, logits_out, want_grad != 0, st));
+  if (loss_out)
+    RV(cuda_rc(cudaMemcpyAsync(loss_out, w.loss, B * sizeof(float), cudaMemcpyDeviceToDevice, st)));
+  if (pred_out)
+    RV(cuda_rc(cudaMemcpyAsync(pred_out, w.pred, B * sizeof(int), cudaMemcpyDeviceToDevice, st)));
+  if (want_grad) {
+    if (!grad_out) return RVLM_ERR_INVAL;
+    RV(run_backward(E, w, B, st));
+    RV(run_patch_grad(E, w, B, st));
+    RV(launch_unpatchify(w.gp, grad_out, B, E.geom, st));
+  }
+  return 0;
+}
+
+extern "C" int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                            const float* x, const float* delta0, int B,
+                            const rvlm_loss_config* loss, int norm, float eps, float stepsize,
+                            int iterations, int maximize, float momentum, float* x_adv_out,
+                            float* loss_trace, void* stream) {
+  if (!h || !workspace || !x || !loss || !x_adv_out || B <= 0 || iterations < 0)
+    return RVLM_ERR_INVAL;
+  if (norm != RVLM_NORM_LINF && norm != RVLM_NORM_L2) return RVLM_ERR_INVAL;
+  const Engine& E = *reinterpret_cast<Engine*>(h);
+  Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 1);
+  if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)E.np * E.kp;
+  RV(prep_state(E, w, B, x, delta0, true, st));
+  for (int it = 0; it < iterations; ++it) {
+    RV(run_forward(E, w, B, st));
+    RV(run_head(E, w, B, loss, 0, nullptr, nullptr, true, st));
+    if (loss_trace)
+      RV(cuda_rc(cudaMemcpyAsync(loss_trace + (size_t)it * B, w.loss, B * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, st)));
+    RV(run_backward(E, w, B, st));
+    if (norm == RVLM_NORM_LINF) {
+      // delta-update fused into the last backward kernel (also emits the next operand)
+      RV(run_patch_pgd_linf(E, w, B, stepsize, eps, maximize, momentum, st));
+    } else {
+      RV(run_patch_grad(E, w, B, st));
+      RV(rvlm_pgd_update_l2(w.dp, w.vp, w.gp, w.xp, B, n, stepsize, eps, maximize, momentum, w.upd,
+                            (void*)st));
+      RV(launch_patch_operand(w.xp, w.dp, w.a16, E.kld, (long long)B * E.np, E.geom,
+                              E.cfg.fmt_fwd, st));
+    }
+  }
+  return launch_unpatchify_add(w.xp, w.dp, x_adv_out, B, E.geom, st);
+}
+
+// Debug / test access to internal buffers of the last call (same B / with_backward).
+extern "C" int rvlm_vit_debug_buffer(rvlm_vit_handle h, void* workspace, int B, int with_backward,
+                                     int which, int layer, void** ptr_out) {
+  if (!h || !workspace || !ptr_out) return RVLM_ERR_INVAL;
+  const Engine& E = *reinterpret_cast<Engine*>(h);
+  Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, with_backward);
+  const size_t MW = (size_t)B * E.T * E.W;
+  const size_t s = with_backward ? (size_t)layer : 0;
+  switch (which) {
+    case 0: *ptr_out = w.tok32; break;
+    case 1: *ptr_out = w.x32 + (with_backward ? (size_t)layer : (size_t)(layer & 1)) * MW; break;
+    case 2: *ptr_out = w.xm32 + s * MW; break;
+    case 3: *ptr_out = w.qkv16 + s * MW * 3; break;
+    case 4: *ptr_out = w.o16 + s * MW; break;
+    case 5: *ptr_out = w.h16 + s * (size_t)B * E.T * E.F; break;
+    case 6: *ptr_out = w.dx32; break;
+    case 7: *ptr_out = w.gp; break;
+    case 8: *ptr_out = w.dp; break;
+    case 9: *ptr_out = w.a16; break;
+    case 10: *ptr_out = w.lse + s * (size_t)B * E.H * E.T; break;
+    case 11: *ptr_out = w.dqkv16; break;
+    case 12: *ptr_out = w.dtok16; break;
+    default: return RVLM_ERR_INVAL;
+  }
+  return 0;
+}

@@ -1,0 +1,162 @@
+"""The reference-facing call surface (robustvlm_b200.attacks / .model) vs the CPU oracle.
+
+The tests read like the reference's own usage (train/adversarial_training_clip.py:300-333,
+CLIP_eval/clip_robustbench.py:289-300): build ClipVisionModel + ComputeLossWrapper, call
+pgd / apgd_train / APGDAttack.perturb with the reference's argument conventions."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import attacks as oa
+from oracle import vit as ovit
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+NAME = "tiny-32"
+
+
+def _log(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "test_metrics.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **kw}) + "\n")
+    print(name, kw)
+
+
+def _pair(seed):
+    """(ours on cuda, oracle on cpu) with identical weights."""
+    from robustvlm_b200 import model as rm
+    o = ovit.build(NAME, seed=seed)
+    vt = rm.VisionTransformer(NAME)
+    vt.load_state_dict(o.state_dict())
+    vt = vt.cuda()
+    return rm.ClipVisionModel(vt, None, None).eval(), ovit.ClipVisionModel(o).eval()
+
+
+def _data(B, seed, eps):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(B, 3, 224, 224, generator=g)
+    d0 = (torch.rand(B, 3, 224, 224, generator=g) * 2 - 1) * eps
+    return x, d0
+
+
+def _loss_after(model_cpu, wrap_cpu, x_adv, y, normalize):
+    with torch.no_grad():
+        return float(wrap_cpu(model_cpu(x_adv.cpu(), output_normalize=normalize), y).mean())
+
+
+@pytest.mark.parametrize("norm,eps,step", [("linf", 4 / 255, 1 / 255), ("l2", 2.0, 0.5)])
+@pytest.mark.parametrize("path", ["fused", "generic"])
+def test_pgd_fare(path, norm, eps, step):
+    from robustvlm_b200 import attacks, model as rm
+    B, iters = 4, 3
+    ours, ref_m = _pair(1)
+    ours_o, ref_o = _pair(2)
+    x, d0 = _data(B, 7, min(eps, 0.05))
+    with torch.no_grad():
+        e_ref = ref_o(x, output_normalize=False)
+        e_our = ours_o(x.cuda(), output_normalize=False)
+    assert float((e_our.cpu() - e_ref).norm() / e_ref.norm()) < 1e-3
+    wrap_ref = oa.ComputeLossWrapper(e_ref, None, "mean", "l2", 100.0)
+    ref = oa.pgd(ref_m, wrap_ref, x, None, norm, eps, iters, step, False, perturbation=d0.clone(),
+                 mode="max")
+    if path == "fused":
+        wrap = rm.ComputeLossWrapper(e_our, None, "mean", "l2", 100.0)
+    else:  # a plain callable defeats the fused dispatch -> autograd through the engine VJP
+        w0 = rm.ComputeLossWrapper(e_our, None, "mean", "l2", 100.0)
+        wrap = lambda out, t: w0(out, t)  # noqa: E731
+    out = attacks.pgd(ours, wrap, x.cuda(), None, norm, eps, iters, step, False,
+                      perturbation=d0.clone().cuda(), mode="max")
+    torch.cuda.synchronize()
+    out = out.cpu()
+    assert out.min() >= 0 and out.max() <= 1
+    if norm == "linf":
+        assert float((out - x).abs().max()) <= eps + 1e-6
+    else:
+        assert float((out - x).flatten(1).norm(dim=1).max()) <= eps * (1 + 1e-5)
+    l_ours = _loss_after(ref_m, wrap_ref, out, None, False)
+    l_ref = _loss_after(ref_m, wrap_ref, ref, None, False)
+    same = float(((out - x) == (ref - x)).float().mean())
+    _log("pgd_fare", path=path, norm=norm, same=same, loss_ours=l_ours, loss_ref=l_ref,
+         max_abs_err=float((out - ref).abs().max()))
+    assert abs(l_ours - l_ref) <= 0.05 * abs(l_ref)
+    if norm == "linf":
+        assert same > 0.9
+
+
+def test_pgd_tecoa_ce():
+    from robustvlm_b200 import attacks, model as rm
+    B, iters, eps, step = 4, 3, 2 / 255, 1 / 255
+    ours, ref_m = _pair(1)
+    x, d0 = _data(B, 11, eps)
+    torch.manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(64, 10), dim=0)
+    y = torch.randint(0, 10, (B,))
+    wrap_ref = oa.ComputeLossWrapper(None, text, "mean", "ce", 100.0)
+    ref = oa.pgd(ref_m, wrap_ref, x, y, "linf", eps, iters, step, True, perturbation=d0.clone(),
+                 mode="max")
+    wrap = rm.ComputeLossWrapper(None, text.cuda(), "mean", "ce", 100.0)
+    out = attacks.pgd(ours, wrap, x.cuda(), y.cuda(), "linf", eps, iters, step, True,
+                      perturbation=d0.clone().cuda(), mode="max").cpu()
+    l_ours = _loss_after(ref_m, wrap_ref, out, y, True)
+    l_ref = _loss_after(ref_m, wrap_ref, ref, y, True)
+    same = float(((out - x) == (ref - x)).float().mean())
+    _log("pgd_tecoa", same=same, loss_ours=l_ours, loss_ref=l_ref)
+    assert same > 0.9 and abs(l_ours - l_ref) <= 0.05 * abs(l_ref)
+
+
+@pytest.mark.parametrize("norm,eps", [("linf", 4 / 255), ("l2", 2.0)])
+def test_apgd_train(norm, eps):
+    from robustvlm_b200 import attacks, model as rm
+    B = 4
+    ours, ref_m = _pair(1)
+    x, _ = _data(B, 13, 0.01)
+    torch.manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(64, 10), dim=0)
+    y = torch.randint(0, 10, (B,))
+    wrap_ref = oa.ComputeLossWrapper(None, text, "none", "ce", 100.0)
+    ref = oa.apgd_train(ref_m, x, y, norm, eps, n_iter=10, loss_fn=wrap_ref)
+    wrap = rm.ComputeLossWrapper(None, text.cuda(), "none", "ce", 100.0)
+    out = attacks.apgd_train(ours, x.cuda(), y.cuda(), norm, eps, n_iter=10, loss_fn=wrap).cpu()
+    l_ours = _loss_after(ref_m, wrap_ref, out, y, True)
+    l_ref = _loss_after(ref_m, wrap_ref, ref, y, True)
+    _log("apgd_train", norm=norm, loss_ours=l_ours, loss_ref=l_ref,
+         max_abs_err=float((out - ref).abs().max()),
+         pert=float((out - x).abs().max()))
+    assert out.min() >= 0 and out.max() <= 1
+    if norm == "linf":
+        assert float((out - x).abs().max()) <= eps + 1e-6
+    else:
+        assert float((out - x).flatten(1).norm(dim=1).max()) <= eps * (1 + 1e-4)
+    assert l_ours >= 0.9 * l_ref
+
+
+@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 2.0)])
+def test_apgd_attack_perturb(norm, eps):
+    from robustvlm_b200 import attacks, model as rm
+    B = 6
+    ours, ref_m = _pair(1)
+    x, _ = _data(B, 17, 0.01)
+    torch.manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(64, 10), dim=0)
+    cm_ref = ovit.ClassificationModel(ref_m.model, text, 100.0)
+    cm = rm.ClassificationModel(ours, text.cuda())
+    with torch.no_grad():
+        logits_ref = cm_ref(x)
+        logits = cm(x.cuda()).cpu()
+    assert float((logits - logits_ref).abs().max()) < 0.05 * float(logits_ref.abs().max())
+    y = logits_ref.argmax(1)
+    R = oa.APGDAttack(cm_ref, n_iter=20, norm=norm, n_restarts=2, eps=eps, seed=0, alpha=2.0)
+    A = attacks.APGDAttack(cm, n_iter=20, norm=norm, n_restarts=2, eps=eps, seed=0, alpha=2.0)
+    ref = R.perturb(x, y)
+    out = A.perturb(x.cuda(), y.cuda()).cpu()
+    with torch.no_grad():
+        racc_ref = float((cm_ref(ref).argmax(1) == y).float().mean())
+        racc_ours = float((cm_ref(out).argmax(1) == y).float().mean())
+    _log("apgd_attack", norm=norm, racc_ref=racc_ref, racc_ours=racc_ours,
+         pert=float((out - x).abs().max()))
+    assert out.min() >= 0 and out.max() <= 1
+    if norm == "Linf":
+        assert float((out - x).abs().max()) <= eps + 1e-6
+    assert racc_ours <= racc_ref + 0.34

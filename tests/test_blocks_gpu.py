@@ -1,0 +1,166 @@
+"""Building-block kernels vs plain PyTorch fp32 references of the same op."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _nat():
+    from robustvlm_b200 import _native as nat
+    return nat
+
+
+def _log(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "test_metrics.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **kw}) + "\n")
+
+
+def _dt(fmt):
+    return torch.bfloat16 if fmt else torch.float16
+
+
+@pytest.mark.parametrize("M,N,K,fmt,flags", [
+    (128, 256, 64, 0, 0), (1000, 768, 1024, 0, 0), (514, 640, 1024, 1, 0),
+    (4112, 3072, 1024, 0, 0), (256, 512, 512, 0, 1), (256, 256, 512, 0, 6), (300, 96, 192, 1, 0),
+])
+def test_gemm16(M, N, K, fmt, flags):
+    nat = _nat()
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda").to(_dt(fmt))
+    B = torch.randn(N, K, device="cuda").to(_dt(fmt))
+    bias = torch.randn(N, device="cuda")
+    ref = A.float() @ B.float().t() + bias
+    A_in = A.t().contiguous() if flags & 2 else A
+    B_in = B.t().contiguous() if flags & 1 else B
+    C = torch.empty(M, N, device="cuda", dtype=_dt(fmt))
+    nat.call("rvlm_gemm16_out16", nat.ptr(A_in), nat.c_int(A_in.stride(0)), nat.ptr(B_in),
+             nat.c_int(B_in.stride(0)), nat.ptr(C), nat.c_int(N), nat.ptr(bias), nat.c_int(M),
+             nat.c_int(N), nat.c_int(K), nat.c_int(fmt), nat.c_int(flags), nat.stream_ptr())
+    torch.cuda.synchronize()
+    tol = (2e-2 if fmt else 3e-3)
+    err = (C.float() - ref).abs().max().item()
+    _log("gemm16", M=M, N=N, K=K, fmt=fmt, flags=flags, err=err)
+    assert err <= tol * ref.abs().max().item()
+
+
+def test_gemm_fp32_residual_and_gelu():
+    nat = _nat()
+    torch.manual_seed(0)
+    M, N, K = 700, 512, 256
+    A = (torch.randn(M, K, device="cuda") * 0.5).half()
+    B = (torch.randn(N, K, device="cuda") * 0.1).half()
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    ref = A.float() @ B.float().t() + bias
+    C = torch.empty(M, N, device="cuda")
+    nat.call("rvlm_gemm16_out32", nat.ptr(A), nat.c_int(K), nat.ptr(B), nat.c_int(K), nat.ptr(C),
+             nat.c_int(N), nat.ptr(bias), nat.ptr(resid), nat.c_int(N), nat.c_int(M), nat.c_int(N),
+             nat.c_int(K), nat.c_int(0), nat.c_int(0), nat.stream_ptr())
+    Hh = torch.empty(M, N, device="cuda", dtype=torch.half)
+    Act = torch.empty(M, N, device="cuda", dtype=torch.half)
+    nat.call("rvlm_gemm16_gelu", nat.ptr(A), nat.c_int(K), nat.ptr(B), nat.c_int(K), nat.ptr(Hh),
+             nat.ptr(Act), nat.c_int(N), nat.ptr(bias), nat.c_int(M), nat.c_int(N), nat.c_int(K),
+             nat.c_int(0), nat.stream_ptr())
+    # gelu backward: out = (G @ Bt^T) * gelu'(H), G [M, K2] bf16, Bt [N, K2]
+    K2 = 128
+    G = torch.randn(M, K2, device="cuda").bfloat16()
+    Bt = (torch.randn(N, K2, device="cuda") * 0.1).bfloat16()
+    dH = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    nat.call("rvlm_gemm16_gelu_bwd", nat.ptr(G), nat.c_int(K2), nat.ptr(Bt), nat.c_int(K2),
+             nat.ptr(dH), nat.ptr(Hh), nat.c_int(N), nat.c_int(M), nat.c_int(N), nat.c_int(K2),
+             nat.c_int(1), nat.c_int(0), nat.stream_ptr())
+    torch.cuda.synchronize()
+    assert (C - (ref + resid)).abs().max() < 2e-3
+    assert (Hh.float() - ref).abs().max() < 2e-2
+    gel = ref * torch.sigmoid(1.702 * ref)
+    assert (Act.float() - gel).abs().max() < 2e-2
+    h = Hh.float()
+    s = torch.sigmoid(1.702 * h)
+    dref = (G.float() @ Bt.float().t()) * (s * (1 + 1.702 * h * (1 - s)))
+    assert (dH.float() - dref).abs().max() <= 2e-2 * dref.abs().max()
+
+
+@pytest.mark.parametrize("W", [128, 768, 1024])
+def test_layernorm_fwd_bwd(W):
+    nat = _nat()
+    torch.manual_seed(W)
+    M = 515
+    x = (torch.randn(M, W, device="cuda") * 2 + 0.3).requires_grad_(True)
+    g = torch.randn(W, device="cuda") * 0.1 + 1
+    b = torch.randn(W, device="cuda") * 0.1
+    y_ref = F.layer_norm(x, (W,), g, b, 1e-5)
+    dy = torch.randn(M, W, device="cuda")
+    dres = torch.randn(M, W, device="cuda")
+    (dx_ref,) = torch.autograd.grad(y_ref, x, dy)
+    y16 = torch.empty(M, W, device="cuda", dtype=torch.half)
+    y32 = torch.empty(M, W, device="cuda")
+    stats = torch.empty(M, 2, device="cuda")
+    nat.call("rvlm_layernorm_fwd", nat.ptr(x.detach()), nat.ptr(g), nat.ptr(b), nat.ptr(y16),
+             nat.ptr(y32), nat.ptr(stats), nat.c_int(M), nat.c_int(W), nat.c_int(0),
+             nat.stream_ptr())
+    dx32 = dres.clone()
+    dx16 = torch.empty(M, W, device="cuda", dtype=torch.bfloat16)
+    nat.call("rvlm_layernorm_bwd", nat.ptr(dy), nat.ptr(x.detach()), nat.ptr(stats), nat.ptr(g),
+             nat.ptr(dx32), nat.ptr(dx32), nat.ptr(dx16), nat.c_int(M), nat.c_int(W), nat.c_int(1),
+             nat.c_int(0), nat.stream_ptr())
+    torch.cuda.synchronize()
+    assert (y32 - y_ref).abs().max() < 1e-5
+    assert (y16.float() - y_ref).abs().max() < 5e-3
+    assert (dx32 - (dx_ref + dres)).abs().max() < 2e-5
+    assert (dx16.float() - (dx_ref + dres)).abs().max() < 5e-2
+    # compaction: drop every T-th row
+    T = 103
+    dxc = torch.zeros(M - M // T, W, device="cuda", dtype=torch.bfloat16)
+    nat.call("rvlm_layernorm_bwd", nat.ptr(dy), nat.ptr(x.detach()), nat.ptr(stats), nat.ptr(g),
+             nat.c_void_p(0), nat.c_void_p(0), nat.ptr(dxc), nat.c_int(M), nat.c_int(W),
+             nat.c_int(1), nat.c_int(T), nat.stream_ptr())
+    torch.cuda.synchronize()
+    keep = torch.arange(M, device="cuda") % T != 0
+    assert (dxc.float() - dx_ref[keep]).abs().max() < 5e-2
+
+
+def _attn_ref(qkv, B, T, H):
+    W = H * 64
+    q, k, v = qkv.float().view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    p = s.softmax(-1)
+    o = (p @ v).permute(0, 2, 1, 3).reshape(B * T, W)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("B,T,H", [(2, 50, 2), (3, 257, 4), (1, 257, 16)])
+def test_attention_fwd_bwd(impl, B, T, H):
+    nat = _nat()
+    torch.manual_seed(B * T + H)
+    W = H * 64
+    qkv = (torch.randn(B * T, 3 * W, device="cuda") * 1.5).half()
+    o = torch.empty(B * T, W, device="cuda", dtype=torch.half)
+    lse = torch.empty(B, H, T, device="cuda")
+    sfx = "_simt" if impl == "simt" else ""
+    nat.call("rvlm_attn_fwd" + sfx, nat.ptr(qkv), nat.ptr(o), nat.ptr(lse), nat.c_int(B),
+             nat.c_int(T), nat.c_int(H), nat.c_int(0), nat.stream_ptr())
+    torch.cuda.synchronize()
+    qf = qkv.float().requires_grad_(True)
+    o_ref, lse_ref = _attn_ref(qf, B, T, H)
+    e_o = (o.float() - o_ref).abs().max().item()
+    e_l = (lse - lse_ref).abs().max().item()
+    _log("attn_fwd", impl=impl, B=B, T=T, H=H, err_o=e_o, err_lse=e_l)
+    assert e_o < 4e-3 and e_l < 2e-3
+    d_o = (torch.randn(B * T, W, device="cuda") * 0.1).bfloat16()
+    (dqkv_ref,) = torch.autograd.grad(o_ref, qf, d_o.float())
+    dqkv = torch.empty(B * T, 3 * W, device="cuda", dtype=torch.bfloat16)
+    nat.call("rvlm_attn_bwd" + sfx, nat.ptr(qkv), nat.ptr(o), nat.ptr(d_o), nat.ptr(lse),
+             nat.ptr(dqkv), nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.c_int(0), nat.c_int(1),
+             nat.stream_ptr())
+    torch.cuda.synchronize()
+    err = (dqkv.float() - dqkv_ref).abs().max().item()
+    scale = dqkv_ref.abs().max().item()
+    _log("attn_bwd", impl=impl, B=B, T=T, H=H, err=err, scale=scale)
+    assert err <= 3e-2 * scale

@@ -1,0 +1,114 @@
+"""Fused engine vs the CPU oracle (oracle/ = checker; see oracle/__init__.py).
+
+Tolerances: forward embeddings within 1e-3 relative (north_star); gradients are
+compared by relative error and sign agreement (end-to-end
+delta can never be bit-identical -- a different fp32 summation order alone flips
+signs of near-zero gradients)."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import attacks as oa
+from oracle import vit as ovit
+from util import make_engine, rel_err, sign_agreement, synth_batch
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _log(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "test_metrics.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **kw}) + "\n")
+    print(name, kw)
+
+
+ATTN = [pytest.param(1, id="attn_simt"), pytest.param(0, id="attn_tc")]
+
+
+@pytest.mark.parametrize("flags", ATTN)
+@pytest.mark.parametrize("name,B", [("tiny-32", 4), ("tiny-14", 3)])
+def test_forward_matches_oracle(name, B, flags):
+    eng, model = make_engine(name, seed=1, flags=flags)
+    x, d0 = synth_batch(B, seed=0)
+    with torch.no_grad():
+        ref = model(x + d0, output_normalize=False)
+        refn = model(x + d0, output_normalize=True)
+    emb = eng.forward(x.cuda(), d0.cuda(), output_normalize=False)
+    embn = eng.forward(x.cuda(), d0.cuda(), output_normalize=True)
+    torch.cuda.synchronize()
+    e1, e2 = rel_err(emb, ref), rel_err(embn, refn)
+    _log("forward", name=name, flags=flags, rel=e1, rel_norm=e2)
+    assert e1 < 1e-3 and e2 < 1e-3
+
+
+def _oracle_grad(model, x, d0, loss_fn, y, normalize):
+    xa = (x + d0).requires_grad_(True)
+    out = model(xa, output_normalize=normalize)
+    li = loss_fn(out, y)
+    (g,) = torch.autograd.grad(li.sum(), xa)
+    return g, li.detach(), out.detach()
+
+
+@pytest.mark.parametrize("flags", ATTN)
+@pytest.mark.parametrize("loss", ["l2", "ce"])
+def test_loss_grad_matches_oracle(loss, flags):
+    from robustvlm_b200.engine import LossSpec
+    name, B = "tiny-32", 4
+    eng, model = make_engine(name, seed=1, flags=flags)
+    model_orig = ovit.ClipVisionModel(ovit.build(name, seed=2)).eval()
+    x, d0 = synth_batch(B, seed=3)
+    D = eng.arch["out_dim"]
+    torch.manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(D, 10), dim=0)
+    y = torch.randint(0, 10, (B,))
+    with torch.no_grad():
+        e_orig = model_orig(x, output_normalize=False)
+    normalize = loss == "ce"
+    wrap = oa.ComputeLossWrapper(e_orig, text, "none", loss, 100.0)
+    g_ref, li_ref, out_ref = _oracle_grad(model, x, d0, wrap, y, normalize)
+    spec = LossSpec(loss, normalize, emb_orig=e_orig.cuda(), text=text.cuda(), targets=y.cuda())
+    r = eng.loss_grad(x.cuda(), spec, delta=d0.cuda())
+    torch.cuda.synchronize()
+    g = r["grad"].cpu()
+    # per-sample positive rescaling is allowed: compare directions per sample
+    cos = torch.nn.functional.cosine_similarity(g.flatten(1).double(), g_ref.flatten(1).double())
+    agree, big_mism = sign_agreement(g, g_ref, tau=0.05)
+    el = rel_err(r["loss"], li_ref)
+    _log("loss_grad", loss=loss, flags=flags, cos_min=float(cos.min()), sign_agree=agree,
+         big_mismatch=big_mism, loss_rel=el, emb_rel=rel_err(r["emb"], out_ref))
+    assert el < 5e-2 if loss == "l2" else el < 5e-3
+    assert float(cos.min()) > 0.99
+    assert big_mism < 0.02
+
+
+@pytest.mark.parametrize("flags", ATTN)
+def test_pgd_run_matches_oracle(flags):
+    from robustvlm_b200.engine import NORM_LINF, LossSpec
+    name, B = "tiny-32", 4
+    eng, model = make_engine(name, seed=1, flags=flags)
+    model_orig = ovit.ClipVisionModel(ovit.build(name, seed=2)).eval()
+    x, d0 = synth_batch(B, seed=5)
+    eps, step, iters = 4 / 255, 1 / 255, 3
+    with torch.no_grad():
+        e_orig = model_orig(x, output_normalize=False)
+    wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+    ref = oa.pgd(model, wrap, x, None, "linf", eps, iters, step, False, perturbation=d0.clone(),
+                 mode="max")
+    spec = LossSpec("l2", False, emb_orig=e_orig.cuda())
+    out, tr = eng.pgd_run(x.cuda(), spec, norm=NORM_LINF, eps=eps, stepsize=step,
+                          iterations=iters, maximize=True, delta0=d0.cuda(), trace=True)
+    torch.cuda.synchronize()
+    out = out.cpu()
+    dl, dr = out - x, ref - x
+    same = float((dl == dr).float().mean())
+    assert float(dl.abs().max()) <= eps + 1e-6 and float(out.min()) >= 0 and float(out.max()) <= 1
+    with torch.no_grad():
+        loss_ours = wrap(model(out, output_normalize=False), None).item()
+        loss_ref = wrap(model(ref, output_normalize=False), None).item()
+    _log("pgd_run", flags=flags, delta_equal_frac=same, max_abs_delta_err=float((dl - dr).abs().max()),
+         loss_ours=loss_ours, loss_ref=loss_ref, trace=tr.mean(1).tolist())
+    assert same > 0.9
+    assert abs(loss_ours - loss_ref) <= 0.05 * abs(loss_ref)

@@ -1,0 +1,72 @@
+"""Oracle vs the live reference, imported in place from /root/reference (skipped where
+the tree is absent, e.g. on the GPU box).  CPU, bit-exact."""
+import pytest
+import torch
+
+from oracle import attacks as oa
+from oracle import ref_import, vit
+
+pytestmark = pytest.mark.skipif(not ref_import.available(), reason="/root/reference not mounted")
+
+
+@pytest.fixture(scope="module")
+def ns():
+    return ref_import.load()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    cfg = vit.VitConfig(image_size=64, patch=32, width=128, layers=2, heads=2, mlp=512, out_dim=64)
+    m = vit.ClipVisionModel(vit.build(cfg, seed=3)).eval()
+    mo = vit.ClipVisionModel(vit.build(cfg, seed=4)).eval()
+    g = torch.Generator().manual_seed(99)
+    x = torch.rand(4, 3, 64, 64, generator=g)
+    d0 = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1) * 4 / 255
+    y = torch.randint(0, 10, (4,), generator=g)
+    text = torch.nn.functional.normalize(torch.randn(64, 10, generator=g), dim=0)
+    with torch.no_grad():
+        eo = mo(x, output_normalize=False)
+    return m, x, d0, y, text, eo
+
+
+@pytest.mark.parametrize("norm,eps,step", [("linf", 4 / 255, 1 / 255), ("l2", 2.0, 0.5)])
+@pytest.mark.parametrize("mode", ["max", "min"])
+def test_pgd(ns, setup, norm, eps, step, mode):
+    m, x, d0, y, text, eo = setup
+    a = oa.pgd(m, oa.ComputeLossWrapper(eo, None, "mean", "l2", 100.0), x, y, norm, eps, 3, step,
+               False, perturbation=d0.clone(), mode=mode)
+    b = ns.pgd(m, ns.ComputeLossWrapper(eo, None, "mean", "l2", 100.0), x, y, norm, eps, 3, step,
+               False, perturbation=d0.clone(), mode=mode)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("norm,eps", [("linf", 4 / 255), ("l2", 2.0)])
+@pytest.mark.parametrize("n_iter", [10, 25])
+def test_apgd_train(ns, setup, norm, eps, n_iter):
+    m, x, d0, y, text, eo = setup
+    a = oa.apgd_train(m, x, y, norm, eps, n_iter=n_iter,
+                      loss_fn=oa.ComputeLossWrapper(eo, text, "none", "ce", 100.0))
+    b = ns.apgd_train(m, x, y, norm, eps, n_iter=n_iter,
+                      loss_fn=ns.ComputeLossWrapper(eo, text, "none", "ce", 100.0))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 2.0)])
+@pytest.mark.parametrize("loss", ["ce", "dlr"])
+def test_apgd_attack(ns, setup, norm, eps, loss):
+    m, x, d0, y, text, eo = setup
+    cm = vit.ClassificationModel(m.model, text, 100.0)
+    with torch.no_grad():
+        yc = cm(x).argmax(1)
+    A = oa.APGDAttack(cm, n_iter=15, norm=norm, n_restarts=2, eps=eps, seed=0, loss=loss, alpha=2.0)
+    R = ns.APGDAttack(cm, n_iter=15, norm=norm, n_restarts=2, eps=eps, seed=0, loss=loss, alpha=2.0)
+    assert torch.equal(A.perturb(x, yc), R.perturb(x, yc))
+    ra, rr = A.attack_single_run(x, yc), R.attack_single_run(x, yc)  # consumes the CPU RNG equally
+
+
+def test_model_wrappers(ns, setup):
+    m, x, d0, y, text, eo = setup
+    r = ns.ClipVisionModel(m.model, None, m.normalize)
+    with torch.no_grad():
+        for flag in (False, True):
+            assert torch.equal(m(x, output_normalize=flag), r(x, output_normalize=flag))

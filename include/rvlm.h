@@ -147,12 +147,18 @@ int rvlm_layernorm_bwd(const float* dy, const float* x, const float* stats, cons
  * tcgen05 kernels (production) and CUDA-core kernels (on-device checker). */
 int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H, int fmt,
                   void* stream);
-int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16, const float* lse,
-                  void* dqkv16, int B, int T, int H, int fmt, int fmt_g, void* stream);
+/* Backward: qkv16 is the backward's copy of q|k|v in fmt_qkv, do16 the output gradient and
+ * dqkv16 the result in fmt_g, o16 the forward output in fmt_o.  The softmax statistics
+ * are recomputed from the operands given (lse_tmp [B,H,T] is scratch).  The tcgen05
+ * kernels need fmt_qkv == fmt_g (one operand format per MMA). */
+int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16, float* lse_tmp,
+                  void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o, int fmt_g,
+                  void* stream);
 int rvlm_attn_fwd_simt(const void* qkv16, void* o16, float* lse, int B, int T, int H, int fmt,
                        void* stream);
-int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void* do16, const float* lse,
-                       void* dqkv16, int B, int T, int H, int fmt, int fmt_g, void* stream);
+int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void* do16, float* lse_tmp,
+                       void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o, int fmt_g,
+                       void* stream);
 
 /* ------------------------------------------------------------------------ *
  * 4. The fused engine.  Replaces, for a CLIP vision tower in open_clip

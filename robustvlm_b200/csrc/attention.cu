@@ -35,10 +35,13 @@ constexpr uint32_t AT_TMEM_S = 0, AT_TMEM_ACC = 320, AT_TMEM_ACC2 = 384;
 struct AttnParams {
   int B, T, H, W;
   int kvp, nblk, ntile, nbox, boxrows;
-  int fmt, fmt_g;
+  int fmt;               // operand format of every MMA in this launch (FWD: the qkv format;
+                         // DQ / DKV: the gradient format -- qkv here is the backward's copy)
+  int fmt_o;             // format of the forward output o (read by threads only)
+  int fmt_g;             // format of the dqkv output
   const uint16_t* o;     // [B*T, W]   (DQ / DKV: forward output, for D = rowsum(dO * O))
   const uint16_t* d_o;   // [B*T, W]
-  const float* lse;      // [B, H, T]  (DQ / DKV)
+  float* lse_tmp;        // [B, H, T]  softmax log2-sum-exp recomputed by DQ, read by DKV
   uint16_t* o_out;       // FWD
   float* lse_out;        // FWD
   uint16_t* dqkv;        // [B*T, 3W]  (DQ / DKV)
@@ -150,7 +153,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_items = P.B * P.H;
-  const uint32_t f = (uint32_t)P.fmt, fg = (uint32_t)P.fmt_g;
+  const uint32_t f = (uint32_t)P.fmt;
   // column offsets (elements) of q / k / v inside a qkv row
   const int colQ = 0, colK = W, colV = 2 * W;
 
@@ -209,13 +212,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
             umma_commit(bar_s);
             mbar_wait(bar_p, (2 * g) & 1, 13);
             tc_fence_after();
-            issue_mma1(tmem + AT_TMEM_S, t1, f1, kvp, fg, f);         // dP = dO V^T
+            issue_mma1(tmem + AT_TMEM_S, t1, f1, kvp, f, f);          // dP = dO V^T
             umma_commit(bar_s);
             mbar_wait(bar_p, (2 * g + 1) & 1, 15);
             tc_fence_after();
             if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 14);
             tc_fence_after();
-            issue_mma2(tmem + AT_TMEM_ACC, pa, f0, kvp, fg, f);       // dQ = dS K
+            issue_mma2(tmem + AT_TMEM_ACC, pa, f0, kvp, f, f);        // dQ = dS K
             umma_commit(bar_acc);
           } else {
             issue_mma1(tmem + AT_TMEM_S, t0, f0, kvp, f, f);          // S^T = K Q^T
@@ -224,12 +227,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
             tc_fence_after();
             if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 14);
             tc_fence_after();
-            issue_mma2(tmem + AT_TMEM_ACC, pa, f1, kvp, f, fg);       // dV = P^T dO
-            issue_mma1(tmem + AT_TMEM_S, t1, f1, kvp, f, fg);         // dP^T = V dO^T
+            issue_mma2(tmem + AT_TMEM_ACC, pa, f1, kvp, f, f);        // dV = P^T dO
+            issue_mma1(tmem + AT_TMEM_S, t1, f1, kvp, f, f);          // dP^T = V dO^T
             umma_commit(bar_s);                                       // (also: dV retired)
             mbar_wait(bar_p, (2 * g + 1) & 1, 15);
             tc_fence_after();
-            issue_mma2(tmem + AT_TMEM_ACC2, pa, f0, kvp, fg, f);      // dK = dS^T Q
+            issue_mma2(tmem + AT_TMEM_ACC2, pa, f0, kvp, f, f);       // dK = dS^T Q
             umma_commit(bar_acc);
           }
         }
@@ -249,9 +252,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
         for (int q = r; q < kvp; q += 128) {
           float L = INFINITY, Dv = 0.f;
           if (q < T) {
-            L = P.lse[((size_t)b * P.H + h) * T + q] * 1.4426950408889634f;
+            L = P.lse_tmp[((size_t)b * P.H + h) * T + q];
             const size_t ro = ((size_t)b * T + q) * W + h * 64;
-            Dv = dot_rows16(P.o + ro, P.fmt, P.d_o + ro, P.fmt_g);
+            Dv = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, P.fmt);
           }
           s_lse[q] = L;
           s_dvec[q] = Dv;
@@ -334,14 +337,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
           mbar_arrive(bar_acc_free);
         } else {
           // ---------------- backward modes ----------------
-          float Lr = 0.f, Dr = 0.f;  // DQ: this row's lse (log2 units) and D
-          if (MODE == AT_DQ && valid) {
-            Lr = P.lse[((size_t)b * P.H + h) * T + row] * 1.4426950408889634f;
-            Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt, P.d_o + grow * W + h * 64, P.fmt_g);
-          }
+          // DQ recomputes the row softmax statistics from the backward's own operand
+          // copies (self-consistent P), DKV reuses them per column through lse_tmp.
+          float Lr = 0.f, Dr = 0.f, rsum = 0.f;  // DQ: row max (log2 units), D, sum of exps
+          if (MODE == AT_DQ && valid)
+            Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, P.fmt);
           // pass 1: P = exp(S/8 - lse)
           mbar_wait(bar_s, (2 * g) & 1, 22);
           tc_fence_after();
+          if (MODE == AT_DQ && warp_valid) {
+            float mx = -INFINITY;
+            for (int c = 0; c < n32 + rem16; ++c) {
+              uint32_t v[32];
+              const int nv = c < n32 ? 32 : 16;
+              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
+              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nv && c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            Lr = mx * c2;
+          }
           if (warp_valid) {
             for (int c = 0; c < n32 + rem16; ++c) {
               uint32_t v[32];
@@ -359,6 +376,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
                 } else {
                   p[i] = 0.f;
                 }
+                rsum += p[i];
               }
 #pragma unroll
               for (int q8 = 0; q8 < 4; ++q8) {
@@ -373,10 +391,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
               }
             }
           }
+          float rinv = 1.f;
+          if (MODE == AT_DQ && valid) {
+            rinv = 1.f / rsum;
+            P.lse_tmp[((size_t)b * P.H + h) * T + row] = Lr + log2f(rsum);
+          }
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(bar_p);
-          // pass 2: dS = P (dP - D) / 8, in place over P
+          // pass 2: dS = P (dP - D) / 8, in place over P (DQ: P normalised here by 1/rowsum)
           mbar_wait(bar_s, (2 * g + 1) & 1, 23);
           tc_fence_after();
           if (warp_valid) {
@@ -399,14 +422,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
                     const int col = c * 32 + q8 * 8 + 2 * i;
                     const float D0 = (MODE == AT_DQ) ? Dr : s_dvec[col];
                     const float D1 = (MODE == AT_DQ) ? Dr : s_dvec[col + 1];
-                    d[2 * i] = pp.x * (__uint_as_float(v[q8 * 8 + 2 * i]) - D0) * 0.125f;
-                    d[2 * i + 1] = pp.y * (__uint_as_float(v[q8 * 8 + 2 * i + 1]) - D1) * 0.125f;
+                    d[2 * i] = pp.x * rinv * (__uint_as_float(v[q8 * 8 + 2 * i]) - D0) * 0.125f;
+                    d[2 * i + 1] =
+                        pp.y * rinv * (__uint_as_float(v[q8 * 8 + 2 * i + 1]) - D1) * 0.125f;
                   }
                   uint4 u;
-                  u.x = pack2(d[0], d[1], P.fmt_g);
-                  u.y = pack2(d[2], d[3], P.fmt_g);
-                  u.z = pack2(d[4], d[5], P.fmt_g);
-                  u.w = pack2(d[6], d[7], P.fmt_g);
+                  u.x = pack2(d[0], d[1], P.fmt);
+                  u.y = pack2(d[2], d[3], P.fmt);
+                  u.z = pack2(d[4], d[5], P.fmt);
+                  u.w = pack2(d[6], d[7], P.fmt);
                   *sp = u;
                 }
               }
@@ -466,7 +490,7 @@ struct AttnPlan {
 };
 
 static int make_plan(AttnPlan& pl, const void* qkv, const void* d_o, int B, int T, int H, int fmt,
-                     int fmt_g) {
+                     int fmt_o, int fmt_g) {
   if (B <= 0 || T <= 0 || T > 272 || H <= 0) return RVLM_ERR_UNSUPPORTED;
   AttnParams& P = pl.P;
   P.B = B; P.T = T; P.H = H; P.W = H * 64;
@@ -475,7 +499,7 @@ static int make_plan(AttnPlan& pl, const void* qkv, const void* d_o, int B, int 
   P.ntile = (T + 127) / 128;
   P.nbox = P.kvp > 256 ? 2 : 1;
   P.boxrows = P.kvp / P.nbox;
-  P.fmt = fmt; P.fmt_g = fmt_g;
+  P.fmt = fmt; P.fmt_o = fmt_o; P.fmt_g = fmt_g;
   pl.smem = (size_t)2 * P.kvp * 128 + 4 * 16384 + (size_t)P.nblk * 16384 + (size_t)2 * P.kvp * 4 +
             128 + 1024;
   const uint64_t W3 = 3ull * P.W;
@@ -515,7 +539,7 @@ using namespace rvlm;
 extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H,
                              int fmt, void* stream) {
   AttnPlan pl{};
-  int rc = make_plan(pl, qkv16, nullptr, B, T, H, fmt, fmt);
+  int rc = make_plan(pl, qkv16, nullptr, B, T, H, fmt, fmt, fmt);
   if (rc) return rc;
   pl.P.o_out = reinterpret_cast<uint16_t*>(o16);
   pl.P.lse_out = lse;
@@ -523,14 +547,17 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
 }
 
 extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16,
-                             const float* lse, void* dqkv16, int B, int T, int H, int fmt,
-                             int fmt_g, void* stream) {
+                             float* lse_tmp, void* dqkv16, int B, int T, int H, int fmt_qkv,
+                             int fmt_o, int fmt_g, void* stream) {
+  // every MMA operand of the backward (qkv copy, dO, P, dS) must share one 16-bit format
+  if (fmt_qkv != fmt_g) return RVLM_ERR_UNSUPPORTED;
+  if (!lse_tmp) return RVLM_ERR_INVAL;
   AttnPlan pl{};
-  int rc = make_plan(pl, qkv16, do16, B, T, H, fmt, fmt_g);
+  int rc = make_plan(pl, qkv16, do16, B, T, H, fmt_g, fmt_o, fmt_g);
   if (rc) return rc;
   pl.P.o = reinterpret_cast<const uint16_t*>(o16);
   pl.P.d_o = reinterpret_cast<const uint16_t*>(do16);
-  pl.P.lse = lse;
+  pl.P.lse_tmp = lse_tmp;
   pl.P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
   rc = launch_attn<AT_DQ>(pl, (cudaStream_t)stream);
   if (rc) return rc;

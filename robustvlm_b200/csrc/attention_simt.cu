@@ -104,9 +104,8 @@ __global__ void attn_fwd_simt_kernel(const uint16_t* __restrict__ qkv, uint16_t*
 // column-wise for dK / dV), scores recomputed in each.
 __global__ void attn_bwd_simt_kernel(const uint16_t* __restrict__ qkv,
                                      const uint16_t* __restrict__ o,
-                                     const uint16_t* __restrict__ d_o,
-                                     const float* __restrict__ lse, uint16_t* __restrict__ dqkv,
-                                     int T, int H, int fmt, int fmt_g) {
+                                     const uint16_t* __restrict__ d_o, uint16_t* __restrict__ dqkv,
+                                     int T, int H, int fmt, int fmt_o, int fmt_g) {
   extern __shared__ uint8_t sm[];
   const int W = H * HD;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -124,21 +123,38 @@ __global__ void attn_bwd_simt_kernel(const uint16_t* __restrict__ qkv,
   load_head(sV, base + 2 * W, T, 3 * W);
   load_head(sdO, d_o + (size_t)b * T * W + h * HD, T, W);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) sL[t] = lse[((size_t)b * H + h) * T + t];
-  __syncthreads();
-  for (int t = warp; t < T; t += nw) {
-    const uint16_t* op = o + ((size_t)b * T + t) * W + h * HD;
-    float s = ld16(op + lane, fmt) * ld16(sdO + t * ROWP + lane, fmt_g) +
-              ld16(op + lane + 32, fmt) * ld16(sdO + t * ROWP + lane + 32, fmt_g);
-    s = wsum(s);
-    if (lane == 0) sD[t] = s;
-  }
   __syncthreads();
   const float scale = 0.125f;
   float* pp = sP + warp * 2 * T;
   float* ds = pp + T;
   float* ra = sR + warp * 128;
   float* rb = ra + 64;
+  // softmax statistics recomputed from the operands given (self-consistent with P below)
+  for (int t = warp; t < T; t += nw) {
+    const uint16_t* op = o + ((size_t)b * T + t) * W + h * HD;
+    float s = ld16(op + lane, fmt_o) * ld16(sdO + t * ROWP + lane, fmt_g) +
+              ld16(op + lane + 32, fmt_o) * ld16(sdO + t * ROWP + lane + 32, fmt_g);
+    s = wsum(s);
+    if (lane == 0) sD[t] = s;
+    ra[lane] = ld16(sQ + t * ROWP + lane, fmt);
+    ra[lane + 32] = ld16(sQ + t * ROWP + lane + 32, fmt);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int kv = lane; kv < T; kv += 32) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < HD; ++d) a += ra[d] * ld16(sK + kv * ROWP + d, fmt);
+      pp[kv] = a * scale;
+      mx = fmaxf(mx, a * scale);
+    }
+    mx = wmax(mx);
+    float sum = 0.f;
+    for (int kv = lane; kv < T; kv += 32) sum += __expf(pp[kv] - mx);
+    sum = wsum(sum);
+    if (lane == 0) sL[t] = mx + logf(sum);
+    __syncwarp();
+  }
+  __syncthreads();
   // ---- pass A: one q row per warp -> dQ
   for (int t = warp; t < T; t += nw) {
     ra[lane] = ld16(sQ + t * ROWP + lane, fmt);
@@ -229,8 +245,9 @@ extern "C" int rvlm_attn_fwd_simt(const void* qkv16, void* o16, float* lse, int 
 }
 
 extern "C" int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void* do16,
-                                  const float* lse, void* dqkv16, int B, int T, int H, int fmt,
-                                  int fmt_g, void* stream) {
+                                  float* lse_tmp, void* dqkv16, int B, int T, int H, int fmt,
+                                  int fmt_o, int fmt_g, void* stream) {
+  (void)lse_tmp;
   const int threads = 256, nw = threads / 32;
   const size_t smem = (size_t)4 * T * ROWP * 2 + (size_t)2 * T * 4 + (size_t)nw * 2 * T * 4 +
                       (size_t)nw * 128 * 4;
@@ -243,8 +260,8 @@ extern "C" int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void
   }
   attn_bwd_simt_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint16_t*>(qkv16), reinterpret_cast<const uint16_t*>(o16),
-      reinterpret_cast<const uint16_t*>(do16), lse, reinterpret_cast<uint16_t*>(dqkv16), T, H, fmt,
-      fmt_g);
+      reinterpret_cast<const uint16_t*>(do16), reinterpret_cast<uint16_t*>(dqkv16), T, H, fmt,
+      fmt_o, fmt_g);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;

@@ -46,6 +46,25 @@ struct EpiStore16 {
   }
 };
 
+// Same value written twice in two 16-bit formats: C (fmt) feeds the forward attention,
+// C2 (fmt2) is the copy the backward keeps, in the gradient operand format -- a
+// tcgen05.mma needs both operands in one format, and the backward's other operand is
+// a gradient.
+struct EpiStore16Dual {
+  uint16_t* C;
+  uint16_t* C2;  // may be null
+  int ldc;
+  const float* bias;
+  int fmt, fmt2;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = acc[j] + (bias ? __ldg(bias + col0 + j) : 0.f);
+    store16x32(C + (size_t)row * ldc + col0, v, fmt);
+    if (C2) store16x32(C2 + (size_t)row * ldc + col0, v, fmt2);
+  }
+};
+
 // C32[row, col] = acc + bias[col] + resid[row, col]   (fp32 residual stream)
 struct EpiStore32 {
   float* C;

@@ -22,10 +22,10 @@
 using namespace rvlm;
 
 extern "C" int rvlm_attn_fwd_simt(const void*, void*, float*, int, int, int, int, void*);
-extern "C" int rvlm_attn_bwd_simt(const void*, const void*, const void*, const float*, void*, int,
+extern "C" int rvlm_attn_bwd_simt(const void*, const void*, const void*, float*, void*, int, int,
                                   int, int, int, int, void*);
 extern "C" int rvlm_attn_fwd(const void*, void*, float*, int, int, int, int, void*);
-extern "C" int rvlm_attn_bwd(const void*, const void*, const void*, const float*, void*, int, int,
+extern "C" int rvlm_attn_bwd(const void*, const void*, const void*, float*, void*, int, int, int,
                              int, int, int, void*);
 extern "C" int rvlm_layernorm_fwd(const float*, const float*, const float*, void*, float*, float*,
                                   int, int, int, void*);
@@ -64,7 +64,8 @@ struct Ws {
   float *x32;     // [(L+1)] or [2] x [M, W]
   float *xm32;    // [L] or [1]
   float *stats1, *stats2;  // [L] x [M, 2]
-  uint16_t *qkv16, *o16, *h16;  // [L] or [1]
+  uint16_t *qkv16, *o16, *h16;  // [L] or [1]; qkv16 is the backward's copy (fmt_bwd)
+  uint16_t* qkvf16;             // [M, 3W] transient forward-format q|k|v
   float* lse;     // [L] x [B, H, T]
   uint16_t *y16, *act16;
   // backward
@@ -109,6 +110,7 @@ Ws carve(const Engine& E, uint8_t* base, int B, int stash) {
   w.stats1 = take<float>(p, used, nl * M * 2);
   w.stats2 = take<float>(p, used, nl * M * 2);
   w.qkv16 = take<uint16_t>(p, used, nl * M * 3 * W);
+  w.qkvf16 = take<uint16_t>(p, used, M * 3 * W);
   w.o16 = take<uint16_t>(p, used, nl * M * W);
   w.h16 = take<uint16_t>(p, used, nl * M * F);
   w.lse = take<float>(p, used, nl * (size_t)B * E.H * E.T);
@@ -165,12 +167,12 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     float* st1 = w.stats1 + s * (size_t)M * 2;
     float* st2 = w.stats2 + s * (size_t)M * 2;
     RV(rvlm_layernorm_fwd(x_in, Lw.ln1_g, Lw.ln1_b, w.y16, nullptr, st1, M, W, ff, stv));
-    {
-      EpiStore16 epi{qkv, 3 * W, Lw.bqkv, ff};
+    {  // q|k|v in the forward format (transient) + the backward's copy in the gradient format
+      EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd};
       RV((launch_gemm16<256, false, false>(w.y16, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
     }
-    if (E.attn_simt) RV(rvlm_attn_fwd_simt(qkv, o, lse, B, E.T, E.H, ff, stv));
-    else RV(rvlm_attn_fwd(qkv, o, lse, B, E.T, E.H, ff, stv));
+    if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
+    else RV(rvlm_attn_fwd(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     {
       EpiStore32 epi{xm, W, Lw.bo, x_in, W};
       RV((launch_gemm16<256, false, false>(o, W, Lw.wo, W, M, W, W, ff, epi, st)));
@@ -239,7 +241,7 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     const uint16_t* qkv = w.qkv16 + (size_t)l * MW * 3;
     const uint16_t* o = w.o16 + (size_t)l * MW;
     const uint16_t* h = w.h16 + (size_t)l * M * F;
-    const float* lse = w.lse + (size_t)l * B * E.H * E.T;
+    float* lse = w.lse + (size_t)l * B * E.H * E.T;  // scratch for the recomputed statistics
     const float* st1 = w.stats1 + (size_t)l * M * 2;
     const float* st2 = w.stats2 + (size_t)l * M * 2;
     {  // d act -> d h (through QuickGELU)
@@ -255,8 +257,9 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       EpiStore16 epi{w.do16, W, nullptr, fg};
       RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
     }
-    if (E.attn_simt) RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, ff, fg, stv));
-    else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, ff, fg, stv));
+    if (E.attn_simt)
+      RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
+    else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     {  // d ln_1 output
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
       RV((launch_gemm16<256, false, false>(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,

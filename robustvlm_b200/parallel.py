@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), batch-sharded.
+
+The inner attack loop is per-sample: every rank attacks its own shard with
+its own model replica and NO data-path collective.  The only exchange in the whole FARE /
+TeCoA step is the all-reduce of the outer model gradients (replacing the reference's
+torch.nn.DataParallel replicate/scatter/gather, train/adversarial_training_clip.py:184-190),
+issued once per step over NCCL / NVLink on a flat fp32 bucket.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init(backend: str | None = None) -> tuple[int, int]:
+    """(rank, world) from the torchrun environment; initialises the process group if N > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world
+
+
+def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous shard [lo, hi) of n samples; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    lo, hi = shard_bounds(t.shape[0], rank, world)
+    return t[lo:hi]
+
+
+def allreduce_mean_(flat_grad: torch.Tensor, local_count: int, global_count: int) -> torch.Tensor:
+    """In-place: sum over ranks of (per-rank mean gradient * local_count) / global_count, i.e.
+    the gradient of the mean loss over the GLOBAL batch (the loss is a batch mean,
+    train/adversarial_training_clip.py:517,528) even when shards are uneven."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        flat_grad.mul_(float(local_count))
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        flat_grad.div_(float(global_count))
+    return flat_grad
+
+
+def gather_batch(t: torch.Tensor) -> torch.Tensor:
+    """All-gather shards along dim 0 (uneven shards allowed); used by tests / evaluation."""
+    if not (dist.is_initialized() and dist.get_world_size() > 1):
+        return t
+    world = dist.get_world_size()
+    sizes = [torch.zeros(1, dtype=torch.long, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.shape[0]], dtype=torch.long, device=t.device))
+    mx = int(max(s.item() for s in sizes))
+    pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return torch.cat([o[: int(s.item())] for o, s in zip(outs, sizes)], dim=0)

@@ -153,12 +153,17 @@ def test_attention_fwd_bwd(impl, B, T, H):
     e_l = (lse - lse_ref).abs().max().item()
     _log("attn_fwd", impl=impl, B=B, T=T, H=H, err_o=e_o, err_lse=e_l)
     assert e_o < 4e-3 and e_l < 2e-3
+    # backward: every operand in the gradient format (bf16 copy of q|k|v), statistics recomputed
     d_o = (torch.randn(B * T, W, device="cuda") * 0.1).bfloat16()
-    (dqkv_ref,) = torch.autograd.grad(o_ref, qf, d_o.float())
+    qkv_b = qkv.float().bfloat16()
+    qb = qkv_b.float().requires_grad_(True)
+    o_ref_b, _ = _attn_ref(qb, B, T, H)
+    (dqkv_ref,) = torch.autograd.grad(o_ref_b, qb, d_o.float())
     dqkv = torch.empty(B * T, 3 * W, device="cuda", dtype=torch.bfloat16)
-    nat.call("rvlm_attn_bwd" + sfx, nat.ptr(qkv), nat.ptr(o), nat.ptr(d_o), nat.ptr(lse),
-             nat.ptr(dqkv), nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.c_int(0), nat.c_int(1),
-             nat.stream_ptr())
+    lse_tmp = torch.empty(B, H, T, device="cuda")
+    nat.call("rvlm_attn_bwd" + sfx, nat.ptr(qkv_b), nat.ptr(o), nat.ptr(d_o), nat.ptr(lse_tmp),
+             nat.ptr(dqkv), nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.c_int(1), nat.c_int(0),
+             nat.c_int(1), nat.stream_ptr())
     torch.cuda.synchronize()
     err = (dqkv.float() - dqkv_ref).abs().max().item()
     scale = dqkv_ref.abs().max().item()

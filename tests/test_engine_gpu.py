@@ -40,7 +40,7 @@ def test_forward_matches_oracle(name, B, flags):
     embn = eng.forward(x.cuda(), d0.cuda(), output_normalize=True)
     torch.cuda.synchronize()
     e1, e2 = rel_err(emb, ref), rel_err(embn, refn)
-    _log("forward", name=name, flags=flags, rel=e1, rel_norm=e2)
+    _log("forward", model=name, flags=flags, rel=e1, rel_norm=e2)
     assert e1 < 1e-3 and e2 < 1e-3
 
 

@@ -232,7 +232,8 @@ int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weights* weights,
 int rvlm_vit_update_weights(rvlm_vit_handle h, const rvlm_vit_weights* weights, void* stream);
 int rvlm_vit_destroy(rvlm_vit_handle h);
 /* Caller-owned scratch for a batch of B images; with_backward = 1 also holds the
- * per-layer activations the input-gradient backward needs. */
+ * per-layer activations the input-gradient backward needs, 2 those of the outer
+ * training step as well. */
 size_t rvlm_vit_workspace_bytes(rvlm_vit_handle h, int B, int with_backward);
 
 /* emb_out[B, out_dim] = model(x + delta) (delta may be NULL); x, delta: [B,3,H,W] in [0,1].
@@ -264,6 +265,48 @@ int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, con
                  const float* delta0, int B, const rvlm_loss_config* loss, int norm, float eps,
                  float stepsize, int iterations, int maximize, float momentum, float* x_adv_out,
                  float* loss_trace, void* stream);
+/* ------------------------------------------------------------------------ *
+ * 5. Outer training step (the model update of FARE / TeCoA,
+ *    train/adversarial_training_clip.py:340-366): forward of x (the adversarial batch),
+ *    loss, full backward.  Writes d(loss_scale * sum_b loss_b)/d(parameter) for every
+ *    parameter into `grads` (same layout as rvlm_vit_weights, fp32, overwritten); pass
+ *    loss_scale = 1 / global_batch for the reference's batch-mean loss.  The engine must
+ *    have fmt_fwd == fmt_bwd (weight-gradient GEMMs need one operand format; bf16
+ *    recommended) and the workspace must be sized with with_backward = 2.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  float* conv1_weight;
+  float* class_embedding;
+  float* positional_embedding;
+  float* ln_pre_weight;
+  float* ln_pre_bias;
+  float* ln_post_weight;
+  float* ln_post_bias;
+  float* proj;
+  float* const* ln_1_weight;
+  float* const* ln_1_bias;
+  float* const* attn_in_proj_weight;
+  float* const* attn_in_proj_bias;
+  float* const* attn_out_proj_weight;
+  float* const* attn_out_proj_bias;
+  float* const* ln_2_weight;
+  float* const* ln_2_bias;
+  float* const* mlp_c_fc_weight;
+  float* const* mlp_c_fc_bias;
+  float* const* mlp_c_proj_weight;
+  float* const* mlp_c_proj_bias;
+} rvlm_vit_grads;
+
+int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                         const float* x, int B, const rvlm_loss_config* loss, float loss_scale,
+                         const rvlm_vit_grads* grads, float* loss_out, float* emb_out,
+                         void* stream);
+/* torch.optim.AdamW semantics on a flat fp32 buffer (train/adversarial_training_clip.py:196-197,363):
+ * decoupled weight decay, bias correction with the 1-based step count. */
+int rvlm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                    long long n, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, void* stream);
+
 /* Test hook: pointer of an internal workspace buffer (see vit_engine.cu). */
 int rvlm_vit_debug_buffer(rvlm_vit_handle h, void* workspace, int B, int with_backward, int which,
                           int layer, void** ptr_out);

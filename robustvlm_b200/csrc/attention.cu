@@ -28,7 +28,8 @@
 
 namespace rvlm {
 
-constexpr int AT_THREADS = 160;
+constexpr int AT_THREADS = 288;  // 8 worker warps + 1 control warp
+constexpr int AT_CTRL_WARP = 8;
 enum { AT_FWD = 0, AT_DQ = 1, AT_DKV = 2 };
 constexpr uint32_t AT_TMEM_S = 0, AT_TMEM_ACC = 320, AT_TMEM_ACC2 = 384;
 
@@ -105,6 +106,18 @@ __device__ __forceinline__ float dot_rows16(const uint16_t* a, int fa, const uin
   return acc;
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 32 (or, for the ragged tail chunk, 16) fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void ld_chunk(uint32_t taddr, int c, int n32, uint32_t (&v)[32]) {
+  if (c < n32) tmem_ld32(taddr + c * 32, v);
+  else tmem_ld16(taddr + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
+  tmem_ld_wait();
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
@@ -124,7 +137,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
   uint8_t* s_p = s_tile1 + 2 * 16384;       // [nblk][16384]
   float* s_lse = reinterpret_cast<float*>(s_p + P.nblk * 16384);  // [kvp] (DKV)
   float* s_dvec = s_lse + kvp;                                    // [kvp] (DKV)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_dvec + kvp);
+  float* s_red = s_dvec + kvp;   // [2][128] row max of each column half
+  float* s_red2 = s_red + 256;   // [2][128] row sum of each column half
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red2 + 256);
   uint64_t* bar_full = bars + 0;     // full0 + full1 landed
   uint64_t* bar_tile = bars + 1;     // [2]
   uint64_t* bar_s = bars + 3;        // mma1 result ready
@@ -139,12 +154,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
     mbar_init(&bar_tile[0], 1);
     mbar_init(&bar_tile[1], 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, 256);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_acc_free, 128);
+    mbar_init(bar_acc_free, 256);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == AT_CTRL_WARP) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -157,7 +172,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
   // column offsets (elements) of q / k / v inside a qkv row
   const int colQ = 0, colK = W, colV = 2 * W;
 
-  if (warp == 4) {
+  if (warp == AT_CTRL_WARP) {
     if (lane == 0) {
       // ===================== TMA + MMA issuer =====================
       uint32_t g = 0;  // global tile counter
@@ -240,16 +255,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
     }
   } else {
     // ===================== row workers =====================
-    const int r = threadIdx.x;  // tile row == TMEM lane
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    // 8 warps: thread (r, hsel) owns tile row r (TMEM lane) and one half of the columns;
+    // the two halves exchange the row max / row sum through shared memory.
+    const int r = threadIdx.x & 127, hsel = threadIdx.x >> 7;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float c2 = 0.125f * 1.4426950408889634f;  // scale * log2(e)
-    const int n32 = kvp >> 5, rem16 = (kvp & 31) >> 4;
+    const int n32 = kvp >> 5, nch = n32 + ((kvp & 31) >> 4);
+    const int c_lo = hsel ? (nch + 1) / 2 : 0, c_hi = hsel ? nch : (nch + 1) / 2;
+    const uint32_t ts = tmem + lane_off + AT_TMEM_S;
     uint32_t g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int b = item / P.H, h = item % P.H;
       if (MODE == AT_DKV) {
-        // per-token lse and D = rowsum(dO * O) for all q of this (b, h)
-        for (int q = r; q < kvp; q += 128) {
+        // per-token log2-sum-exp (from the DQ pass) and D = rowsum(dO * O) of this (b, h)
+        for (int q = threadIdx.x; q < kvp; q += 256) {
           float L = INFINITY, Dv = 0.f;
           if (q < T) {
             L = P.lse_tmp[((size_t)b * P.H + h) * T + q];
@@ -259,156 +278,109 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
           s_lse[q] = L;
           s_dvec[q] = Dv;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       for (int j = 0; j < P.ntile; ++j, ++g) {
-        const int row = j * 128 + r;        // q row (FWD/DQ) or kv row (DKV) inside the image
+        const int row = j * 128 + r;  // q row (FWD/DQ) or kv row (DKV) inside the image
         const bool valid = row < T;
-        const bool warp_valid = (j * 128 + warp * 32) < T;
+        const bool warp_valid = (j * 128 + (warp & 3) * 32) < T;
         const size_t grow = (size_t)b * T + row;
-        if (MODE == AT_FWD) {
-          mbar_wait(bar_s, g & 1, 20);
-          tc_fence_after();
-          float mx = -INFINITY, sum = 0.f;
+        float Dr = 0.f;
+        if (MODE == AT_DQ && valid)
+          Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, P.fmt);
+        // ---------------- pass 1: P from the mma1 result ----------------
+        mbar_wait(bar_s, (MODE == AT_FWD ? g : 2 * g) & 1, 20);
+        tc_fence_after();
+        float mc = 0.f, rsum = 0.f;
+        if (MODE != AT_DKV) {
+          // row max over this thread's columns, then across the two halves
+          float mx = -INFINITY;
           if (warp_valid) {
-            for (int c = 0; c < n32 + rem16; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
               uint32_t v[32];
+              ld_chunk(ts, c, n32, v);
               const int nv = c < n32 ? 32 : 16;
-              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
-              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
-              tmem_ld_wait();
+              if (c * 32 + nv <= T) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < nv && c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
+              }
+            }
+          }
+          s_red[hsel * 128 + r] = mx;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          mc = fmaxf(s_red[r], s_red[128 + r]) * c2;
+        }
+        if (warp_valid) {
+          for (int c = c_lo; c < c_hi; ++c) {
+            uint32_t v[32];
+            ld_chunk(ts, c, n32, v);
+            const int nv = c < n32 ? 32 : 16;
+            float p[32];
+            if (MODE == AT_DKV) {
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (i < nv && c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
-            }
-            const float mc = mx * c2;
-            for (int c = 0; c < n32 + rem16; ++c) {
-              uint32_t v[32];
-              const int nv = c < n32 ? 32 : 16;
-              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
-              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
-              tmem_ld_wait();
-              float p[32];
+                p[i] = (i < nv && valid)
+                           ? fast_ex2(fmaf(__uint_as_float(v[i]), c2, -s_lse[c * 32 + i]))
+                           : 0.f;
+            } else if (c * 32 + nv <= T) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                p[i] = (i < nv && c * 32 + i < T) ? exp2f(__uint_as_float(v[i]) * c2 - mc) : 0.f;
-                sum += p[i];
-              }
-#pragma unroll
-              for (int q8 = 0; q8 < 4; ++q8) {
-                if (q8 * 8 < nv) {
-                  uint4 u;
-                  u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
-                  u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
-                  u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
-                  u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
-                  *reinterpret_cast<uint4*>(s_p + p_off(r, c * 32 + q8 * 8)) = u;
-                }
-              }
-            }
-          }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(bar_p);
-          mbar_wait(bar_acc, g & 1, 21);
-          tc_fence_after();
-          if (warp_valid) {
-            uint32_t v0[32], v1[32];
-            tmem_ld32(tmem + lane_off + AT_TMEM_ACC, v0);
-            tmem_ld32(tmem + lane_off + AT_TMEM_ACC + 32, v1);
-            tmem_ld_wait();
-            if (valid) {
-              const float inv = 1.f / sum;
-              uint4* dst = reinterpret_cast<uint4*>(P.o_out + grow * W + h * 64);
-#pragma unroll
-              for (int q8 = 0; q8 < 8; ++q8) {
-                const uint32_t* s = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
-                uint4 u;
-                u.x = pack2(__uint_as_float(s[0]) * inv, __uint_as_float(s[1]) * inv, P.fmt);
-                u.y = pack2(__uint_as_float(s[2]) * inv, __uint_as_float(s[3]) * inv, P.fmt);
-                u.z = pack2(__uint_as_float(s[4]) * inv, __uint_as_float(s[5]) * inv, P.fmt);
-                u.w = pack2(__uint_as_float(s[6]) * inv, __uint_as_float(s[7]) * inv, P.fmt);
-                dst[q8] = u;
-              }
-              P.lse_out[((size_t)b * P.H + h) * T + row] = mx * 0.125f + logf(sum);
-            }
-          }
-          tc_fence_before();
-          mbar_arrive(bar_acc_free);
-        } else {
-          // ---------------- backward modes ----------------
-          // DQ recomputes the row softmax statistics from the backward's own operand
-          // copies (self-consistent P), DKV reuses them per column through lse_tmp.
-          float Lr = 0.f, Dr = 0.f, rsum = 0.f;  // DQ: row max (log2 units), D, sum of exps
-          if (MODE == AT_DQ && valid)
-            Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, P.fmt);
-          // pass 1: P = exp(S/8 - lse)
-          mbar_wait(bar_s, (2 * g) & 1, 22);
-          tc_fence_after();
-          if (MODE == AT_DQ && warp_valid) {
-            float mx = -INFINITY;
-            for (int c = 0; c < n32 + rem16; ++c) {
-              uint32_t v[32];
-              const int nv = c < n32 ? 32 : 16;
-              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
-              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nv && c * 32 + i < T) mx = fmaxf(mx, __uint_as_float(v[i]));
-            }
-            Lr = mx * c2;
-          }
-          if (warp_valid) {
-            for (int c = 0; c < n32 + rem16; ++c) {
-              uint32_t v[32];
-              const int nv = c < n32 ? 32 : 16;
-              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
-              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
-              tmem_ld_wait();
-              float p[32];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (i < nv) {
-                  const float L = (MODE == AT_DQ) ? Lr : s_lse[c * 32 + i];
-                  const bool colv = (MODE == AT_DQ) ? (c * 32 + i < T) : true;
-                  p[i] = (colv && valid) ? exp2f(__uint_as_float(v[i]) * c2 - L) : 0.f;
-                } else {
-                  p[i] = 0.f;
-                }
+                p[i] = (i < nv) ? fast_ex2(fmaf(__uint_as_float(v[i]), c2, -mc)) : 0.f;
                 rsum += p[i];
               }
+            } else {
 #pragma unroll
-              for (int q8 = 0; q8 < 4; ++q8) {
-                if (q8 * 8 < nv) {
-                  uint4 u;
-                  u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
-                  u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
-                  u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
-                  u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
-                  *reinterpret_cast<uint4*>(s_p + p_off(r, c * 32 + q8 * 8)) = u;
-                }
+              for (int i = 0; i < 32; ++i) {
+                p[i] = (i < nv && c * 32 + i < T)
+                           ? fast_ex2(fmaf(__uint_as_float(v[i]), c2, -mc))
+                           : 0.f;
+                rsum += p[i];
+              }
+            }
+            if (MODE == AT_DQ && !valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) p[i] = 0.f;
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              if (q8 * 8 < nv) {
+                uint4 u;
+                u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
+                u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
+                u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
+                u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
+                *reinterpret_cast<uint4*>(s_p + p_off(r, c * 32 + q8 * 8)) = u;
               }
             }
           }
-          float rinv = 1.f;
-          if (MODE == AT_DQ && valid) {
-            rinv = 1.f / rsum;
-            P.lse_tmp[((size_t)b * P.H + h) * T + row] = Lr + log2f(rsum);
-          }
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(bar_p);
-          // pass 2: dS = P (dP - D) / 8, in place over P (DQ: P normalised here by 1/rowsum)
+        }
+        if (MODE != AT_DKV) s_red2[hsel * 128 + r] = rsum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        float rinv = 1.f;
+        if (MODE != AT_DKV) {
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          rsum = s_red2[r] + s_red2[128 + r];
+          rinv = 1.f / rsum;
+          if (MODE == AT_DQ && valid && hsel == 0)
+            P.lse_tmp[((size_t)b * P.H + h) * T + row] = mc + log2f(rsum);
+        }
+        if (MODE != AT_FWD) {
+          // ------------- pass 2: dS = P (dP - D) / 8, in place over P -------------
           mbar_wait(bar_s, (2 * g + 1) & 1, 23);
           tc_fence_after();
           if (warp_valid) {
-            for (int c = 0; c < n32 + rem16; ++c) {
+            const float sc = 0.125f * rinv;  // DQ: P is normalised here by 1 / rowsum
+            for (int c = c_lo; c < c_hi; ++c) {
               uint32_t v[32];
+              ld_chunk(ts, c, n32, v);
               const int nv = c < n32 ? 32 : 16;
-              if (c < n32) tmem_ld32(tmem + lane_off + AT_TMEM_S + c * 32, v);
-              else tmem_ld16(tmem + lane_off + AT_TMEM_S + c * 32, *reinterpret_cast<uint32_t(*)[16]>(v));
-              tmem_ld_wait();
 #pragma unroll
               for (int q8 = 0; q8 < 4; ++q8) {
                 if (q8 * 8 < nv) {
@@ -422,9 +394,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
                     const int col = c * 32 + q8 * 8 + 2 * i;
                     const float D0 = (MODE == AT_DQ) ? Dr : s_dvec[col];
                     const float D1 = (MODE == AT_DQ) ? Dr : s_dvec[col + 1];
-                    d[2 * i] = pp.x * rinv * (__uint_as_float(v[q8 * 8 + 2 * i]) - D0) * 0.125f;
-                    d[2 * i + 1] =
-                        pp.y * rinv * (__uint_as_float(v[q8 * 8 + 2 * i + 1]) - D1) * 0.125f;
+                    d[2 * i] = pp.x * sc * (__uint_as_float(v[q8 * 8 + 2 * i]) - D0);
+                    d[2 * i + 1] = pp.y * sc * (__uint_as_float(v[q8 * 8 + 2 * i + 1]) - D1);
                   }
                   uint4 u;
                   u.x = pack2(d[0], d[1], P.fmt);
@@ -439,45 +410,69 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(bar_p);
-          // epilogue
-          mbar_wait(bar_acc, g & 1, 24);
-          tc_fence_after();
-          if (warp_valid) {
-            const int nacc = (MODE == AT_DKV) ? 2 : 1;
-            for (int a = 0; a < nacc; ++a) {
-              uint32_t v0[32], v1[32];
-              const uint32_t col = (a == 0) ? AT_TMEM_ACC : AT_TMEM_ACC2;
-              tmem_ld32(tmem + lane_off + col, v0);
-              tmem_ld32(tmem + lane_off + col + 32, v1);
-              tmem_ld_wait();
-              if (valid) {
-                // DQ: dQ at column 0; DKV: a == 0 -> dV (2W), a == 1 -> dK (W)
-                const int cofs = (MODE == AT_DQ) ? 0 : (a == 0 ? 2 * W : W);
-                uint4* dst = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + cofs + h * 64);
+        }
+        // ---------------- epilogue: accumulators -> HBM ----------------
+        mbar_wait(bar_acc, g & 1, 24);
+        tc_fence_after();
+        if (warp_valid) {
+          if (MODE == AT_DKV) {
+            // hsel 0: dV (ACC, columns 2W..), hsel 1: dK (ACC2, columns W..)
+            uint32_t v0[32], v1[32];
+            const uint32_t col = hsel ? AT_TMEM_ACC2 : AT_TMEM_ACC;
+            tmem_ld32(tmem + lane_off + col, v0);
+            tmem_ld32(tmem + lane_off + col + 32, v1);
+            tmem_ld_wait();
+            if (valid) {
+              uint4* dst = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + (hsel ? W : 2 * W) +
+                                                    h * 64);
 #pragma unroll
-                for (int q8 = 0; q8 < 8; ++q8) {
-                  const uint32_t* s = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
-                  uint4 u;
-                  u.x = pack2(__uint_as_float(s[0]), __uint_as_float(s[1]), P.fmt_g);
-                  u.y = pack2(__uint_as_float(s[2]), __uint_as_float(s[3]), P.fmt_g);
-                  u.z = pack2(__uint_as_float(s[4]), __uint_as_float(s[5]), P.fmt_g);
-                  u.w = pack2(__uint_as_float(s[6]), __uint_as_float(s[7]), P.fmt_g);
-                  dst[q8] = u;
-                }
+              for (int q8 = 0; q8 < 8; ++q8) {
+                const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+                uint4 u;
+                u.x = pack2(__uint_as_float(sv[0]), __uint_as_float(sv[1]), P.fmt_g);
+                u.y = pack2(__uint_as_float(sv[2]), __uint_as_float(sv[3]), P.fmt_g);
+                u.z = pack2(__uint_as_float(sv[4]), __uint_as_float(sv[5]), P.fmt_g);
+                u.w = pack2(__uint_as_float(sv[6]), __uint_as_float(sv[7]), P.fmt_g);
+                dst[q8] = u;
               }
             }
+          } else {
+            // FWD: O * (1 / rowsum); DQ: dQ.  Each half stores 32 of the 64 columns.
+            uint32_t v0[32];
+            tmem_ld32(tmem + lane_off + AT_TMEM_ACC + hsel * 32, v0);
+            tmem_ld_wait();
+            if (valid) {
+              const float sc = (MODE == AT_FWD) ? rinv : 1.f;
+              const int ofmt = (MODE == AT_FWD) ? P.fmt : P.fmt_g;
+              uint16_t* base = (MODE == AT_FWD) ? P.o_out + grow * W + h * 64
+                                                : P.dqkv + grow * 3 * W + h * 64;
+              uint4* dst = reinterpret_cast<uint4*>(base + hsel * 32);
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                const uint32_t* sv = &v0[q8 * 8];
+                uint4 u;
+                u.x = pack2(__uint_as_float(sv[0]) * sc, __uint_as_float(sv[1]) * sc, ofmt);
+                u.y = pack2(__uint_as_float(sv[2]) * sc, __uint_as_float(sv[3]) * sc, ofmt);
+                u.z = pack2(__uint_as_float(sv[4]) * sc, __uint_as_float(sv[5]) * sc, ofmt);
+                u.w = pack2(__uint_as_float(sv[6]) * sc, __uint_as_float(sv[7]) * sc, ofmt);
+                dst[q8] = u;
+              }
+              if (MODE == AT_FWD && hsel == 0)
+                P.lse_out[((size_t)b * P.H + h) * T + row] =
+                    (mc + log2f(rsum)) * 0.6931471805599453f;
+            }
           }
-          tc_fence_before();
-          mbar_arrive(bar_acc_free);
         }
+        tc_fence_before();
+        mbar_arrive(bar_acc_free);
       }
-      if (MODE == AT_DKV) asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (MODE == AT_DKV) asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AT_CTRL_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -501,7 +496,7 @@ static int make_plan(AttnPlan& pl, const void* qkv, const void* d_o, int B, int 
   P.boxrows = P.kvp / P.nbox;
   P.fmt = fmt; P.fmt_o = fmt_o; P.fmt_g = fmt_g;
   pl.smem = (size_t)2 * P.kvp * 128 + 4 * 16384 + (size_t)P.nblk * 16384 + (size_t)2 * P.kvp * 4 +
-            128 + 1024;
+            2048 + 128 + 1024;
   const uint64_t W3 = 3ull * P.W;
   int rc = make_tmap_3d(&pl.tmTile, qkv, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
   if (rc) return rc;

@@ -28,8 +28,38 @@ struct HeadArgs {
   int fmt_g;
   float grad_scale;       // multiplies d loss_b / d emb
   int grad_unit;          // 1: rescale each sample's CLS-row gradient to unit max-abs
+  // outer training step only (may be null): per-sample vectors for the head's parameter grads
+  float* t_xhat;          // [B, W] normalised CLS row
+  float* t_pooled;        // [B, W] ln_post output
+  float* t_dpooled;       // [B, W] d loss / d pooled
+  float* t_demb;          // [B, D] d loss / d (un-normalised) embedding
 };
 int launch_head(const HeadArgs& A, int B, cudaStream_t st);
+
+// ---- train_kernels.cu ------------------------------------------------------
+constexpr int TRAIN_RSPLIT = 64;  // row splits of the two-stage column reductions
+// out[N] = column sums of a 16-bit [M, N] matrix; scratch: TRAIN_RSPLIT * N floats
+int launch_colsum16(const uint16_t* a, int M, int N, int fmt, float* scratch, float* out,
+                    cudaStream_t st);
+// LayerNorm affine gradients; scratch: 2 * TRAIN_RSPLIT * W floats
+int launch_ln_param_grads(const float* dy, const float* x, const float* stats, int M, int W,
+                          float* scratch, float* dgamma, float* dbeta, cudaStream_t st);
+int launch_batch_sum(const float* in, float* out, int B, long long n, cudaStream_t st);
+int launch_head_param_grads(const float* pooled, const float* demb, const float* dpooled,
+                            const float* xhat, int B, int W, int D, float* dproj, float* dgamma,
+                            float* dbeta, cudaStream_t st);
+
+// GEMM epilogue: conv1 weight gradient [W, kp] (the GEMM's N is kp rounded up to 32)
+struct EpiWgradPatch {
+  float* G;
+  int kp;
+  struct Aux {};
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux&) const {
+    if (col < kp) *reinterpret_cast<float4*>(G + (size_t)row * kp + col) = acc;
+  }
+};
 
 // ---- patch.cu ------------------------------------------------------------
 struct PatchGeom {
@@ -54,18 +84,14 @@ struct EpiPatchFwd {
   float* tok;        // [B*T, W]
   const float* pos;  // [T, W]
   int np, T, W;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
+  struct Aux {};
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux&) const {
     const int b = row / np, p = row - b * np;
-    float4* d = reinterpret_cast<float4*>(tok + ((size_t)b * T + 1 + p) * W + col0);
-    const float4* ps = reinterpret_cast<const float4*>(pos + (size_t)(1 + p) * W + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 q = __ldg(ps + j);
-      float4 o;
-      o.x = acc[4 * j + 0] + q.x; o.y = acc[4 * j + 1] + q.y;
-      o.z = acc[4 * j + 2] + q.z; o.w = acc[4 * j + 3] + q.w;
-      d[j] = o;
-    }
+    const float4 q = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(1 + p) * W + col));
+    *reinterpret_cast<float4*>(tok + ((size_t)b * T + 1 + p) * W + col) =
+        make_float4(acc.x + q.x, acc.y + q.y, acc.z + q.z, acc.w + q.w);
   }
 };
 
@@ -73,22 +99,16 @@ struct EpiPatchFwd {
 // G[r, k] = acc / std_c  (chain rule through Normalize, train/adversarial_training_clip.py:254)
 struct EpiPatchGrad {
   float* G;  // [rows, kp]
-  int kp, pp;  // pp = patch*patch
+  int kp, pp;  // pp = patch*patch; kp % 4 == 0
   float inv_std[3];
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    float* g = G + (size_t)row * kp + col0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = col0 + 4 * j;
-      if (k < kp) {  // kp % 4 == 0
-        float4 o;
-        o.x = acc[4 * j + 0] * inv_std[(k + 0) / pp];
-        o.y = acc[4 * j + 1] * inv_std[(k + 1) / pp];
-        o.z = acc[4 * j + 2] * inv_std[(k + 2) / pp];
-        o.w = acc[4 * j + 3] * inv_std[(k + 3) / pp];
-        reinterpret_cast<float4*>(g)[j] = o;
-      }
-    }
+  struct Aux {};
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux&) const {
+    if (col >= kp) return;
+    *reinterpret_cast<float4*>(G + (size_t)row * kp + col) =
+        make_float4(acc.x * inv_std[(col + 0) / pp], acc.y * inv_std[(col + 1) / pp],
+                    acc.z * inv_std[(col + 2) / pp], acc.w * inv_std[(col + 3) / pp]);
   }
 };
 
@@ -104,41 +124,50 @@ struct EpiPatchPgdLinf {
   int kp, pp, lda, fmt;
   float stepsize, eps, dir, momentum;
   float mean[3], inv_std[3];
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    const size_t off = (size_t)row * kp + col0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = col0 + 4 * j;
-      if (k >= kp) break;
-      const float4 x4 = *reinterpret_cast<const float4*>(xp + off + 4 * j);
-      float4 d4 = *reinterpret_cast<float4*>(dp + off + 4 * j);
-      float4 v4 = *reinterpret_cast<float4*>(vp + off + 4 * j);
-      const float* xx = &x4.x;
-      float* dd = &d4.x;
-      float* vv = &v4.x;
-      float nx[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float g = acc[4 * j + i];
-        if (g != g) g = 0.f;
-        const float gs = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
-        const float m = __fadd_rn(__fmul_rn(momentum, vv[i]), gs);
-        const float vn = (m > 0.f) ? 1.f : ((m < 0.f) ? -1.f : 0.f);
-        float dn = __fadd_rn(dd[i], __fmul_rn(__fmul_rn(stepsize, vn), dir));
-        dn = fminf(fmaxf(dn, -eps), eps);
-        const float xa = fminf(fmaxf(__fadd_rn(xx[i], dn), 0.f), 1.f);
-        dd[i] = __fsub_rn(xa, xx[i]);
-        vv[i] = vn;
-        const int c = (k + i) / pp;
-        nx[i] = (__fadd_rn(xx[i], dd[i]) - mean[c]) * inv_std[c];
-      }
-      *reinterpret_cast<float4*>(dp + off + 4 * j) = d4;
-      *reinterpret_cast<float4*>(vp + off + 4 * j) = v4;
-      uint2 pk;
-      pk.x = pack2(nx[0], nx[1], fmt);
-      pk.y = pack2(nx[2], nx[3], fmt);
-      *reinterpret_cast<uint2*>(a16 + (size_t)row * lda + k) = pk;
+  struct Aux { float4 x, d, v; };
+  __device__ __forceinline__ Aux load(int row, int col) const {
+    Aux a;
+    if (col < kp) {
+      const size_t off = (size_t)row * kp + col;
+      a.x = *reinterpret_cast<const float4*>(xp + off);
+      a.d = *reinterpret_cast<const float4*>(dp + off);
+      a.v = *reinterpret_cast<const float4*>(vp + off);
     }
+    return a;
+  }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux& a) const {
+    if (col >= kp) return;
+    const size_t off = (size_t)row * kp + col;
+    const float4 x4 = a.x;
+    float4 d4 = a.d;
+    float4 v4 = a.v;
+    const float* gg = &acc.x;
+    const float* xx = &x4.x;
+    float* dd = &d4.x;
+    float* vv = &v4.x;
+    float nx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float g = gg[i];
+      if (g != g) g = 0.f;
+      const float gs = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+      const float m = __fadd_rn(__fmul_rn(momentum, vv[i]), gs);
+      const float vn = (m > 0.f) ? 1.f : ((m < 0.f) ? -1.f : 0.f);
+      float dn = __fadd_rn(dd[i], __fmul_rn(__fmul_rn(stepsize, vn), dir));
+      dn = fminf(fmaxf(dn, -eps), eps);
+      const float xa = fminf(fmaxf(__fadd_rn(xx[i], dn), 0.f), 1.f);
+      dd[i] = __fsub_rn(xa, xx[i]);
+      vv[i] = vn;
+      const int c = (col + i) / pp;
+      nx[i] = (__fadd_rn(xx[i], dd[i]) - mean[c]) * inv_std[c];
+    }
+    *reinterpret_cast<float4*>(dp + off) = d4;
+    *reinterpret_cast<float4*>(vp + off) = v4;
+    uint2 pk;
+    pk.x = pack2(nx[0], nx[1], fmt);
+    pk.y = pack2(nx[2], nx[3], fmt);
+    *reinterpret_cast<uint2*>(a16 + (size_t)row * lda + col) = pk;
   }
 };
 

@@ -1,48 +1,60 @@
-// Fused GEMM epilogues.  Each functor receives one output row's 32 consecutive
-// fp32 accumulators (the thread owns the row: TMEM lane == tile row) and writes
-// them to HBM after the fused elementwise work.  Per thread the 32 columns are
-// contiguous in memory, so every store instruction fills whole 32-byte sectors.
+// Fused GEMM epilogues.
+//
+// The GEMM's epilogue warps read 32 accumulator columns per thread-row out of TMEM,
+// transpose them through a swizzled warp-private shared-memory tile and then hand each
+// lane a float4 of FOUR CONSECUTIVE COLUMNS OF ONE ROW, 8 lanes per row: a warp-wide
+// access covers 4 rows x 128 B (fp32) or 4 rows x 64 B (16-bit) of contiguous global
+// memory, i.e. whole cache lines instead of 32 scattered 16-byte pieces.
+//
+// Functor interface (col % 4 == 0, row < M, col < N guaranteed by the caller, N % 32 == 0):
+//   Aux  load(row, col)                       HBM operands of the epilogue, requested early
+//   void operator()(row, col, acc, aux)       math + stores
 #pragma once
 #include "ptx.cuh"
 
 namespace rvlm {
 
-__device__ __forceinline__ void store16x32(uint16_t* dst, const float (&v)[32], int fmt) {
-  uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u;
-    u.x = pack2(v[8 * j + 0], v[8 * j + 1], fmt);
-    u.y = pack2(v[8 * j + 2], v[8 * j + 3], fmt);
-    u.z = pack2(v[8 * j + 4], v[8 * j + 5], fmt);
-    u.w = pack2(v[8 * j + 6], v[8 * j + 7], fmt);
-    d[j] = u;
-  }
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-__device__ __forceinline__ void load16x32(const uint16_t* src, float (&v)[32], int fmt) {
-  const uint4* s = reinterpret_cast<const uint4*>(src);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u = s[j];
-    float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt), c = unpack2(u.z, fmt),
-           d = unpack2(u.w, fmt);
-    v[8 * j + 0] = a.x; v[8 * j + 1] = a.y; v[8 * j + 2] = b.x; v[8 * j + 3] = b.y;
-    v[8 * j + 4] = c.x; v[8 * j + 5] = c.y; v[8 * j + 6] = d.x; v[8 * j + 7] = d.y;
-  }
+__device__ __forceinline__ uint2 pack4(const float4& v, int fmt) {
+  uint2 u;
+  u.x = pack2(v.x, v.y, fmt);
+  u.y = pack2(v.z, v.w, fmt);
+  return u;
+}
+__device__ __forceinline__ float4 unpack4(const uint2& u, int fmt) {
+  const float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 add_bias(const float4& a, const float* bias, int col) {
+  if (!bias) return a;
+  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
 // C16[row, col] = acc + bias[col]
+struct NoAux {};
+
 struct EpiStore16 {
   uint16_t* C;
   int ldc;
   const float* bias;  // may be null
   int fmt;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = acc[j] + (bias ? __ldg(bias + col0 + j) : 0.f);
-    store16x32(C + (size_t)row * ldc + col0, v, fmt);
+  using Aux = NoAux;
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux&) const {
+    const float4 v = add_bias(acc, bias, col);
+    *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(v, fmt);
   }
 };
 
@@ -56,12 +68,13 @@ struct EpiStore16Dual {
   int ldc;
   const float* bias;
   int fmt, fmt2;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = acc[j] + (bias ? __ldg(bias + col0 + j) : 0.f);
-    store16x32(C + (size_t)row * ldc + col0, v, fmt);
-    if (C2) store16x32(C2 + (size_t)row * ldc + col0, v, fmt2);
+  using Aux = NoAux;
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux&) const {
+    const float4 v = add_bias(acc, bias, col);
+    *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(v, fmt);
+    if (C2) *reinterpret_cast<uint2*>(C2 + (size_t)row * ldc + col) = pack4(v, fmt2);
   }
 };
 
@@ -72,52 +85,45 @@ struct EpiStore32 {
   const float* bias;   // may be null
   const float* resid;  // may be null
   int ldr;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    float4* d = reinterpret_cast<float4*>(C + (size_t)row * ldc + col0);
-    const float4* r = resid ? reinterpret_cast<const float4*>(resid + (size_t)row * ldr + col0)
-                            : nullptr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 o;
-      o.x = acc[4 * j + 0]; o.y = acc[4 * j + 1]; o.z = acc[4 * j + 2]; o.w = acc[4 * j + 3];
-      if (bias) {
-        o.x += __ldg(bias + col0 + 4 * j + 0); o.y += __ldg(bias + col0 + 4 * j + 1);
-        o.z += __ldg(bias + col0 + 4 * j + 2); o.w += __ldg(bias + col0 + 4 * j + 3);
-      }
-      if (r) {
-        float4 rr = r[j];
-        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-      }
-      d[j] = o;
-    }
+  using Aux = float4;
+  __device__ __forceinline__ Aux load(int row, int col) const {
+    return resid ? *reinterpret_cast<const float4*>(resid + (size_t)row * ldr + col)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux& r) const {
+    float4 v = add_bias(acc, bias, col);
+    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = v;
   }
 };
 
-// QuickGELU (open_clip QuickGELU: x * sigmoid(1.702 x))
+// QuickGELU (open_clip QuickGELU: x * sigmoid(1.702 x)), with
+// MUFU ex2 / rcp approximations (relative error ~1e-7, far below the 16-bit output).
 __device__ __forceinline__ float quick_gelu(float x) {
-  return x / (1.f + __expf(-1.702f * x));
+  return x * fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x));  // 1.702 * log2(e)
 }
 __device__ __forceinline__ float quick_gelu_grad(float x) {
-  const float s = 1.f / (1.f + __expf(-1.702f * x));
+  const float s = fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x));
   return s * (1.f + 1.702f * x * (1.f - s));
 }
 
 // H16 = acc + bias (pre-activation, kept for the backward); A16 = quick_gelu(H)
 struct EpiGelu {
-  uint16_t* H;
+  uint16_t* H;  // may be null
   uint16_t* A;
   int ld;
   const float* bias;
   int fmt;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    float h[32], a[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      h[j] = acc[j] + (bias ? __ldg(bias + col0 + j) : 0.f);
-      a[j] = quick_gelu(h[j]);
-    }
-    if (H) store16x32(H + (size_t)row * ld + col0, h, fmt);
-    store16x32(A + (size_t)row * ld + col0, a, fmt);
+  using Aux = NoAux;
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux&) const {
+    const float4 h = add_bias(acc, bias, col);
+    const float4 a = make_float4(quick_gelu(h.x), quick_gelu(h.y), quick_gelu(h.z),
+                                 quick_gelu(h.w));
+    if (H) *reinterpret_cast<uint2*>(H + (size_t)row * ld + col) = pack4(h, fmt);
+    *reinterpret_cast<uint2*>(A + (size_t)row * ld + col) = pack4(a, fmt);
   }
 };
 
@@ -128,12 +134,16 @@ struct EpiGeluBwd {
   const uint16_t* H;
   int fmt_h;
   int fmt_out;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&acc)[32]) const {
-    float h[32], o[32];
-    load16x32(H + (size_t)row * ld + col0, h, fmt_h);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] = acc[j] * quick_gelu_grad(h[j]);
-    store16x32(out + (size_t)row * ld + col0, o, fmt_out);
+  using Aux = uint2;
+  __device__ __forceinline__ Aux load(int row, int col) const {
+    return *reinterpret_cast<const uint2*>(H + (size_t)row * ld + col);
+  }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
+                                             const Aux& hu) const {
+    const float4 h = unpack4(hu, fmt_h);
+    const float4 o = make_float4(acc.x * quick_gelu_grad(h.x), acc.y * quick_gelu_grad(h.y),
+                                 acc.z * quick_gelu_grad(h.z), acc.w * quick_gelu_grad(h.w));
+    *reinterpret_cast<uint2*>(out + (size_t)row * ld + col) = pack4(o, fmt_out);
   }
 };
 

@@ -13,7 +13,10 @@
 //   warp 0 lane 0 : TMA producer   (kStages-deep smem ring, full/empty mbarriers)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma, double-buffered TMEM accumulator)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue       (tcgen05.ld -> registers -> Epi functor -> HBM)
+//   warps 4..11   : epilogue       (tcgen05.ld -> registers -> swizzled smem transpose ->
+//                                   Epi functor on row-contiguous float4 pieces -> HBM);
+//                                   two warps per TMEM lane quarter, each takes half the
+//                                   accumulator columns
 //
 // Tile: BLOCK_M = 128 (UMMA M, one TMEM lane per row), BLOCK_N = BN (UMMA N),
 // BLOCK_K = 64 elements (= one 128-byte swizzle row).
@@ -29,7 +32,8 @@ namespace rvlm {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
 
 template <int BN>
 struct GemmSmem {
@@ -38,12 +42,16 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /*align slack*/;
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * 32 * 4;  // per-warp transpose tiles
+  static constexpr int kTotal =
+      kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /*align slack*/;
 };
 
 // The epilogue functor interface:
-//   __device__ void operator()(int row, int col0, const float (&acc)[32]) const
-// is called once per (row, 32-column chunk) with row < M and col0 < N already
+//   struct Aux;                                     // what the functor reads from HBM
+//   __device__ Aux  load(int row, int col) const;   // issued early (latency hidden)
+//   __device__ void operator()(int row, int col, const float4& acc, const Aux&) const
+// called once per (row, 4 consecutive columns) with row < M and col < N already
 // guaranteed (N is required to be a multiple of 32 by the host wrappers).
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -57,7 +65,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
   uint64_t* full_bar = bars;                    // [kStages]
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
@@ -84,7 +94,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -160,7 +170,10 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the accumulator columns
+    float* stg = staging + (warp - 4) * 1024;
+    const int rl = lane >> 3, c4 = lane & 7;  // piece owned after the transpose
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -168,21 +181,39 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
-      const int row = m_blk * GEMM_BM + q * 32 + lane;
+      const int row0 = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= N) break;  // warp-uniform
+        // operands the epilogue reads from HBM (residual, pre-activation, ...) are requested
+        // first, so their latency overlaps the TMEM read and the transpose
+        typename Epi::Aux aux[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + rl + 4 * i;
+          if (row < M) aux[i] = epi.load(row, col0 + 4 * c4);
+        }
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (row < M) {
-          float v[32];
+        // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          epi(row, col0, v);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rl + 4 * i;
+          const float4 v =
+              *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+          const int row = row0 + rr;
+          if (row < M) epi(row, col0 + 4 * c4, v, aux[i]);
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);

@@ -172,6 +172,15 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
     for (int d = tid; d < D; d += HEAD_THREADS) de[d] = (de[d] - e[d] * dot) / nrm;
   }
   __syncthreads();
+  if (A.t_demb) {  // outer training step: keep what the head's parameter gradients need
+    for (int d = tid; d < D; d += HEAD_THREADS)
+      A.t_demb[(size_t)b * D + d] = de[d] * A.grad_scale;
+    for (int i = tid; i < W; i += HEAD_THREADS) {
+      A.t_xhat[(size_t)b * W + i] = xh[i];
+      A.t_pooled[(size_t)b * W + i] = pooled[i];
+    }
+    __syncthreads();
+  }
   // ---- d pooled = proj @ d emb  (reuse `pooled` as g = dpooled * gamma)
   {
     const int warp = tid >> 5, lane = tid & 31;
@@ -180,7 +189,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
       for (int d = lane; d < D; d += 32) acc += __ldg(A.proj + (size_t)w * D + d) * de[d];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
-      if (lane == 0) pooled[w] = acc * A.ln_g[w] * A.grad_scale;
+      if (lane == 0) {
+        if (A.t_dpooled) A.t_dpooled[(size_t)b * W + w] = acc * A.grad_scale;
+        pooled[w] = acc * A.ln_g[w] * A.grad_scale;
+      }
     }
   }
   __syncthreads();

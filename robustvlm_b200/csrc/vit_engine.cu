@@ -68,6 +68,10 @@ struct Ws {
   uint16_t* qkvf16;             // [M, 3W] transient forward-format q|k|v
   float* lse;     // [L] x [B, H, T]
   uint16_t *y16, *act16;
+  // outer training step (stash == 2): per-layer GEMM inputs kept for the weight gradients
+  uint16_t *ty16, *tz16, *tact16;   // [L] x [M, W], [M, W], [M, F]
+  float *red;                        // column-reduction scratch
+  float *t_xhat, *t_pooled, *t_dpooled, *t_demb;
   // backward
   float *dx32, *dz32;
   uint16_t *dx16, *dh16, *do16, *dqkv16, *dtok16;
@@ -120,6 +124,16 @@ Ws carve(const Engine& E, uint8_t* base, int B, int stash) {
   w.loss = take<float>(p, used, B);
   w.pred = take<int>(p, used, B);
   w.upd = take<float>(p, used, (size_t)B * 32 * 3);
+  if (stash == 2) {
+    w.ty16 = take<uint16_t>(p, used, L * M * W);
+    w.tz16 = take<uint16_t>(p, used, L * M * W);
+    w.tact16 = take<uint16_t>(p, used, L * M * F);
+    w.red = take<float>(p, used, (size_t)2 * TRAIN_RSPLIT * (3 * W > F ? 3 * W : F));
+    w.t_xhat = take<float>(p, used, (size_t)B * W);
+    w.t_pooled = take<float>(p, used, (size_t)B * W);
+    w.t_dpooled = take<float>(p, used, (size_t)B * W);
+    w.t_demb = take<float>(p, used, (size_t)B * E.D);
+  }
   if (stash) {
     w.dx32 = take<float>(p, used, M * W);
     w.dz32 = take<float>(p, used, M * W);
@@ -166,10 +180,14 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     float* lse = w.lse + s * (size_t)B * E.H * E.T;
     float* st1 = w.stats1 + s * (size_t)M * 2;
     float* st2 = w.stats2 + s * (size_t)M * 2;
-    RV(rvlm_layernorm_fwd(x_in, Lw.ln1_g, Lw.ln1_b, w.y16, nullptr, st1, M, W, ff, stv));
+    const bool train = w.stash == 2;
+    uint16_t* y1 = train ? w.ty16 + (size_t)l * MW : w.y16;
+    uint16_t* z1 = train ? w.tz16 + (size_t)l * MW : w.y16;
+    uint16_t* act = train ? w.tact16 + (size_t)l * M * F : w.act16;
+    RV(rvlm_layernorm_fwd(x_in, Lw.ln1_g, Lw.ln1_b, y1, nullptr, st1, M, W, ff, stv));
     {  // q|k|v in the forward format (transient) + the backward's copy in the gradient format
       EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd};
-      RV((launch_gemm16<256, false, false>(w.y16, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
+      RV((launch_gemm16<256, false, false>(y1, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
     }
     if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     else RV(rvlm_attn_fwd(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
@@ -177,14 +195,14 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       EpiStore32 epi{xm, W, Lw.bo, x_in, W};
       RV((launch_gemm16<256, false, false>(o, W, Lw.wo, W, M, W, W, ff, epi, st)));
     }
-    RV(rvlm_layernorm_fwd(xm, Lw.ln2_g, Lw.ln2_b, w.y16, nullptr, st2, M, W, ff, stv));
+    RV(rvlm_layernorm_fwd(xm, Lw.ln2_g, Lw.ln2_b, z1, nullptr, st2, M, W, ff, stv));
     {
-      EpiGelu epi{w.stash ? h : nullptr, w.act16, F, Lw.bfc, ff};
-      RV((launch_gemm16<256, false, false>(w.y16, W, Lw.wfc, W, M, F, W, ff, epi, st)));
+      EpiGelu epi{w.stash ? h : nullptr, act, F, Lw.bfc, ff};
+      RV((launch_gemm16<256, false, false>(z1, W, Lw.wfc, W, M, F, W, ff, epi, st)));
     }
     {
       EpiStore32 epi{x_out, W, Lw.bpr, xm, W};
-      RV((launch_gemm16<256, false, false>(w.act16, F, Lw.wpr, F, M, W, F, ff, epi, st)));
+      RV((launch_gemm16<256, false, false>(act, F, Lw.wpr, F, M, W, F, ff, epi, st)));
     }
   }
   return 0;
@@ -196,7 +214,8 @@ const float* final_x(const Engine& E, const Ws& w, int B) {
 }
 
 int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, int normalize,
-             float* emb_out, float* logits_out, bool backward, cudaStream_t st) {
+             float* emb_out, float* logits_out, bool backward, cudaStream_t st,
+             float grad_scale = 1.f) {
   HeadArgs A{};
   A.xL = final_x(E, w, B);
   A.T = E.T; A.W = E.W; A.D = E.D;
@@ -214,8 +233,11 @@ int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, in
   A.loss = w.loss;
   A.pred = w.pred;
   A.fmt_g = E.cfg.fmt_bwd;
-  A.grad_scale = 1.f;
-  A.grad_unit = (E.cfg.fmt_bwd == RVLM_FMT_F16) ? 1 : 0;
+  A.grad_scale = grad_scale;
+  A.grad_unit = (E.cfg.fmt_bwd == RVLM_FMT_F16 && w.stash != 2) ? 1 : 0;
+  if (w.stash == 2) {
+    A.t_xhat = w.t_xhat; A.t_pooled = w.t_pooled; A.t_dpooled = w.t_dpooled; A.t_demb = w.t_demb;
+  }
   if (backward) {
     const size_t MW = (size_t)B * E.T * E.W;
     cudaError_t e = cudaMemsetAsync(w.dx32, 0, MW * sizeof(float), st);
@@ -270,6 +292,92 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
   // ln_pre backward, compacted to patch rows (the CLS row's input is a constant)
   RV(rvlm_layernorm_bwd(w.dx32, w.tok32, w.stats_pre, E.lnpre_g, nullptr, nullptr, w.dtok16, M, W,
                         fg, E.T, stv));
+  return 0;
+}
+
+// Weight gradient dW[Nw, Kw] = dY^T X with dY [Mtok, Nw] and X [Mtok, Kw], both consumed
+// MN-major (the token dimension is the contraction), fp32 output.
+int wgrad(const uint16_t* dY, int Nw, const uint16_t* X, int Kw, int Mtok, int fmt, float* dW,
+          cudaStream_t st) {
+  EpiStore32 epi{dW, Kw, nullptr, nullptr, 0};
+  return launch_gemm16<128, true, true>(dY, Nw, X, Kw, Nw, Kw, Mtok, fmt, epi, st);
+}
+
+// Full backward of the outer training step: dgrad chain as in run_backward plus every
+// parameter gradient, written (overwritten) into `g` (open_clip layout, fp32).
+int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads* g,
+                       cudaStream_t st) {
+  const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
+  const int ff = E.cfg.fmt_fwd, fg = E.cfg.fmt_bwd;
+  const size_t MW = (size_t)M * W;
+  void* stv = (void*)st;
+  RV(launch_head_param_grads(w.t_pooled, w.t_demb, w.t_dpooled, w.t_xhat, B, W, E.D, g->proj,
+                             g->ln_post_weight, g->ln_post_bias, st));
+  for (int l = E.L - 1; l >= 0; --l) {
+    const LayerDev& Lw = E.layers[l];
+    const float* x_in = w.x32 + (size_t)l * MW;
+    const float* xm = w.xm32 + (size_t)l * MW;
+    const uint16_t* qkv = w.qkv16 + (size_t)l * MW * 3;
+    const uint16_t* o = w.o16 + (size_t)l * MW;
+    const uint16_t* h = w.h16 + (size_t)l * M * F;
+    float* lse = w.lse + (size_t)l * B * E.H * E.T;
+    const float* st1 = w.stats1 + (size_t)l * M * 2;
+    const float* st2 = w.stats2 + (size_t)l * M * 2;
+    const uint16_t* y1 = w.ty16 + (size_t)l * MW;
+    const uint16_t* z1 = w.tz16 + (size_t)l * MW;
+    const uint16_t* act = w.tact16 + (size_t)l * M * F;
+    // mlp.c_proj: x_{l+1} = xm + act W_pr^T + b_pr ; dY = dx
+    RV(wgrad(w.dx16, W, act, F, M, fg, g->mlp_c_proj_weight[l], st));
+    RV(launch_colsum16(w.dx16, M, W, fg, w.red, g->mlp_c_proj_bias[l], st));
+    {
+      EpiGeluBwd epi{w.dh16, F, h, ff, fg};
+      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
+    }
+    // mlp.c_fc: dY = dh
+    RV(wgrad(w.dh16, F, z1, W, M, fg, g->mlp_c_fc_weight[l], st));
+    RV(launch_colsum16(w.dh16, M, F, fg, w.red, g->mlp_c_fc_bias[l], st));
+    {
+      EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
+      RV((launch_gemm16<256, false, false>(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
+    }
+    RV(launch_ln_param_grads(w.dz32, xm, st2, M, W, w.red, g->ln_2_weight[l], g->ln_2_bias[l], st));
+    RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+    // attn.out_proj: xm = x + o W_o^T + b_o ; dY = dx (now the gradient w.r.t. xm)
+    RV(wgrad(w.dx16, W, o, W, M, fg, g->attn_out_proj_weight[l], st));
+    RV(launch_colsum16(w.dx16, M, W, fg, w.red, g->attn_out_proj_bias[l], st));
+    {
+      EpiStore16 epi{w.do16, W, nullptr, fg};
+      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
+    }
+    if (E.attn_simt)
+      RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
+    else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
+    // attn.in_proj: dY = dqkv
+    RV(wgrad(w.dqkv16, 3 * W, y1, W, M, fg, g->attn_in_proj_weight[l], st));
+    RV(launch_colsum16(w.dqkv16, M, 3 * W, fg, w.red, g->attn_in_proj_bias[l], st));
+    {
+      EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
+      RV((launch_gemm16<256, false, false>(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
+                                           st)));
+    }
+    RV(launch_ln_param_grads(w.dz32, x_in, st1, M, W, w.red, g->ln_1_weight[l], g->ln_1_bias[l], st));
+    RV(rvlm_layernorm_bwd(w.dz32, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+  }
+  // ln_pre: parameter grads, fp32 token gradient (positional / class embedding), 16-bit
+  // compact patch rows (conv1 weight gradient)
+  RV(launch_ln_param_grads(w.dx32, w.tok32, w.stats_pre, M, W, w.red, g->ln_pre_weight,
+                           g->ln_pre_bias, st));
+  RV(rvlm_layernorm_bwd(w.dx32, w.tok32, w.stats_pre, E.lnpre_g, nullptr, w.dz32, nullptr, M, W,
+                        fg, 0, stv));
+  RV(rvlm_layernorm_bwd(w.dx32, w.tok32, w.stats_pre, E.lnpre_g, nullptr, nullptr, w.dtok16, M, W,
+                        fg, E.T, stv));
+  RV(launch_batch_sum(w.dz32, g->positional_embedding, B, (long long)E.T * W, st));
+  RV(cuda_rc(cudaMemcpyAsync(g->class_embedding, g->positional_embedding, W * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st)));
+  {
+    EpiWgradPatch epi{g->conv1_weight, E.kp};
+    RV((launch_gemm16<128, true, true>(w.dtok16, W, w.a16, E.kld, W, E.kp32, R, fg, epi, st)));
+  }
   return 0;
 }
 
@@ -359,7 +467,7 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
   E->np = g * g;
   E->T = E->np + 1;
   E->kp = 3 * cfg->patch * cfg->patch;
-  E->kld = (int)align_up(E->kp, 8);
+  E->kld = (int)align_up(E->kp, 32);  // row pitch of the patch operand / conv weight
   E->kp32 = (int)align_up(E->kp, 32);
   E->geom.image = cfg->image; E->geom.patch = cfg->patch; E->geom.grid = g;
   E->geom.np = E->np; E->geom.kp = E->kp;
@@ -480,6 +588,25 @@ extern "C" int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t wor
     RV(launch_unpatchify(w.gp, grad_out, B, E.geom, st));
   }
   return 0;
+}
+
+extern "C" int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                                    const float* x, int B, const rvlm_loss_config* loss,
+                                    float loss_scale, const rvlm_vit_grads* grads,
+                                    float* loss_out, float* emb_out, void* stream) {
+  if (!h || !workspace || !x || !loss || !grads || B <= 0) return RVLM_ERR_INVAL;
+  if (loss->mode != 1 && loss->mode != 2) return RVLM_ERR_INVAL;
+  const Engine& E = *reinterpret_cast<Engine*>(h);
+  if (E.cfg.fmt_fwd != E.cfg.fmt_bwd) return RVLM_ERR_UNSUPPORTED;  // wgrad: one operand format
+  Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 2);
+  if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
+  cudaStream_t st = (cudaStream_t)stream;
+  RV(prep_state(E, w, B, x, nullptr, false, st));
+  RV(run_forward(E, w, B, st));
+  RV(run_head(E, w, B, loss, 0, emb_out, nullptr, true, st, loss_scale));
+  if (loss_out)
+    RV(cuda_rc(cudaMemcpyAsync(loss_out, w.loss, B * sizeof(float), cudaMemcpyDeviceToDevice, st)));
+  return run_backward_train(E, w, B, grads, st);
 }
 
 extern "C" int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,

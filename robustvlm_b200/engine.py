@@ -42,6 +42,10 @@ class VitWeightsC(Structure):
             "mlp_c_fc_weight", "mlp_c_fc_bias", "mlp_c_proj_weight", "mlp_c_proj_bias")]
 
 
+class VitGradsC(Structure):
+    _fields_ = VitWeightsC._fields_
+
+
 class LossConfigC(Structure):
     _fields_ = [("mode", c_int), ("output_normalize", c_int), ("pred_on_logits", c_int),
                 ("emb_orig", c_void_p), ("text", c_void_p), ("n_classes", c_int),
@@ -259,6 +263,31 @@ class VitEngine:
             if trace:
                 tr[:, lo:hi] = trc
         return (out, tr) if trace else out
+
+    def train_grads(self, x, loss: LossSpec, grads: dict, loss_scale: float):
+        """Outer training step: forward(x) + loss + full backward.  `grads` maps every
+        state-dict key to a contiguous fp32 CUDA tensor of the parameter's shape; they are
+        overwritten with d(loss_scale * sum_b loss_b)/d(param).  Returns (loss[B], emb[B,D])."""
+        x = self._chk(x)
+        B = x.shape[0]
+        ws, nbytes = self._workspace(B, 2)
+        gc, keep = VitGradsC(), []
+        for f, k in _TOP_KEYS.items():
+            setattr(gc, f, grads[k].data_ptr())
+        L = self.arch["layers"]
+        for f, k in _LAYER_KEYS.items():
+            arr = (c_void_p * L)(*[grads[f"transformer.resblocks.{i}.{k}"].data_ptr()
+                                   for i in range(L)])
+            keep.append(arr)
+            setattr(gc, f, ctypes.cast(arr, _PP))
+        lc = loss.to_c()
+        out_loss = torch.empty(B, device=self.device, dtype=torch.float32)
+        emb = torch.empty(B, self.arch["out_dim"], device=self.device, dtype=torch.float32)
+        nat.call("rvlm_vit_train_grads", self.handle, nat.ptr(ws), c_size_t(nbytes), nat.ptr(x),
+                 c_int(B), byref(lc), c_float(loss_scale), byref(gc), nat.ptr(out_loss),
+                 nat.ptr(emb), nat.stream_ptr())
+        del keep
+        return out_loss, emb
 
     def debug_buffer(self, B, with_backward, which, layer, shape, dtype):
         ws, _ = self._workspace(B, with_backward)

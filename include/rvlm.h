@@ -307,6 +307,10 @@ int rvlm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     long long n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, void* stream);
 
+/* Self-test of tcgen05.mma with the A operand in TMEM: C[128,64] = A[128,64] * B[64,64]^T
+ * (16-bit A, B row-major; fp32 C). */
+int rvlm_selftest_ts_mma(const void* A, const void* B, float* C, int fmt, void* stream);
+
 /* Test hook: pointer of an internal workspace buffer (see vit_engine.cu). */
 int rvlm_vit_debug_buffer(rvlm_vit_handle h, void* workspace, int B, int with_backward, int which,
                           int layer, void** ptr_out);

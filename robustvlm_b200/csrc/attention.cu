@@ -478,6 +478,280 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
   }
 }
 
+
+// =====================================================================================
+// Forward, version 2: two row groups in flight, one thread per row.
+//
+// The 257 = 256 + 1 token count of ViT-L/14 is peeled: the tensor cores handle query rows
+// and keys [0, 256) -- two 128-row tiles per (image, head), processed CONCURRENTLY by two
+// groups of four warps, each thread owning one whole row (no cross-thread softmax
+// reduction) -- while the one remaining key is a 64-MAC dot product per row on the CUDA
+// cores, folded into the same softmax, and the one remaining query row is computed by the
+// CUDA-core kernel.  This removes the 1-valid-row third tile and fits two S accumulators
+// (2 x 256 columns, the O accumulator aliasing the consumed S) into the 512 TMEM columns.
+// =====================================================================================
+struct AttnFwd2Params {
+  int B, T, H, W;
+  int tm;      // rows / keys handled on the tensor cores: min(T, 256)
+  int kvm;     // tm rounded up to 16 (UMMA N extent, P / V K-extent)
+  int nblk;    // 64-column blocks of P
+  int ntile;   // 128-row tiles: 1 or 2
+  int tail;    // 1 if key index 256 exists (T == 257)
+  int fmt;
+  const uint16_t* qkv;
+  uint16_t* o_out;
+  float* lse_out;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x kvm
+                 AttnFwd2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int kvm = P.kvm, T = P.T, W = P.W;
+  const int full_bytes = kvm * 128;
+  uint8_t* s_k = smem;
+  uint8_t* s_v = s_k + full_bytes;
+  uint8_t* s_q = s_v + full_bytes;                 // [2][16384]
+  uint8_t* s_p = s_q + 2 * 16384;                  // [2][nblk * 16384]
+  uint16_t* s_tail = reinterpret_cast<uint16_t*>(s_p + 2 * P.nblk * 16384);  // [2][2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + 256);
+  uint64_t* bar_k = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_q = bars + 2;       // [2]
+  uint64_t* bar_s = bars + 4;       // [2]
+  uint64_t* bar_p = bars + 6;       // [2] 128 arrivals
+  uint64_t* bar_o = bars + 8;       // [2]
+  uint64_t* bar_ofree = bars + 10;  // [2] 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&bar_q[g], 1);
+      mbar_init(&bar_s[g], 1);
+      mbar_init(&bar_p[g], 128);
+      mbar_init(&bar_o[g], 1);
+      mbar_init(&bar_ofree[g], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == AT_CTRL_WARP) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = P.B * P.H;
+  const uint32_t f = (uint32_t)P.fmt;
+  const int ng = P.ntile;  // active groups (group g <-> tile g)
+
+  if (warp == AT_CTRL_WARP) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issuer =====================
+      auto load_k = [&](int item) {
+        mbar_arrive_expect_tx(bar_k, full_bytes);
+        tma_load_3d(s_k, &tmFull, bar_k, W + (item % P.H) * 64, 0, item / P.H);
+      };
+      auto load_v = [&](int item) {
+        mbar_arrive_expect_tx(bar_v, full_bytes);
+        tma_load_3d(s_v, &tmFull, bar_v, 2 * W + (item % P.H) * 64, 0, item / P.H);
+      };
+      auto load_q = [&](int item, int g) {
+        mbar_arrive_expect_tx(&bar_q[g], 16384);
+        tma_load_3d(s_q + g * 16384, &tmTile, &bar_q[g], (item % P.H) * 64, g * 128, item / P.H);
+      };
+      const uint32_t idS = idesc_ab(f, f, 128, kvm, 0, 0);
+      int it = 0;
+      if ((int)blockIdx.x < n_items) {
+        load_k(blockIdx.x);
+        load_v(blockIdx.x);
+        for (int g = 0; g < ng; ++g) load_q(blockIdx.x, g);
+      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int next = item + gridDim.x;
+        mbar_wait(bar_k, ph, 30);
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(&bar_q[g], ph, 31);
+          if (it > 0) mbar_wait(&bar_ofree[g], ph ^ 1, 32);
+          tc_fence_after();
+          const uint32_t qa = smem_u32(s_q + g * 16384), ka = smem_u32(s_k);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem + g * 256, make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                     make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(&bar_s[g]);
+        }
+        for (int g = 0; g < ng; ++g) mbar_wait(&bar_s[g], ph, 33);   // K consumed
+        if (next < n_items) load_k(next);
+        mbar_wait(bar_v, ph, 34);
+        for (int g = 0; g < ng; ++g) {
+          mbar_wait(&bar_p[g], ph, 35);                              // P written, Q consumed
+          tc_fence_after();
+          if (next < n_items) load_q(next, g);
+          issue_mma2(tmem + g * 256, smem_u32(s_p + g * P.nblk * 16384), smem_u32(s_v), kvm, f, f);
+          umma_commit(&bar_o[g]);
+        }
+        for (int g = 0; g < ng; ++g) mbar_wait(&bar_o[g], ph, 36);   // V consumed
+        if (next < n_items) load_v(next);
+      }
+    }
+  } else {
+    // ===================== row workers: group g = warp / 4, thread = one row =====================
+    const int g = warp >> 2, r = threadIdx.x & 127;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t ts = tmem + lane_off + g * 256;
+    const float c2 = 0.125f * 1.4426950408889634f;
+    const int n32 = kvm >> 5, nch = n32 + ((kvm & 31) >> 4);
+    uint8_t* my_p = s_p + g * P.nblk * 16384;
+    const uint16_t* kt = s_tail + g * 128;       // k_tail[64]
+    const uint16_t* vt = kt + 64;                // v_tail[64]
+    if (g < ng) {
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const int b = item / P.H, h = item % P.H;
+        const int row = g * 128 + r;
+        const bool valid = row < P.tm;
+        const bool warp_valid = (g * 128 + (warp & 3) * 32) < P.tm;
+        if (P.tail) {
+          if (r < 16) {  // this group's copy of the peeled key / value row (index 256)
+            const uint16_t* src = P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 +
+                                  (r < 8 ? W : 2 * W) + (r & 7) * 8;
+            *reinterpret_cast<uint4*>(s_tail + g * 128 + r * 8) =
+                *reinterpret_cast<const uint4*>(src);
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        }
+        mbar_wait(&bar_q[g], ph, 42);  // (complete long ago) makes the TMA-written Q tile visible
+        mbar_wait(&bar_s[g], ph, 40);
+        tc_fence_after();
+        float mx = -INFINITY, s_t = 0.f, sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+        float p_t = 0.f;
+        if (warp_valid) {
+          if (P.tail) {  // score against the peeled key: q_row . k_tail from swizzled smem
+            const uint8_t* qrow = s_q + g * 16384 + r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 qu = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+              const uint4 ku = *reinterpret_cast<const uint4*>(kt + c * 8);
+              const uint32_t* qa = &qu.x;
+              const uint32_t* ka = &ku.x;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 x = unpack2(qa[i], P.fmt), y = unpack2(ka[i], P.fmt);
+                s_t = fmaf(x.x, y.x, fmaf(x.y, y.y, s_t));
+              }
+            }
+            mx = s_t;
+          }
+          for (int c = 0; c < nch; ++c) {
+            uint32_t v[32];
+            ld_chunk(ts, c, n32, v);
+            const int nv = c < n32 ? 32 : 16;
+            if (c * 32 + nv <= P.tm) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nv && c * 32 + i < P.tm) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+          }
+          const float mc = mx * c2;
+          if (P.tail) p_t = fast_ex2(fmaf(s_t, c2, -mc));
+          for (int c = 0; c < nch; ++c) {
+            uint32_t v[32];
+            ld_chunk(ts, c, n32, v);
+            const int nv = c < n32 ? 32 : 16;
+            float p[32];
+            const bool full = c * 32 + nv <= P.tm;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              p[i] = (i < nv && (full || c * 32 + i < P.tm))
+                         ? fast_ex2(fmaf(__uint_as_float(v[i]), c2, -mc))
+                         : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              sum0 += p[i]; sum1 += p[i + 1]; sum2 += p[i + 2]; sum3 += p[i + 3];
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              if (q8 * 8 < nv) {
+                uint4 u;
+                u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
+                u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
+                u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
+                u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
+                *reinterpret_cast<uint4*>(my_p + p_off(r, c * 32 + q8 * 8)) = u;
+              }
+            }
+          }
+          mx = mc;  // keep in log2 units
+        }
+        const float rsum = (sum0 + sum1) + (sum2 + sum3) + p_t;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&bar_p[g]);
+        mbar_wait(&bar_o[g], ph, 41);
+        tc_fence_after();
+        if (warp_valid) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(ts, v0);
+          tmem_ld32(ts + 32, v1);
+          tmem_ld_wait();
+          if (valid) {
+            const float inv = 1.f / rsum;
+            const size_t grow = (size_t)b * T + row;
+            uint4* dst = reinterpret_cast<uint4*>(P.o_out + grow * W + h * 64);
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+              const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
+              if (P.tail) {
+                const uint4 vu = *reinterpret_cast<const uint4*>(vt + q8 * 8);
+                const uint32_t* va = &vu.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 y = unpack2(va[i], P.fmt);
+                  o[2 * i] = fmaf(p_t, y.x, o[2 * i]);
+                  o[2 * i + 1] = fmaf(p_t, y.y, o[2 * i + 1]);
+                }
+              }
+              uint4 u;
+              u.x = pack2(o[0] * inv, o[1] * inv, P.fmt);
+              u.y = pack2(o[2] * inv, o[3] * inv, P.fmt);
+              u.z = pack2(o[4] * inv, o[5] * inv, P.fmt);
+              u.w = pack2(o[6] * inv, o[7] * inv, P.fmt);
+              dst[q8] = u;
+            }
+            P.lse_out[((size_t)b * P.H + h) * T + row] = (mx + log2f(rsum)) * 0.6931471805599453f;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&bar_ofree[g]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT_CTRL_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 struct AttnPlan {
   AttnParams P;
   size_t smem;
@@ -531,14 +805,47 @@ static int launch_attn(const AttnPlan& pl, cudaStream_t st) {
 
 using namespace rvlm;
 
+extern "C" int rvlm_attn_fwd_simt_rows(const void* qkv16, void* o16, float* lse, int B, int T,
+                                       int H, int fmt, int t_begin, int t_end, void* stream);
+
 extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H,
                              int fmt, void* stream) {
-  AttnPlan pl{};
-  int rc = make_plan(pl, qkv16, nullptr, B, T, H, fmt, fmt, fmt);
+  if (B <= 0 || T <= 0 || T > 257 || H <= 0) return RVLM_ERR_UNSUPPORTED;
+  AttnFwd2Params P{};
+  P.B = B; P.T = T; P.H = H; P.W = H * 64;
+  P.tm = T < 256 ? T : 256;
+  P.kvm = (P.tm + 15) / 16 * 16;
+  P.nblk = (P.kvm + 63) / 64;
+  P.ntile = (P.tm + 127) / 128;
+  P.tail = T > 256 ? 1 : 0;
+  P.fmt = fmt;
+  P.qkv = reinterpret_cast<const uint16_t*>(qkv16);
+  P.o_out = reinterpret_cast<uint16_t*>(o16);
+  P.lse_out = lse;
+  CUtensorMap tmTile, tmFull;
+  const uint64_t W3 = 3ull * P.W;
+  int rc = make_tmap_3d(&tmTile, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
   if (rc) return rc;
-  pl.P.o_out = reinterpret_cast<uint16_t*>(o16);
-  pl.P.lse_out = lse;
-  return launch_attn<AT_FWD>(pl, (cudaStream_t)stream);
+  rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
+  if (rc) return rc;
+  const size_t smem = (size_t)2 * P.kvm * 128 + 2 * 16384 + (size_t)2 * P.nblk * 16384 + 512 +
+                      128 + 1024;
+  static size_t set = 0;
+  if (smem > set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    set = smem;
+  }
+  int grid = sm_count();
+  if (B * H < grid) grid = B * H;
+  attn_fwd2_kernel<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(tmTile, tmFull, P);
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return -(int)e - 1000;
+  // the one query row beyond the 128-row tiles (token 256 of ViT-L/14) on the CUDA cores
+  if (T > 256) return rvlm_attn_fwd_simt_rows(qkv16, o16, lse, B, T, H, fmt, 256, T, stream);
+  return 0;
 }
 
 extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16,

@@ -46,7 +46,8 @@ __device__ void load_head(uint16_t* dst, const uint16_t* src, int T, int ld) {
 }
 
 __global__ void attn_fwd_simt_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ o,
-                                     float* __restrict__ lse, int T, int H, int fmt) {
+                                     float* __restrict__ lse, int T, int H, int fmt, int t_begin,
+                                     int t_end) {
   extern __shared__ uint8_t sm[];
   const int W = H * HD;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -62,7 +63,7 @@ __global__ void attn_fwd_simt_kernel(const uint16_t* __restrict__ qkv, uint16_t*
   float* p = sP + warp * T;
   float* q = sQ + warp * HD;
   const float scale = 0.125f;
-  for (int t = warp; t < T; t += nw) {
+  for (int t = t_begin + warp; t < t_end; t += nw) {
     const uint16_t* qp = base + (size_t)t * 3 * W;
     q[lane] = ld16(qp + lane, fmt);
     q[lane + 32] = ld16(qp + lane + 32, fmt);
@@ -226,8 +227,17 @@ __global__ void attn_bwd_simt_kernel(const uint16_t* __restrict__ qkv,
 
 using namespace rvlm;
 
+extern "C" int rvlm_attn_fwd_simt_rows(const void* qkv16, void* o16, float* lse, int B, int T,
+                                       int H, int fmt, int t_begin, int t_end, void* stream);
+
 extern "C" int rvlm_attn_fwd_simt(const void* qkv16, void* o16, float* lse, int B, int T, int H,
                                   int fmt, void* stream) {
+  return rvlm_attn_fwd_simt_rows(qkv16, o16, lse, B, T, H, fmt, 0, T, stream);
+}
+
+// query rows [t_begin, t_end) only (all keys)
+extern "C" int rvlm_attn_fwd_simt_rows(const void* qkv16, void* o16, float* lse, int B, int T,
+                                       int H, int fmt, int t_begin, int t_end, void* stream) {
   const int threads = 128, nw = threads / 32;
   const size_t smem = (size_t)2 * T * ROWP * 2 + (size_t)nw * T * 4 + (size_t)nw * HD * 4;
   static size_t set = 0;
@@ -238,7 +248,8 @@ extern "C" int rvlm_attn_fwd_simt(const void* qkv16, void* o16, float* lse, int 
     set = smem;
   }
   attn_fwd_simt_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
-      reinterpret_cast<const uint16_t*>(qkv16), reinterpret_cast<uint16_t*>(o16), lse, T, H, fmt);
+      reinterpret_cast<const uint16_t*>(qkv16), reinterpret_cast<uint16_t*>(o16), lse, T, H, fmt,
+      t_begin, t_end);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;

@@ -169,3 +169,20 @@ def test_attention_fwd_bwd(impl, B, T, H):
     scale = dqkv_ref.abs().max().item()
     _log("attn_bwd", impl=impl, B=B, T=T, H=H, err=err, scale=scale)
     assert err <= 3e-2 * scale
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_ts_mma_operand_packing(fmt):
+    """tcgen05.mma with A in TMEM: A[i,k] at lane i, 32-bit column k/2 (low half = even k)."""
+    nat = _nat()
+    torch.manual_seed(fmt)
+    A = torch.randn(128, 64, device="cuda").to(_dt(fmt))
+    B = torch.randn(64, 64, device="cuda").to(_dt(fmt))
+    C = torch.zeros(128, 64, device="cuda")
+    nat.call("rvlm_selftest_ts_mma", nat.ptr(A), nat.ptr(B), nat.ptr(C), nat.c_int(fmt),
+             nat.stream_ptr())
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t()
+    err = (C - ref).abs().max().item()
+    _log("ts_mma", fmt=fmt, err=err)
+    assert err < 1e-2

@@ -517,7 +517,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint8_t* s_q = s_v + full_bytes;                 // [2][16384]
   uint8_t* s_p = s_q + 2 * 16384;                  // [2][nblk * 16384]
   uint16_t* s_tail = reinterpret_cast<uint16_t*>(s_p + 2 * P.nblk * 16384);  // [2][2][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + 256);
+  uint16_t* s_qtail = s_tail + 256;                // [64] the peeled query row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qtail + 64);
   uint64_t* bar_k = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_q = bars + 2;       // [2]
@@ -525,12 +526,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint64_t* bar_p = bars + 6;       // [2] 128 arrivals
   uint64_t* bar_o = bars + 8;       // [2]
   uint64_t* bar_ofree = bars + 10;  // [2] 128 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_tail = bars + 12;   // 128 arrivals: peeled query row done with K / V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bar_k, 1);
     mbar_init(bar_v, 1);
+    mbar_init(bar_tail, 128);
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bar_q[g], 1);
       mbar_init(&bar_s[g], 1);
@@ -589,7 +592,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                      make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
           umma_commit(&bar_s[g]);
         }
-        for (int g = 0; g < ng; ++g) mbar_wait(&bar_s[g], ph, 33);   // K consumed
+        for (int g = 0; g < ng; ++g) mbar_wait(&bar_s[g], ph, 33);   // K consumed by the MMAs
+        if (P.tail) mbar_wait(bar_tail, ph, 37);                     // ... and by the peeled row
         if (next < n_items) load_k(next);
         mbar_wait(bar_v, ph, 34);
         for (int g = 0; g < ng; ++g) {
@@ -629,6 +633,108 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 *reinterpret_cast<const uint4*>(src);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        }
+        if (P.tail && g == ng - 1) {
+          // ---- the peeled QUERY row (token 256) on the CUDA cores, in the shadow of the S
+          // MMAs: scores against all 257 keys, softmax, P V.  Scratch = this group's P buffer.
+          float* sc = reinterpret_cast<float*>(my_p);   // [272] scores / probabilities
+          float* red = sc + 288;                        // [8] warp partials
+          float* oh = red + 8;                          // [2][64] output halves
+          if (r < 8)
+            *reinterpret_cast<uint4*>(s_qtail + r * 8) = *reinterpret_cast<const uint4*>(
+                P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 + r * 8);
+          mbar_wait(bar_k, ph, 43);
+          mbar_wait(bar_v, ph, 44);
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          float qv[64];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 qu = *reinterpret_cast<const uint4*>(s_qtail + c * 8);
+            const uint32_t* qa = &qu.x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 x = unpack2(qa[i], P.fmt);
+              qv[c * 8 + 2 * i] = x.x;
+              qv[c * 8 + 2 * i + 1] = x.y;
+            }
+          }
+          float lmax = -INFINITY;
+          for (int kv = r; kv < T; kv += 128) {
+            float acc = 0.f;
+            if (kv < 256) {
+              const uint8_t* krow = s_k + kv * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 ku = *reinterpret_cast<const uint4*>(krow + ((c ^ (kv & 7)) << 4));
+                const uint32_t* ka = &ku.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 y = unpack2(ka[i], P.fmt);
+                  acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
+                }
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 ku = *reinterpret_cast<const uint4*>(kt + c * 8);
+                const uint32_t* ka = &ku.x;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 y = unpack2(ka[i], P.fmt);
+                  acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
+                }
+              }
+            }
+            sc[kv] = acc;
+            lmax = fmaxf(lmax, acc);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffff, lmax, o));
+          if (lane == 0) red[warp & 3] = lmax;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          const float tmc = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * c2;
+          float lsum = 0.f;
+          for (int kv = r; kv < T; kv += 128) {
+            const float e = fast_ex2(fmaf(sc[kv], c2, -tmc));
+            sc[kv] = e;
+            lsum += e;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffff, lsum, o);
+          if (lane == 0) red[4 + (warp & 3)] = lsum;
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          const float tsum = (red[4] + red[5]) + (red[6] + red[7]);
+          {  // o[d] over this thread's half of the keys
+            const int d = r & 63, hf = r >> 6;
+            const int k0 = hf * 128, k1 = hf ? 256 : 128;
+            float acc = 0.f;
+            for (int kv = k0; kv < k1; ++kv) {
+              const uint16_t hv = *reinterpret_cast<const uint16_t*>(
+                  s_v + kv * 128 + (((d >> 3) ^ (kv & 7)) << 4) + (d & 7) * 2);
+              const float v = P.fmt ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&hv))
+                                    : __half2float(*reinterpret_cast<const __half*>(&hv));
+              acc = fmaf(sc[kv], v, acc);
+            }
+            if (hf == 1) {
+              const uint16_t hv = vt[d];
+              const float v = P.fmt ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&hv))
+                                    : __half2float(*reinterpret_cast<const __half*>(&hv));
+              acc = fmaf(sc[256], v, acc);
+            }
+            oh[hf * 64 + d] = acc;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          if (r < 32) {
+            const float inv = 1.f / tsum;
+            const float o0 = (oh[2 * r] + oh[64 + 2 * r]) * inv;
+            const float o1 = (oh[2 * r + 1] + oh[64 + 2 * r + 1]) * inv;
+            reinterpret_cast<uint32_t*>(P.o_out + ((size_t)b * T + 256) * W + h * 64)[r] =
+                pack2(o0, o1, P.fmt);
+            if (r == 0)
+              P.lse_out[((size_t)b * P.H + h) * T + 256] = (tmc + log2f(tsum)) * 0.6931471805599453f;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");  // scratch free again
+          mbar_arrive(bar_tail);
         }
         mbar_wait(&bar_q[g], ph, 42);  // (complete long ago) makes the TMA-written Q tile visible
         mbar_wait(&bar_s[g], ph, 40);
@@ -829,7 +935,7 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
   const size_t smem = (size_t)2 * P.kvm * 128 + 2 * 16384 + (size_t)2 * P.nblk * 16384 + 512 +
-                      128 + 1024;
+                      128 + 128 + 1024;
   static size_t set = 0;
   if (smem > set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel,
@@ -842,10 +948,7 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   attn_fwd2_kernel<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(tmTile, tmFull, P);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return -(int)e - 1000;
-  // the one query row beyond the 128-row tiles (token 256 of ViT-L/14) on the CUDA cores
-  if (T > 256) return rvlm_attn_fwd_simt_rows(qkv16, o16, lse, B, T, H, fmt, 256, T, stream);
-  return 0;
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
 extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16,

@@ -66,10 +66,12 @@ int rvlm_profile_gemm_collect(double* total_ms, double* total_flops, long long* 
  *    flags: bit0 = B is given as [K,N] row-major (MN-major operand)
  *           bit1 = A is given as [K,M] row-major (MN-major operand)
  *           bit2 = 128-column tiles instead of 256
+ *           bit3 = 2-CTA kernel (256 x 256 tile per SM pair)
  * ------------------------------------------------------------------------ */
 #define RVLM_GEMM_B_MN 1
 #define RVLM_GEMM_A_MN 2
 #define RVLM_GEMM_BN128 4
+#define RVLM_GEMM_2CTA 8 /* cluster of two CTAs, tcgen05.mma.cta_group::2 (K-major operands) */
 
 /* 16-bit output */
 int rvlm_gemm16_out16(const void* A, int lda, const void* B, int ldb, void* C, int ldc,

@@ -24,6 +24,7 @@
 // Warp roles: warps 0-3 = row workers (TMEM lane == tile row), warp 4 = TMEM allocator
 // and, lane 0, the TMA + MMA issuer.
 #include "gemm.cuh"
+#include <cstdlib>
 #include "../../include/rvlm.h"
 
 namespace rvlm {
@@ -479,6 +480,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
 }
 
 
+template <int FMT>
+__device__ __forceinline__ uint32_t packc(float a, float b) {
+  return FMT ? pack2_bf16(a, b) : pack2_f16(a, b);
+}
+template <int FMT>
+__device__ __forceinline__ float2 unpackc(uint32_t u) {
+  return unpack2(u, FMT);
+}
+template <int FMT>
+__device__ __forceinline__ float ld1(const uint16_t* p) {
+  return FMT ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p))
+             : __half2float(*reinterpret_cast<const __half*>(p));
+}
 // =====================================================================================
 // Forward, version 2: two row groups in flight, one thread per row.
 //
@@ -503,6 +517,7 @@ struct AttnFwd2Params {
   float* lse_out;
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
                  const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x kvm
@@ -552,7 +567,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_items = P.B * P.H;
-  const uint32_t f = (uint32_t)P.fmt;
+  const uint32_t f = (uint32_t)FMT;
   const int ng = P.ntile;  // active groups (group g <-> tile g)
 
   if (warp == AT_CTRL_WARP) {
@@ -653,7 +668,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             const uint32_t* qa = &qu.x;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float2 x = unpack2(qa[i], P.fmt);
+              const float2 x = unpackc<FMT>(qa[i]);
               qv[c * 8 + 2 * i] = x.x;
               qv[c * 8 + 2 * i + 1] = x.y;
             }
@@ -669,7 +684,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 const uint32_t* ka = &ku.x;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 y = unpack2(ka[i], P.fmt);
+                  const float2 y = unpackc<FMT>(ka[i]);
                   acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
                 }
               }
@@ -680,7 +695,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 const uint32_t* ka = &ku.x;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 y = unpack2(ka[i], P.fmt);
+                  const float2 y = unpackc<FMT>(ka[i]);
                   acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
                 }
               }
@@ -711,14 +726,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             for (int kv = k0; kv < k1; ++kv) {
               const uint16_t hv = *reinterpret_cast<const uint16_t*>(
                   s_v + kv * 128 + (((d >> 3) ^ (kv & 7)) << 4) + (d & 7) * 2);
-              const float v = P.fmt ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&hv))
-                                    : __half2float(*reinterpret_cast<const __half*>(&hv));
+              const float v = ld1<FMT>(&hv);
               acc = fmaf(sc[kv], v, acc);
             }
             if (hf == 1) {
               const uint16_t hv = vt[d];
-              const float v = P.fmt ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&hv))
-                                    : __half2float(*reinterpret_cast<const __half*>(&hv));
+              const float v = ld1<FMT>(&hv);
               acc = fmaf(sc[256], v, acc);
             }
             oh[hf * 64 + d] = acc;
@@ -729,7 +742,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             const float o0 = (oh[2 * r] + oh[64 + 2 * r]) * inv;
             const float o1 = (oh[2 * r + 1] + oh[64 + 2 * r + 1]) * inv;
             reinterpret_cast<uint32_t*>(P.o_out + ((size_t)b * T + 256) * W + h * 64)[r] =
-                pack2(o0, o1, P.fmt);
+                packc<FMT>(o0, o1);
             if (r == 0)
               P.lse_out[((size_t)b * P.H + h) * T + 256] = (tmc + log2f(tsum)) * 0.6931471805599453f;
           }
@@ -752,7 +765,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               const uint32_t* ka = &ku.x;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 x = unpack2(qa[i], P.fmt), y = unpack2(ka[i], P.fmt);
+                const float2 x = unpackc<FMT>(qa[i]), y = unpackc<FMT>(ka[i]);
                 s_t = fmaf(x.x, y.x, fmaf(x.y, y.y, s_t));
               }
             }
@@ -793,10 +806,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             for (int q8 = 0; q8 < 4; ++q8) {
               if (q8 * 8 < nv) {
                 uint4 u;
-                u.x = pack2(p[q8 * 8 + 0], p[q8 * 8 + 1], P.fmt);
-                u.y = pack2(p[q8 * 8 + 2], p[q8 * 8 + 3], P.fmt);
-                u.z = pack2(p[q8 * 8 + 4], p[q8 * 8 + 5], P.fmt);
-                u.w = pack2(p[q8 * 8 + 6], p[q8 * 8 + 7], P.fmt);
+                u.x = packc<FMT>(p[q8 * 8 + 0], p[q8 * 8 + 1]);
+                u.y = packc<FMT>(p[q8 * 8 + 2], p[q8 * 8 + 3]);
+                u.z = packc<FMT>(p[q8 * 8 + 4], p[q8 * 8 + 5]);
+                u.w = packc<FMT>(p[q8 * 8 + 6], p[q8 * 8 + 7]);
                 *reinterpret_cast<uint4*>(my_p + p_off(r, c * 32 + q8 * 8)) = u;
               }
             }
@@ -829,16 +842,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 const uint32_t* va = &vu.x;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 y = unpack2(va[i], P.fmt);
+                  const float2 y = unpackc<FMT>(va[i]);
                   o[2 * i] = fmaf(p_t, y.x, o[2 * i]);
                   o[2 * i + 1] = fmaf(p_t, y.y, o[2 * i + 1]);
                 }
               }
               uint4 u;
-              u.x = pack2(o[0] * inv, o[1] * inv, P.fmt);
-              u.y = pack2(o[2] * inv, o[3] * inv, P.fmt);
-              u.z = pack2(o[4] * inv, o[5] * inv, P.fmt);
-              u.w = pack2(o[6] * inv, o[7] * inv, P.fmt);
+              u.x = packc<FMT>(o[0] * inv, o[1] * inv);
+              u.y = packc<FMT>(o[2] * inv, o[3] * inv);
+              u.z = packc<FMT>(o[4] * inv, o[5] * inv);
+              u.w = packc<FMT>(o[6] * inv, o[7] * inv);
               dst[q8] = u;
             }
             P.lse_out[((size_t)b * P.H + h) * T + row] = (mx + log2f(rsum)) * 0.6931471805599453f;
@@ -856,6 +869,612 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+}
+
+
+// =====================================================================================
+// Backward, version 2 (ViT-L/14: T = 257, ViT-B/32: T = 50).
+//   * the 257th token is peeled exactly as in the forward: tensor-core tiles cover rows and
+//     columns [0, 256); the peeled key / query COLUMN is a pair of 64-MAC dot products per
+//     thread-row folded into the epilogue as a rank-1 update, and the peeled ROW is computed
+//     by all worker threads on the CUDA cores in the shadow of the first tile's MMAs;
+//   * S and dP are issued back to back into separate TMEM regions (2 x 256 columns), the
+//     64-column output accumulators alias the consumed S region: three issuer<->worker
+//     hand-offs per tile instead of five, two tiles per item instead of three;
+//   * each thread keeps its 32*NCH probabilities in registers between the two passes (one
+//     TMEM sweep of S, one of dP); operand format is a template parameter.
+// =====================================================================================
+struct AttnBwd2Params {
+  int B, T, H, W;
+  int tm, kvm, nblk, ntile, tail;
+  int fmt_o;             // format of the forward output o (read by threads only)
+  const uint16_t* qkv;   // [B*T, 3W] backward copy of q|k|v (operand format)
+  const uint16_t* o;     // [B*T, W]
+  const uint16_t* d_o;   // [B*T, W]  (operand format)
+  float* lse_tmp;        // [B, H, T] log2-sum-exp, written by DQ, read by DKV
+  uint16_t* dqkv;        // [B*T, 3W] (operand format)
+};
+
+// dot product of a 64-element row of a 128B-swizzled K-major smem tile with a 64-element
+// vector held in plain shared memory
+template <int FMT>
+__device__ __forceinline__ float dot_swz_row(const uint8_t* tile, int r, const uint16_t* vec) {
+  float acc = 0.f;
+  const uint8_t* row = tile + r * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 a = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+    const uint4 b = *reinterpret_cast<const uint4*>(vec + c * 8);
+    const uint32_t* pa = &a.x;
+    const uint32_t* pb = &b.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpackc<FMT>(pa[i]), y = unpackc<FMT>(pb[i]);
+      acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+    }
+  }
+  return acc;
+}
+template <int FMT>
+__device__ __forceinline__ float dot_vec(const uint16_t* a, const uint16_t* b) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 ua = *reinterpret_cast<const uint4*>(a + c * 8);
+    const uint4 ub = *reinterpret_cast<const uint4*>(b + c * 8);
+    const uint32_t* pa = &ua.x;
+    const uint32_t* pb = &ub.x;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpackc<FMT>(pa[i]), y = unpackc<FMT>(pb[i]);
+      acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+    }
+  }
+  return acc;
+}
+// element (row kv, column d) of a 128B-swizzled [rows x 64] 16-bit tile
+template <int FMT>
+__device__ __forceinline__ float swz_at(const uint8_t* tile, int kv, int d) {
+  return ld1<FMT>(reinterpret_cast<const uint16_t*>(tile + kv * 128 + (((d >> 3) ^ (kv & 7)) << 4) +
+                                                    (d & 7) * 2));
+}
+__device__ __forceinline__ float blk256_max(float v, float* red, int warp, int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffff, v, o));
+  if (lane == 0) red[warp] = v;
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+  float t = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t = fmaxf(t, red[i]);
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+  return t;
+}
+__device__ __forceinline__ float blk256_sum(float v, float* red, int warp, int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  if (lane == 0) red[warp] = v;
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += red[i];
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+  return t;
+}
+
+template <int MODE, int NCH, int FMT>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x kvm
+                 const __grid_constant__ CUtensorMap tmDoTile, // dO,  box 64 x 128
+                 const __grid_constant__ CUtensorMap tmDoFull, // dO,  box 64 x kvm
+                 AttnBwd2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr int KVM = NCH * 64;          // columns on the tensor cores (64 or 256)
+  constexpr int NBLK = KVM / 64;
+  const int T = P.T, W = P.W;
+  constexpr int full_bytes = KVM * 128;
+  uint8_t* s_full0 = smem;                   // DQ: K      DKV: Q
+  uint8_t* s_full1 = s_full0 + full_bytes;   // DQ: V      DKV: dO
+  uint8_t* s_tile0 = s_full1 + full_bytes;   // [2][16384] DQ: Q_i   DKV: K_j
+  uint8_t* s_tile1 = s_tile0 + 2 * 16384;    // [2][16384] DQ: dO_i  DKV: V_j
+  uint8_t* s_p = s_tile1 + 2 * 16384;        // [NBLK][16384] P / dS operand
+  float* s_lse = reinterpret_cast<float*>(s_p + NBLK * 16384);  // [272] (DKV) per-q lse
+  float* s_dvec = s_lse + 272;                                  // [272] (DKV) per-q D
+  float* s_red = s_dvec + 272;    // [256]
+  float* s_red2 = s_red + 256;    // [256]
+  float* s_tt = s_red2 + 256;     // [256] per-row tail terms: p_t | ds_t
+  float* s_misc = s_tt + 256;     // [16]
+  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_misc + 16);  // [4][64] peeled vectors
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 256);
+  uint64_t* bar_full = bars + 0;
+  uint64_t* bar_tile = bars + 1;      // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_dp = bars + 4;
+  uint64_t* bar_p = bars + 5;         // 256 arrivals, 1 (DQ) or 2 (DKV) uses per tile
+  uint64_t* bar_dv = bars + 6;        // DKV: dV MMA retired (P may be overwritten)
+  uint64_t* bar_acc = bars + 7;
+  uint64_t* bar_acc_free = bars + 8;  // 256 arrivals
+  uint64_t* bar_trow = bars + 9;      // 256 arrivals: peeled row done with the full matrices
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(&bar_tile[0], 1);
+    mbar_init(&bar_tile[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_dv, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc_free, 256);
+    mbar_init(bar_trow, 256);
+    fence_barrier_init();
+  }
+  if (warp == AT_CTRL_WARP) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = P.B * P.H;
+  const int colQ = 0, colK = W, colV = 2 * W;
+  constexpr uint32_t TS = 0, TDP = 256, TACC = 0, TACC2 = 64;
+
+  if (warp == AT_CTRL_WARP) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issuer =====================
+      auto load_full = [&](int item) {
+        const int b = item / P.H, h = item % P.H;
+        mbar_arrive_expect_tx(bar_full, 2 * full_bytes);
+        if (MODE == AT_DKV) {
+          tma_load_3d(s_full0, &tmFull, bar_full, colQ + h * 64, 0, b);
+          tma_load_3d(s_full1, &tmDoFull, bar_full, h * 64, 0, b);
+        } else {
+          tma_load_3d(s_full0, &tmFull, bar_full, colK + h * 64, 0, b);
+          tma_load_3d(s_full1, &tmFull, bar_full, colV + h * 64, 0, b);
+        }
+      };
+      auto load_tile = [&](int item, int j, uint32_t gg) {
+        const int b = item / P.H, h = item % P.H, buf = gg & 1;
+        mbar_arrive_expect_tx(&bar_tile[buf], 32768);
+        if (MODE == AT_DKV) {
+          tma_load_3d(s_tile0 + buf * 16384, &tmTile, &bar_tile[buf], colK + h * 64, j * 128, b);
+          tma_load_3d(s_tile1 + buf * 16384, &tmTile, &bar_tile[buf], colV + h * 64, j * 128, b);
+        } else {
+          tma_load_3d(s_tile0 + buf * 16384, &tmTile, &bar_tile[buf], colQ + h * 64, j * 128, b);
+          tma_load_3d(s_tile1 + buf * 16384, &tmDoTile, &bar_tile[buf], h * 64, j * 128, b);
+        }
+      };
+      const uint32_t idS = idesc_ab(FMT, FMT, 128, KVM, 0, 0);
+      uint32_t g = 0;
+      int it = 0;
+      if ((int)blockIdx.x < n_items) {
+        load_full(blockIdx.x);
+        load_tile(blockIdx.x, 0, 0);
+      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int next = item + gridDim.x;
+        mbar_wait(bar_full, it & 1, 50);
+        for (int j = 0; j < P.ntile; ++j, ++g) {
+          const int buf = g & 1;
+          if (j + 1 < P.ntile) load_tile(item, j + 1, g + 1);
+          else if (next < n_items) load_tile(next, 0, g + 1);
+          mbar_wait(&bar_tile[buf], (g >> 1) & 1, 51);
+          if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 52);   // accumulators alias S
+          tc_fence_after();
+          const uint32_t t0 = smem_u32(s_tile0 + buf * 16384), t1 = smem_u32(s_tile1 + buf * 16384);
+          const uint32_t f0 = smem_u32(s_full0), f1 = smem_u32(s_full1), pa = smem_u32(s_p);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // S = Q_i K^T   |  S^T = K_j Q^T
+            umma_f16(tmem + TS, make_smem_desc_sw128(t0 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(f0 + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_s);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dP = dO_i V^T |  dP^T = V_j dO^T
+            umma_f16(tmem + TDP, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(f1 + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_dp);
+          if (MODE == AT_DKV) {
+            mbar_wait(bar_p, (2 * g) & 1, 53);                   // P^T written, S^T consumed
+            tc_fence_after();
+            issue_mma2(tmem + TACC, pa, f1, KVM, FMT, FMT);      // dV = P^T dO
+            umma_commit(bar_dv);
+            mbar_wait(bar_p, (2 * g + 1) & 1, 54);               // dS^T written
+            tc_fence_after();
+            issue_mma2(tmem + TACC2, pa, f0, KVM, FMT, FMT);     // dK = dS^T Q
+          } else {
+            mbar_wait(bar_p, g & 1, 53);                         // dS written, S / dP consumed
+            tc_fence_after();
+            issue_mma2(tmem + TACC, pa, f0, KVM, FMT, FMT);      // dQ = dS K
+          }
+          umma_commit(bar_acc);
+        }
+        mbar_wait(bar_acc, (g - 1) & 1, 55);                     // every MMA of this item retired
+        if (P.tail) mbar_wait(bar_trow, it & 1, 56);
+        if (next < n_items) load_full(next);
+      }
+    }
+  } else {
+    // ===================== row workers =====================
+    const int r = threadIdx.x & 127, hsel = threadIdx.x >> 7, tid = threadIdx.x;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float c2 = 0.125f * 1.4426950408889634f;
+    const uint32_t ts = tmem + lane_off;
+    constexpr int NH = NCH;                 // 32-column chunks per thread (half of the columns)
+    const int c0 = hsel * NH;
+    const uint16_t* tv0 = s_tv;             // DQ: k_256   DKV: q_256
+    const uint16_t* tv1 = s_tv + 64;        // DQ: v_256   DKV: dO_256
+    const uint16_t* tv2 = s_tv + 128;       // DQ: q_256   DKV: k_256
+    const uint16_t* tv3 = s_tv + 192;       // DQ: dO_256  DKV: v_256
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int b = item / P.H, h = item % P.H;
+      const size_t lse_base = ((size_t)b * P.H + h) * T;
+      // ---- stage the peeled vectors and (DKV) the per-query statistics
+      if (P.tail && tid < 32) {
+        const int which = tid >> 3, c = tid & 7;
+        const size_t rowq = ((size_t)b * T + 256) * 3 * W + h * 64 + c * 8;
+        const size_t rowd = ((size_t)b * T + 256) * W + h * 64 + c * 8;
+        const uint16_t* src;
+        if (MODE == AT_DQ)
+          src = which == 0 ? P.qkv + rowq + colK : which == 1 ? P.qkv + rowq + colV
+              : which == 2 ? P.qkv + rowq + colQ : P.d_o + rowd;
+        else
+          src = which == 0 ? P.qkv + rowq + colQ : which == 1 ? P.d_o + rowd
+              : which == 2 ? P.qkv + rowq + colK : P.qkv + rowq + colV;
+        *reinterpret_cast<uint4*>(s_tv + which * 64 + c * 8) = *reinterpret_cast<const uint4*>(src);
+      }
+      if (MODE == AT_DKV) {
+        for (int q = tid; q < 272; q += 256) {
+          float L = INFINITY, Dv = 0.f;
+          if (q < T) {
+            L = P.lse_tmp[lse_base + q];
+            const size_t ro = ((size_t)b * T + q) * W + h * 64;
+            Dv = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);
+          }
+          s_lse[q] = L;
+          s_dvec[q] = Dv;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (P.tail) {
+        // ================= the peeled ROW (token 256) on the CUDA cores =================
+        float* sc = reinterpret_cast<float*>(s_p);   // [272] p / weights (scratch: P buffer)
+        float* sc2 = sc + 272;                       // [272] ds
+        float* part = sc2 + 272;                     // [2][4][64] partial sums
+        mbar_wait(bar_full, it & 1, 60);
+        if (MODE == AT_DQ) {
+          // dq_256 = sum_kv ds[kv] K[kv],  ds = softmax(q_256 K^T / 8) (dO_256 V^T - D) / 8
+          float sv = -INFINITY, dpv = 0.f;
+          if (tid < 256) {
+            sv = dot_swz_row<FMT>(s_full0, tid, tv2);
+            dpv = dot_swz_row<FMT>(s_full1, tid, tv3);
+          }
+          float s_last = dot_vec<FMT>(tv0, tv2), dp_last = dot_vec<FMT>(tv1, tv3);
+          const float mx = blk256_max(fmaxf(sv, s_last), s_misc, warp, lane) * c2;
+          const float e = fast_ex2(fmaf(sv, c2, -mx));
+          const float e_last = fast_ex2(fmaf(s_last, c2, -mx));
+          const float sum = blk256_sum(e, s_misc, warp, lane) + e_last;
+          const float inv = 1.f / sum;
+          const size_t ro = ((size_t)b * T + 256) * W + h * 64;
+          const float D = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);
+          sc2[tid] = e * inv * (dpv - D) * 0.125f;
+          if (tid == 0) {
+            sc2[256] = e_last * inv * (dp_last - D) * 0.125f;
+            P.lse_tmp[lse_base + 256] = mx + log2f(sum);
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          {
+            const int d = tid & 63, qt = tid >> 6;
+            float acc = 0.f;
+            for (int kv = qt * 64; kv < qt * 64 + 64; ++kv)
+              acc = fmaf(sc2[kv], swz_at<FMT>(s_full0, kv, d), acc);
+            if (qt == 3) acc = fmaf(sc2[256], ld1<FMT>(tv0 + d), acc);
+            part[qt * 64 + d] = acc;
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (tid < 32) {
+            const float a0 = part[2 * tid] + part[64 + 2 * tid] + part[128 + 2 * tid] +
+                             part[192 + 2 * tid];
+            const float a1 = part[2 * tid + 1] + part[64 + 2 * tid + 1] + part[128 + 2 * tid + 1] +
+                             part[192 + 2 * tid + 1];
+            reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64)[tid] =
+                packc<FMT>(a0, a1);
+          }
+        } else {
+          // dv_256 = sum_q p[q] dO[q],  dk_256 = sum_q ds[q] Q[q]   (column 256 of P, dS)
+          float pv = 0.f, dsv = 0.f;
+          {
+            const float sT = dot_swz_row<FMT>(s_full0, tid, tv2);   // q_tid . k_256
+            const float dpT = dot_swz_row<FMT>(s_full1, tid, tv3);  // dO_tid . v_256
+            pv = fast_ex2(fmaf(sT, c2, -s_lse[tid]));
+            dsv = pv * (dpT - s_dvec[tid]) * 0.125f;
+          }
+          sc[tid] = pv;
+          sc2[tid] = dsv;
+          if (tid == 0) {
+            const float sT = dot_vec<FMT>(tv0, tv2), dpT = dot_vec<FMT>(tv1, tv3);
+            const float pl = fast_ex2(fmaf(sT, c2, -s_lse[256]));
+            sc[256] = pl;
+            sc2[256] = pl * (dpT - s_dvec[256]) * 0.125f;
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          {
+            const int d = tid & 63, qt = tid >> 6;
+            float av = 0.f, ak = 0.f;
+            for (int q = qt * 64; q < qt * 64 + 64; ++q) {
+              av = fmaf(sc[q], swz_at<FMT>(s_full1, q, d), av);
+              ak = fmaf(sc2[q], swz_at<FMT>(s_full0, q, d), ak);
+            }
+            if (qt == 3) {
+              av = fmaf(sc[256], ld1<FMT>(tv1 + d), av);
+              ak = fmaf(sc2[256], ld1<FMT>(tv0 + d), ak);
+            }
+            part[qt * 64 + d] = av;
+            part[256 + qt * 64 + d] = ak;
+          }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (tid < 64) {
+            const int which = tid >> 5, l2 = tid & 31;   // 0: dv, 1: dk
+            const float* pp = part + which * 256;
+            const float a0 = pp[2 * l2] + pp[64 + 2 * l2] + pp[128 + 2 * l2] + pp[192 + 2 * l2];
+            const float a1 = pp[2 * l2 + 1] + pp[64 + 2 * l2 + 1] + pp[128 + 2 * l2 + 1] +
+                             pp[192 + 2 * l2 + 1];
+            reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W +
+                                        (which ? colK : colV) + h * 64)[l2] = packc<FMT>(a0, a1);
+          }
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");   // scratch (P buffer) free again
+        mbar_arrive(bar_trow);
+      }
+      for (int j = 0; j < P.ntile; ++j, ++g) {
+        const int buf = g & 1;
+        const int row = j * 128 + r;
+        const bool valid = row < P.tm;
+        const bool warp_valid = (j * 128 + (warp & 3) * 32) < P.tm;
+        const size_t grow = (size_t)b * T + row;
+        mbar_wait(&bar_tile[buf], (g >> 1) & 1, 61);     // tile rows visible to generic loads
+        float Dr = 0.f, a_t = 0.f, b_t = 0.f;
+        if (MODE == AT_DQ && valid)
+          Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, FMT);
+        if (P.tail && hsel == 1 && warp_valid) {
+          a_t = dot_swz_row<FMT>(s_tile0 + buf * 16384, r, tv0);   // DQ: q_r.k_256  DKV: k_r.q_256
+          b_t = dot_swz_row<FMT>(s_tile1 + buf * 16384, r, tv1);   // DQ: dO_r.v_256 DKV: v_r.dO_256
+        }
+        // ---------------- pass 1: probabilities (kept in registers) ----------------
+        mbar_wait(bar_s, g & 1, 62);
+        tc_fence_after();
+        // probabilities are kept PACKED (operand format, two per register) between the passes:
+        // pass 2 then uses exactly the values the tensor core sees in P
+        uint32_t pk[NH * 16];
+        float mc = 0.f, rinv = 1.f, p_t = 0.f;
+        if (MODE == AT_DQ) {
+          float mx = -INFINITY;
+          if (warp_valid) {
+#pragma unroll
+            for (int c = 0; c < NH; ++c) {
+              uint32_t v[32];
+              tmem_ld32(ts + TS + (c0 + c) * 32, v);
+              tmem_ld_wait();
+              if ((c0 + c) * 32 + 32 <= P.tm) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if ((c0 + c) * 32 + i < P.tm) mx = fmaxf(mx, __uint_as_float(v[i]));
+              }
+            }
+            if (P.tail && hsel == 1) mx = fmaxf(mx, a_t);
+          }
+          s_red[hsel * 128 + r] = mx;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          mc = fmaxf(s_red[r], s_red[128 + r]) * c2;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          if (warp_valid) {
+#pragma unroll
+            for (int c = 0; c < NH; ++c) {
+              uint32_t v[32];
+              tmem_ld32(ts + TS + (c0 + c) * 32, v);
+              tmem_ld_wait();
+              const bool full = (c0 + c) * 32 + 32 <= P.tm;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                float e[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  e[u] = (valid && (full || (c0 + c) * 32 + i + u < P.tm))
+                             ? fast_ex2(fmaf(__uint_as_float(v[i + u]), c2, -mc)) : 0.f;
+                s0 += e[0]; s1 += e[1]; s2 += e[2]; s3 += e[3];
+                pk[c * 16 + i / 2] = packc<FMT>(e[0], e[1]);
+                pk[c * 16 + i / 2 + 1] = packc<FMT>(e[2], e[3]);
+              }
+            }
+            if (P.tail && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -mc));
+          }
+          s_red2[hsel * 128 + r] = (s0 + s1) + (s2 + s3) + p_t;
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          const float rsum = s_red2[r] + s_red2[128 + r];
+          rinv = 1.f / rsum;
+          if (valid && hsel == 0) P.lse_tmp[lse_base + row] = mc + log2f(rsum);
+        } else {
+          if (warp_valid) {
+#pragma unroll
+            for (int c = 0; c < NH; ++c) {
+              uint32_t v[32];
+              tmem_ld32(ts + TS + (c0 + c) * 32, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float e0 = valid ? fast_ex2(fmaf(__uint_as_float(v[i]), c2,
+                                                       -s_lse[(c0 + c) * 32 + i])) : 0.f;
+                const float e1 = valid ? fast_ex2(fmaf(__uint_as_float(v[i + 1]), c2,
+                                                       -s_lse[(c0 + c) * 32 + i + 1])) : 0.f;
+                pk[c * 16 + i / 2] = packc<FMT>(e0, e1);
+              }
+              // P^T -> shared memory (A operand of dV = P^T dO)
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8)
+                *reinterpret_cast<uint4*>(s_p + p_off(r, (c0 + c) * 32 + q8 * 8)) =
+                    make_uint4(pk[c * 16 + q8 * 4], pk[c * 16 + q8 * 4 + 1],
+                               pk[c * 16 + q8 * 4 + 2], pk[c * 16 + q8 * 4 + 3]);
+            }
+            if (P.tail && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -s_lse[256]));
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(bar_p);
+        }
+        // ---------------- pass 2: dS = P (dP - D) / 8 ----------------
+        mbar_wait(bar_dp, g & 1, 63);
+        tc_fence_after();
+        if (MODE == AT_DKV) mbar_wait(bar_dv, g & 1, 64);   // dV no longer reads the P buffer
+        float ds_t = 0.f;
+        if (warp_valid) {
+          const float sc = 0.125f * rinv;
+#pragma unroll
+          for (int c = 0; c < NH; ++c) {
+            uint32_t v[32];
+            tmem_ld32(ts + TDP + (c0 + c) * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float d[8];
+#pragma unroll
+              for (int u = 0; u < 8; u += 2) {
+                const float2 pp = unpackc<FMT>(pk[c * 16 + (i + u) / 2]);
+                const float D0 = (MODE == AT_DQ) ? Dr : s_dvec[(c0 + c) * 32 + i + u];
+                const float D1 = (MODE == AT_DQ) ? Dr : s_dvec[(c0 + c) * 32 + i + u + 1];
+                d[u] = pp.x * sc * (__uint_as_float(v[i + u]) - D0);
+                d[u + 1] = pp.y * sc * (__uint_as_float(v[i + u + 1]) - D1);
+              }
+              uint4 u4;
+              u4.x = packc<FMT>(d[0], d[1]);
+              u4.y = packc<FMT>(d[2], d[3]);
+              u4.z = packc<FMT>(d[4], d[5]);
+              u4.w = packc<FMT>(d[6], d[7]);
+              *reinterpret_cast<uint4*>(s_p + p_off(r, (c0 + c) * 32 + i)) = u4;
+            }
+          }
+          if (P.tail && hsel == 1) {
+            const float Dv = (MODE == AT_DQ) ? Dr : s_dvec[256];
+            ds_t = p_t * sc * (b_t - Dv);
+            s_tt[r] = p_t * rinv;
+            s_tt[128 + r] = ds_t;
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        // ---------------- epilogue ----------------
+        mbar_wait(bar_acc, g & 1, 65);
+        tc_fence_after();
+        if (warp_valid) {
+          const float pt = P.tail ? s_tt[r] : 0.f, dst = P.tail ? s_tt[128 + r] : 0.f;
+          if (MODE == AT_DKV) {
+            uint32_t v0[32], v1[32];
+            const uint32_t col = hsel ? TACC2 : TACC;
+            tmem_ld32(ts + col, v0);
+            tmem_ld32(ts + col + 32, v1);
+            tmem_ld_wait();
+            if (valid) {
+              // hsel 0: dV_r += p_t dO_256     hsel 1: dK_r += ds_t q_256
+              const float w = hsel ? dst : pt;
+              const uint16_t* tvx = hsel ? tv0 : tv1;
+              uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + (hsel ? colK : colV) +
+                                                     h * 64);
+#pragma unroll
+              for (int q8 = 0; q8 < 8; ++q8) {
+                const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
+                if (P.tail) {
+                  const uint4 tu = *reinterpret_cast<const uint4*>(tvx + q8 * 8);
+                  const uint32_t* ta = &tu.x;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 y = unpackc<FMT>(ta[i]);
+                    o[2 * i] = fmaf(w, y.x, o[2 * i]);
+                    o[2 * i + 1] = fmaf(w, y.y, o[2 * i + 1]);
+                  }
+                }
+                uint4 u;
+                u.x = packc<FMT>(o[0], o[1]); u.y = packc<FMT>(o[2], o[3]);
+                u.z = packc<FMT>(o[4], o[5]); u.w = packc<FMT>(o[6], o[7]);
+                dst4[q8] = u;
+              }
+            }
+          } else {
+            uint32_t v0[32];
+            tmem_ld32(ts + TACC + hsel * 32, v0);
+            tmem_ld_wait();
+            if (valid) {   // dQ_r += ds_t k_256 ; each half stores 32 of the 64 columns
+              uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + colQ + h * 64 +
+                                                     hsel * 32);
+#pragma unroll
+              for (int q8 = 0; q8 < 4; ++q8) {
+                float o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v0[q8 * 8 + i]);
+                if (P.tail) {
+                  const uint4 tu = *reinterpret_cast<const uint4*>(tv0 + hsel * 32 + q8 * 8);
+                  const uint32_t* ta = &tu.x;
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 y = unpackc<FMT>(ta[i]);
+                    o[2 * i] = fmaf(dst, y.x, o[2 * i]);
+                    o[2 * i + 1] = fmaf(dst, y.y, o[2 * i + 1]);
+                  }
+                }
+                uint4 u;
+                u.x = packc<FMT>(o[0], o[1]); u.y = packc<FMT>(o[2], o[3]);
+                u.z = packc<FMT>(o[4], o[5]); u.w = packc<FMT>(o[6], o[7]);
+                dst4[q8] = u;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_acc_free);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT_CTRL_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int MODE, int NCH, int FMT>
+static int launch_bwd2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                       const CUtensorMap& d, const AttnBwd2Params& P, cudaStream_t st) {
+  auto kern = attn_bwd2_kernel<MODE, NCH, FMT>;
+  const size_t smem = (size_t)2 * NCH * 64 * 128 + 4 * 16384 + (size_t)NCH * 16384 +
+                      (272 * 2 + 256 * 3 + 16) * 4 + 512 + 128 + 1024;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    set = true;
+  }
+  int grid = sm_count();
+  if (P.B * P.H < grid) grid = P.B * P.H;
+  kern<<<grid, AT_THREADS, smem, st>>>(a, b, c, d, P);
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
 struct AttnPlan {
@@ -936,16 +1555,17 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   if (rc) return rc;
   const size_t smem = (size_t)2 * P.kvm * 128 + 2 * 16384 + (size_t)2 * P.nblk * 16384 + 512 +
                       128 + 128 + 1024;
-  static size_t set = 0;
-  if (smem > set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd2_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = fmt ? attn_fwd2_kernel<1> : attn_fwd2_kernel<0>;
+  static size_t set[2] = {0, 0};
+  if (smem > set[fmt ? 1 : 0]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;
-    set = smem;
+    set[fmt ? 1 : 0] = smem;
   }
   int grid = sm_count();
   if (B * H < grid) grid = B * H;
-  attn_fwd2_kernel<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(tmTile, tmFull, P);
+  kern<<<grid, AT_THREADS, smem, (cudaStream_t)stream>>>(tmTile, tmFull, P);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
@@ -957,6 +1577,42 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
   // every MMA operand of the backward (qkv copy, dO, P, dS) must share one 16-bit format
   if (fmt_qkv != fmt_g) return RVLM_ERR_UNSUPPORTED;
   if (!lse_tmp) return RVLM_ERR_INVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tm = T < 256 ? T : 256;
+  const int kvm = (tm + 15) / 16 * 16;
+  static int use_v2 = -1;   // RVLM_ATTN_BWD2=1 selects the peeled / register-resident variant
+  if (use_v2 < 0) {
+    const char* e = getenv("RVLM_ATTN_BWD2");
+    use_v2 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (use_v2 && T <= 257 && (kvm == 64 || kvm == 256)) {
+    AttnBwd2Params P{};
+    P.B = B; P.T = T; P.H = H; P.W = H * 64;
+    P.tm = tm; P.kvm = kvm; P.nblk = kvm / 64; P.ntile = (tm + 127) / 128;
+    P.tail = T > 256 ? 1 : 0;
+    P.fmt_o = fmt_o;
+    P.qkv = reinterpret_cast<const uint16_t*>(qkv16);
+    P.o = reinterpret_cast<const uint16_t*>(o16);
+    P.d_o = reinterpret_cast<const uint16_t*>(do16);
+    P.lse_tmp = lse_tmp;
+    P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
+    CUtensorMap tmTile, tmFull, tmDoTile, tmDoFull;
+    const uint64_t W3 = 3ull * P.W, Wd = P.W;
+    int rc = make_tmap_3d(&tmTile, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
+    if (!rc) rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, kvm);
+    if (!rc) rc = make_tmap_3d(&tmDoTile, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);
+    if (!rc) rc = make_tmap_3d(&tmDoFull, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, kvm);
+    if (rc) return rc;
+#define RVLM_BWD2(MODE)                                                                          \
+    (kvm == 256 ? (fmt_g ? launch_bwd2<MODE, 4, 1>(tmTile, tmFull, tmDoTile, tmDoFull, P, st)    \
+                         : launch_bwd2<MODE, 4, 0>(tmTile, tmFull, tmDoTile, tmDoFull, P, st))   \
+                : (fmt_g ? launch_bwd2<MODE, 1, 1>(tmTile, tmFull, tmDoTile, tmDoFull, P, st)    \
+                         : launch_bwd2<MODE, 1, 0>(tmTile, tmFull, tmDoTile, tmDoFull, P, st)))
+    rc = RVLM_BWD2(AT_DQ);
+    if (rc) return rc;
+    return RVLM_BWD2(AT_DKV);
+#undef RVLM_BWD2
+  }
   AttnPlan pl{};
   int rc = make_plan(pl, qkv16, do16, B, T, H, fmt_g, fmt_o, fmt_g);
   if (rc) return rc;
@@ -964,7 +1620,7 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
   pl.P.d_o = reinterpret_cast<const uint16_t*>(do16);
   pl.P.lse_tmp = lse_tmp;
   pl.P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
-  rc = launch_attn<AT_DQ>(pl, (cudaStream_t)stream);
+  rc = launch_attn<AT_DQ>(pl, st);
   if (rc) return rc;
-  return launch_attn<AT_DKV>(pl, (cudaStream_t)stream);
+  return launch_attn<AT_DKV>(pl, st);
 }

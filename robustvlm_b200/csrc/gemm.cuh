@@ -229,6 +229,235 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------------------
+// 2-CTA variant: a cluster of two CTAs (one SM pair) computes a 256 x 256 output tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and HALF of the B tile
+// (128 of the 256 N-rows), so per 128x256 of output an SM pulls 32 KB per k-block from L2
+// instead of 48 KB -- the L2 -> SM fill rate is what bounds the 1-CTA kernel -- and the
+// ring is 6 stages deep.  The leader CTA (cluster rank 0) issues every MMA; both CTAs run
+// TMA producers (completing on the LEADER's full barrier) and epilogues (each drains its own
+// 128 TMEM lanes).  K-major operands only.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (count 1) on the mbarrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's barrier (bit 24 of a
+// shared::cluster address selects the CTA of the pair)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m,
+                                                 uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: arrive on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+struct Gemm2Smem {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;   // 128 x 64
+  static constexpr int kBBytes = 128 * GEMM_BK * 2;       // half of the 256-row B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 256 + 1024;
+};
+
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   int M, int N, int K, int fmt, Epi epi) {
+  using S = Gemm2Smem;
+  constexpr int kStages = S::kStages;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
+  uint64_t* full_bar = bars;                      // [kStages]  (used in the leader only)
+  uint64_t* empty_bar = bars + kStages;           // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;       // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]        (used in the leader only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_m = (M + 255) / 256;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = (K + GEMM_BK - 1) / GEMM_BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 2);    // one arrival per CTA's producer (+ the transaction bytes)
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
+        else mbar_arrive_cluster(&full_bar[stage], 0);
+        tma_load_2d_pair(smem_a + stage * S::kABytes, &tmA, &full_bar[stage], kb * GEMM_BK,
+                         m_blk * 256 + (int)rank * 128);
+        tma_load_2d_pair(smem_b + stage * S::kBBytes, &tmB, &full_bar[stage], kb * GEMM_BK,
+                         n_blk * BN + (int)rank * 128);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================== MMA issuer (leader only) =====================
+    const uint32_t idesc = make_idesc_f16((uint32_t)fmt, 256, BN, 0u, 0u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
+        const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k)
+          umma_f16_2cta(tmem_d, make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
+                        make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+        umma_commit_2cta(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit_2cta(&tfull_bar[acc]);
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    float* stg = staging + (warp - 4) * 1024;
+    const int rl = lane >> 3, c4 = lane & 7;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int m_blk = tile / num_n, n_blk = tile % num_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const int row0 = m_blk * 256 + (int)rank * 128 + q * 32;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 64; ++cc) {
+        const int c = half * (BN / 64) + cc;
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= N) break;
+        typename Epi::Aux aux[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = row0 + rl + 4 * i;
+          if (row < M) aux[i] = epi.load(row, col0 + 4 * c4);
+        }
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = rl + 4 * i;
+          const float4 v =
+              *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+          const int row = row0 + rr;
+          if (row < M) epi(row, col0 + 4 * c4, v, aux[i]);
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      if (leader) mbar_arrive(&tempty_bar[acc]);
+      else mbar_arrive_cluster(&tempty_bar[acc], 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(512u)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Host side: tensor-map construction + launch
 // ---------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -289,6 +518,46 @@ int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   }
   count_launch();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+bool gemm_use_2cta();
+
+template <class Epi>
+int launch_gemm16_2cta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int fmt,
+                       const Epi& epi, cudaStream_t stream) {
+  if (N % 32 != 0 || M <= 0 || K <= 0) return -22;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
+  if (rc) return rc;
+  rc = make_tmap_2d(&tmB, B, N, K, ldb, 128);
+  if (rc) return rc;
+  auto kern = gemm16_2cta_kernel<Epi>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Gemm2Smem::kTotal);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    attr_set = true;
+  }
+  const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  int grid = sm_count() & ~1;
+  if (2 * num_tiles < grid) grid = 2 * num_tiles;
+  cudaError_t e;
+  {
+    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K);
+    kern<<<grid, GEMM_THREADS, Gemm2Smem::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
+    e = cudaGetLastError();
+  }
+  count_launch();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+// K-major GEMM used by the engine: the 2-CTA kernel unless disabled (RVLM_GEMM_2CTA=0)
+template <class Epi>
+int launch_gemm_kmajor(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                       int fmt, const Epi& epi, cudaStream_t stream) {
+  if (gemm_use_2cta()) return launch_gemm16_2cta(A, lda, B, ldb, M, N, K, fmt, epi, stream);
+  return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, stream);
 }
 
 }  // namespace rvlm

@@ -13,6 +13,10 @@ int dispatch(const void* A, int lda, const void* B, int ldb, int M, int N, int K
   const bool bmn = flags & RVLM_GEMM_B_MN, amn = flags & RVLM_GEMM_A_MN,
              bn128 = flags & RVLM_GEMM_BN128;
   if (fmt != 0 && fmt != 1) return RVLM_ERR_INVAL;
+  if (flags & RVLM_GEMM_2CTA) {
+    if (amn || bmn || bn128) return RVLM_ERR_UNSUPPORTED;
+    return launch_gemm16_2cta(A, lda, B, ldb, M, N, K, fmt, epi, st);
+  }
   if (!amn && !bmn) {
     return bn128 ? launch_gemm16<128, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, st)
                  : launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, st);

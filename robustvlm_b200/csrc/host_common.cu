@@ -3,6 +3,7 @@
 // dlopen'ed on a machine with no GPU), SM count, error strings.
 #include "gemm.cuh"
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 #include "../../include/rvlm.h"
 
@@ -71,6 +72,15 @@ GemmProfScope::GemmProfScope(cudaStream_t s, double flops) : st(s), slot(-1) {
 }
 GemmProfScope::~GemmProfScope() {
   if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
+bool gemm_use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RVLM_GEMM_2CTA");
+    v = (e && e[0] == '1') ? 1 : 0;   // opt-in until validated on hardware
+  }
+  return v == 1;
 }
 
 int sm_count() {

@@ -165,7 +165,7 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
   RV(launch_cls_rows(w.tok32, E.cls, E.pos, B, E.T, W, st));
   {
     EpiPatchFwd epi{w.tok32, E.pos, E.np, E.T, W};
-    RV((launch_gemm16<256, false, false>(w.a16, E.kld, E.conv_w, E.kld, R, W, E.kp, ff, epi, st)));
+    RV((launch_gemm_kmajor(w.a16, E.kld, E.conv_w, E.kld, R, W, E.kp, ff, epi, st)));
   }
   RV(rvlm_layernorm_fwd(w.tok32, E.lnpre_g, E.lnpre_b, nullptr, w.x32, w.stats_pre, M, W, ff, stv));
   for (int l = 0; l < E.L; ++l) {
@@ -187,22 +187,22 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     RV(rvlm_layernorm_fwd(x_in, Lw.ln1_g, Lw.ln1_b, y1, nullptr, st1, M, W, ff, stv));
     {  // q|k|v in the forward format (transient) + the backward's copy in the gradient format
       EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd};
-      RV((launch_gemm16<256, false, false>(y1, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
+      RV((launch_gemm_kmajor(y1, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
     }
     if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     else RV(rvlm_attn_fwd(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     {
       EpiStore32 epi{xm, W, Lw.bo, x_in, W};
-      RV((launch_gemm16<256, false, false>(o, W, Lw.wo, W, M, W, W, ff, epi, st)));
+      RV((launch_gemm_kmajor(o, W, Lw.wo, W, M, W, W, ff, epi, st)));
     }
     RV(rvlm_layernorm_fwd(xm, Lw.ln2_g, Lw.ln2_b, z1, nullptr, st2, M, W, ff, stv));
     {
       EpiGelu epi{w.stash ? h : nullptr, act, F, Lw.bfc, ff};
-      RV((launch_gemm16<256, false, false>(z1, W, Lw.wfc, W, M, F, W, ff, epi, st)));
+      RV((launch_gemm_kmajor(z1, W, Lw.wfc, W, M, F, W, ff, epi, st)));
     }
     {
       EpiStore32 epi{x_out, W, Lw.bpr, xm, W};
-      RV((launch_gemm16<256, false, false>(act, F, Lw.wpr, F, M, W, F, ff, epi, st)));
+      RV((launch_gemm_kmajor(act, F, Lw.wpr, F, M, W, F, ff, epi, st)));
     }
   }
   return 0;
@@ -268,23 +268,23 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     const float* st2 = w.stats2 + (size_t)l * M * 2;
     {  // d act -> d h (through QuickGELU)
       EpiGeluBwd epi{w.dh16, F, h, ff, fg};
-      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
+      RV((launch_gemm_kmajor(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
     }
     {  // d ln_2 output
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
-      RV((launch_gemm16<256, false, false>(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
+      RV((launch_gemm_kmajor(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
     }
     RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
     {  // d attention output
       EpiStore16 epi{w.do16, W, nullptr, fg};
-      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
+      RV((launch_gemm_kmajor(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
     }
     if (E.attn_simt)
       RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     {  // d ln_1 output
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
-      RV((launch_gemm16<256, false, false>(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
+      RV((launch_gemm_kmajor(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
                                            st)));
     }
     RV(rvlm_layernorm_bwd(w.dz32, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
@@ -331,14 +331,14 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
     RV(launch_colsum16(w.dx16, M, W, fg, w.red, g->mlp_c_proj_bias[l], st));
     {
       EpiGeluBwd epi{w.dh16, F, h, ff, fg};
-      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
+      RV((launch_gemm_kmajor(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
     }
     // mlp.c_fc: dY = dh
     RV(wgrad(w.dh16, F, z1, W, M, fg, g->mlp_c_fc_weight[l], st));
     RV(launch_colsum16(w.dh16, M, F, fg, w.red, g->mlp_c_fc_bias[l], st));
     {
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
-      RV((launch_gemm16<256, false, false>(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
+      RV((launch_gemm_kmajor(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
     }
     RV(launch_ln_param_grads(w.dz32, xm, st2, M, W, w.red, g->ln_2_weight[l], g->ln_2_bias[l], st));
     RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
@@ -347,7 +347,7 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
     RV(launch_colsum16(w.dx16, M, W, fg, w.red, g->attn_out_proj_bias[l], st));
     {
       EpiStore16 epi{w.do16, W, nullptr, fg};
-      RV((launch_gemm16<256, false, false>(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
+      RV((launch_gemm_kmajor(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
     }
     if (E.attn_simt)
       RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
@@ -357,7 +357,7 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
     RV(launch_colsum16(w.dqkv16, M, 3 * W, fg, w.red, g->attn_in_proj_bias[l], st));
     {
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
-      RV((launch_gemm16<256, false, false>(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
+      RV((launch_gemm_kmajor(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
                                            st)));
     }
     RV(launch_ln_param_grads(w.dz32, x_in, st1, M, W, w.red, g->ln_1_weight[l], g->ln_1_bias[l], st));
@@ -384,7 +384,7 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
 int run_patch_grad(const Engine& E, const Ws& w, int B, cudaStream_t st) {
   EpiPatchGrad epi{w.gp, E.kp, E.cfg.patch * E.cfg.patch,
                    {E.geom.inv_std[0], E.geom.inv_std[1], E.geom.inv_std[2]}};
-  return launch_gemm16<256, false, false>(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
+  return launch_gemm_kmajor(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
                                           E.cfg.fmt_bwd, epi, st);
 }
 
@@ -394,7 +394,7 @@ int run_patch_pgd_linf(const Engine& E, const Ws& w, int B, float stepsize, floa
                       E.cfg.fmt_fwd, stepsize, eps, maximize ? 1.f : -1.f, momentum,
                       {E.geom.mean[0], E.geom.mean[1], E.geom.mean[2]},
                       {E.geom.inv_std[0], E.geom.inv_std[1], E.geom.inv_std[2]}};
-  return launch_gemm16<256, false, false>(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
+  return launch_gemm_kmajor(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
                                           E.cfg.fmt_bwd, epi, st);
 }
 

@@ -28,6 +28,9 @@ def _dt(fmt):
 @pytest.mark.parametrize("M,N,K,fmt,flags", [
     (128, 256, 64, 0, 0), (1000, 768, 1024, 0, 0), (514, 640, 1024, 1, 0),
     (4112, 3072, 1024, 0, 0), (256, 512, 512, 0, 1), (256, 256, 512, 0, 6), (300, 96, 192, 1, 0),
+    # 2-CTA kernel (tcgen05.mma.cta_group::2)
+    (256, 256, 64, 0, 8), (512, 512, 1024, 0, 8), (1000, 768, 1024, 1, 8), (4112, 3072, 1024, 0, 8),
+    (300, 96, 192, 1, 8),
 ])
 def test_gemm16(M, N, K, fmt, flags):
     nat = _nat()

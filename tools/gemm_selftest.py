@@ -143,6 +143,9 @@ if __name__ == "__main__":
     case(128, 128, 64, 0, 2 | 4, tag="amn_one_tile_")
     case(256, 256, 512, 0, 2 | 4, tag="amn_")
     case(256, 256, 512, 0, 3 | 4, tag="abmn_")
+    case(256, 256, 64, 0, 8, tag="2cta_one_tile_")
+    case(1000, 768, 1024, 0, 8, True, tag="2cta_ragged_")
+    case(4112, 3072, 1024, 0, 8, True, tag="2cta_qkv_")
     ok = all(c.get("bad_frac", 1.0) == 0.0 for c in report["cases"][:8])
     report["kmajor_ok"] = ok
     if ok:
@@ -150,6 +153,9 @@ if __name__ == "__main__":
                           (65792, 1024, 4096)]:
             bench(M, N, K, 0, 0)
         bench(65792, 1024, 1024, 0, 4)
+        for (M, N, K) in [(65792, 3072, 1024), (65792, 1024, 1024), (65792, 4096, 1024),
+                          (65792, 1024, 4096)]:
+            bench(M, N, K, 0, 8)
     report["seconds"] = time.time() - t0
     with open(os.path.join(OUT, "gemm_selftest.json"), "w") as f:
         json.dump(report, f, indent=1)

@@ -961,7 +961,7 @@ __device__ __forceinline__ float blk256_sum(float v, float* red, int warp, int l
   return t;
 }
 
-template <int MODE, int NCH, int FMT>
+template <int MODE, int NCH, int FMT, bool TAIL, bool FULL>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
                  const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x kvm
@@ -1095,7 +1095,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           umma_commit(bar_acc);
         }
         mbar_wait(bar_acc, (g - 1) & 1, 55);                     // every MMA of this item retired
-        if (P.tail) mbar_wait(bar_trow, it & 1, 56);
+        if (TAIL) mbar_wait(bar_trow, it & 1, 56);
         if (next < n_items) load_full(next);
       }
     }
@@ -1117,7 +1117,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       const int b = item / P.H, h = item % P.H;
       const size_t lse_base = ((size_t)b * P.H + h) * T;
       // ---- stage the peeled vectors and (DKV) the per-query statistics
-      if (P.tail && tid < 32) {
+      if (TAIL && tid < 32) {
         const int which = tid >> 3, c = tid & 7;
         const size_t rowq = ((size_t)b * T + 256) * 3 * W + h * 64 + c * 8;
         const size_t rowd = ((size_t)b * T + 256) * W + h * 64 + c * 8;
@@ -1143,7 +1143,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (P.tail) {
+      if (TAIL) {
         // ================= the peeled ROW (token 256) on the CUDA cores =================
         float* sc = reinterpret_cast<float*>(s_p);   // [272] p / weights (scratch: P buffer)
         float* sc2 = sc + 272;                       // [272] ds
@@ -1236,14 +1236,14 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       for (int j = 0; j < P.ntile; ++j, ++g) {
         const int buf = g & 1;
         const int row = j * 128 + r;
-        const bool valid = row < P.tm;
-        const bool warp_valid = (j * 128 + (warp & 3) * 32) < P.tm;
+        const bool valid = FULL || row < P.tm;
+        const bool warp_valid = FULL || (j * 128 + (warp & 3) * 32) < P.tm;
         const size_t grow = (size_t)b * T + row;
         mbar_wait(&bar_tile[buf], (g >> 1) & 1, 61);     // tile rows visible to generic loads
         float Dr = 0.f, a_t = 0.f, b_t = 0.f;
         if (MODE == AT_DQ && valid)
           Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, FMT);
-        if (P.tail && hsel == 1 && warp_valid) {
+        if (TAIL && hsel == 1 && warp_valid) {
           a_t = dot_swz_row<FMT>(s_tile0 + buf * 16384, r, tv0);   // DQ: q_r.k_256  DKV: k_r.q_256
           b_t = dot_swz_row<FMT>(s_tile1 + buf * 16384, r, tv1);   // DQ: dO_r.v_256 DKV: v_r.dO_256
         }
@@ -1262,7 +1262,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               uint32_t v[32];
               tmem_ld32(ts + TS + (c0 + c) * 32, v);
               tmem_ld_wait();
-              if ((c0 + c) * 32 + 32 <= P.tm) {
+              if (FULL || (c0 + c) * 32 + 32 <= P.tm) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
               } else {
@@ -1271,7 +1271,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                   if ((c0 + c) * 32 + i < P.tm) mx = fmaxf(mx, __uint_as_float(v[i]));
               }
             }
-            if (P.tail && hsel == 1) mx = fmaxf(mx, a_t);
+            if (TAIL && hsel == 1) mx = fmaxf(mx, a_t);
           }
           s_red[hsel * 128 + r] = mx;
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -1283,7 +1283,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               uint32_t v[32];
               tmem_ld32(ts + TS + (c0 + c) * 32, v);
               tmem_ld_wait();
-              const bool full = (c0 + c) * 32 + 32 <= P.tm;
+              const bool full = FULL || (c0 + c) * 32 + 32 <= P.tm;
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 float e[4];
@@ -1296,7 +1296,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 pk[c * 16 + i / 2 + 1] = packc<FMT>(e[2], e[3]);
               }
             }
-            if (P.tail && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -mc));
+            if (TAIL && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -mc));
           }
           s_red2[hsel * 128 + r] = (s0 + s1) + (s2 + s3) + p_t;
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -1325,7 +1325,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                     make_uint4(pk[c * 16 + q8 * 4], pk[c * 16 + q8 * 4 + 1],
                                pk[c * 16 + q8 * 4 + 2], pk[c * 16 + q8 * 4 + 3]);
             }
-            if (P.tail && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -s_lse[256]));
+            if (TAIL && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -s_lse[256]));
           }
           fence_proxy_async_smem();
           tc_fence_before();
@@ -1362,7 +1362,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               *reinterpret_cast<uint4*>(s_p + p_off(r, (c0 + c) * 32 + i)) = u4;
             }
           }
-          if (P.tail && hsel == 1) {
+          if (TAIL && hsel == 1) {
             const float Dv = (MODE == AT_DQ) ? Dr : s_dvec[256];
             ds_t = p_t * sc * (b_t - Dv);
             s_tt[r] = p_t * rinv;
@@ -1376,7 +1376,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         mbar_wait(bar_acc, g & 1, 65);
         tc_fence_after();
         if (warp_valid) {
-          const float pt = P.tail ? s_tt[r] : 0.f, dst = P.tail ? s_tt[128 + r] : 0.f;
+          const float pt = TAIL ? s_tt[r] : 0.f, dst = TAIL ? s_tt[128 + r] : 0.f;
           if (MODE == AT_DKV) {
             uint32_t v0[32], v1[32];
             const uint32_t col = hsel ? TACC2 : TACC;
@@ -1395,7 +1395,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
-                if (P.tail) {
+                if (TAIL) {
                   const uint4 tu = *reinterpret_cast<const uint4*>(tvx + q8 * 8);
                   const uint32_t* ta = &tu.x;
 #pragma unroll
@@ -1423,7 +1423,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                 float o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v0[q8 * 8 + i]);
-                if (P.tail) {
+                if (TAIL) {
                   const uint4 tu = *reinterpret_cast<const uint4*>(tv0 + hsel * 32 + q8 * 8);
                   const uint32_t* ta = &tu.x;
 #pragma unroll
@@ -1456,10 +1456,10 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   }
 }
 
-template <int MODE, int NCH, int FMT>
+template <int MODE, int NCH, int FMT, bool TAIL, bool FULL>
 static int launch_bwd2(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                        const CUtensorMap& d, const AttnBwd2Params& P, cudaStream_t st) {
-  auto kern = attn_bwd2_kernel<MODE, NCH, FMT>;
+  auto kern = attn_bwd2_kernel<MODE, NCH, FMT, TAIL, FULL>;
   const size_t smem = (size_t)2 * NCH * 64 * 128 + 4 * 16384 + (size_t)NCH * 16384 +
                       (272 * 2 + 256 * 3 + 16) * 4 + 512 + 128 + 1024;
   static bool set = false;
@@ -1603,15 +1603,20 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
     if (!rc) rc = make_tmap_3d(&tmDoTile, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);
     if (!rc) rc = make_tmap_3d(&tmDoFull, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, kvm);
     if (rc) return rc;
+    // ViT-L/14 (T = 257): every tile row / column valid, one peeled token -> fully static code
+#define RVLM_BWD2_ARGS tmTile, tmFull, tmDoTile, tmDoFull, P, st
 #define RVLM_BWD2(MODE)                                                                          \
-    (kvm == 256 ? (fmt_g ? launch_bwd2<MODE, 4, 1>(tmTile, tmFull, tmDoTile, tmDoFull, P, st)    \
-                         : launch_bwd2<MODE, 4, 0>(tmTile, tmFull, tmDoTile, tmDoFull, P, st))   \
-                : (fmt_g ? launch_bwd2<MODE, 1, 1>(tmTile, tmFull, tmDoTile, tmDoFull, P, st)    \
-                         : launch_bwd2<MODE, 1, 0>(tmTile, tmFull, tmDoTile, tmDoFull, P, st)))
+    (T == 257 ? (fmt_g ? launch_bwd2<MODE, 4, 1, true, true>(RVLM_BWD2_ARGS)                      \
+                       : launch_bwd2<MODE, 4, 0, true, true>(RVLM_BWD2_ARGS))                     \
+     : kvm == 256 ? (fmt_g ? launch_bwd2<MODE, 4, 1, false, false>(RVLM_BWD2_ARGS)                \
+                           : launch_bwd2<MODE, 4, 0, false, false>(RVLM_BWD2_ARGS))               \
+                  : (fmt_g ? launch_bwd2<MODE, 1, 1, false, false>(RVLM_BWD2_ARGS)                \
+                           : launch_bwd2<MODE, 1, 0, false, false>(RVLM_BWD2_ARGS)))
     rc = RVLM_BWD2(AT_DQ);
     if (rc) return rc;
     return RVLM_BWD2(AT_DKV);
 #undef RVLM_BWD2
+#undef RVLM_BWD2_ARGS
   }
   AttnPlan pl{};
   int rc = make_plan(pl, qkv16, do16, B, T, H, fmt_g, fmt_o, fmt_g);

@@ -332,7 +332,7 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 2);    // one arrival per CTA's producer (+ the transaction bytes)
+      mbar_init(&full_bar[i], 1);    // the leader's arrive.expect_tx (+ both CTAs' TMA bytes)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -361,8 +361,11 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        // Both producers are released by the same multicast commit (their empty barriers), so
+        // the peer needs no arrival of its own on the leader's full barrier: its TMA bytes
+        // simply count against the leader's expect_tx (a transiently negative tx-count is
+        // legal while the leader's arrival is still pending).  No cross-CTA hop in the loop.
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-        else mbar_arrive_cluster(&full_bar[stage], 0);
         tma_load_2d_pair(smem_a + stage * S::kABytes, &tmA, &full_bar[stage], kb * GEMM_BK,
                          m_blk * 256 + (int)rank * 128);
         tma_load_2d_pair(smem_b + stage * S::kBBytes, &tmB, &full_bar[stage], kb * GEMM_BK,

@@ -771,46 +771,79 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             }
             mx = s_t;
           }
-          for (int c = 0; c < nch; ++c) {
-            uint32_t v[32];
-            ld_chunk(ts, c, n32, v);
-            const int nv = c < n32 ? 32 : 16;
-            if (c * 32 + nv <= P.tm) {
+          // TMEM sweeps in 16-column pieces with the next tcgen05.ld in flight
+          const int nq = kvm >> 4;
+          const bool allcols = P.tm == kvm;          // ViT-L/14: every column valid
+          uint8_t* prow = my_p + r * 128;
+          const uint32_t rx = (uint32_t)(r & 7) << 4;
+          {
+            float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            auto pmax = [&](const uint32_t (&v)[16], int q) {
+              if (allcols || q * 16 + 16 <= P.tm) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nv) mx = fmaxf(mx, __uint_as_float(v[i]));
-            } else {
+                for (int i = 0; i < 16; i += 4) {
+                  m0 = fmaxf(m0, __uint_as_float(v[i]));
+                  m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+                  m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+                  m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+                }
+              } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (i < nv && c * 32 + i < P.tm) mx = fmaxf(mx, __uint_as_float(v[i]));
+                for (int i = 0; i < 16; ++i)
+                  if (q * 16 + i < P.tm) m0 = fmaxf(m0, __uint_as_float(v[i]));
+              }
+            };
+            uint32_t va[16], vb[16];
+            tmem_ld16(ts, va);
+            for (int q = 0; q < nq; q += 2) {
+              tmem_ld_wait();
+              if (q + 1 < nq) tmem_ld16(ts + (q + 1) * 16, vb);
+              pmax(va, q);
+              if (q + 1 < nq) {
+                tmem_ld_wait();
+                if (q + 2 < nq) tmem_ld16(ts + (q + 2) * 16, va);
+                pmax(vb, q + 1);
+              }
             }
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           }
           const float mc = mx * c2;
           if (P.tail) p_t = fast_ex2(fmaf(s_t, c2, -mc));
-          for (int c = 0; c < nch; ++c) {
-            uint32_t v[32];
-            ld_chunk(ts, c, n32, v);
-            const int nv = c < n32 ? 32 : 16;
-            float p[32];
-            const bool full = c * 32 + nv <= P.tm;
+          {
+            auto pexp = [&](const uint32_t (&v)[16], int q) {
+              float e[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              p[i] = (i < nv && (full || c * 32 + i < P.tm))
-                         ? fast_ex2(fmaf(__uint_as_float(v[i]), c2, -mc))
-                         : 0.f;
+              for (int i = 0; i < 16; ++i) e[i] = fast_ex2(fmaf(__uint_as_float(v[i]), c2, -mc));
+              if (!(allcols || q * 16 + 16 <= P.tm)) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              sum0 += p[i]; sum1 += p[i + 1]; sum2 += p[i + 2]; sum3 += p[i + 3];
-            }
+                for (int i = 0; i < 16; ++i)
+                  if (q * 16 + i >= P.tm) e[i] = 0.f;
+              }
 #pragma unroll
-            for (int q8 = 0; q8 < 4; ++q8) {
-              if (q8 * 8 < nv) {
-                uint4 u;
-                u.x = packc<FMT>(p[q8 * 8 + 0], p[q8 * 8 + 1]);
-                u.y = packc<FMT>(p[q8 * 8 + 2], p[q8 * 8 + 3]);
-                u.z = packc<FMT>(p[q8 * 8 + 4], p[q8 * 8 + 5]);
-                u.w = packc<FMT>(p[q8 * 8 + 6], p[q8 * 8 + 7]);
-                *reinterpret_cast<uint4*>(my_p + p_off(r, c * 32 + q8 * 8)) = u;
+              for (int i = 0; i < 16; i += 4) {
+                sum0 += e[i]; sum1 += e[i + 1]; sum2 += e[i + 2]; sum3 += e[i + 3];
+              }
+#pragma unroll
+              for (int q8 = 0; q8 < 2; ++q8) {
+                const int cc = q * 16 + q8 * 8;
+                *reinterpret_cast<uint4*>(prow + (cc >> 6) * 16384 +
+                                          (((uint32_t)((cc & 63) >> 3) << 4) ^ rx)) =
+                    make_uint4(packc<FMT>(e[q8 * 8 + 0], e[q8 * 8 + 1]),
+                               packc<FMT>(e[q8 * 8 + 2], e[q8 * 8 + 3]),
+                               packc<FMT>(e[q8 * 8 + 4], e[q8 * 8 + 5]),
+                               packc<FMT>(e[q8 * 8 + 6], e[q8 * 8 + 7]));
+              }
+            };
+            uint32_t va[16], vb[16];
+            tmem_ld16(ts, va);
+            for (int q = 0; q < nq; q += 2) {
+              tmem_ld_wait();
+              if (q + 1 < nq) tmem_ld16(ts + (q + 1) * 16, vb);
+              pexp(va, q);
+              if (q + 1 < nq) {
+                tmem_ld_wait();
+                if (q + 2 < nq) tmem_ld16(ts + (q + 2) * 16, va);
+                pexp(vb, q + 1);
               }
             }
           }
@@ -1139,7 +1172,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             Dv = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);
           }
           s_lse[q] = L;
-          s_dvec[q] = Dv;
+          s_dvec[q] = Dv * 0.125f;   // pre-scaled: dS = P (dP/8 - D/8)
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -1194,7 +1227,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             const float sT = dot_swz_row<FMT>(s_full0, tid, tv2);   // q_tid . k_256
             const float dpT = dot_swz_row<FMT>(s_full1, tid, tv3);  // dO_tid . v_256
             pv = fast_ex2(fmaf(sT, c2, -s_lse[tid]));
-            dsv = pv * (dpT - s_dvec[tid]) * 0.125f;
+            dsv = pv * fmaf(dpT, 0.125f, -s_dvec[tid]);
           }
           sc[tid] = pv;
           sc2[tid] = dsv;
@@ -1202,7 +1235,7 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             const float sT = dot_vec<FMT>(tv0, tv2), dpT = dot_vec<FMT>(tv1, tv3);
             const float pl = fast_ex2(fmaf(sT, c2, -s_lse[256]));
             sc[256] = pl;
-            sc2[256] = pl * (dpT - s_dvec[256]) * 0.125f;
+            sc2[256] = pl * fmaf(dpT, 0.125f, -s_dvec[256]);
           }
           asm volatile("bar.sync 3, 256;" ::: "memory");
           {
@@ -1247,53 +1280,71 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           a_t = dot_swz_row<FMT>(s_tile0 + buf * 16384, r, tv0);   // DQ: q_r.k_256  DKV: k_r.q_256
           b_t = dot_swz_row<FMT>(s_tile1 + buf * 16384, r, tv1);   // DQ: dO_r.v_256 DKV: v_r.dO_256
         }
-        // ---------------- pass 1: probabilities (kept in registers) ----------------
+        // ---------------- pass 1: probabilities ----------------
+        // TMEM is swept in 16-column pieces, the next piece's tcgen05.ld in flight while the
+        // current one is processed.  Probabilities stay PACKED (operand format) in registers
+        // between the passes: pass 2 uses exactly the values the tensor core sees in P.
         mbar_wait(bar_s, g & 1, 62);
         tc_fence_after();
-        // probabilities are kept PACKED (operand format, two per register) between the passes:
-        // pass 2 then uses exactly the values the tensor core sees in P
-        uint32_t pk[NH * 16];
+        constexpr int NQ = NH * 2;                 // 16-column pieces owned by this thread
+        const uint32_t tcol = ts + c0 * 32;        // first TMEM column of this thread's half
+        const int col0 = c0 * 32;
+        uint8_t* prow = s_p + (size_t)(col0 >> 6) * 16384 + r * 128;   // this row, first block
+        const uint32_t rx = (uint32_t)(r & 7) << 4;
+        // byte offset of 8 columns starting at (thread-relative) column cc (cc % 8 == 0)
+        auto poff = [&](int cc) -> uint32_t {
+          return (uint32_t)(((col0 & 63) + cc) >> 6) * 16384u +
+                 ((((uint32_t)(((col0 & 63) + cc) & 63) >> 3) << 4) ^ rx);
+        };
+        uint32_t pk[NQ * 8];
         float mc = 0.f, rinv = 1.f, p_t = 0.f;
         if (MODE == AT_DQ) {
-          float mx = -INFINITY;
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
           if (warp_valid) {
+            uint32_t v[2][16];
+            tmem_ld16(tcol + TS, v[0]);
 #pragma unroll
-            for (int c = 0; c < NH; ++c) {
-              uint32_t v[32];
-              tmem_ld32(ts + TS + (c0 + c) * 32, v);
+            for (int q = 0; q < NQ; ++q) {
               tmem_ld_wait();
-              if (FULL || (c0 + c) * 32 + 32 <= P.tm) {
+              if (q + 1 < NQ) tmem_ld16(tcol + TS + (q + 1) * 16, v[(q + 1) & 1]);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-              } else {
+              for (int i = 0; i < 16; i += 4) {
+                if (FULL || col0 + q * 16 + i + 3 < P.tm) {
+                  m0 = fmaxf(m0, __uint_as_float(v[q & 1][i]));
+                  m1 = fmaxf(m1, __uint_as_float(v[q & 1][i + 1]));
+                  m2 = fmaxf(m2, __uint_as_float(v[q & 1][i + 2]));
+                  m3 = fmaxf(m3, __uint_as_float(v[q & 1][i + 3]));
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if ((c0 + c) * 32 + i < P.tm) mx = fmaxf(mx, __uint_as_float(v[i]));
+                  for (int u = 0; u < 4; ++u)
+                    if (col0 + q * 16 + i + u < P.tm) m0 = fmaxf(m0, __uint_as_float(v[q & 1][i + u]));
+                }
               }
             }
-            if (TAIL && hsel == 1) mx = fmaxf(mx, a_t);
+            if (TAIL && hsel == 1) m0 = fmaxf(m0, a_t);
           }
-          s_red[hsel * 128 + r] = mx;
+          s_red[hsel * 128 + r] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           asm volatile("bar.sync 2, 256;" ::: "memory");
           mc = fmaxf(s_red[r], s_red[128 + r]) * c2;
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           if (warp_valid) {
+            uint32_t v[2][16];
+            tmem_ld16(tcol + TS, v[0]);
 #pragma unroll
-            for (int c = 0; c < NH; ++c) {
-              uint32_t v[32];
-              tmem_ld32(ts + TS + (c0 + c) * 32, v);
+            for (int q = 0; q < NQ; ++q) {
               tmem_ld_wait();
-              const bool full = FULL || (c0 + c) * 32 + 32 <= P.tm;
+              if (q + 1 < NQ) tmem_ld16(tcol + TS + (q + 1) * 16, v[(q + 1) & 1]);
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
+              for (int i = 0; i < 16; i += 4) {
                 float e[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                  e[u] = (valid && (full || (c0 + c) * 32 + i + u < P.tm))
-                             ? fast_ex2(fmaf(__uint_as_float(v[i + u]), c2, -mc)) : 0.f;
+                for (int u = 0; u < 4; ++u) {
+                  e[u] = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + u]), c2, -mc));
+                  if (!FULL && !(valid && col0 + q * 16 + i + u < P.tm)) e[u] = 0.f;
+                }
                 s0 += e[0]; s1 += e[1]; s2 += e[2]; s3 += e[3];
-                pk[c * 16 + i / 2] = packc<FMT>(e[0], e[1]);
-                pk[c * 16 + i / 2 + 1] = packc<FMT>(e[2], e[3]);
+                pk[q * 8 + i / 2] = packc<FMT>(e[0], e[1]);
+                pk[q * 8 + i / 2 + 1] = packc<FMT>(e[2], e[3]);
               }
             }
             if (TAIL && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -mc));
@@ -1305,25 +1356,29 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           if (valid && hsel == 0) P.lse_tmp[lse_base + row] = mc + log2f(rsum);
         } else {
           if (warp_valid) {
+            uint32_t v[2][16];
+            tmem_ld16(tcol + TS, v[0]);
 #pragma unroll
-            for (int c = 0; c < NH; ++c) {
-              uint32_t v[32];
-              tmem_ld32(ts + TS + (c0 + c) * 32, v);
+            for (int q = 0; q < NQ; ++q) {
               tmem_ld_wait();
+              if (q + 1 < NQ) tmem_ld16(tcol + TS + (q + 1) * 16, v[(q + 1) & 1]);
 #pragma unroll
-              for (int i = 0; i < 32; i += 2) {
-                const float e0 = valid ? fast_ex2(fmaf(__uint_as_float(v[i]), c2,
-                                                       -s_lse[(c0 + c) * 32 + i])) : 0.f;
-                const float e1 = valid ? fast_ex2(fmaf(__uint_as_float(v[i + 1]), c2,
-                                                       -s_lse[(c0 + c) * 32 + i + 1])) : 0.f;
-                pk[c * 16 + i / 2] = packc<FMT>(e0, e1);
+              for (int i = 0; i < 16; i += 4) {
+                const float4 L4 = *reinterpret_cast<const float4*>(s_lse + col0 + q * 16 + i);
+                float e0 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i]), c2, -L4.x));
+                float e1 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + 1]), c2, -L4.y));
+                float e2 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + 2]), c2, -L4.z));
+                float e3 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + 3]), c2, -L4.w));
+                if (!FULL && !valid) { e0 = 0.f; e1 = 0.f; e2 = 0.f; e3 = 0.f; }
+                pk[q * 8 + i / 2] = packc<FMT>(e0, e1);
+                pk[q * 8 + i / 2 + 1] = packc<FMT>(e2, e3);
               }
               // P^T -> shared memory (A operand of dV = P^T dO)
 #pragma unroll
-              for (int q8 = 0; q8 < 4; ++q8)
-                *reinterpret_cast<uint4*>(s_p + p_off(r, (c0 + c) * 32 + q8 * 8)) =
-                    make_uint4(pk[c * 16 + q8 * 4], pk[c * 16 + q8 * 4 + 1],
-                               pk[c * 16 + q8 * 4 + 2], pk[c * 16 + q8 * 4 + 3]);
+              for (int q8 = 0; q8 < 2; ++q8)
+                *reinterpret_cast<uint4*>(prow + poff(q * 16 + q8 * 8)) =
+                    make_uint4(pk[q * 8 + q8 * 4], pk[q * 8 + q8 * 4 + 1], pk[q * 8 + q8 * 4 + 2],
+                               pk[q * 8 + q8 * 4 + 3]);
             }
             if (TAIL && hsel == 1 && valid) p_t = fast_ex2(fmaf(a_t, c2, -s_lse[256]));
           }
@@ -1332,39 +1387,46 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           mbar_arrive(bar_p);
         }
         // ---------------- pass 2: dS = P (dP - D) / 8 ----------------
+        // d = p * fma(dP, sc, -D*sc); DKV keeps D pre-multiplied by 1/8 in s_dvec.
         mbar_wait(bar_dp, g & 1, 63);
         tc_fence_after();
         if (MODE == AT_DKV) mbar_wait(bar_dv, g & 1, 64);   // dV no longer reads the P buffer
         float ds_t = 0.f;
         if (warp_valid) {
           const float sc = 0.125f * rinv;
+          const float nDsc = -Dr * sc;
+          uint32_t v[2][16];
+          tmem_ld16(tcol + TDP, v[0]);
 #pragma unroll
-          for (int c = 0; c < NH; ++c) {
-            uint32_t v[32];
-            tmem_ld32(ts + TDP + (c0 + c) * 32, v);
+          for (int q = 0; q < NQ; ++q) {
             tmem_ld_wait();
+            if (q + 1 < NQ) tmem_ld16(tcol + TDP + (q + 1) * 16, v[(q + 1) & 1]);
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+            for (int q8 = 0; q8 < 2; ++q8) {
               float d[8];
 #pragma unroll
-              for (int u = 0; u < 8; u += 2) {
-                const float2 pp = unpackc<FMT>(pk[c * 16 + (i + u) / 2]);
-                const float D0 = (MODE == AT_DQ) ? Dr : s_dvec[(c0 + c) * 32 + i + u];
-                const float D1 = (MODE == AT_DQ) ? Dr : s_dvec[(c0 + c) * 32 + i + u + 1];
-                d[u] = pp.x * sc * (__uint_as_float(v[i + u]) - D0);
-                d[u + 1] = pp.y * sc * (__uint_as_float(v[i + u + 1]) - D1);
+              for (int u = 0; u < 8; u += 4) {
+                const int i = q8 * 8 + u;
+                const float2 pa = unpackc<FMT>(pk[q * 8 + i / 2]);
+                const float2 pb = unpackc<FMT>(pk[q * 8 + i / 2 + 1]);
+                float4 nd = make_float4(nDsc, nDsc, nDsc, nDsc);
+                if (MODE == AT_DKV) {
+                  const float4 D4 = *reinterpret_cast<const float4*>(s_dvec + col0 + q * 16 + i);
+                  nd = make_float4(-D4.x, -D4.y, -D4.z, -D4.w);
+                }
+                d[u] = pa.x * fmaf(__uint_as_float(v[q & 1][i]), sc, nd.x);
+                d[u + 1] = pa.y * fmaf(__uint_as_float(v[q & 1][i + 1]), sc, nd.y);
+                d[u + 2] = pb.x * fmaf(__uint_as_float(v[q & 1][i + 2]), sc, nd.z);
+                d[u + 3] = pb.y * fmaf(__uint_as_float(v[q & 1][i + 3]), sc, nd.w);
               }
-              uint4 u4;
-              u4.x = packc<FMT>(d[0], d[1]);
-              u4.y = packc<FMT>(d[2], d[3]);
-              u4.z = packc<FMT>(d[4], d[5]);
-              u4.w = packc<FMT>(d[6], d[7]);
-              *reinterpret_cast<uint4*>(s_p + p_off(r, (c0 + c) * 32 + i)) = u4;
+              *reinterpret_cast<uint4*>(prow + poff(q * 16 + q8 * 8)) =
+                  make_uint4(packc<FMT>(d[0], d[1]), packc<FMT>(d[2], d[3]),
+                             packc<FMT>(d[4], d[5]), packc<FMT>(d[6], d[7]));
             }
           }
           if (TAIL && hsel == 1) {
-            const float Dv = (MODE == AT_DQ) ? Dr : s_dvec[256];
-            ds_t = p_t * sc * (b_t - Dv);
+            const float nd = (MODE == AT_DQ) ? nDsc : -s_dvec[256];
+            ds_t = p_t * fmaf(b_t, sc, nd);
             s_tt[r] = p_t * rinv;
             s_tt[128 + r] = ds_t;
           }
@@ -1580,10 +1642,10 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
   cudaStream_t st = (cudaStream_t)stream;
   const int tm = T < 256 ? T : 256;
   const int kvm = (tm + 15) / 16 * 16;
-  static int use_v2 = -1;   // RVLM_ATTN_BWD2=1 selects the peeled / register-resident variant
+  static int use_v2 = -1;   // the peeled / register-resident variant (version 2) by default
   if (use_v2 < 0) {
     const char* e = getenv("RVLM_ATTN_BWD2");
-    use_v2 = (e && e[0] == '1') ? 1 : 0;
+    use_v2 = (e && e[0] == '0') ? 0 : 1;   // default on; RVLM_ATTN_BWD2=0 selects version 1
   }
   if (use_v2 && T <= 257 && (kvm == 64 || kvm == 256)) {
     AttnBwd2Params P{};

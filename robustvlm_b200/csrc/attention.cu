@@ -1539,6 +1539,488 @@ static int launch_bwd2(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
+
+// =====================================================================================
+// Backward, version 3: ONE fused kernel for dQ, dK and dV (the standard flash-attention
+// backward shape).  Per (image, head) and 128-row q tile the scores and dP are computed
+// ONCE; the 16-bit P / dS tile written by the row-owner threads is consumed by the tensor
+// cores twice -- K-major as the A operand of dQ_i = dS K, and MN-major (its transpose, no
+// data movement) as the A operand of dV += P^T dO_i and dK += dS^T Q_i, whose accumulators
+// (2 x 2 x [128 kv x 64]) stay in TMEM across the q tiles.  5 matmuls and one exp pass per
+// tile instead of the 7 matmuls and two exp passes of the dQ + dK/dV kernel pair.
+//   TMEM (512 columns): [0,256) S, then dP (same region), then the dQ accumulator in [0,64);
+//                       [256,384) dV (2 kv tiles x 64); [384,512) dK.
+//   The softmax normalisation 1/rowsum is folded into the dO_i tile (each row scaled once in
+//   shared memory), so P is stored un-normalised straight after the exp sweep.
+//   The 257th token is peeled as in the forward (see above).
+// =====================================================================================
+template <int FMT, bool TAIL>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x 256
+                 const __grid_constant__ CUtensorMap tmDoTile, // dO,  box 64 x 128
+                 AttnBwd2Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  constexpr int KVM = 256, NBLK = 4, NH = 4, NQ = 8;
+  const int T = P.T, W = P.W;
+  constexpr int full_bytes = KVM * 128;
+  uint8_t* s_k = smem;
+  uint8_t* s_v = s_k + full_bytes;
+  uint8_t* s_tile0 = s_v + full_bytes;       // [2][16384] Q_i
+  uint8_t* s_tile1 = s_tile0 + 2 * 16384;    // [2][16384] dO_i (rows scaled by 1/rowsum in place)
+  uint8_t* s_p = s_tile1 + 2 * 16384;        // [4][16384] P, then dS
+  float* s_p256 = reinterpret_cast<float*>(s_p + NBLK * 16384);  // [272] P[256, kv]  (peeled row)
+  float* s_ds256 = s_p256 + 272;                                 // [272] dS[256, kv]
+  float* s_red = s_ds256 + 272;   // [256]
+  float* s_red2 = s_red + 256;    // [256]
+  float* s_tt = s_red2 + 256;     // [256] per-row peeled-column terms: p_t | ds_t
+  float* s_part = s_tt + 256;     // [2][4][64] partial sums of the peeled kv row
+  float* s_misc = s_part + 512;   // [16]
+  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_misc + 16);  // [4][64] k_256 v_256 q_256 dO_256
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 256);
+  uint64_t* bar_full = bars + 0;
+  uint64_t* bar_tile = bars + 1;      // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_dp = bars + 4;
+  uint64_t* bar_p = bars + 5;         // 256 arrivals, two uses per tile
+  uint64_t* bar_acc = bars + 6;       // dQ (and, on the last tile, dK / dV) complete
+  uint64_t* bar_acc_free = bars + 7;  // 256 arrivals: dQ accumulator drained
+  uint64_t* bar_kv_free = bars + 8;   // 256 arrivals: dK / dV accumulators drained
+  uint64_t* bar_trow = bars + 9;      // 256 arrivals: peeled row done with K / V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(&bar_tile[0], 1);
+    mbar_init(&bar_tile[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_p, 256);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc_free, 256);
+    mbar_init(bar_kv_free, 256);
+    mbar_init(bar_trow, 256);
+    fence_barrier_init();
+  }
+  if (warp == AT_CTRL_WARP) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = P.B * P.H;
+  const int colQ = 0, colK = W, colV = 2 * W;
+  constexpr uint32_t TR = 0, TDV = 256, TDK = 384;
+  const int ntile = P.ntile;   // 2 for T = 257
+
+  if (warp == AT_CTRL_WARP) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issuer =====================
+      auto load_full = [&](int item) {
+        const int b = item / P.H, h = item % P.H;
+        mbar_arrive_expect_tx(bar_full, 2 * full_bytes);
+        tma_load_3d(s_k, &tmFull, bar_full, colK + h * 64, 0, b);
+        tma_load_3d(s_v, &tmFull, bar_full, colV + h * 64, 0, b);
+      };
+      auto load_tile = [&](int item, int j, uint32_t gg) {
+        const int b = item / P.H, h = item % P.H, buf = gg & 1;
+        mbar_arrive_expect_tx(&bar_tile[buf], 32768);
+        tma_load_3d(s_tile0 + buf * 16384, &tmTile, &bar_tile[buf], colQ + h * 64, j * 128, b);
+        tma_load_3d(s_tile1 + buf * 16384, &tmDoTile, &bar_tile[buf], h * 64, j * 128, b);
+      };
+      const uint32_t idS = idesc_ab(FMT, FMT, 128, KVM, 0, 0);
+      const uint32_t idT = idesc_ab(FMT, FMT, 128, 64, 1, 1);   // A and B both MN-major
+      uint32_t g = 0;
+      int it = 0;
+      if ((int)blockIdx.x < n_items) {
+        load_full(blockIdx.x);
+        load_tile(blockIdx.x, 0, 0);
+      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int next = item + gridDim.x;
+        mbar_wait(bar_full, it & 1, 70);
+        if (it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 71);   // dK / dV accumulators drained
+        for (int j = 0; j < ntile; ++j, ++g) {
+          const int buf = g & 1;
+          // tile g-1 fully consumed (its MMAs retired, the workers done with its Q / dO tile
+          // and with the dQ accumulator, which aliases S): its buffer may be refilled
+          if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 73);
+          if (j + 1 < ntile) load_tile(item, j + 1, g + 1);
+          else if (next < n_items) load_tile(next, 0, g + 1);
+          mbar_wait(&bar_tile[buf], (g >> 1) & 1, 72);
+          tc_fence_after();
+          const uint32_t t0 = smem_u32(s_tile0 + buf * 16384), t1 = smem_u32(s_tile1 + buf * 16384);
+          const uint32_t ka = smem_u32(s_k), va = smem_u32(s_v), pa = smem_u32(s_p);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // S = Q_i K^T
+            umma_f16(tmem + TR, make_smem_desc_sw128(t0 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_s);
+          mbar_wait(bar_p, (2 * g) & 1, 74);        // P written (and dO_i rows scaled), S consumed
+          tc_fence_after();
+          // dV_jj += P^T dO_i : A = P (MN-major: 64-wide kv atoms 16 KB apart), B = dO_i (MN-major)
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              umma_f16(tmem + TDV + jj * 64,
+                       make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
+                       make_smem_desc_sw128(t1 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // dP' = dO'_i V^T into the (consumed) S region
+            umma_f16(tmem + TR, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(va + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_dp);                      // (also: the dV MMAs have retired)
+          mbar_wait(bar_p, (2 * g + 1) & 1, 75);    // dS written over P
+          tc_fence_after();
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)            // dK_jj += dS^T Q_i
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              umma_f16(tmem + TDK + jj * 64,
+                       make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
+                       make_smem_desc_sw128(t0 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
+          issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
+          umma_commit(bar_acc);
+        }
+        mbar_wait(bar_acc, (g - 1) & 1, 76);        // every MMA of this item retired
+        if (TAIL) mbar_wait(bar_trow, it & 1, 77);
+        if (next < n_items) load_full(next);
+      }
+    }
+  } else {
+    // ===================== row workers =====================
+    const int r = threadIdx.x & 127, hsel = threadIdx.x >> 7, tid = threadIdx.x;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const float c2 = 0.125f * 1.4426950408889634f;
+    const uint32_t ts = tmem + lane_off;
+    const int c0 = hsel * NH;
+    const uint16_t* tv0 = s_tv;             // k_256
+    const uint16_t* tv1 = s_tv + 64;        // v_256
+    const uint16_t* tv2 = s_tv + 128;       // q_256
+    const uint16_t* tv3 = s_tv + 192;       // dO_256
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int b = item / P.H, h = item % P.H;
+      float tdv = 0.f, tdk = 0.f;   // this thread's share of dv_256[d], dk_256[d] (d = tid & 63)
+      if (TAIL && tid < 32) {
+        const int which = tid >> 3, c = tid & 7;
+        const size_t rowq = ((size_t)b * T + 256) * 3 * W + h * 64 + c * 8;
+        const size_t rowd = ((size_t)b * T + 256) * W + h * 64 + c * 8;
+        const uint16_t* src = which == 0 ? P.qkv + rowq + colK : which == 1 ? P.qkv + rowq + colV
+                            : which == 2 ? P.qkv + rowq + colQ : P.d_o + rowd;
+        *reinterpret_cast<uint4*>(s_tv + which * 64 + c * 8) = *reinterpret_cast<const uint4*>(src);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (TAIL) {
+        // ============ the peeled QUERY row (token 256) on the CUDA cores ============
+        // p256[kv], ds256[kv] for all 257 keys; dq_256; kept for the dK / dV epilogue.
+        mbar_wait(bar_full, it & 1, 80);
+        const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
+        const float dpv = dot_swz_row<FMT>(s_v, tid, tv3);
+        const float s_last = dot_vec<FMT>(tv0, tv2), dp_last = dot_vec<FMT>(tv1, tv3);
+        const float mx = blk256_max(fmaxf(sv, s_last), s_misc, warp, lane) * c2;
+        const float e = fast_ex2(fmaf(sv, c2, -mx));
+        const float e_last = fast_ex2(fmaf(s_last, c2, -mx));
+        const float inv = 1.f / (blk256_sum(e, s_misc, warp, lane) + e_last);
+        const size_t ro = ((size_t)b * T + 256) * W + h * 64;
+        const float D = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);
+        s_p256[tid] = e * inv;
+        s_ds256[tid] = e * inv * (dpv - D) * 0.125f;
+        if (tid == 0) {
+          s_p256[256] = e_last * inv;
+          s_ds256[256] = e_last * inv * (dp_last - D) * 0.125f;
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        {
+          const int d = tid & 63, qt = tid >> 6;
+          float acc = 0.f;
+          for (int kv = qt * 64; kv < qt * 64 + 64; ++kv)
+            acc = fmaf(s_ds256[kv], swz_at<FMT>(s_k, kv, d), acc);
+          if (qt == 3) acc = fmaf(s_ds256[256], ld1<FMT>(tv0 + d), acc);
+          s_part[qt * 64 + d] = acc;
+          // the (q = 256, kv = 256) corner of dk_256 / dv_256
+          if (qt == 0) {
+            tdv = s_p256[256] * ld1<FMT>(tv3 + d);
+            tdk = s_ds256[256] * ld1<FMT>(tv2 + d);
+          }
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (tid < 32) {
+          const float a0 = s_part[2 * tid] + s_part[64 + 2 * tid] + s_part[128 + 2 * tid] +
+                           s_part[192 + 2 * tid];
+          const float a1 = s_part[2 * tid + 1] + s_part[64 + 2 * tid + 1] +
+                           s_part[128 + 2 * tid + 1] + s_part[192 + 2 * tid + 1];
+          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64)[tid] =
+              packc<FMT>(a0, a1);
+        }
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        mbar_arrive(bar_trow);
+      }
+      for (int j = 0; j < ntile; ++j, ++g) {
+        const int buf = g & 1;
+        const int row = j * 128 + r;
+        const size_t grow = (size_t)b * T + row;
+        uint8_t* tq = s_tile0 + buf * 16384;
+        uint8_t* tdo = s_tile1 + buf * 16384;
+        mbar_wait(&bar_tile[buf], (g >> 1) & 1, 81);
+        const float Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, FMT);
+        float a_t = 0.f, b_t = 0.f;
+        if (TAIL && hsel == 1) {
+          a_t = dot_swz_row<FMT>(tq, r, tv0);    // q_r . k_256
+          b_t = dot_swz_row<FMT>(tdo, r, tv1);   // dO_r . v_256   (before the row is scaled)
+        }
+        // ---------------- pass 1 ----------------
+        mbar_wait(bar_s, g & 1, 82);
+        tc_fence_after();
+        const uint32_t tcol = ts + c0 * 32;
+        const int col0 = c0 * 32;
+        uint8_t* prow = s_p + (size_t)(col0 >> 6) * 16384 + r * 128;
+        const uint32_t rx = (uint32_t)(r & 7) << 4;
+        auto poff = [&](int cc) -> uint32_t {
+          return (uint32_t)(cc >> 6) * 16384u + ((((uint32_t)(cc & 63) >> 3) << 4) ^ rx);
+        };
+        uint32_t pk[NQ * 8];
+        float p_t = 0.f;
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        {
+          uint32_t v[2][16];
+          tmem_ld16(tcol + TR, v[0]);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            tmem_ld_wait();
+            if (q + 1 < NQ) tmem_ld16(tcol + TR + (q + 1) * 16, v[(q + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[q & 1][i]));
+              m1 = fmaxf(m1, __uint_as_float(v[q & 1][i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[q & 1][i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[q & 1][i + 3]));
+            }
+          }
+          if (TAIL && hsel == 1) m0 = fmaxf(m0, a_t);
+        }
+        s_red[hsel * 128 + r] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float mc = fmaxf(s_red[r], s_red[128 + r]) * c2;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        {
+          uint32_t v[2][16];
+          tmem_ld16(tcol + TR, v[0]);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            tmem_ld_wait();
+            if (q + 1 < NQ) tmem_ld16(tcol + TR + (q + 1) * 16, v[(q + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float e[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                e[u] = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + u]), c2, -mc));
+              s0 += e[0]; s1 += e[1]; s2 += e[2]; s3 += e[3];
+              pk[q * 8 + i / 2] = packc<FMT>(e[0], e[1]);
+              pk[q * 8 + i / 2 + 1] = packc<FMT>(e[2], e[3]);
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8)   // un-normalised P -> shared memory
+              *reinterpret_cast<uint4*>(prow + poff(q * 16 + q8 * 8)) =
+                  make_uint4(pk[q * 8 + q8 * 4], pk[q * 8 + q8 * 4 + 1], pk[q * 8 + q8 * 4 + 2],
+                             pk[q * 8 + q8 * 4 + 3]);
+          }
+          if (TAIL && hsel == 1) p_t = fast_ex2(fmaf(a_t, c2, -mc));
+        }
+        s_red2[hsel * 128 + r] = (s0 + s1) + (s2 + s3) + p_t;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float rinv = 1.f / (s_red2[r] + s_red2[128 + r]);
+        if (hsel == 0) {
+          // fold 1/rowsum into this row of dO_i (used by dV = P^T dO' and dP' = dO' V^T)
+          uint8_t* drow = tdo + r * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4* pp = reinterpret_cast<uint4*>(drow + ((c ^ (r & 7)) << 4));
+            const uint4 u = *pp;
+            const uint32_t* ua = &u.x;
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 x = unpackc<FMT>(ua[i]);
+              o[i] = packc<FMT>(x.x * rinv, x.y * rinv);
+            }
+            *pp = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        // ---------------- pass 2: dS = p (dP' - D/rowsum) / 8 ----------------
+        mbar_wait(bar_dp, g & 1, 83);
+        tc_fence_after();
+        float ds_t = 0.f;
+        {
+          const float nDsc = -Dr * rinv * 0.125f;
+          uint32_t v[2][16];
+          tmem_ld16(tcol + TR, v[0]);
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            tmem_ld_wait();
+            if (q + 1 < NQ) tmem_ld16(tcol + TR + (q + 1) * 16, v[(q + 1) & 1]);
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+              float d[8];
+#pragma unroll
+              for (int u = 0; u < 8; u += 2) {
+                const int i = q8 * 8 + u;
+                const float2 pp = unpackc<FMT>(pk[q * 8 + i / 2]);
+                d[u] = pp.x * fmaf(__uint_as_float(v[q & 1][i]), 0.125f, nDsc);
+                d[u + 1] = pp.y * fmaf(__uint_as_float(v[q & 1][i + 1]), 0.125f, nDsc);
+              }
+              *reinterpret_cast<uint4*>(prow + poff(q * 16 + q8 * 8)) =
+                  make_uint4(packc<FMT>(d[0], d[1]), packc<FMT>(d[2], d[3]),
+                             packc<FMT>(d[4], d[5]), packc<FMT>(d[6], d[7]));
+            }
+          }
+          if (TAIL && hsel == 1) {
+            ds_t = p_t * rinv * (b_t - Dr) * 0.125f;
+            s_tt[r] = p_t;            // un-normalised: multiplies the scaled dO' rows
+            s_tt[128 + r] = ds_t;
+          }
+        }
+        if (TAIL) {
+          // peeled KEY row (kv = 256): dv_256 += sum_q p_t[q] dO'_q ; dk_256 += sum_q ds_t[q] Q_q
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          const int d = tid & 63, qt = tid >> 6;
+          for (int q = qt * 32; q < qt * 32 + 32; ++q) {
+            tdv = fmaf(s_tt[q], swz_at<FMT>(tdo, q, d), tdv);
+            tdk = fmaf(s_tt[128 + q], swz_at<FMT>(tq, q, d), tdk);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        // ---------------- dQ epilogue ----------------
+        mbar_wait(bar_acc, g & 1, 84);
+        tc_fence_after();
+        {
+          const float dst = TAIL ? s_tt[128 + r] : 0.f;
+          uint32_t v0[32];
+          tmem_ld32(ts + TR + hsel * 32, v0);
+          tmem_ld_wait();
+          uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + colQ + h * 64 + hsel * 32);
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v0[q8 * 8 + i]);
+            if (TAIL) {
+              const uint4 tu = *reinterpret_cast<const uint4*>(tv0 + hsel * 32 + q8 * 8);
+              const uint32_t* ta = &tu.x;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = unpackc<FMT>(ta[i]);
+                o[2 * i] = fmaf(dst, y.x, o[2 * i]);
+                o[2 * i + 1] = fmaf(dst, y.y, o[2 * i + 1]);
+              }
+            }
+            dst4[q8] = make_uint4(packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
+                                  packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_acc_free);
+      }
+      // ---------------- dK / dV epilogue (accumulated over the q tiles) ----------------
+      // (bar_acc of the last tile, waited above, covers the dK / dV MMAs too)
+      {
+        const uint32_t base = hsel ? TDK : TDV;           // hsel 0: dV, hsel 1: dK
+        const uint16_t* tvx = hsel ? tv2 : tv3;           // rank-1 term of the peeled query row
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int kv = jj * 128 + r;
+          uint32_t v0[32], v1[32];
+          tmem_ld32(ts + base + jj * 64, v0);
+          tmem_ld32(ts + base + jj * 64 + 32, v1);
+          tmem_ld_wait();
+          const float w = TAIL ? (hsel ? s_ds256[kv] : s_p256[kv]) : 0.f;
+          uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + ((size_t)b * T + kv) * 3 * W +
+                                                 (hsel ? colK : colV) + h * 64);
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8) {
+            const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
+            if (TAIL) {
+              const uint4 tu = *reinterpret_cast<const uint4*>(tvx + q8 * 8);
+              const uint32_t* ta = &tu.x;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = unpackc<FMT>(ta[i]);
+                o[2 * i] = fmaf(w, y.x, o[2 * i]);
+                o[2 * i + 1] = fmaf(w, y.y, o[2 * i + 1]);
+              }
+            }
+            dst4[q8] = make_uint4(packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
+                                  packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_kv_free);
+      if (TAIL) {
+        // dk_256 / dv_256: reduce the four row-quarter partials
+        const int d = tid & 63, qt = tid >> 6;
+        s_part[qt * 64 + d] = tdv;
+        s_part[256 + qt * 64 + d] = tdk;
+        asm volatile("bar.sync 3, 256;" ::: "memory");
+        if (tid < 64) {
+          const int which = tid >> 5, l2 = tid & 31;   // 0: dv, 1: dk
+          const float* pp = s_part + which * 256;
+          const float a0 = pp[2 * l2] + pp[64 + 2 * l2] + pp[128 + 2 * l2] + pp[192 + 2 * l2];
+          const float a1 = pp[2 * l2 + 1] + pp[64 + 2 * l2 + 1] + pp[128 + 2 * l2 + 1] +
+                           pp[192 + 2 * l2 + 1];
+          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W +
+                                      (which ? colK : colV) + h * 64)[l2] = packc<FMT>(a0, a1);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT_CTRL_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int FMT, bool TAIL>
+static int launch_bwd3(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                       const AttnBwd2Params& P, cudaStream_t st) {
+  auto kern = attn_bwd3_kernel<FMT, TAIL>;
+  const size_t smem = (size_t)2 * 256 * 128 + 4 * 16384 + (size_t)4 * 16384 +
+                      (272 * 2 + 256 * 3 + 512 + 16) * 4 + 512 + 128 + 1024;
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    set = true;
+  }
+  int grid = sm_count();
+  if (P.B * P.H < grid) grid = P.B * P.H;
+  kern<<<grid, AT_THREADS, smem, st>>>(a, b, c, P);
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
 struct AttnPlan {
   AttnParams P;
   size_t smem;
@@ -1660,6 +2142,20 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
     P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
     CUtensorMap tmTile, tmFull, tmDoTile, tmDoFull;
     const uint64_t W3 = 3ull * P.W, Wd = P.W;
+    // the fused dQ / dK / dV kernel (RVLM_ATTN_BWD3=1; read per call so tests can toggle it)
+    const char* e3 = getenv("RVLM_ATTN_BWD3");
+    const int use_v3 = (e3 && e3[0] == '1') ? 1 : 0;
+    if (use_v3 && (T == 257 || T == 256)) {
+      int rc3 = make_tmap_3d(&tmTile, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
+      if (!rc3) rc3 = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 256);
+      if (!rc3) rc3 = make_tmap_3d(&tmDoTile, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);
+      if (rc3) return rc3;
+      if (T == 257)
+        return fmt_g ? launch_bwd3<1, true>(tmTile, tmFull, tmDoTile, P, st)
+                     : launch_bwd3<0, true>(tmTile, tmFull, tmDoTile, P, st);
+      return fmt_g ? launch_bwd3<1, false>(tmTile, tmFull, tmDoTile, P, st)
+                   : launch_bwd3<0, false>(tmTile, tmFull, tmDoTile, P, st);
+    }
     int rc = make_tmap_3d(&tmTile, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
     if (!rc) rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, kvm);
     if (!rc) rc = make_tmap_3d(&tmDoTile, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);

@@ -137,10 +137,17 @@ def _attn_ref(qkv, B, T, H):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc"])
-@pytest.mark.parametrize("B,T,H", [(2, 50, 2), (3, 257, 4), (1, 257, 16)])
-def test_attention_fwd_bwd(impl, B, T, H):
+@pytest.mark.parametrize("impl", ["simt", "tc", "tc3"])
+@pytest.mark.parametrize("B,T,H", [(2, 50, 2), (3, 257, 4), (1, 257, 16), (2, 256, 4), (40, 257, 8)])
+def test_attention_fwd_bwd(impl, B, T, H, monkeypatch):
     nat = _nat()
+    if impl == "tc3":   # the fused dQ/dK/dV backward kernel (T in {256, 257})
+        if T < 256:
+            pytest.skip("fused backward covers T in {256, 257}")
+        monkeypatch.setenv("RVLM_ATTN_BWD3", "1")
+        impl = "tc"
+    else:
+        monkeypatch.setenv("RVLM_ATTN_BWD3", "0")
     torch.manual_seed(B * T + H)
     W = H * 64
     qkv = (torch.randn(B * T, 3 * W, device="cuda") * 1.5).half()

@@ -124,13 +124,12 @@ def test_fullsize_vitl14_properties():
     from robustvlm_b200 import attacks, model as rm
     B, eps = 32, 4 / 255
     vt = rm.VisionTransformer("ViT-L-14", seed=1).cuda()
-    vto = rm.VisionTransformer("ViT-L-14", seed=2).cuda()
-    m, mo = rm.ClipVisionModel(vt, None, None).eval(), rm.ClipVisionModel(vto, None, None).eval()
+    m = rm.ClipVisionModel(vt, None, None).eval()
     g = torch.Generator().manual_seed(0)
     x = torch.rand(B, 3, 224, 224, generator=g).cuda()
     d0 = ((torch.rand(B, 3, 224, 224, generator=g) * 2 - 1) * eps).cuda()
     with torch.no_grad():
-        eo = mo(x, output_normalize=False)
+        eo = m(x, output_normalize=False)   # FARE at step 0: the frozen copy equals the model
     w = rm.ComputeLossWrapper(eo, None, "mean", "l2", 100.0)
     a = attacks.pgd(m, w, x, None, "linf", eps, 10, 1 / 255, False, perturbation=d0, mode="max")
     b = attacks.pgd(m, w, x, None, "linf", eps, 10, 1 / 255, False, perturbation=d0, mode="max")

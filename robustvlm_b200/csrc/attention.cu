@@ -127,8 +127,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 12
                const __grid_constant__ CUtensorMap tmDoFull, // dO,  box 64 x boxrows
                AttnParams P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
+  // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int kvp = P.kvp, T = P.T, W = P.W;
   const int full_bytes = kvp * 128;
   uint8_t* s_full0 = smem;
@@ -490,7 +491,7 @@ __device__ __forceinline__ float2 unpackc(uint32_t u) {
 }
 template <int FMT>
 __device__ __forceinline__ float ld1(const uint16_t* p) {
-  return FMT ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p))
+  return FMT ? __uint_as_float((uint32_t)*p << 16)
              : __half2float(*reinterpret_cast<const __half*>(p));
 }
 // =====================================================================================
@@ -523,8 +524,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                  const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x kvm
                  AttnFwd2Params P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
+  // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int kvm = P.kvm, T = P.T, W = P.W;
   const int full_bytes = kvm * 128;
   uint8_t* s_k = smem;
@@ -1002,8 +1004,9 @@ attn_bwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                  const __grid_constant__ CUtensorMap tmDoFull, // dO,  box 64 x kvm
                  AttnBwd2Params P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
+  // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int KVM = NCH * 64;          // columns on the tensor cores (64 or 256)
   constexpr int NBLK = KVM / 64;
   const int T = P.T, W = P.W;
@@ -1561,8 +1564,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                  const __grid_constant__ CUtensorMap tmDoTile, // dO,  box 64 x 128
                  AttnBwd2Params P) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
+  // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int KVM = 256, NBLK = 4, NH = 4, NQ = 8;
   const int T = P.T, W = P.W;
   constexpr int full_bytes = KVM * 128;
@@ -1577,7 +1581,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   float* s_red2 = s_red + 256;    // [256]
   float* s_tt = s_red2 + 256;     // [256] per-row peeled-column terms: p_t | ds_t
   float* s_part = s_tt + 256;     // [2][4][64] partial sums of the peeled kv row
-  float* s_misc = s_part + 512;   // [16]
+  float* s_dd = s_part + 512;     // [256] partial row sums of o . dO
+  float* s_misc = s_dd + 256;     // [16]
   uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_misc + 16);  // [4][64] k_256 v_256 q_256 dO_256
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 256);
   uint64_t* bar_full = bars + 0;
@@ -1589,7 +1594,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint64_t* bar_acc_free = bars + 7;  // 256 arrivals: dQ accumulator drained
   uint64_t* bar_kv_free = bars + 8;   // 256 arrivals: dK / dV accumulators drained
   uint64_t* bar_trow = bars + 9;      // 256 arrivals: peeled row done with K / V
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* bar_kdone = bars + 10;    // last tensor-core read of K / V of this item retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1603,6 +1609,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
     mbar_init(bar_acc_free, 256);
     mbar_init(bar_kv_free, 256);
     mbar_init(bar_trow, 256);
+    mbar_init(bar_kdone, 1);
     fence_barrier_init();
   }
   if (warp == AT_CTRL_WARP) {
@@ -1644,7 +1651,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const int next = item + gridDim.x;
         mbar_wait(bar_full, it & 1, 70);
-        if (it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 71);   // dK / dV accumulators drained
         for (int j = 0; j < ntile; ++j, ++g) {
           const int buf = g & 1;
           // tile g-1 fully consumed (its MMAs retired, the workers done with its Q / dO tile
@@ -1662,6 +1668,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                      make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
           umma_commit(bar_s);
           mbar_wait(bar_p, (2 * g) & 1, 74);        // P written (and dO_i rows scaled), S consumed
+          if (j == 0 && it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 71);   // dK / dV drained
           tc_fence_after();
           // dV_jj += P^T dO_i : A = P (MN-major: 64-wide kv atoms 16 KB apart), B = dO_i (MN-major)
 #pragma unroll
@@ -1678,6 +1685,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           umma_commit(bar_dp);                      // (also: the dV MMAs have retired)
           mbar_wait(bar_p, (2 * g + 1) & 1, 75);    // dS written over P
           tc_fence_after();
+          issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
+          if (j + 1 == ntile) umma_commit(bar_kdone);     // K (and, earlier, V) no longer read
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)            // dK_jj += dS^T Q_i
 #pragma unroll
@@ -1685,10 +1694,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               umma_f16(tmem + TDK + jj * 64,
                        make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
                        make_smem_desc_sw128(t0 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
-          issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
           umma_commit(bar_acc);
         }
-        mbar_wait(bar_acc, (g - 1) & 1, 76);        // every MMA of this item retired
+        // refill K / V for the next item under this item's last dK MMAs and its epilogues
+        mbar_wait(bar_kdone, it & 1, 76);
         if (TAIL) mbar_wait(bar_trow, it & 1, 77);
         if (next < n_items) load_full(next);
       }
@@ -1721,6 +1730,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       if (TAIL) {
         // ============ the peeled QUERY row (token 256) on the CUDA cores ============
         // p256[kv], ds256[kv] for all 257 keys; dq_256; kept for the dK / dV epilogue.
+        const size_t ro = ((size_t)b * T + 256) * W + h * 64;
+        const float D = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);   // (latency under the K/V load)
         mbar_wait(bar_full, it & 1, 80);
         const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
         const float dpv = dot_swz_row<FMT>(s_v, tid, tv3);
@@ -1729,8 +1740,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         const float e = fast_ex2(fmaf(sv, c2, -mx));
         const float e_last = fast_ex2(fmaf(s_last, c2, -mx));
         const float inv = 1.f / (blk256_sum(e, s_misc, warp, lane) + e_last);
-        const size_t ro = ((size_t)b * T + 256) * W + h * 64;
-        const float D = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);
         s_p256[tid] = e * inv;
         s_ds256[tid] = e * inv * (dpv - D) * 0.125f;
         if (tid == 0) {
@@ -1769,8 +1778,19 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         const size_t grow = (size_t)b * T + row;
         uint8_t* tq = s_tile0 + buf * 16384;
         uint8_t* tdo = s_tile1 + buf * 16384;
+        // D_r = o_r . dO_r: this thread's half of the row, requested now, reduced after the
+        // first TMEM sweep (the HBM / L2 latency hides under the tile load and the S MMA)
+        uint4 g_o[4], g_d[4];
+        {
+          const uint4* po = reinterpret_cast<const uint4*>(P.o + grow * W + h * 64 + hsel * 32);
+          const uint4* pd = reinterpret_cast<const uint4*>(P.d_o + grow * W + h * 64 + hsel * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            g_o[i] = po[i];
+            g_d[i] = pd[i];
+          }
+        }
         mbar_wait(&bar_tile[buf], (g >> 1) & 1, 81);
-        const float Dr = dot_rows16(P.o + grow * W + h * 64, P.fmt_o, P.d_o + grow * W + h * 64, FMT);
         float a_t = 0.f, b_t = 0.f;
         if (TAIL && hsel == 1) {
           a_t = dot_swz_row<FMT>(tq, r, tv0);    // q_r . k_256
@@ -1807,7 +1827,22 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           if (TAIL && hsel == 1) m0 = fmaxf(m0, a_t);
         }
         s_red[hsel * 128 + r] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        {
+          float dd = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t* pa = &g_o[i].x;
+            const uint32_t* pb = &g_d[i].x;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 x = unpack2(pa[u], P.fmt_o), y = unpackc<FMT>(pb[u]);
+              dd = fmaf(x.x, y.x, fmaf(x.y, y.y, dd));
+            }
+          }
+          s_dd[hsel * 128 + r] = dd;
+        }
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float Dr = s_dd[r] + s_dd[128 + r];
         const float mc = fmaxf(s_red[r], s_red[128 + r]) * c2;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         {
@@ -2005,7 +2040,7 @@ static int launch_bwd3(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
                        const AttnBwd2Params& P, cudaStream_t st) {
   auto kern = attn_bwd3_kernel<FMT, TAIL>;
   const size_t smem = (size_t)2 * 256 * 128 + 4 * 16384 + (size_t)4 * 16384 +
-                      (272 * 2 + 256 * 3 + 512 + 16) * 4 + 512 + 128 + 1024;
+                      (272 * 2 + 256 * 4 + 512 + 16) * 4 + 512 + 128 + 1024;
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2142,9 +2177,10 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
     P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
     CUtensorMap tmTile, tmFull, tmDoTile, tmDoFull;
     const uint64_t W3 = 3ull * P.W, Wd = P.W;
-    // the fused dQ / dK / dV kernel (RVLM_ATTN_BWD3=1; read per call so tests can toggle it)
+    // the fused dQ / dK / dV kernel, default for T in {256, 257}; RVLM_ATTN_BWD3=0 selects the
+    // dQ + dK/dV kernel pair (read per call so that the tests can cover both)
     const char* e3 = getenv("RVLM_ATTN_BWD3");
-    const int use_v3 = (e3 && e3[0] == '1') ? 1 : 0;
+    const int use_v3 = (e3 && e3[0] == '0') ? 0 : 1;
     if (use_v3 && (T == 257 || T == 256)) {
       int rc3 = make_tmap_3d(&tmTile, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
       if (!rc3) rc3 = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 256);

@@ -61,8 +61,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
+  // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
   float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
@@ -304,8 +305,9 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int kStages = S::kStages;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
+  // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
   float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);

@@ -329,6 +329,10 @@ class APGDAttack:
             return torch.nn.CrossEntropyLoss(reduction="none")             # :244
         if self.loss == "dlr":
             return dlr_loss
+        if self.loss == "dlr-targeted":
+            return self.dlr_loss_targeted                                  # :255-256
+        if self.loss == "ce-targeted":
+            return self.ce_loss_targeted
         raise ValueError("unknowkn loss")
 
     def _fwd_bwd(self, x_adv, y, crit):
@@ -411,4 +415,56 @@ class APGDAttack:
             fooled = (acc_curr == 0).nonzero().flatten()
             acc[idx[fooled]] = 0                                           # :521-525
             adv[idx[fooled]] = adv_curr[fooled].clone()
+        return adv
+
+
+class APGDAttack_targeted(APGDAttack):
+    """AutoPGD on the targeted DLR loss (autoattack/autopgd_base.py:584-707): for every target
+    rank 2..n_target_classes+1 (by clean-logit order of the still-robust points) run
+    n_restarts attacks towards that class."""
+
+    def __init__(self, predict, n_iter=100, norm="Linf", n_restarts=1, eps=None, seed=0,
+                 eot_iter=1, rho=0.75, topk=None, n_target_classes=9, verbose=False, device=None,
+                 use_largereps=False, is_tf_model=False, logger=None, alpha=None, use_rs=True):
+        super().__init__(predict, n_iter=n_iter, norm=norm, n_restarts=n_restarts, eps=eps,
+                         seed=seed, loss="dlr-targeted", eot_iter=eot_iter, rho=rho, topk=topk,
+                         verbose=verbose, device=device, use_largereps=use_largereps,
+                         is_tf_model=is_tf_model, logger=logger, alpha=alpha, use_rs=use_rs)
+        self.y_target = None
+        self.n_target_classes = n_target_classes
+
+    def dlr_loss_targeted(self, x, y):
+        """:616-621"""
+        x_sorted, _ = x.sort(dim=1)
+        u = torch.arange(x.shape[0])
+        return -(x[u, y] - x[u, self.y_target]) / (
+            x_sorted[:, -1] - 0.5 * (x_sorted[:, -3] + x_sorted[:, -4]) + 1e-12)
+
+    def ce_loss_targeted(self, x, y):
+        """:623-624"""
+        return -1.0 * F.cross_entropy(x, self.y_target, reduction="none")
+
+    def perturb(self, x, y=None, x_init=None):
+        """:627-707"""
+        assert self.loss in ("dlr-targeted",)
+        if self.device is None:
+            self.device = x.device
+        x = x.detach().clone().float().to(self.device)
+        y_pred = self.model(x).max(1)[1]
+        y = y_pred.detach().clone().long() if y is None else y.detach().clone().long().to(self.device)
+        adv = x.clone()
+        acc = y_pred == y
+        torch.random.manual_seed(self.seed)                                # :661
+        for target_class in range(2, self.n_target_classes + 2):           # :678
+            for _ in range(self.n_restarts):
+                idx = acc.nonzero().flatten()
+                if idx.numel() == 0:
+                    continue
+                x_to_fool, y_to_fool = x[idx].clone(), y[idx].clone()
+                output = self.model(x_to_fool)
+                self.y_target = output.sort(dim=1)[1][:, -target_class]    # :691
+                _, acc_curr, _, adv_curr = self.attack_single_run(x_to_fool, y_to_fool)
+                fooled = (acc_curr == 0).nonzero().flatten()
+                acc[idx[fooled]] = 0
+                adv[idx[fooled]] = adv_curr[fooled].clone()
         return adv

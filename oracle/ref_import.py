@@ -49,6 +49,7 @@ def load():
     ns.attack_utils = importlib.import_module("vlm_eval.attacks.utils")
     apgd_base = importlib.import_module("autoattack.autopgd_base")
     ns.APGDAttack = apgd_base.APGDAttack
+    ns.APGDAttack_targeted = apgd_base.APGDAttack_targeted
     try:
         atc = importlib.import_module("train.adversarial_training_clip")
         ns.ClipVisionModel = atc.ClipVisionModel

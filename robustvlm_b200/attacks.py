@@ -3,6 +3,7 @@
   pgd                  train/pgd_train.py:5-68            (same signature)
   apgd_train           train/apgd_train.py:125-373        (same signature)
   APGDAttack           autoattack/autopgd_base.py:89-582  (same ctor / perturb / attack_single_run)
+  APGDAttack_targeted  autoattack/autopgd_base.py:584-707 (targeted DLR, n_target_classes)
   project_perturbation, normalize_grad   vlm_eval/attacks/utils.py:8-26
 
 Two execution paths behind each entry point, both on the GPU and both ending in the
@@ -276,6 +277,10 @@ class APGDAttack:
             crit = torch.nn.CrossEntropyLoss(reduction="none")                     # :244
         elif self.loss == "dlr":
             crit = dlr_loss
+        elif self.loss == "dlr-targeted":
+            crit = self.dlr_loss_targeted                                          # :255-256
+        elif self.loss == "ce-targeted":
+            crit = self.ce_loss_targeted
         else:
             raise ValueError("unknowkn loss")
         base = _autograd_fwd_bwd(m, crit, y)
@@ -313,6 +318,9 @@ class APGDAttack:
         """:453-548"""
         assert self.loss in ("ce", "dlr")
         _need_cuda(x, "x")
+        if y is not None and y.dim() == 0:                                         # :462-464
+            x.unsqueeze_(0)
+            y.unsqueeze_(0)
         if self.device is None:
             self.device = x.device
         x = x.detach().clone().float().to(self.device)
@@ -339,4 +347,63 @@ class APGDAttack:
             fooled = (acc_curr == 0).nonzero().flatten()
             acc[idx[fooled]] = False                                               # :521-525
             adv[idx[fooled]] = adv_curr[fooled].clone()
+        return adv
+
+
+class APGDAttack_targeted(APGDAttack):
+    """AutoPGD on the targeted DLR loss (autoattack/autopgd_base.py:584-707): for each target
+    rank 2 .. n_target_classes+1 of the still-robust points' logits, n_restarts runs towards
+    that class.  The loss needs a per-row sort (top-4), so the gradient comes from autograd
+    through the engine's VJP; step / projection / bookkeeping are the CUDA update kernels."""
+
+    def __init__(self, predict, n_iter=100, norm="Linf", n_restarts=1, eps=None, seed=0,
+                 eot_iter=1, rho=0.75, topk=None, n_target_classes=9, verbose=False, device=None,
+                 use_largereps=False, is_tf_model=False, logger=None, alpha=None, use_rs=True):
+        super().__init__(predict, n_iter=n_iter, norm=norm, n_restarts=n_restarts, eps=eps,
+                         seed=seed, loss="dlr-targeted", eot_iter=eot_iter, rho=rho, topk=topk,
+                         verbose=verbose, device=device, use_largereps=use_largereps,
+                         is_tf_model=is_tf_model, logger=logger, alpha=alpha, use_rs=use_rs)
+        self.y_target = None
+        self.n_target_classes = n_target_classes
+
+    def dlr_loss_targeted(self, x, y):
+        """:616-621"""
+        x_sorted, _ = x.sort(dim=1)
+        u = torch.arange(x.shape[0], device=x.device)
+        return -(x[u, y] - x[u, self.y_target]) / (
+            x_sorted[:, -1] - 0.5 * (x_sorted[:, -3] + x_sorted[:, -4]) + 1e-12)
+
+    def ce_loss_targeted(self, x, y):
+        """:623-624"""
+        return -1.0 * torch.nn.functional.cross_entropy(x, self.y_target, reduction="none")
+
+    def perturb(self, x, y=None, x_init=None):
+        """:627-707"""
+        assert self.loss in ("dlr-targeted",)
+        _need_cuda(x, "x")
+        if y is not None and y.dim() == 0:                                         # :634-636
+            x.unsqueeze_(0)
+            y.unsqueeze_(0)
+        if self.device is None:
+            self.device = x.device
+        x = x.detach().clone().float().to(self.device)
+        with torch.no_grad():
+            y_pred = self.model(x).max(1)[1]
+        y = y_pred.detach().clone().long() if y is None else y.detach().clone().long().to(self.device)
+        adv = x.clone()
+        acc = y_pred == y
+        torch.random.manual_seed(self.seed)                                        # :661
+        for target_class in range(2, self.n_target_classes + 2):                   # :678
+            for _ in range(self.n_restarts):
+                idx = acc.nonzero().flatten()
+                if idx.numel() == 0:
+                    continue
+                x_to_fool, y_to_fool = x[idx].clone(), y[idx].clone()
+                with torch.no_grad():
+                    output = self.model(x_to_fool)
+                self.y_target = output.sort(dim=1)[1][:, -target_class]            # :691
+                _, acc_curr, _, adv_curr = self.attack_single_run(x_to_fool, y_to_fool)
+                fooled = (acc_curr == 0).nonzero().flatten()
+                acc[idx[fooled]] = False
+                adv[idx[fooled]] = adv_curr[fooled].clone()
         return adv

@@ -117,6 +117,69 @@ def test_golden_apgd_eval(gold, models, norm, eps):
     assert int(fooled_o.sum()) >= int(fooled_r.sum()) - 1
 
 
+@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 1.0)])
+def test_golden_apgd_targeted(gold, models, norm, eps):
+    """APGDAttack_targeted (autoattack/autopgd_base.py:584-707) vs the reference's output:
+    constraints exact, at least as many points fooled (minus one) as the reference."""
+    from robustvlm_b200 import attacks, model as rm
+    gt = torch.load(GOLD.replace("reference_vectors.pt", "reference_vectors_targeted.pt"),
+                    weights_only=False)
+    k = gt["meta"]
+    ours, ref_m = models
+    x, text, yc = gold["x"], gold["text"], gold["y_clean"]
+    cm = rm.ClassificationModel(ours, text.cuda())
+    atk = attacks.APGDAttack_targeted(cm, n_iter=k["n_iter"], norm=norm, n_restarts=k["n_restarts"],
+                                      eps=eps, seed=k["seed"],
+                                      n_target_classes=k["n_target_classes"], alpha=k["alpha"])
+    out = atk.perturb(x.cuda(), yc.cuda()).cpu()
+    ref = gt[f"apgd_t_{norm}"]
+    cm_ref = ovit.ClassificationModel(ref_m.model, text, 100.0)
+    with torch.no_grad():
+        fooled_o = (cm_ref(out).argmax(1) != yc)
+        fooled_r = (cm_ref(ref).argmax(1) != yc)
+    d = out - x
+    pert = float(d.abs().max()) if norm == "Linf" else float(d.flatten(1).norm(dim=1).max())
+    _log("golden_apgd_targeted", norm=norm, fooled_ours=int(fooled_o.sum()),
+         fooled_ref=int(fooled_r.sum()), pert=pert)
+    assert pert <= eps * (1 + 1e-4) + 1e-6 and out.min() >= 0 and out.max() <= 1
+    assert int(fooled_o.sum()) >= int(fooled_r.sum()) - 1
+
+
+def test_golden_autoattack(gold, models):
+    """AutoAttack.run_standard_evaluation, version='custom', ['apgd-ce', 'apgd-t']
+    (autoattack/autoattack.py:82-261 as driven by CLIP_eval/clip_robustbench.py:289-300) vs the
+    reference's run on CPU: constraints exact, untouched points returned unchanged, robust
+    accuracy within one point of the reference's."""
+    from robustvlm_b200 import model as rm
+    from robustvlm_b200.autoattack import AutoAttack
+    gt = torch.load(GOLD.replace("reference_vectors.pt", "reference_vectors_targeted.pt"),
+                    weights_only=False)["aa"]
+    ours, ref_m = models
+    cm = rm.ClassificationModel(ours, gold["text"].cuda())
+    x, y, eps = gt["x"].cuda(), gt["y"].cuda(), gt["eps"]
+    A = AutoAttack(cm, norm="Linf", eps=eps, version="custom", attacks_to_run=["apgd-ce", "apgd-t"],
+                   alpha=2.0, verbose=False, device="cuda", iterations_apgd=gt["iterations_apgd"],
+                   seed=0)
+    A.apgd.n_restarts = 1
+    A.apgd_targeted.n_target_classes = gt["n_target_classes"]
+    x_adv, y_adv = A.run_standard_evaluation(x, y, bs=gt["bs"], return_labels=True)
+    cm_ref = ovit.ClassificationModel(ref_m.model, gold["text"], 100.0)
+    with torch.no_grad():
+        pred = cm_ref(x_adv.cpu()).argmax(1)
+    racc = float((pred == gt["y"]).float().mean())
+    _log("golden_autoattack", racc_ours=racc, racc_ref=gt["robust_acc"],
+         acc_dict=A.robust_accuracy_dict)
+    d = (x_adv - x).flatten(1).abs().max(1)[0]
+    assert float(d.max()) <= eps + 1e-6 and float(x_adv.min()) >= 0 and float(x_adv.max()) <= 1
+    still_robust = (y_adv == y)
+    assert torch.equal(x_adv[still_robust], x[still_robust])      # only successes are written back
+    assert torch.equal(x_adv[0], x[0])                            # initially misclassified: untouched
+    assert abs(racc - gt["robust_acc"]) <= 1.0 / x.shape[0] + 1e-6
+    with pytest.raises(NotImplementedError):
+        AutoAttack(cm, norm="Linf", eps=eps, version="custom", attacks_to_run=["square"],
+                   verbose=False).run_standard_evaluation(x[:2], y[:2], bs=2)
+
+
 def test_fullsize_vitl14_properties():
     """BASELINE.json configs[1] at reduced batch: size-independent properties of the fused
     10-step PGD on ViT-L/14 -- constraints, determinism, invariance to micro-batching (the

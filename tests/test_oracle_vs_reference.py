@@ -64,6 +64,18 @@ def test_apgd_attack(ns, setup, norm, eps, loss):
     ra, rr = A.attack_single_run(x, yc), R.attack_single_run(x, yc)  # consumes the CPU RNG equally
 
 
+@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 2.0)])
+def test_apgd_targeted(ns, setup, norm, eps):
+    """autoattack/autopgd_base.py:584-707 (targeted DLR over the 2nd..4th ranked classes)"""
+    m, x, d0, y, text, eo = setup
+    cm = vit.ClassificationModel(m.model, text, 100.0)
+    with torch.no_grad():
+        yc = cm(x).argmax(1)
+    kw = dict(n_iter=12, norm=norm, n_restarts=1, eps=eps, seed=0, n_target_classes=3, alpha=2.0)
+    A, R = oa.APGDAttack_targeted(cm, **kw), ns.APGDAttack_targeted(cm, **kw)
+    assert torch.equal(A.perturb(x, yc), R.perturb(x, yc))
+
+
 def test_model_wrappers(ns, setup):
     m, x, d0, y, text, eo = setup
     r = ns.ClipVisionModel(m.model, None, m.normalize)

@@ -140,12 +140,54 @@ def _cpu_arm_setup(model_name, Bs):
     return oa, model, wrap, x, d0, best, n
 
 
+def run_reference_cuda(args):
+    """Informal extra baseline (NOT the reference arm the driver runs): the same oracle port of
+    the reference's pgd() around the restated ViT, executed by stock PyTorch on cuda:0 -- the
+    "reference's single-GPU PyTorch path" of BASELINE.json's target -- in fp32 and with TF32
+    matmuls allowed.  CUDA-event timing, 1 warm-up + `steps` timed calls, median."""
+    import torch
+    from oracle import attacks as oa
+    from oracle import vit as ovit
+    dev = torch.device("cuda", 0)
+    Bs = args.ref_batch
+    model = ovit.ClipVisionModel(ovit.build(args.model, seed=1)).eval().to(dev)
+    model_orig = ovit.ClipVisionModel(ovit.build(args.model, seed=2)).eval().to(dev)
+    x, d0 = synth(Bs, seed=0, device=dev)
+    res = {}
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        with torch.no_grad():
+            e_orig = model_orig(x, output_normalize=False)
+        wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+
+        def one():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            oa.pgd(model, wrap, x, None, "linf", EPS, ITERS, STEPSIZE, False,
+                   perturbation=d0.clone(), mode="max")
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 1e3
+        one()
+        ts = sorted(one() for _ in range(max(1, args.steps)))
+        res["tf32" if tf32 else "fp32"] = Bs / ts[len(ts) // 2]
+    line = {"impl": "reference-torch-cuda", "metric": METRIC, "unit": "img/s", "n_gpus": 1,
+            "value": res["fp32"], "value_tf32": res["tf32"], "steps": args.steps, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, Bs),
+            "note": "oracle port of train/pgd_train.py::pgd + restated open_clip ViT on stock "
+                    f"PyTorch {torch.__version__} CUDA (cuBLAS/cuDNN), batch {Bs}; informal"}
+    print(json.dumps(line), flush=True)
+
+
 def run_reference(args):
     """CPU baseline arm: the oracle port of the reference's pgd() around the restated ViT."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.ref_device == "cuda":
+        return run_reference_cuda(args)
     name = args.model
     Bs = 8
     oa, model, wrap, x, d0, cores, avail = _cpu_arm_setup(name, Bs)
@@ -337,6 +379,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--chunk", type=int, default=256, help="engine micro-batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' times stock PyTorch on the GPU (informal)")
+    ap.add_argument("--ref-batch", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,9 +54,11 @@ struct EpiWgradPatch {
   float* G;
   int kp;
   struct Aux {};
+  struct Col {};
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux&) const {
+  __device__ __forceinline__ Col col(int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col&) const {
     if (col < kp) *reinterpret_cast<float4*>(G + (size_t)row * kp + col) = acc;
   }
 };
@@ -85,9 +87,11 @@ struct EpiPatchFwd {
   const float* pos;  // [T, W]
   int np, T, W;
   struct Aux {};
+  struct Col {};
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux&) const {
+  __device__ __forceinline__ Col col(int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col&) const {
     const int b = row / np, p = row - b * np;
     const float4 q = __ldg(reinterpret_cast<const float4*>(pos + (size_t)(1 + p) * W + col));
     *reinterpret_cast<float4*>(tok + ((size_t)b * T + 1 + p) * W + col) =
@@ -102,9 +106,11 @@ struct EpiPatchGrad {
   int kp, pp;  // pp = patch*patch; kp % 4 == 0
   float inv_std[3];
   struct Aux {};
+  struct Col {};
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux&) const {
+  __device__ __forceinline__ Col col(int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col&) const {
     if (col >= kp) return;
     *reinterpret_cast<float4*>(G + (size_t)row * kp + col) =
         make_float4(acc.x * inv_std[(col + 0) / pp], acc.y * inv_std[(col + 1) / pp],
@@ -124,21 +130,20 @@ struct EpiPatchPgdLinf {
   int kp, pp, lda, fmt;
   float stepsize, eps, dir, momentum;
   float mean[3], inv_std[3];
-  struct Aux { float4 x, d, v; };
-  __device__ __forceinline__ Aux load(int row, int col) const {
-    Aux a;
-    if (col < kp) {
-      const size_t off = (size_t)row * kp + col;
-      a.x = *reinterpret_cast<const float4*>(xp + off);
-      a.d = *reinterpret_cast<const float4*>(dp + off);
-      a.v = *reinterpret_cast<const float4*>(vp + off);
-    }
-    return a;
-  }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux& a) const {
+  // x / delta / velocity are read inside operator() (3 float4 per piece x 8 pieces held
+  // early would not fit the register budget; this GEMM runs once per PGD step)
+  struct Aux {};
+  struct Col {};
+  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ Col col(int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col&) const {
     if (col >= kp) return;
     const size_t off = (size_t)row * kp + col;
+    struct { float4 x, d, v; } a;
+    a.x = *reinterpret_cast<const float4*>(xp + off);
+    a.d = *reinterpret_cast<const float4*>(dp + off);
+    a.v = *reinterpret_cast<const float4*>(vp + off);
     const float4 x4 = a.x;
     float4 d4 = a.d;
     float4 v4 = a.v;

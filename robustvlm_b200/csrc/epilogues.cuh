@@ -8,7 +8,8 @@
 //
 // Functor interface (col % 4 == 0, row < M, col < N guaranteed by the caller, N % 32 == 0):
 //   Aux  load(row, col)                       HBM operands of the epilogue, requested early
-//   void operator()(row, col, acc, aux)       math + stores
+//   Col  col(col)                             per-column operand (bias), once per 32-column chunk
+//   void operator()(row, col, acc, aux, col)  math + stores
 #pragma once
 #include "ptx.cuh"
 
@@ -35,9 +36,11 @@ __device__ __forceinline__ float4 unpack4(const uint2& u, int fmt) {
   const float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt);
   return make_float4(a.x, a.y, b.x, b.y);
 }
-__device__ __forceinline__ float4 add_bias(const float4& a, const float* bias, int col) {
-  if (!bias) return a;
-  const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col));
+// per-column operand of an epilogue (the bias of 4 consecutive columns), loaded once per chunk
+__device__ __forceinline__ float4 load_bias(const float* bias, int col) {
+  return bias ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
@@ -50,11 +53,12 @@ struct EpiStore16 {
   const float* bias;  // may be null
   int fmt;
   using Aux = NoAux;
+  using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux&) const {
-    const float4 v = add_bias(acc, bias, col);
-    *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(v, fmt);
+  __device__ __forceinline__ Col col(int c) const { return load_bias(bias, c); }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col& b) const {
+    *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(add4(acc, b), fmt);
   }
 };
 
@@ -69,10 +73,12 @@ struct EpiStore16Dual {
   const float* bias;
   int fmt, fmt2;
   using Aux = NoAux;
+  using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux&) const {
-    const float4 v = add_bias(acc, bias, col);
+  __device__ __forceinline__ Col col(int c) const { return load_bias(bias, c); }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col& b) const {
+    const float4 v = add4(acc, b);
     *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(v, fmt);
     if (C2) *reinterpret_cast<uint2*>(C2 + (size_t)row * ldc + col) = pack4(v, fmt2);
   }
@@ -86,15 +92,15 @@ struct EpiStore32 {
   const float* resid;  // may be null
   int ldr;
   using Aux = float4;
+  using Col = float4;
   __device__ __forceinline__ Aux load(int row, int col) const {
     return resid ? *reinterpret_cast<const float4*>(resid + (size_t)row * ldr + col)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux& r) const {
-    float4 v = add_bias(acc, bias, col);
-    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-    *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = v;
+  __device__ __forceinline__ Col col(int c) const { return load_bias(bias, c); }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& r,
+                                             const Col& b) const {
+    *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = add4(add4(acc, b), r);
   }
 };
 
@@ -116,10 +122,12 @@ struct EpiGelu {
   const float* bias;
   int fmt;
   using Aux = NoAux;
+  using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux&) const {
-    const float4 h = add_bias(acc, bias, col);
+  __device__ __forceinline__ Col col(int c) const { return load_bias(bias, c); }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+                                             const Col& b) const {
+    const float4 h = add4(acc, b);
     const float4 a = make_float4(quick_gelu(h.x), quick_gelu(h.y), quick_gelu(h.z),
                                  quick_gelu(h.w));
     if (H) *reinterpret_cast<uint2*>(H + (size_t)row * ld + col) = pack4(h, fmt);
@@ -135,11 +143,13 @@ struct EpiGeluBwd {
   int fmt_h;
   int fmt_out;
   using Aux = uint2;
+  using Col = NoAux;
   __device__ __forceinline__ Aux load(int row, int col) const {
     return *reinterpret_cast<const uint2*>(H + (size_t)row * ld + col);
   }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc,
-                                             const Aux& hu) const {
+  __device__ __forceinline__ Col col(int) const { return {}; }
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& hu,
+                                             const Col&) const {
     const float4 h = unpack4(hu, fmt_h);
     const float4 o = make_float4(acc.x * quick_gelu_grad(h.x), acc.y * quick_gelu_grad(h.y),
                                  acc.z * quick_gelu_grad(h.z), acc.w * quick_gelu_grad(h.w));

@@ -49,10 +49,77 @@ struct GemmSmem {
 
 // The epilogue functor interface:
 //   struct Aux;                                     // what the functor reads from HBM
+//   struct Col;                                     // per-column operand (bias), once per chunk
 //   __device__ Aux  load(int row, int col) const;   // issued early (latency hidden)
-//   __device__ void operator()(int row, int col, const float4& acc, const Aux&) const
+//   __device__ Col  col(int col) const;
+//   __device__ void operator()(int row, int col, const float4& acc, const Aux&, const Col&) const
 // called once per (row, 4 consecutive columns) with row < M and col < N already
 // guaranteed (N is required to be a multiple of 32 by the host wrappers).
+
+
+// Epilogue of one accumulator tile for one epilogue warp: drains this warp's 32 TMEM lanes x
+// (BN/2) columns in 32-column chunks.  Per chunk: tcgen05.ld -> registers -> XOR-swizzled
+// warp-private smem transpose -> each lane owns float4 pieces (4 consecutive columns of one
+// row, 8 lanes per row) -> Epi functor.  Latency is hidden inside the warp instead of across
+// warps (only two epilogue warps share an SM sub-partition): the HBM operands of the
+// epilogue and the per-column operand (bias) are requested first, the NEXT chunk's
+// tcgen05.ld is issued as soon as the registers are staged, and the eight transposed pieces
+// are read back in one batch before any math / store is issued.
+template <int BN, bool GUARD, class Epi>
+__device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, uint32_t taddr,
+                                                    int row0, int n0, int half, int M, int N,
+                                                    int lane) {
+  constexpr int NCH = BN / 64;
+  const int rl = lane >> 3, c4 = lane & 7;
+  const int cfirst = half * NCH;
+  const int rem = N - (n0 + cfirst * 32);  // columns left for this half (N % 32 == 0)
+  const int nch = rem <= 0 ? 0 : (rem >= NCH * 32 ? NCH : rem / 32);  // warp-uniform
+  if (nch == 0) return;
+  uint32_t r[32];
+  tmem_ld32(taddr + cfirst * 32, r);
+#pragma unroll 1
+  for (int cc = 0; cc < nch; ++cc) {
+    const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
+    typename Epi::Aux aux[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + rl + 4 * i;
+      if (!GUARD || row < M) aux[i] = epi.load(row, col);
+    }
+    const typename Epi::Col ca = epi.col(col);
+    tmem_ld_wait();
+    // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+          make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    if (cc + 1 < nch) tmem_ld32(taddr + (cfirst + cc + 1) * 32, r);
+    float4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = rl + 4 * i;
+      v[i] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + rl + 4 * i;
+      if (!GUARD || row < M) epi(row, col, v[i], aux[i], ca);
+    }
+  }
+}
+
+// The row guard is hoisted to the warp's 32-row slab: full slabs (all but the last M tile)
+// run branch-free, so the eight pieces' dependent chains (MUFU, conversions, stores)
+// interleave instead of executing one piece at a time.
+template <int BN, class Epi>
+__device__ __forceinline__ void epilogue_drain(const Epi& epi, float* stg, uint32_t taddr,
+                                               int row0, int n0, int half, int M, int N,
+                                               int lane) {
+  if (row0 + 32 <= M) epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, half, M, N, lane);
+  else if (row0 < M) epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, half, M, N, lane);
+}
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -174,7 +241,6 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the accumulator columns
     float* stg = staging + (warp - 4) * 1024;
-    const int rl = lane >> 3, c4 = lane & 7;  // piece owned after the transpose
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -184,38 +250,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after();
       const int row0 = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        const int c = half * (BN / 64) + cc;
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        // operands the epilogue reads from HBM (residual, pre-activation, ...) are requested
-        // first, so their latency overlaps the TMEM read and the transpose
-        typename Epi::Aux aux[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row0 + rl + 4 * i;
-          if (row < M) aux[i] = epi.load(row, col0 + 4 * c4);
-        }
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = rl + 4 * i;
-          const float4 v =
-              *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-          const int row = row0 + rr;
-          if (row < M) epi(row, col0 + 4 * c4, v, aux[i]);
-        }
-        __syncwarp();
-      }
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -407,7 +442,6 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     float* stg = staging + (warp - 4) * 1024;
-    const int rl = lane >> 3, c4 = lane & 7;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -417,35 +451,7 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const int row0 = m_blk * 256 + (int)rank * 128 + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int cc = 0; cc < BN / 64; ++cc) {
-        const int c = half * (BN / 64) + cc;
-        const int col0 = n_blk * BN + c * 32;
-        if (col0 >= N) break;
-        typename Epi::Aux aux[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = row0 + rl + 4 * i;
-          if (row < M) aux[i] = epi.load(row, col0 + 4 * c4);
-        }
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = rl + 4 * i;
-          const float4 v =
-              *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-          const int row = row0 + rr;
-          if (row < M) epi(row, col0 + 4 * c4, v, aux[i]);
-        }
-        __syncwarp();
-      }
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[acc]);
       else mbar_arrive_cluster(&tempty_bar[acc], 0);

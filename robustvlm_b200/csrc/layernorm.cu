@@ -88,13 +88,25 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
   }
   const float2 st = stats[row];
   const float mean = st.x, rstd = st.y;
-  float4 g[NV], xh[NV];
+  float4 g[NV], xh[NV], res[NV];
   float s1 = 0.f, s2 = 0.f;
+  // every HBM read of the row (dy, x, residual gradient) is requested before the first
+  // reduction, so one round of memory latency covers all three streams
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const float4 d = reinterpret_cast<const float4*>(dy + (size_t)row * W)[i * 32 + lane];
-    const float4 xv = reinterpret_cast<const float4*>(x + (size_t)row * W)[i * 32 + lane];
-    const float4 gm = reinterpret_cast<const float4*>(gamma)[i * 32 + lane];
+    g[i] = reinterpret_cast<const float4*>(dy + (size_t)row * W)[i * 32 + lane];
+    xh[i] = reinterpret_cast<const float4*>(x + (size_t)row * W)[i * 32 + lane];
+  }
+  if (dres) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      res[i] = reinterpret_cast<const float4*>(dres + (size_t)row * W)[i * 32 + lane];
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 d = g[i];
+    const float4 xv = xh[i];
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
     g[i].x = d.x * gm.x; g[i].y = d.y * gm.y; g[i].z = d.z * gm.z; g[i].w = d.w * gm.w;
     xh[i].x = (xv.x - mean) * rstd; xh[i].y = (xv.y - mean) * rstd;
     xh[i].z = (xv.z - mean) * rstd; xh[i].w = (xv.w - mean) * rstd;
@@ -111,7 +123,7 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
     o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
     o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
     if (dres) {
-      const float4 r = reinterpret_cast<const float4*>(dres + (size_t)row * W)[i * 32 + lane];
+      const float4 r = res[i];
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
     if (dx32) reinterpret_cast<float4*>(dx32 + (size_t)orow * W)[i * 32 + lane] = o;

@@ -143,6 +143,10 @@ int rvlm_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
 int rvlm_layernorm_bwd(const float* dy, const float* x, const float* stats, const float* gamma,
                        const float* dres, float* dx32, void* dx16, int M, int W, int fmt,
                        int drop_T, void* stream);
+/* Same with dy given as a 16-bit matrix in `fmt` (also the format of dx16). */
+int rvlm_layernorm_bwd16(const void* dy16, const float* x, const float* stats, const float* gamma,
+                         const float* dres, float* dx32, void* dx16, int M, int W, int fmt,
+                         int drop_T, void* stream);
 /* Multi-head attention core, head dim 64, no mask: softmax(q k^T / 8) v.
  *   qkv16 [B*T, 3W] (q | k | v per token; head h at columns 64h..64h+63), W = 64 H
  *   o16 [B*T, W]; lse [B, H, T] (log-sum-exp of the scaled scores)

@@ -1583,8 +1583,9 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   float* s_part = s_tt + 256;     // [2][4][64] partial sums of the peeled kv row
   float* s_dd = s_part + 512;     // [256] partial row sums of o . dO
   float* s_misc = s_dd + 256;     // [16]
-  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_misc + 16);  // [4][64] k_256 v_256 q_256 dO_256
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 256);
+  // [2][5][64] k_256 v_256 q_256 dO_256 o_256 of the current / the next item
+  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_misc + 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 2 * 320);
   uint64_t* bar_full = bars + 0;
   uint64_t* bar_tile = bars + 1;      // [2]
   uint64_t* bar_s = bars + 3;
@@ -1595,7 +1596,8 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint64_t* bar_kv_free = bars + 8;   // 256 arrivals: dK / dV accumulators drained
   uint64_t* bar_trow = bars + 9;      // 256 arrivals: peeled row done with K / V
   uint64_t* bar_kdone = bars + 10;    // last tensor-core read of K / V of this item retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* bar_dk = bars + 11;       // dK MMAs of a tile retired (Q_i / dS no longer read)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1610,6 +1612,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
     mbar_init(bar_kv_free, 256);
     mbar_init(bar_trow, 256);
     mbar_init(bar_kdone, 1);
+    mbar_init(bar_dk, 1);
     fence_barrier_init();
   }
   if (warp == AT_CTRL_WARP) {
@@ -1655,7 +1658,10 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           const int buf = g & 1;
           // tile g-1 fully consumed (its MMAs retired, the workers done with its Q / dO tile
           // and with the dQ accumulator, which aliases S): its buffer may be refilled
-          if (g > 0) mbar_wait(bar_acc_free, (g - 1) & 1, 73);
+          if (g > 0) {
+            mbar_wait(bar_acc_free, (g - 1) & 1, 73);
+            mbar_wait(bar_dk, (g - 1) & 1, 78);
+          }
           if (j + 1 < ntile) load_tile(item, j + 1, g + 1);
           else if (next < n_items) load_tile(next, 0, g + 1);
           mbar_wait(&bar_tile[buf], (g >> 1) & 1, 72);
@@ -1686,6 +1692,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           mbar_wait(bar_p, (2 * g + 1) & 1, 75);    // dS written over P
           tc_fence_after();
           issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
+          umma_commit(bar_acc);                           // the dQ epilogue starts under the dK MMAs
           if (j + 1 == ntile) umma_commit(bar_kdone);     // K (and, earlier, V) no longer read
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)            // dK_jj += dS^T Q_i
@@ -1694,7 +1701,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               umma_f16(tmem + TDK + jj * 64,
                        make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
                        make_smem_desc_sw128(t0 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
-          umma_commit(bar_acc);
+          umma_commit(bar_dk);
         }
         // refill K / V for the next item under this item's last dK MMAs and its epilogues
         mbar_wait(bar_kdone, it & 1, 76);
@@ -1709,29 +1716,37 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
     const float c2 = 0.125f * 1.4426950408889634f;
     const uint32_t ts = tmem + lane_off;
     const int c0 = hsel * NH;
-    const uint16_t* tv0 = s_tv;             // k_256
-    const uint16_t* tv1 = s_tv + 64;        // v_256
-    const uint16_t* tv2 = s_tv + 128;       // q_256
-    const uint16_t* tv3 = s_tv + 192;       // dO_256
+    // the five 64-element vectors of the peeled token (k, v, q, dO, o of token 256): 40 threads
+    // fetch 16 bytes each; the NEXT item's vectors are requested under this item's dK / dV
+    // epilogue and parked in the other buffer, so no worker ever waits on these loads
+    auto tail_src = [&](int item_) -> const uint4* {
+      const int b_ = item_ / P.H, h_ = item_ % P.H;
+      const int which = tid >> 3, c = tid & 7;
+      const size_t rowq = ((size_t)b_ * T + 256) * 3 * W + h_ * 64 + c * 8;
+      const size_t rowd = ((size_t)b_ * T + 256) * W + h_ * 64 + c * 8;
+      const uint16_t* src = which == 0 ? P.qkv + rowq + colK : which == 1 ? P.qkv + rowq + colV
+                          : which == 2 ? P.qkv + rowq + colQ : which == 3 ? P.d_o + rowd
+                                                                          : P.o + rowd;
+      return reinterpret_cast<const uint4*>(src);
+    };
+    if (TAIL && tid < 40 && (int)blockIdx.x < n_items)
+      *reinterpret_cast<uint4*>(s_tv + tid * 8) = *tail_src(blockIdx.x);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     uint32_t g = 0;
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / P.H, h = item % P.H;
+      const uint16_t* tvb = s_tv + (it & 1) * 320;
+      const uint16_t* tv0 = tvb;              // k_256
+      const uint16_t* tv1 = tvb + 64;         // v_256
+      const uint16_t* tv2 = tvb + 128;        // q_256
+      const uint16_t* tv3 = tvb + 192;        // dO_256
+      const uint16_t* tv4 = tvb + 256;        // o_256 (forward format)
       float tdv = 0.f, tdk = 0.f;   // this thread's share of dv_256[d], dk_256[d] (d = tid & 63)
-      if (TAIL && tid < 32) {
-        const int which = tid >> 3, c = tid & 7;
-        const size_t rowq = ((size_t)b * T + 256) * 3 * W + h * 64 + c * 8;
-        const size_t rowd = ((size_t)b * T + 256) * W + h * 64 + c * 8;
-        const uint16_t* src = which == 0 ? P.qkv + rowq + colK : which == 1 ? P.qkv + rowq + colV
-                            : which == 2 ? P.qkv + rowq + colQ : P.d_o + rowd;
-        *reinterpret_cast<uint4*>(s_tv + which * 64 + c * 8) = *reinterpret_cast<const uint4*>(src);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (TAIL) {
         // ============ the peeled QUERY row (token 256) on the CUDA cores ============
         // p256[kv], ds256[kv] for all 257 keys; dq_256; kept for the dK / dV epilogue.
-        const size_t ro = ((size_t)b * T + 256) * W + h * 64;
-        const float D = dot_rows16(P.o + ro, P.fmt_o, P.d_o + ro, FMT);   // (latency under the K/V load)
+        const float D = dot_rows16(tv4, P.fmt_o, tv3, FMT);
         mbar_wait(bar_full, it & 1, 80);
         const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
         const float dpv = dot_swz_row<FMT>(s_v, tid, tv3);
@@ -1778,18 +1793,6 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         const size_t grow = (size_t)b * T + row;
         uint8_t* tq = s_tile0 + buf * 16384;
         uint8_t* tdo = s_tile1 + buf * 16384;
-        // D_r = o_r . dO_r: this thread's half of the row, requested now, reduced after the
-        // first TMEM sweep (the HBM / L2 latency hides under the tile load and the S MMA)
-        uint4 g_o[4], g_d[4];
-        {
-          const uint4* po = reinterpret_cast<const uint4*>(P.o + grow * W + h * 64 + hsel * 32);
-          const uint4* pd = reinterpret_cast<const uint4*>(P.d_o + grow * W + h * 64 + hsel * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            g_o[i] = po[i];
-            g_d[i] = pd[i];
-          }
-        }
         mbar_wait(&bar_tile[buf], (g >> 1) & 1, 81);
         float a_t = 0.f, b_t = 0.f;
         if (TAIL && hsel == 1) {
@@ -1827,22 +1830,16 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           if (TAIL && hsel == 1) m0 = fmaxf(m0, a_t);
         }
         s_red[hsel * 128 + r] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        // D_r = o_r . dO_r: this thread's half of the o row is requested HERE and consumed after
+        // the exp sweep (its HBM / L2 latency hides under ~2 us of MUFU work); the dO half comes
+        // from the TMA-loaded tile in shared memory
+        uint4 g_o[4];
         {
-          float dd = 0.f;
+          const uint4* po = reinterpret_cast<const uint4*>(P.o + grow * W + h * 64 + hsel * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t* pa = &g_o[i].x;
-            const uint32_t* pb = &g_d[i].x;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 x = unpack2(pa[u], P.fmt_o), y = unpackc<FMT>(pb[u]);
-              dd = fmaf(x.x, y.x, fmaf(x.y, y.y, dd));
-            }
-          }
-          s_dd[hsel * 128 + r] = dd;
+          for (int i = 0; i < 4; ++i) g_o[i] = po[i];
         }
         asm volatile("bar.sync 2, 256;" ::: "memory");
-        const float Dr = s_dd[r] + s_dd[128 + r];
         const float mc = fmaxf(s_red[r], s_red[128 + r]) * c2;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         {
@@ -1871,7 +1868,25 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           if (TAIL && hsel == 1) p_t = fast_ex2(fmaf(a_t, c2, -mc));
         }
         s_red2[hsel * 128 + r] = (s0 + s1) + (s2 + s3) + p_t;
+        {
+          float dd = 0.f;
+          const uint8_t* drow = tdo + r * 128;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 ud =
+                *reinterpret_cast<const uint4*>(drow + (((hsel * 4 + i) ^ (r & 7)) << 4));
+            const uint32_t* pa = &g_o[i].x;
+            const uint32_t* pb = &ud.x;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 x = unpack2(pa[u], P.fmt_o), y = unpackc<FMT>(pb[u]);
+              dd = fmaf(x.x, y.x, fmaf(x.y, y.y, dd));
+            }
+          }
+          s_dd[hsel * 128 + r] = dd;
+        }
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        const float Dr = s_dd[r] + s_dd[128 + r];
         const float rinv = 1.f / (s_red2[r] + s_red2[128 + r]);
         if (hsel == 0) {
           // fold 1/rowsum into this row of dO_i (used by dV = P^T dO' and dP' = dO' V^T)
@@ -1970,7 +1985,11 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         mbar_arrive(bar_acc_free);
       }
       // ---------------- dK / dV epilogue (accumulated over the q tiles) ----------------
-      // (bar_acc of the last tile, waited above, covers the dK / dV MMAs too)
+      uint4 tv_next = make_uint4(0u, 0u, 0u, 0u);
+      const bool tv_fetch = TAIL && tid < 40 && item + (int)gridDim.x < n_items;
+      if (tv_fetch) tv_next = *tail_src(item + gridDim.x);
+      mbar_wait(bar_dk, (g - 1) & 1, 85);   // the last tile's dK MMAs (dV retired earlier)
+      tc_fence_after();
       {
         const uint32_t base = hsel ? TDK : TDV;           // hsel 0: dV, hsel 1: dK
         const uint16_t* tvx = hsel ? tv2 : tv3;           // rank-1 term of the peeled query row
@@ -2023,6 +2042,7 @@ attn_bwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                                       (which ? colK : colV) + h * 64)[l2] = packc<FMT>(a0, a1);
         }
       }
+      if (tv_fetch) *reinterpret_cast<uint4*>(s_tv + ((it + 1) & 1) * 320 + tid * 8) = tv_next;
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
   }
@@ -2040,7 +2060,7 @@ static int launch_bwd3(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
                        const AttnBwd2Params& P, cudaStream_t st) {
   auto kern = attn_bwd3_kernel<FMT, TAIL>;
   const size_t smem = (size_t)2 * 256 * 128 + 4 * 16384 + (size_t)4 * 16384 +
-                      (272 * 2 + 256 * 4 + 512 + 16) * 4 + 512 + 128 + 1024;
+                      (272 * 2 + 256 * 4 + 512 + 16) * 4 + 2 * 640 + 128 + 1024;
   static bool set = false;
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

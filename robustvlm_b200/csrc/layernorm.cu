@@ -70,9 +70,11 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
 // drop_T > 0: rows with (row % drop_T == 0) (the CLS token of each image) are not
 // written and the remaining rows are compacted (used by the ln_pre backward, whose
 // consumer is the patch-embedding dgrad over patch rows only).
-template <int NV>
+// DY16: dy is a 16-bit matrix in `fmt` (the dgrad GEMM's epilogue output on the attack path:
+// 2 B/elem written + 2 read instead of 4 + 4).
+template <int NV, bool DY16>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float2* __restrict__ stats, const float* __restrict__ gamma,
               const float* dres, float* dx32,
               uint16_t* __restrict__ dx16, int M, int fmt, int drop_T) {
@@ -94,7 +96,14 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
   // reduction, so one round of memory latency covers all three streams
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    g[i] = reinterpret_cast<const float4*>(dy + (size_t)row * W)[i * 32 + lane];
+    if (DY16) {
+      const uint2 u =
+          reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy_) + (size_t)row * W)[i * 32 + lane];
+      const float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt);
+      g[i] = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      g[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * W)[i * 32 + lane];
+    }
     xh[i] = reinterpret_cast<const float4*>(x + (size_t)row * W)[i * 32 + lane];
   }
   if (dres) {
@@ -159,22 +168,37 @@ extern "C" int rvlm_layernorm_fwd(const float* x, const float* gamma, const floa
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
-extern "C" int rvlm_layernorm_bwd(const float* dy, const float* x, const float* stats,
-                                  const float* gamma, const float* dres, float* dx32, void* dx16,
-                                  int M, int W, int fmt, int drop_T, void* stream) {
+namespace {
+template <bool DY16>
+int launch_ln_bwd(const void* dy, const float* x, const float* stats, const float* gamma,
+                  const float* dres, float* dx32, void* dx16, int M, int W, int fmt, int drop_T,
+                  void* stream) {
   if (M <= 0) return RVLM_ERR_INVAL;
   const dim3 grid((M + LN_WARPS - 1) / LN_WARPS), block(LN_WARPS * 32);
   cudaStream_t st = (cudaStream_t)stream;
   uint16_t* d16 = reinterpret_cast<uint16_t*>(dx16);
   const float2* s = reinterpret_cast<const float2*>(stats);
   switch (W) {
-    case 128: ln_bwd_kernel<1><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
-    case 256: ln_bwd_kernel<2><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
-    case 768: ln_bwd_kernel<6><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
-    case 1024: ln_bwd_kernel<8><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
+    case 128: ln_bwd_kernel<1, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
+    case 256: ln_bwd_kernel<2, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
+    case 768: ln_bwd_kernel<6, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
+    case 1024: ln_bwd_kernel<8, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
     default: return RVLM_ERR_UNSUPPORTED;
   }
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+}  // namespace
+
+extern "C" int rvlm_layernorm_bwd(const float* dy, const float* x, const float* stats,
+                                  const float* gamma, const float* dres, float* dx32, void* dx16,
+                                  int M, int W, int fmt, int drop_T, void* stream) {
+  return launch_ln_bwd<false>(dy, x, stats, gamma, dres, dx32, dx16, M, W, fmt, drop_T, stream);
+}
+
+extern "C" int rvlm_layernorm_bwd16(const void* dy16, const float* x, const float* stats,
+                                    const float* gamma, const float* dres, float* dx32, void* dx16,
+                                    int M, int W, int fmt, int drop_T, void* stream) {
+  return launch_ln_bwd<true>(dy16, x, stats, gamma, dres, dx32, dx16, M, W, fmt, drop_T, stream);
 }

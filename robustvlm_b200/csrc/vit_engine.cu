@@ -16,6 +16,7 @@
 #include "engine_internal.cuh"
 #include "../../include/rvlm.h"
 
+#include <cstdlib>
 #include <vector>
 #include <new>
 
@@ -31,6 +32,8 @@ extern "C" int rvlm_layernorm_fwd(const float*, const float*, const float*, void
                                   int, int, int, void*);
 extern "C" int rvlm_layernorm_bwd(const float*, const float*, const float*, const float*,
                                   const float*, float*, void*, int, int, int, int, void*);
+extern "C" int rvlm_layernorm_bwd16(const void*, const float*, const float*, const float*,
+                                    const float*, float*, void*, int, int, int, int, void*);
 
 namespace {
 
@@ -52,6 +55,7 @@ struct Engine {
   uint16_t *conv_w, *conv_wT;
   std::vector<LayerDev> layers;
   int attn_simt = 0;
+  int ln_dz16 = 1;   // attack-path dgrad GEMMs hand LayerNorm' a 16-bit gradient (RVLM_LN_DZ16=0: fp32)
 };
 
 // ---- workspace carving --------------------------------------------------------
@@ -270,11 +274,18 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       EpiGeluBwd epi{w.dh16, F, h, ff, fg};
       RV((launch_gemm_kmajor(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
     }
-    {  // d ln_2 output
+    // d ln_2 output.  The gradient w.r.t. a LayerNorm output is handed over in the 16-bit
+    // gradient format (w.do16 is free at both hand-overs): every other link of this chain is
+    // already a 16-bit GEMM operand, and the LayerNorm' kernel is HBM-bound (18 -> 16 B/elem).
+    if (E.ln_dz16) {
+      EpiStore16 epi{w.do16, W, nullptr, fg};
+      RV((launch_gemm_kmajor(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
+      RV(rvlm_layernorm_bwd16(w.do16, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+    } else {
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
       RV((launch_gemm_kmajor(w.dh16, F, Lw.wfcT, F, M, W, F, fg, epi, st)));
+      RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
     }
-    RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
     {  // d attention output
       EpiStore16 epi{w.do16, W, nullptr, fg};
       RV((launch_gemm_kmajor(w.dx16, W, Lw.woT, W, M, W, W, fg, epi, st)));
@@ -282,12 +293,15 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     if (E.attn_simt)
       RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
-    {  // d ln_1 output
+    if (E.ln_dz16) {  // d ln_1 output
+      EpiStore16 epi{w.do16, W, nullptr, fg};
+      RV((launch_gemm_kmajor(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi, st)));
+      RV(rvlm_layernorm_bwd16(w.do16, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+    } else {
       EpiStore32 epi{w.dz32, W, nullptr, nullptr, 0};
-      RV((launch_gemm_kmajor(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi,
-                                           st)));
+      RV((launch_gemm_kmajor(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi, st)));
+      RV(rvlm_layernorm_bwd(w.dz32, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
     }
-    RV(rvlm_layernorm_bwd(w.dz32, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
   }
   // ln_pre backward, compacted to patch rows (the CLS row's input is a constant)
   RV(rvlm_layernorm_bwd(w.dx32, w.tok32, w.stats_pre, E.lnpre_g, nullptr, nullptr, w.dtok16, M, W,
@@ -474,6 +488,10 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
   for (int c = 0; c < 3; ++c) { E->geom.mean[c] = cfg->mean[c]; E->geom.inv_std[c] = 1.f / cfg->std[c]; }
   if (E->T > 272 || (E->kp & 3)) { delete E; return RVLM_ERR_UNSUPPORTED; }
   E->attn_simt = (cfg->flags & RVLM_VIT_ATTN_SIMT) ? 1 : 0;
+  {
+    const char* e = getenv("RVLM_LN_DZ16");
+    E->ln_dz16 = (e && e[0] == '0') ? 0 : 1;
+  }
   // size the slab
   const size_t W = E->W, F = E->F, D = E->D, L = E->L;
   size_t used = 0;

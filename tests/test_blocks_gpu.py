@@ -126,6 +126,15 @@ def test_layernorm_fwd_bwd(W):
     torch.cuda.synchronize()
     keep = torch.arange(M, device="cuda") % T != 0
     assert (dxc.float() - dx_ref[keep]).abs().max() < 5e-2
+    # 16-bit dy (the attack path's hand-over format): exact w.r.t. the rounded dy
+    dy16 = dy.to(torch.bfloat16)
+    (dx_ref16,) = torch.autograd.grad(F.layer_norm(x, (W,), g, b, 1e-5), x, dy16.float())
+    dx32b = dres.clone()
+    nat.call("rvlm_layernorm_bwd16", nat.ptr(dy16), nat.ptr(x.detach()), nat.ptr(stats), nat.ptr(g),
+             nat.ptr(dx32b), nat.ptr(dx32b), nat.ptr(dx16), nat.c_int(M), nat.c_int(W),
+             nat.c_int(1), nat.c_int(0), nat.stream_ptr())
+    torch.cuda.synchronize()
+    assert (dx32b - (dx_ref16 + dres)).abs().max() < 2e-5
 
 
 def _attn_ref(qkv, B, T, H):

@@ -160,6 +160,13 @@ int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H,
 int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16, float* lse_tmp,
                   void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o, int fmt_g,
                   void* stream);
+/* Class-token row only (the last block of the tower needs nothing else):
+ * forward writes o16[b*T, :] for every image b; backward takes the class-token output
+ * gradient do_cls16 [B, W] and writes the dense dqkv16 [B*T, 3W] (dQ rows t > 0 are zero).
+ * One 16-bit format for all operands of a call. */
+int rvlm_attn_cls_fwd(const void* qkv16, void* o16, int B, int T, int H, int fmt, void* stream);
+int rvlm_attn_cls_bwd(const void* qkv16, const void* do_cls16, void* dqkv16, int B, int T, int H,
+                      int fmt, void* stream);
 int rvlm_attn_fwd_simt(const void* qkv16, void* o16, float* lse, int B, int T, int H, int fmt,
                        void* stream);
 int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void* do16, float* lse_tmp,
@@ -176,6 +183,8 @@ int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void* do16, flo
 typedef void* rvlm_vit_handle;
 
 #define RVLM_VIT_ATTN_SIMT 1 /* flags: use the CUDA-core attention (debug / checker) */
+#define RVLM_VIT_FULL_LAST_BLOCK 2 /* flags: evaluate all T rows of the last block (default:
+                                      only the class-token row, the only one the output uses) */
 
 typedef struct {
   int image, patch, width, layers, heads, mlp, out_dim;

@@ -15,6 +15,15 @@ namespace rvlm {
 void count_launch(int n);
 constexpr int LN_WARPS = 8;
 
+// Row pitches in elements (W everywhere for a dense [M, W] matrix).  The last-block shortcut of
+// the engine runs LayerNorm on the B class-token rows of a [B*T, W] stream: pitch T*W.
+struct LnStrides {
+  long long x;    // input rows (forward: x; backward: x)
+  long long y;    // forward outputs y16 / y32; backward outputs dx32 / dx16
+  long long dy;   // backward: incoming gradient
+  long long res;  // backward: residual gradient
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
@@ -25,12 +34,13 @@ template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, uint16_t* __restrict__ y16,
-              float* __restrict__ y32, float2* __restrict__ stats, int M, int fmt) {
+              float* __restrict__ y32, float2* __restrict__ stats, int M, int fmt,
+              LnStrides sd) {
   constexpr int W = NV * 128;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * W);
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * sd.x);
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
@@ -56,12 +66,12 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
-    if (y32) reinterpret_cast<float4*>(y32 + (size_t)row * W)[i * 32 + lane] = o;
+    if (y32) reinterpret_cast<float4*>(y32 + (size_t)row * sd.y)[i * 32 + lane] = o;
     if (y16) {
       uint2 p;
       p.x = pack2(o.x, o.y, fmt);
       p.y = pack2(o.z, o.w, fmt);
-      reinterpret_cast<uint2*>(y16 + (size_t)row * W)[i * 32 + lane] = p;
+      reinterpret_cast<uint2*>(y16 + (size_t)row * sd.y)[i * 32 + lane] = p;
     }
   }
 }
@@ -77,7 +87,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
               const float2* __restrict__ stats, const float* __restrict__ gamma,
               const float* dres, float* dx32,
-              uint16_t* __restrict__ dx16, int M, int fmt, int drop_T) {
+              uint16_t* __restrict__ dx16, int M, int fmt, int drop_T, LnStrides sd) {
   constexpr int W = NV * 128;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -98,18 +108,18 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
   for (int i = 0; i < NV; ++i) {
     if (DY16) {
       const uint2 u =
-          reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy_) + (size_t)row * W)[i * 32 + lane];
+          reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(dy_) + (size_t)row * sd.dy)[i * 32 + lane];
       const float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt);
       g[i] = make_float4(a.x, a.y, b.x, b.y);
     } else {
-      g[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * W)[i * 32 + lane];
+      g[i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * sd.dy)[i * 32 + lane];
     }
-    xh[i] = reinterpret_cast<const float4*>(x + (size_t)row * W)[i * 32 + lane];
+    xh[i] = reinterpret_cast<const float4*>(x + (size_t)row * sd.x)[i * 32 + lane];
   }
   if (dres) {
 #pragma unroll
     for (int i = 0; i < NV; ++i)
-      res[i] = reinterpret_cast<const float4*>(dres + (size_t)row * W)[i * 32 + lane];
+      res[i] = reinterpret_cast<const float4*>(dres + (size_t)row * sd.res)[i * 32 + lane];
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -135,12 +145,12 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
       const float4 r = res[i];
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
-    if (dx32) reinterpret_cast<float4*>(dx32 + (size_t)orow * W)[i * 32 + lane] = o;
+    if (dx32) reinterpret_cast<float4*>(dx32 + (size_t)orow * sd.y)[i * 32 + lane] = o;
     if (dx16) {
       uint2 p;
       p.x = pack2(o.x, o.y, fmt);
       p.y = pack2(o.z, o.w, fmt);
-      reinterpret_cast<uint2*>(dx16 + (size_t)orow * W)[i * 32 + lane] = p;
+      reinterpret_cast<uint2*>(dx16 + (size_t)orow * sd.y)[i * 32 + lane] = p;
     }
   }
 }
@@ -149,18 +159,21 @@ ln_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x,
 
 using namespace rvlm;
 
-extern "C" int rvlm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16,
-                                  float* y32, float* stats, int M, int W, int fmt, void* stream) {
+namespace rvlm {
+// strided entry points (engine-internal); pitches in elements, 0 = dense (W)
+int ln_fwd_strided(const float* x, long long ldx, const float* gamma, const float* beta, void* y16,
+                   float* y32, long long ldy, float* stats, int M, int W, int fmt,
+                   cudaStream_t st) {
   if (M <= 0) return RVLM_ERR_INVAL;
   const dim3 grid((M + LN_WARPS - 1) / LN_WARPS), block(LN_WARPS * 32);
-  cudaStream_t st = (cudaStream_t)stream;
   uint16_t* y = reinterpret_cast<uint16_t*>(y16);
   float2* s = reinterpret_cast<float2*>(stats);
+  const LnStrides sd{ldx ? ldx : W, ldy ? ldy : W, 0, 0};
   switch (W) {
-    case 128: ln_fwd_kernel<1><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt); break;
-    case 256: ln_fwd_kernel<2><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt); break;
-    case 768: ln_fwd_kernel<6><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt); break;
-    case 1024: ln_fwd_kernel<8><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt); break;
+    case 128: ln_fwd_kernel<1><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
+    case 256: ln_fwd_kernel<2><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
+    case 768: ln_fwd_kernel<6><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
+    case 1024: ln_fwd_kernel<8><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
     default: return RVLM_ERR_UNSUPPORTED;
   }
   count_launch(1);
@@ -168,37 +181,51 @@ extern "C" int rvlm_layernorm_fwd(const float* x, const float* gamma, const floa
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
-namespace {
 template <bool DY16>
-int launch_ln_bwd(const void* dy, const float* x, const float* stats, const float* gamma,
-                  const float* dres, float* dx32, void* dx16, int M, int W, int fmt, int drop_T,
-                  void* stream) {
+int ln_bwd_strided_t(const void* dy, long long lddy, const float* x, long long ldx,
+                     const float* stats, const float* gamma, const float* dres, long long ldres,
+                     float* dx32, void* dx16, long long ldo, int M, int W, int fmt, int drop_T,
+                     cudaStream_t st) {
   if (M <= 0) return RVLM_ERR_INVAL;
   const dim3 grid((M + LN_WARPS - 1) / LN_WARPS), block(LN_WARPS * 32);
-  cudaStream_t st = (cudaStream_t)stream;
   uint16_t* d16 = reinterpret_cast<uint16_t*>(dx16);
   const float2* s = reinterpret_cast<const float2*>(stats);
+  const LnStrides sd{ldx ? ldx : W, ldo ? ldo : W, lddy ? lddy : W, ldres ? ldres : W};
   switch (W) {
-    case 128: ln_bwd_kernel<1, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
-    case 256: ln_bwd_kernel<2, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
-    case 768: ln_bwd_kernel<6, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
-    case 1024: ln_bwd_kernel<8, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T); break;
+    case 128: ln_bwd_kernel<1, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T, sd); break;
+    case 256: ln_bwd_kernel<2, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T, sd); break;
+    case 768: ln_bwd_kernel<6, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T, sd); break;
+    case 1024: ln_bwd_kernel<8, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T, sd); break;
     default: return RVLM_ERR_UNSUPPORTED;
   }
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
-}  // namespace
+int ln_bwd16_strided(const void* dy16, long long lddy, const float* x, long long ldx,
+                     const float* stats, const float* gamma, const float* dres, long long ldres,
+                     float* dx32, void* dx16, long long ldo, int M, int W, int fmt,
+                     cudaStream_t st) {
+  return ln_bwd_strided_t<true>(dy16, lddy, x, ldx, stats, gamma, dres, ldres, dx32, dx16, ldo, M,
+                                W, fmt, 0, st);
+}
+}  // namespace rvlm
+
+extern "C" int rvlm_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y16,
+                                  float* y32, float* stats, int M, int W, int fmt, void* stream) {
+  return ln_fwd_strided(x, 0, gamma, beta, y16, y32, 0, stats, M, W, fmt, (cudaStream_t)stream);
+}
 
 extern "C" int rvlm_layernorm_bwd(const float* dy, const float* x, const float* stats,
                                   const float* gamma, const float* dres, float* dx32, void* dx16,
                                   int M, int W, int fmt, int drop_T, void* stream) {
-  return launch_ln_bwd<false>(dy, x, stats, gamma, dres, dx32, dx16, M, W, fmt, drop_T, stream);
+  return ln_bwd_strided_t<false>(dy, 0, x, 0, stats, gamma, dres, 0, dx32, dx16, 0, M, W, fmt,
+                                 drop_T, (cudaStream_t)stream);
 }
 
 extern "C" int rvlm_layernorm_bwd16(const void* dy16, const float* x, const float* stats,
                                     const float* gamma, const float* dres, float* dx32, void* dx16,
                                     int M, int W, int fmt, int drop_T, void* stream) {
-  return launch_ln_bwd<true>(dy16, x, stats, gamma, dres, dx32, dx16, M, W, fmt, drop_T, stream);
+  return ln_bwd_strided_t<true>(dy16, 0, x, 0, stats, gamma, dres, 0, dx32, dx16, 0, M, W, fmt,
+                                drop_T, (cudaStream_t)stream);
 }

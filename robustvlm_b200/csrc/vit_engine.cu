@@ -35,6 +35,16 @@ extern "C" int rvlm_layernorm_bwd(const float*, const float*, const float*, cons
 extern "C" int rvlm_layernorm_bwd16(const void*, const float*, const float*, const float*,
                                     const float*, float*, void*, int, int, int, int, void*);
 
+namespace rvlm {
+int attn_cls_fwd(const void*, void*, int, int, int, int, cudaStream_t);
+int attn_cls_bwd(const void*, const void*, void*, int, int, int, int, cudaStream_t);
+int ln_fwd_strided(const float*, long long, const float*, const float*, void*, float*, long long,
+                   float*, int, int, int, cudaStream_t);
+int ln_bwd16_strided(const void*, long long, const float*, long long, const float*, const float*,
+                     const float*, long long, float*, void*, long long, int, int, int,
+                     cudaStream_t);
+}  // namespace rvlm
+
 namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -55,6 +65,7 @@ struct Engine {
   uint16_t *conv_w, *conv_wT;
   std::vector<LayerDev> layers;
   int attn_simt = 0;
+  int cls_last = 1;  // last block: class-token row only (flag RVLM_VIT_FULL_LAST_BLOCK / env RVLM_CLS_LAST=0 disable)
   int ln_dz16 = 1;   // attack-path dgrad GEMMs hand LayerNorm' a 16-bit gradient (RVLM_LN_DZ16=0: fp32)
 };
 
@@ -193,6 +204,26 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd};
       RV((launch_gemm_kmajor(y1, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
     }
+    if (l == E.L - 1 && E.cls_last && !train) {
+      // ---- last block, class-token rows only (row pitch T*W inside the [B*T, W] streams; the
+      // per-row operands of the MLP live compactly in the first B rows of their buffers)
+      const long long TW = (long long)E.T * W;
+      RV(attn_cls_fwd(w.qkvf16, o, B, E.T, E.H, ff, st));
+      {
+        EpiStore32 epi{xm, (int)TW, Lw.bo, x_in, (int)TW};
+        RV((launch_gemm_kmajor(o, (int)TW, Lw.wo, W, B, W, W, ff, epi, st)));
+      }
+      RV(ln_fwd_strided(xm, TW, Lw.ln2_g, Lw.ln2_b, w.y16, nullptr, 0, st2, B, W, ff, st));
+      {
+        EpiGelu epi{w.stash ? h : nullptr, w.act16, F, Lw.bfc, ff};
+        RV((launch_gemm_kmajor(w.y16, W, Lw.wfc, W, B, F, W, ff, epi, st)));
+      }
+      {
+        EpiStore32 epi{x_out, (int)TW, Lw.bpr, xm, (int)TW};
+        RV((launch_gemm_kmajor(w.act16, F, Lw.wpr, F, B, W, F, ff, epi, st)));
+      }
+      break;
+    }
     if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     else RV(rvlm_attn_fwd(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     {
@@ -270,6 +301,31 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     float* lse = w.lse + (size_t)l * B * E.H * E.T;  // scratch for the recomputed statistics
     const float* st1 = w.stats1 + (size_t)l * M * 2;
     const float* st2 = w.stats2 + (size_t)l * M * 2;
+    if (l == E.L - 1 && E.cls_last) {
+      // ---- last block: the incoming gradient is non-zero on the class-token rows only
+      const long long TW = (long long)E.T * W;
+      {
+        EpiGeluBwd epi{w.dh16, F, h, ff, fg};
+        RV((launch_gemm_kmajor(w.dx16, (int)TW, Lw.wprT, W, B, F, W, fg, epi, st)));
+      }
+      {
+        EpiStore16 epi{w.do16, W, nullptr, fg};
+        RV((launch_gemm_kmajor(w.dh16, F, Lw.wfcT, F, B, W, F, fg, epi, st)));
+      }
+      RV(ln_bwd16_strided(w.do16, 0, xm, TW, st2, Lw.ln2_g, w.dx32, TW, w.dx32, w.dx16, TW, B, W,
+                          fg, st));
+      {
+        EpiStore16 epi{w.do16, W, nullptr, fg};
+        RV((launch_gemm_kmajor(w.dx16, (int)TW, Lw.woT, W, B, W, W, fg, epi, st)));
+      }
+      RV(attn_cls_bwd(qkv, w.do16, w.dqkv16, B, E.T, E.H, fg, st));
+      {
+        EpiStore16 epi{w.do16, W, nullptr, fg};
+        RV((launch_gemm_kmajor(w.dqkv16, 3 * W, Lw.wqkvT, 3 * W, M, W, 3 * W, fg, epi, st)));
+      }
+      RV(rvlm_layernorm_bwd16(w.do16, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
+      continue;
+    }
     {  // d act -> d h (through QuickGELU)
       EpiGeluBwd epi{w.dh16, F, h, ff, fg};
       RV((launch_gemm_kmajor(w.dx16, W, Lw.wprT, W, M, F, W, fg, epi, st)));
@@ -488,6 +544,10 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
   for (int c = 0; c < 3; ++c) { E->geom.mean[c] = cfg->mean[c]; E->geom.inv_std[c] = 1.f / cfg->std[c]; }
   if (E->T > 272 || (E->kp & 3)) { delete E; return RVLM_ERR_UNSUPPORTED; }
   E->attn_simt = (cfg->flags & RVLM_VIT_ATTN_SIMT) ? 1 : 0;
+  {
+    const char* e = getenv("RVLM_CLS_LAST");
+    E->cls_last = ((cfg->flags & RVLM_VIT_FULL_LAST_BLOCK) || (e && e[0] == '0')) ? 0 : 1;
+  }
   {
     const char* e = getenv("RVLM_LN_DZ16");
     E->ln_dz16 = (e && e[0] == '0') ? 0 : 1;

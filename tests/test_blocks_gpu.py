@@ -190,6 +190,41 @@ def test_attention_fwd_bwd(impl, B, T, H, monkeypatch):
     assert err <= 3e-2 * scale
 
 
+@pytest.mark.parametrize("B,T,H", [(3, 257, 4), (2, 50, 2), (5, 257, 16)])
+def test_attention_cls_row(B, T, H):
+    """Class-token-only attention of the last block: forward row 0 and the dense dqkv it
+    induces, vs autograd of the full attention with an output gradient on row 0 only."""
+    nat = _nat()
+    torch.manual_seed(B + T + H)
+    W = H * 64
+    qkv = (torch.randn(B * T, 3 * W, device="cuda") * 1.5).half()
+    o = torch.full((B * T, W), 7.0, device="cuda", dtype=torch.half)
+    nat.call("rvlm_attn_cls_fwd", nat.ptr(qkv), nat.ptr(o), nat.c_int(B), nat.c_int(T), nat.c_int(H),
+             nat.c_int(0), nat.stream_ptr())
+    torch.cuda.synchronize()
+    o_ref, _ = _attn_ref(qkv.float(), B, T, H)
+    cls = torch.arange(B, device="cuda") * T
+    assert (o[cls].float() - o_ref[cls]).abs().max().item() < 4e-3
+    rest = torch.ones(B * T, dtype=torch.bool, device="cuda")
+    rest[cls] = False
+    assert bool((o[rest] == 7.0).all())                       # other rows untouched
+    qkv_b = qkv.float().bfloat16()
+    qb = qkv_b.float().requires_grad_(True)
+    o_b, _ = _attn_ref(qb, B, T, H)
+    d_cls = (torch.randn(B, W, device="cuda") * 0.1).bfloat16()
+    d_full = torch.zeros(B * T, W, device="cuda")
+    d_full[cls] = d_cls.float()
+    (dqkv_ref,) = torch.autograd.grad(o_b, qb, d_full)
+    dqkv = torch.full((B * T, 3 * W), float("nan"), device="cuda", dtype=torch.bfloat16)
+    nat.call("rvlm_attn_cls_bwd", nat.ptr(qkv_b), nat.ptr(d_cls), nat.ptr(dqkv), nat.c_int(B),
+             nat.c_int(T), nat.c_int(H), nat.c_int(1), nat.stream_ptr())
+    torch.cuda.synchronize()
+    err = (dqkv.float() - dqkv_ref).abs().max().item()
+    scale = dqkv_ref.abs().max().item()
+    _log("attn_cls_bwd", B=B, T=T, H=H, err=err, scale=scale)
+    assert err <= 1e-2 * scale
+
+
 @pytest.mark.parametrize("fmt", [0, 1])
 def test_ts_mma_operand_packing(fmt):
     """tcgen05.mma with A in TMEM: A[i,k] at lane i, 32-bit column k/2 (low half = even k)."""

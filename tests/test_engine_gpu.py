@@ -112,3 +112,27 @@ def test_pgd_run_matches_oracle(flags):
          loss_ours=loss_ours, loss_ref=loss_ref, trace=tr.mean(1).tolist())
     assert same > 0.9
     assert abs(loss_ours - loss_ref) <= 0.05 * abs(loss_ref)
+
+
+@pytest.mark.parametrize("name,B", [("tiny-32", 4), ("tiny-14", 3)])
+def test_last_block_shortcut_equals_full(name, B):
+    """The class-token-only evaluation of the last block (default) against the engine run
+    with every row of the last block computed (flag RVLM_VIT_FULL_LAST_BLOCK = 2): same
+    embedding and same input gradient up to the rounding of a different summation order."""
+    from robustvlm_b200.engine import LossSpec
+    eng_s, _ = make_engine(name, seed=1, flags=0)
+    eng_f, _ = make_engine(name, seed=1, flags=2)
+    model_orig = ovit.ClipVisionModel(ovit.build(name, seed=2)).eval()
+    x, d0 = synth_batch(B, seed=11)
+    with torch.no_grad():
+        e_orig = model_orig(x, output_normalize=False)
+    spec = LossSpec("l2", False, emb_orig=e_orig.cuda())
+    rs = eng_s.loss_grad(x.cuda(), spec, delta=d0.cuda())
+    rf = eng_f.loss_grad(x.cuda(), spec, delta=d0.cuda())
+    torch.cuda.synchronize()
+    e = rel_err(rs["emb"], rf["emb"])
+    gs, gf = rs["grad"].flatten(1).double(), rf["grad"].flatten(1).double()
+    cos = torch.nn.functional.cosine_similarity(gs, gf)
+    _log("cls_shortcut", model=name, emb_rel=e, cos_min=float(cos.min()))
+    assert e < 2e-4
+    assert float(cos.min()) > 0.9995

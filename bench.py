@@ -220,11 +220,24 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def gemm_traffic():
+    """Measured DRAM bytes per GEMM launch (mean over the four forward GEMM variants of one
+    block) from the committed ncu --set full capture; None when the summary is absent."""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d["mean_per_launch"], d["mean_algorithmic_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def workload_config(args, B):
     return {"workload": f"{args.model} FARE(l2) {ITERS}-step PGD linf eps=4/255 step=1/255, "
                         f"{B} synthetic 224x224x3 images per GPU, random-init weights",
             "per_gpu_batch": B, "chunk": args.chunk, "parallelism": f"dp{args.gpus}",
-            "l2_flush": "inputs larger than L2 (154 MB images + ~40 GB activations per step)"}
+            "l2_flush": "inputs larger than L2 (154 MB images + ~40 GB activations per step)",
+            "shortcuts": "last block evaluated on the class-token rows only (declared, "
+                         "SURVEY.md 8d); FLOP figures stay the full algorithmic ones"}
 
 
 def cpu_baseline_sample(model_name, seconds=20.0):
@@ -356,8 +369,12 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                         "traffic": None, "peak_source": f"{which} bf16_tflops_sustained",
-                         "kernel": "gemm16_kernel (tcgen05)", "launches": gemm_n,
+                         "traffic": gemm_traffic()[0],
+                         "traffic_algorithmic": gemm_traffic()[1],
+                         "traffic_source": "profiles/r01_gemm_traffic.json (ncu dram bytes per "
+                                           "launch, mean of the 4 forward GEMM variants)",
+                         "peak_source": f"{which} bf16_tflops_sustained",
+                         "kernel": "gemm16_2cta_kernel (tcgen05 cta_group::2, all epilogue variants)", "launches": gemm_n,
                          "gemm_ms_per_step": gemm_ms / args.steps,
                          "gemm_share_of_step": gemm_ms / ms if ms else None,
                          "whole_step_algorithmic_tflops": algo_tf / (ms / 1e3)},

@@ -105,6 +105,18 @@ int rvlm_pgd_update_l2(float* delta, float* velocity, const float* grad, const f
                        long long n, float stepsize, float eps, int maximize, float momentum,
                        float* workspace, void* stream);
 
+/* The same two updates for the VLM-evaluation attack (`PGD.perturb`, vlm_eval/attacks/pgd.py:21-73):
+ * `mask` (nullable, [B, n]) multiplies the gradient before the NaN scrub (:39, built by
+ * `_set_mask` :75-87); image_space = 0 skips delta = clamp(x+delta,0,1)-x (:57-59). */
+int rvlm_pgd_update_linf_masked(float* delta, float* velocity, const float* grad, const float* x,
+                                const float* mask, int image_space, int B, long long n,
+                                float stepsize, float eps, int maximize, float momentum,
+                                void* stream);
+int rvlm_pgd_update_l2_masked(float* delta, float* velocity, const float* grad, const float* x,
+                              const float* mask, int image_space, int B, long long n,
+                              float stepsize, float eps, int maximize, float momentum,
+                              float* workspace, void* stream);
+
 /* One APGD proposal step (train/apgd_train.py:205-254 == autoattack/autopgd_base.py:328-350).
  * In place: x_adv_old <- x_adv; x_adv <- new iterate.  step_size is per sample [B];
  * a = 1.0 on the first iteration, 0.75 afterwards. */
@@ -128,6 +140,8 @@ int rvlm_apgd_bookkeep(float* x_adv, float* grad, float* x_best, float* grad_bes
                        float* reduced_last, float* step_size, int* acc, int* flags, int B,
                        long long n, int n_iter, int iter, int k_check, float k_thr, void* stream);
 
+/* out = a * b elementwise (grad *= mask, vlm_eval/attacks/apgd.py:225,297); out may alias a */
+int rvlm_mul_f32(float* out, const float* a, const float* b, long long n, void* stream);
 /* out = a + b (x_adv = x + delta, train/pgd_train.py:68) */
 int rvlm_add_f32(float* out, const float* a, const float* b, long long n, void* stream);
 

@@ -178,9 +178,14 @@ def checkpoints(n_iter):
     return out
 
 
-def _apgd_step(norm, x, x_adv, x_adv_old, grad, step_size, eps, a, normalize_fn):
+def _apgd_step(norm, x, x_adv, x_adv_old, grad, step_size, eps, a, normalize_fn,
+               scale_then_divide=False):
     """One APGD proposal (train/apgd_train.py:205-254 == autopgd_base.py:328-350).
-    Returns (x_adv_new, x_adv_old_new)."""
+    Returns (x_adv_new, x_adv_old_new).  The ell_2 ascent direction is written
+    `step_size * grad / (||grad|| + 1e-12)` in train/apgd_train.py:232-235 and
+    vlm_eval/attacks/apgd.py:259-260 (multiply first: `scale_then_divide`) but
+    `step_size * normalize(grad)` in autopgd_base.py:343 -- one rounding apart unless the step
+    size is a power of two."""
     grad2 = x_adv - x_adv_old
     x_adv_old = x_adv.clone()
     if norm == "Linf":
@@ -189,7 +194,10 @@ def _apgd_step(norm, x, x_adv, x_adv_old, grad, step_size, eps, a, normalize_fn)
         z = torch.clamp(torch.min(torch.max(x_adv + (z - x_adv) * a + grad2 * (1 - a), x - eps),
                                   x + eps), 0.0, 1.0)
     elif norm == "L2":
-        z = x_adv + step_size * normalize_fn(grad)
+        if scale_then_divide:
+            z = x_adv + step_size * grad / (L2_norm(grad, keepdim=True) + 1e-12)
+        else:
+            z = x_adv + step_size * normalize_fn(grad)
         z = torch.clamp(x + normalize_fn(z - x) * torch.min(eps * torch.ones_like(x),
                                                             L2_norm(z - x, keepdim=True)), 0.0, 1.0)
         z = x_adv + (z - x_adv) * a + grad2 * (1 - a)
@@ -279,7 +287,7 @@ def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss_fn=None, ve
     for i in range(n_iter):                                                # :202
         a = 0.75 if i > 0 else 1.0
         x_adv, x_adv_old = _apgd_step(norm, x, x_adv.detach(), x_adv_old, grad, step_size, eps, a,
-                                      _l2_unit)
+                                      _l2_unit, scale_then_divide=True)
         logits, loss_indiv, g_new = fwd_bwd(x_adv, need_grad=i < n_iter - 1)  # :288-295
         if g_new is not None:
             grad = g_new

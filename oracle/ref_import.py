@@ -50,6 +50,8 @@ def load():
     apgd_base = importlib.import_module("autoattack.autopgd_base")
     ns.APGDAttack = apgd_base.APGDAttack
     ns.APGDAttack_targeted = apgd_base.APGDAttack_targeted
+    ns.vlm_pgd = importlib.import_module("vlm_eval.attacks.pgd")     # PGD
+    ns.vlm_apgd = importlib.import_module("vlm_eval.attacks.apgd")   # APGD, apgd
     try:
         atc = importlib.import_module("train.adversarial_training_clip")
         ns.ClipVisionModel = atc.ClipVisionModel

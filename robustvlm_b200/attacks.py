@@ -140,8 +140,10 @@ def apgd_schedule(n_iter):
     return (max(int(0.22 * n_iter), 1), max(int(0.06 * n_iter), 1), max(int(0.03 * n_iter), 1))
 
 
-def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_last_grad):
+def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_last_grad,
+               schedule=None):
     """fwd_bwd(x_adv, need_grad) -> (loss_indiv[B] f32, pred[B] int32, grad | None).
+    `schedule` overrides (k0, n_iter_min, size_decr) (vlm_eval/attacks/apgd.py:194-198).
     Returns (x_best, acc(bool), loss_best, x_best_adv)."""
     B, n, dev = x.shape[0], _flat_n(x), x.device
     x_adv = x_start.clamp(0.0, 1.0).contiguous()
@@ -158,7 +160,7 @@ def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_las
     loss_steps = torch.zeros(n_iter, B, device=dev, dtype=torch.float32)
     flags = torch.zeros(B, device=dev, dtype=torch.int32)
     ws = _upd_ws(B, dev) if norm == "L2" else None
-    k, k_min, k_decr = apgd_schedule(n_iter)
+    k, k_min, k_decr = apgd_schedule(n_iter) if schedule is None else schedule
     counter3 = 0
     for i in range(n_iter):
         a = 0.75 if i > 0 else 1.0

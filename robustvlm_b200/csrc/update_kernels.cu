@@ -51,8 +51,11 @@ __device__ __forceinline__ float sample_sum(const float* partial, int b) {
 // ---------------------------------------------------------------------------
 // PGD ell_inf: one fused pass.  grid = (blocks, B)
 // ---------------------------------------------------------------------------
+// `mask` (nullable) multiplies the gradient first (vlm_eval/attacks/pgd.py:39); image_space = 0
+// skips the [0,1] clamp (vlm_eval/attacks/pgd.py:57).
 __global__ void pgd_update_linf_kernel(float* __restrict__ delta, float* __restrict__ vel,
                                        const float* __restrict__ grad, const float* __restrict__ x,
+                                       const float* __restrict__ mask, int image_space,
                                        long long n, float stepsize, float eps, float dir,
                                        float momentum) {
   const long long base = (long long)blockIdx.y * n;
@@ -63,18 +66,23 @@ __global__ void pgd_update_linf_kernel(float* __restrict__ delta, float* __restr
     float4 d = reinterpret_cast<const float4*>(delta + base)[i];
     float4 v = reinterpret_cast<const float4*>(vel + base)[i];
     float4 xx = reinterpret_cast<const float4*>(x + base)[i];
-    float* gp = &g.x; float* dp = &d.x; float* vp = &v.x; float* xp = &xx.x;
+    float4 mk = mask ? reinterpret_cast<const float4*>(mask + base)[i]
+                     : make_float4(1.f, 1.f, 1.f, 1.f);
+    float* gp = &g.x; float* dp = &d.x; float* vp = &v.x; float* xp = &xx.x; float* mp = &mk.x;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float gj = gp[j];
+      float gj = mask ? __fmul_rn(mp[j], gp[j]) : gp[j];
       if (gj != gj) gj = 0.f;                                  // NaN scrub (:40-42)
       const float gs = fsign(gj);                              // normalize_grad (:44)
       const float m = __fadd_rn(__fmul_rn(momentum, vp[j]), gs);  // :46
       const float vn = fsign(m);                               // :47
       float dn = __fadd_rn(dp[j], __fmul_rn(__fmul_rn(stepsize, vn), dir));  // :49-52
       dn = fminf(fmaxf(dn, -eps), eps);                        // project (:56)
-      const float xa = fminf(fmaxf(__fadd_rn(xp[j], dn), 0.f), 1.f);
-      dp[j] = __fsub_rn(xa, xp[j]);                            // :57-59
+      if (image_space) {
+        const float xa = fminf(fmaxf(__fadd_rn(xp[j], dn), 0.f), 1.f);
+        dn = __fsub_rn(xa, xp[j]);                             // :57-59
+      }
+      dp[j] = dn;
       vp[j] = vn;
     }
     reinterpret_cast<float4*>(delta + base)[i] = d;
@@ -87,7 +95,8 @@ __global__ void pgd_update_linf_kernel(float* __restrict__ delta, float* __restr
 // ---------------------------------------------------------------------------
 // pass 1: partial[b][blk] = sum g^2 (NaN -> 0)
 __global__ void l2_sumsq_kernel(const float* __restrict__ a, const float* __restrict__ bsub,
-                                long long n, float* __restrict__ partial, int scrub_nan) {
+                                long long n, float* __restrict__ partial, int scrub_nan,
+                                const float* __restrict__ mask = nullptr) {
   __shared__ float sh[32];
   const long long base = (long long)blockIdx.y * n;
   float s = 0.f;
@@ -95,6 +104,7 @@ __global__ void l2_sumsq_kernel(const float* __restrict__ a, const float* __rest
        i += (long long)gridDim.x * blockDim.x) {
     float v = a[base + i];
     if (bsub) v = __fsub_rn(v, bsub[base + i]);
+    if (mask) v = __fmul_rn(mask[base + i], v);
     if (scrub_nan && v != v) v = 0.f;
     s = __fadd_rn(s, __fmul_rn(v, v));
   }
@@ -104,7 +114,7 @@ __global__ void l2_sumsq_kernel(const float* __restrict__ a, const float* __rest
 
 // pass 2: m = momentum*v + g / max(||g||, 1e-12)  -> vel (unnormalised); partial = sum m^2
 __global__ void pgd_l2_momentum_kernel(float* __restrict__ vel, const float* __restrict__ grad,
-                                       long long n, float momentum,
+                                       const float* __restrict__ mask, long long n, float momentum,
                                        const float* __restrict__ gpart,
                                        float* __restrict__ mpart) {
   __shared__ float sh[32];
@@ -115,6 +125,7 @@ __global__ void pgd_l2_momentum_kernel(float* __restrict__ vel, const float* __r
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float g = grad[base + i];
+    if (mask) g = __fmul_rn(mask[base + i], g);
     if (g != g) g = 0.f;
     const float m = __fadd_rn(__fmul_rn(momentum, vel[base + i]), __fdiv_rn(g, gn));
     vel[base + i] = m;
@@ -147,17 +158,21 @@ __global__ void pgd_l2_step_kernel(float* __restrict__ delta, float* __restrict_
 
 // pass 4: renorm (torch.renorm: rows with norm > eps scaled by eps/(norm+1e-7)), image clamp
 __global__ void pgd_l2_project_kernel(float* __restrict__ delta, const float* __restrict__ x,
-                                      long long n, float eps, const float* __restrict__ dpart) {
+                                      int image_space, long long n, float eps,
+                                      const float* __restrict__ dpart) {
   const int b = blockIdx.y;
   const long long base = (long long)b * n;
   const float dn = sqrtf(sample_sum(dpart, b));
   const float scale = dn > eps ? __fdiv_rn(eps, __fadd_rn(dn, 1e-7f)) : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
-    const float d = __fmul_rn(delta[base + i], scale);
-    const float xv = x[base + i];
-    const float xa = fminf(fmaxf(__fadd_rn(xv, d), 0.f), 1.f);
-    delta[base + i] = __fsub_rn(xa, xv);
+    float d = __fmul_rn(delta[base + i], scale);
+    if (image_space) {
+      const float xv = x[base + i];
+      const float xa = fminf(fmaxf(__fadd_rn(xv, d), 0.f), 1.f);
+      d = __fsub_rn(xa, xv);
+    }
+    delta[base + i] = d;
   }
 }
 
@@ -372,6 +387,18 @@ __global__ void add_kernel(float* __restrict__ out, const float* __restrict__ a,
   }
 }
 
+// out = a * b   (grad *= mask, vlm_eval/attacks/apgd.py:225,297)
+__global__ void mul_kernel(float* __restrict__ out, const float* __restrict__ a,
+                           const float* __restrict__ b, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+    x.x = __fmul_rn(x.x, y.x); x.y = __fmul_rn(x.y, y.y);
+    x.z = __fmul_rn(x.z, y.z); x.w = __fmul_rn(x.w, y.w);
+    reinterpret_cast<float4*>(out)[i] = x;
+  }
+}
+
 static inline dim3 upd_grid(long long work_items, int B) {
   long long blocks = (work_items + UPD_THREADS - 1) / UPD_THREADS;
   long long cap = (148LL * 8 + B - 1) / B;  // ~8 CTAs per SM in total
@@ -396,29 +423,47 @@ extern "C" size_t rvlm_update_workspace_bytes(int B) {
   return (size_t)B * RED_BLOCKS * sizeof(float) * 3;
 }
 
+extern "C" int rvlm_pgd_update_linf_masked(float* delta, float* velocity, const float* grad,
+                                           const float* x, const float* mask, int image_space,
+                                           int B, long long n, float stepsize, float eps,
+                                           int maximize, float momentum, void* stream) {
+  if (B <= 0 || n <= 0 || (n & 3)) return RVLM_ERR_INVAL;
+  pgd_update_linf_kernel<<<upd_grid(n >> 2, B), UPD_THREADS, 0, (cudaStream_t)stream>>>(
+      delta, velocity, grad, x, mask, image_space, n, stepsize, eps, maximize ? 1.f : -1.f,
+      momentum);
+  return cuda_rc();
+}
+
 extern "C" int rvlm_pgd_update_linf(float* delta, float* velocity, const float* grad,
                                     const float* x, int B, long long n, float stepsize, float eps,
                                     int maximize, float momentum, void* stream) {
-  if (B <= 0 || n <= 0 || (n & 3)) return RVLM_ERR_INVAL;
-  pgd_update_linf_kernel<<<upd_grid(n >> 2, B), UPD_THREADS, 0, (cudaStream_t)stream>>>(
-      delta, velocity, grad, x, n, stepsize, eps, maximize ? 1.f : -1.f, momentum);
-  return cuda_rc();
+  return rvlm_pgd_update_linf_masked(delta, velocity, grad, x, nullptr, 1, B, n, stepsize, eps,
+                                     maximize, momentum, stream);
 }
 
 extern "C" int rvlm_pgd_update_l2(float* delta, float* velocity, const float* grad, const float* x,
                                   int B, long long n, float stepsize, float eps, int maximize,
                                   float momentum, float* workspace, void* stream) {
+  return rvlm_pgd_update_l2_masked(delta, velocity, grad, x, nullptr, 1, B, n, stepsize, eps,
+                                   maximize, momentum, workspace, stream);
+}
+
+extern "C" int rvlm_pgd_update_l2_masked(float* delta, float* velocity, const float* grad,
+                                         const float* x, const float* mask, int image_space,
+                                         int B, long long n, float stepsize, float eps,
+                                         int maximize, float momentum, float* workspace,
+                                         void* stream) {
   if (B <= 0 || n <= 0 || !workspace) return RVLM_ERR_INVAL;
   cudaStream_t st = (cudaStream_t)stream;
   float* pg = workspace;
   float* pm = workspace + (size_t)B * RED_BLOCKS;
   float* pd = workspace + (size_t)2 * B * RED_BLOCKS;
   const dim3 grid(RED_BLOCKS, B);
-  l2_sumsq_kernel<<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, pg, 1);
-  pgd_l2_momentum_kernel<<<grid, UPD_THREADS, 0, st>>>(velocity, grad, n, momentum, pg, pm);
+  l2_sumsq_kernel<<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, pg, 1, mask);
+  pgd_l2_momentum_kernel<<<grid, UPD_THREADS, 0, st>>>(velocity, grad, mask, n, momentum, pg, pm);
   pgd_l2_step_kernel<<<grid, UPD_THREADS, 0, st>>>(delta, velocity, n, stepsize,
                                                    maximize ? 1.f : -1.f, pm, pd);
-  pgd_l2_project_kernel<<<grid, UPD_THREADS, 0, st>>>(delta, x, n, eps, pd);
+  pgd_l2_project_kernel<<<grid, UPD_THREADS, 0, st>>>(delta, x, image_space, n, eps, pd);
   return cuda_rc(4);
 }
 
@@ -461,6 +506,14 @@ extern "C" int rvlm_apgd_bookkeep(float* x_adv, float* grad, float* x_best, floa
                                                                       grad_best, x_best_adv, flags,
                                                                       n);
   return cuda_rc(2);
+}
+
+extern "C" int rvlm_mul_f32(float* out, const float* a, const float* b, long long n, void* stream) {
+  if (n <= 0 || (n & 3)) return RVLM_ERR_INVAL;
+  long long blocks = ((n >> 2) + UPD_THREADS - 1) / UPD_THREADS;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  mul_kernel<<<(unsigned)blocks, UPD_THREADS, 0, (cudaStream_t)stream>>>(out, a, b, n >> 2);
+  return cuda_rc();
 }
 
 extern "C" int rvlm_add_f32(float* out, const float* a, const float* b, long long n, void* stream) {

@@ -1,0 +1,163 @@
+"""BASELINE.json configs as parity / property tests, plus the edge cases of the call surface.
+
+  config 1  ViT-B/32 random-init, 1-step PGD ell_inf eps=4/255, batch 4, CPU reference:
+            the sign / clamp arithmetic bit-exact given the reference's gradient; end-to-end
+            delta identical except where the reference gradient is (near) zero.
+  config 3  ViT-L/14 TeCoA (CE-logit loss), 10-step PGD ell_inf eps=2/255   } full-size models at
+  config 4  ViT-L/14 APGD-CE ell_2 eps=2.0, 100 iterations (AutoAttack APGD) } reduced batch:
+            size-independent properties (constraints, determinism, attack strength).
+  edge cases of `pgd` (train/pgd_train.py:5-68): iterations = 0, perturbation = None, batch of
+  one, ragged micro-batches, the reference's exceptions.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import attacks as oa
+from oracle import vit as ovit
+
+pytestmark = pytest.mark.gpu
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _log(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "test_metrics.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **kw}) + "\n")
+    print(name, kw)
+
+
+def _ours(o):
+    from robustvlm_b200 import model as rm
+    cfg = o.cfg if hasattr(o, "cfg") else None
+    vt = rm.VisionTransformer(dict(image=cfg.image_size, patch=cfg.patch, width=cfg.width,
+                                   layers=cfg.layers, heads=cfg.heads, mlp=cfg.mlp,
+                                   out_dim=cfg.out_dim))
+    vt.load_state_dict(o.state_dict())
+    return rm.ClipVisionModel(vt.cuda(), None, None).eval()
+
+
+def test_config1_vitb32_one_step_pgd():
+    from robustvlm_b200 import _native as nat
+    from robustvlm_b200 import attacks, model as rm
+    from robustvlm_b200._native import c_float, c_int, c_int64
+    torch.manual_seed(0)                                  # train/adversarial_training_clip.py:532
+    o = ovit.build("ViT-B-32", seed=0)
+    ref_m = ovit.ClipVisionModel(o).eval()
+    ours = _ours(o)
+    B, eps, step = 4, 4 / 255, 1 / 255
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(B, 3, 224, 224, generator=g)
+    d0 = (torch.rand(B, 3, 224, 224, generator=g) * 2 - 1) * eps
+    with torch.no_grad():
+        e_orig = ref_m(x, output_normalize=False)         # FARE at step 0: frozen copy == model
+    wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+    ref = oa.pgd(ref_m, wrap, x, None, "linf", eps, 1, step, False, perturbation=d0.clone(),
+                 mode="max")
+    xa = (x + d0).requires_grad_(True)
+    (g_ref,) = torch.autograd.grad(wrap(ref_m(xa, output_normalize=False), None), xa)
+    # (a) the update arithmetic alone, given the reference's gradient: bit-exact
+    delta, vel = d0.clone().cuda(), torch.zeros_like(d0).cuda()
+    nat.call("rvlm_pgd_update_linf", nat.ptr(delta), nat.ptr(vel), nat.ptr(g_ref.cuda().contiguous()),
+             nat.ptr(x.cuda()), c_int(B), c_int64(3 * 224 * 224), c_float(step), c_float(eps),
+             c_int(1), c_float(0.9), nat.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(delta.cpu(), ref - x)
+    # (b) end to end through the fused engine
+    out = attacks.pgd(ours, rm.ComputeLossWrapper(e_orig.cuda(), None, "mean", "l2", 100.0), x.cuda(),
+                      None, "linf", eps, 1, step, False, perturbation=d0.clone().cuda(),
+                      mode="max").cpu()
+    mism = (out - x) != (ref - x)
+    med = g_ref.abs().median()
+    big = g_ref.abs() > 0.05 * med
+    frac, frac_big = float(mism.float().mean()), float((mism & big).float().sum() / big.sum())
+    _log("config1_vitb32", mismatch=int(mism.sum()), n=mism.numel(), frac=frac, frac_big=frac_big,
+         max_abs_delta_err=float(((out - x) - (ref - x)).abs().max()))
+    assert float((out - x).abs().max()) <= eps + 1e-6 and out.min() >= 0 and out.max() <= 1
+    assert frac < 0.04 and frac_big < 0.01
+
+
+@pytest.fixture(scope="module")
+def vitl():
+    from robustvlm_b200 import model as rm
+    vt = rm.VisionTransformer("ViT-L-14", seed=1).cuda()
+    g = torch.Generator().manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(768, 1000, generator=g), dim=0).cuda()
+    return rm.ClipVisionModel(vt, None, None).eval(), text, g
+
+
+def test_config3_tecoa_vitl14_properties(vitl):
+    from robustvlm_b200 import attacks, model as rm
+    m, text, g = vitl
+    B, eps = 16, 2 / 255
+    x = torch.rand(B, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, 1000, (B,), generator=g).cuda()
+    d0 = ((torch.rand(B, 3, 224, 224, generator=g) * 2 - 1) * eps).cuda()
+    wrap = rm.ComputeLossWrapper(None, text, "mean", "ce", 100.0)
+    run = lambda **k: attacks.pgd(m, wrap, x, y, "linf", eps, 10, 1 / 255, True,  # noqa: E731
+                                  perturbation=d0, mode="max", **k)
+    a, b, c = run(), run(), run(chunk=5)                   # ragged micro-batches: 5 + 5 + 5 + 1
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    assert float((a - x).abs().max()) <= eps + 1e-6 and float(a.min()) >= 0 and float(a.max()) <= 1
+    with torch.no_grad():
+        l0 = float(wrap(m(x + d0, output_normalize=True), y))
+        l1 = float(wrap(m(a, output_normalize=True), y))
+    _log("config3_tecoa_vitl14", ce_start=l0, ce_adv=l1)
+    assert l1 > l0 + 1.0
+
+
+def test_config4_apgd_l2_vitl14_properties(vitl):
+    from robustvlm_b200 import attacks, model as rm
+    m, text, g = vitl
+    B, eps = 8, 2.0
+    x = torch.rand(B, 3, 224, 224, generator=g).cuda()
+    cm = rm.ClassificationModel(m, text)
+    with torch.no_grad():
+        y = cm(x).argmax(1)                                # all points start robust (§8d config 4)
+    atk = attacks.APGDAttack(cm, n_iter=100, norm="L2", n_restarts=1, eps=eps, seed=0, alpha=2.0)
+    adv = atk.perturb(x, y)
+    adv2 = atk.perturb(x, y)                               # perturb() reseeds the CPU RNG (:505)
+    torch.cuda.synchronize()
+    l2 = (adv - x).flatten(1).norm(dim=1)
+    with torch.no_grad():
+        racc = float((cm(adv).argmax(1) == y).float().mean())
+    _log("config4_apgd_l2_vitl14", robust_acc=racc, max_l2=float(l2.max()))
+    assert torch.equal(adv, adv2)
+    assert float(l2.max()) <= eps * (1 + 1e-4) and float(adv.min()) >= 0 and float(adv.max()) <= 1
+    assert racc <= 0.25       # a random-init tower has no robustness at eps = 2.0
+
+
+def test_pgd_edge_cases():
+    from robustvlm_b200 import attacks, model as rm
+    o = ovit.build("tiny-32", seed=5)
+    ours, ref_m = _ours(o), ovit.ClipVisionModel(o).eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 3, 224, 224, generator=g)
+    d0 = (torch.rand(5, 3, 224, 224, generator=g) * 2 - 1) * 4 / 255
+    with torch.no_grad():
+        eo = ovit.ClipVisionModel(ovit.build("tiny-32", seed=6)).eval()(x, output_normalize=False)
+    w = rm.ComputeLossWrapper(eo.cuda(), None, "mean", "l2", 100.0)
+    wr = oa.ComputeLossWrapper(eo, None, "mean", "l2", 100.0)
+    kw = dict(norm="linf", eps=4 / 255, stepsize=1 / 255, output_normalize=False, mode="max")
+    # iterations = 0: x + perturbation, untouched (the loop body never runs, :29)
+    out0 = attacks.pgd(ours, w, x.cuda(), None, iterations=0, perturbation=d0.cuda(), **kw)
+    assert torch.equal(out0.cpu(), oa.pgd(ref_m, wr, x, None, iterations=0,
+                                          perturbation=d0.clone(), **kw))
+    # perturbation = None starts from zeros (:26-27); batch of one; ragged micro-batches
+    a = attacks.pgd(ours, w, x.cuda(), None, iterations=2, **kw)
+    b = attacks.pgd(ours, w, x.cuda(), None, iterations=2, chunk=2, **kw)
+    one = attacks.pgd(ours, rm.ComputeLossWrapper(eo[:1].cuda(), None, "mean", "l2", 100.0),
+                      x[:1].cuda(), None, iterations=2, **kw)
+    ref = oa.pgd(ref_m, wr, x, None, iterations=2, **kw)
+    assert torch.equal(a, b) and torch.equal(a[:1], one)
+    assert float(((a.cpu() - x) == (ref - x)).float().mean()) > 0.97
+    # the reference's exceptions
+    with pytest.raises(AssertionError):                    # :24 data outside [0, 1]
+        attacks.pgd(ours, w, (x + 0.5).cuda(), None, iterations=1, **kw)
+    with pytest.raises(ValueError):                        # :54
+        attacks.pgd(ours, w, x.cuda(), None, iterations=1, **{**kw, "mode": "up"})
+    with pytest.raises(NotImplementedError):               # vlm_eval/attacks/utils.py:16
+        attacks.pgd(ours, w, x.cuda(), None, iterations=1, **{**kw, "norm": "l1"})

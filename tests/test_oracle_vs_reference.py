@@ -40,7 +40,7 @@ def test_pgd(ns, setup, norm, eps, step, mode):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("norm,eps", [("linf", 4 / 255), ("l2", 2.0)])
+@pytest.mark.parametrize("norm,eps", [("linf", 4 / 255), ("l2", 2.0), ("l2", 1.5)])
 @pytest.mark.parametrize("n_iter", [10, 25])
 def test_apgd_train(ns, setup, norm, eps, n_iter):
     m, x, d0, y, text, eo = setup
@@ -51,7 +51,7 @@ def test_apgd_train(ns, setup, norm, eps, n_iter):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 2.0)])
+@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 2.0), ("L2", 1.5)])
 @pytest.mark.parametrize("loss", ["ce", "dlr"])
 def test_apgd_attack(ns, setup, norm, eps, loss):
     m, x, d0, y, text, eo = setup

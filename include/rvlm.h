@@ -331,10 +331,15 @@ int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t workspace_by
                          const rvlm_vit_grads* grads, float* loss_out, float* emb_out,
                          void* stream);
 /* torch.optim.AdamW semantics on a flat fp32 buffer (train/adversarial_training_clip.py:196-197,363):
- * decoupled weight decay, bias correction with the 1-based step count. */
+ * decoupled weight decay, bias correction with the 1-based step count.
+ * Hyper-parameters are doubles (what torch.optim holds); bias corrections formed in double. */
 int rvlm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                    long long n, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, void* stream);
+                    long long n, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, int step, void* stream);
+/* torch.optim.SGD semantics (`--opt sgd`, train/adversarial_training_clip.py:198-204): coupled
+ * weight decay, momentum buffer initialised with the first gradient (step == 1), no dampening. */
+int rvlm_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, double lr,
+                  double momentum, double weight_decay, int step, void* stream);
 
 /* Self-test of tcgen05.mma with the A operand in TMEM: C[128,64] = A[128,64] * B[64,64]^T
  * (16-bit A, B row-major; fp32 C). */

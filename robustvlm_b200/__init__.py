@@ -6,7 +6,8 @@ Importing the package does not need a GPU; calling into it does (no CPU fallback
 """
 from . import _native  # noqa: F401
 
-__all__ = ["attacks", "engine", "model"]
+__all__ = ["attacks", "autoattack", "checkpoint", "engine", "model", "parallel", "train",
+           "vlm_attacks"]
 
 
 def __getattr__(name):

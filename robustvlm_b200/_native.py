@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p, c_size_t
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, c_size_t
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "librvlm_b200.so")
@@ -71,5 +71,5 @@ def call(name: str, *args) -> None:
 
 __all__ = [
     "lib", "check", "ptr", "stream_ptr", "call", "declared_symbols", "RvlmError", "LIB_PATH",
-    "c_int", "c_float", "c_void_p", "c_int64", "c_size_t",
+    "c_int", "c_float", "c_double", "c_void_p", "c_int64", "c_size_t",
 ]

@@ -121,6 +121,22 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// torch.optim.SGD semantics (coupled weight decay, momentum without dampening / Nesterov).
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g,
+                           float* __restrict__ buf, long long n, float lr, float momentum,
+                           float wd, int first) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    float gi = g[i] + wd * pi;
+    if (momentum != 0.f) {
+      gi = first ? gi : momentum * buf[i] + gi;
+      buf[i] = gi;
+    }
+    p[i] = pi - lr * gi;
+  }
+}
+
 static inline int rc(int n = 1) {
   count_launch(n);
   cudaError_t e = cudaGetLastError();
@@ -166,14 +182,28 @@ int launch_head_param_grads(const float* pooled, const float* demb, const float*
 using namespace rvlm;
 
 extern "C" int rvlm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
-                               long long n, float lr, float beta1, float beta2, float eps,
-                               float weight_decay, int step, void* stream) {
+                               long long n, double lr, double beta1, double beta2, double eps,
+                               double weight_decay, int step, void* stream) {
   if (n <= 0 || step < 1) return RVLM_ERR_INVAL;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
+  // hyper-parameters arrive as the Python doubles torch.optim holds; the bias corrections are
+  // formed in double as torch does (1 - beta ** step), then rounded once for the kernel
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+      param, grad, exp_avg, exp_avg_sq, n, (float)lr, (float)beta1, (float)beta2, (float)eps,
+      (float)weight_decay, (float)bc1, (float)sqrt(bc2));
+  return rc();
+}
+
+extern "C" int rvlm_sgd_step(float* param, const float* grad, float* momentum_buf, long long n,
+                             double lr, double momentum, double weight_decay, int step,
+                             void* stream) {
+  if (n <= 0 || step < 1 || (momentum != 0.0 && !momentum_buf)) return RVLM_ERR_INVAL;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sgd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      param, grad, momentum_buf, n, (float)lr, (float)momentum, (float)weight_decay, step == 1);
   return rc();
 }

@@ -72,10 +72,29 @@ def test_adamw_matches_torch():
         ref_p.grad = g.clone()
         opt.step()
         nat.call("rvlm_adamw_step", nat.ptr(p), nat.ptr(g), nat.ptr(m), nat.ptr(v), nat.c_int64(n),
-                 nat.c_float(1e-3), nat.c_float(0.9), nat.c_float(0.95), nat.c_float(1e-8),
-                 nat.c_float(1e-2), nat.c_int(step), nat.stream_ptr())
+                 nat.c_double(1e-3), nat.c_double(0.9), nat.c_double(0.95), nat.c_double(1e-8),
+                 nat.c_double(1e-2), nat.c_int(step), nat.stream_ptr())
         torch.cuda.synchronize()
-        assert float((p - ref_p.detach()).abs().max()) < 2e-6
+        assert float((p - ref_p.detach()).abs().max()) < 1e-6
+
+
+def test_sgd_matches_torch():
+    from robustvlm_b200 import _native as nat
+    torch.manual_seed(1)
+    n = 10007
+    p = torch.randn(n, device="cuda")
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([ref_p], lr=1e-2, momentum=0.9, weight_decay=1e-3)
+    buf = torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(n, device="cuda")
+        ref_p.grad = g.clone()
+        opt.step()
+        nat.call("rvlm_sgd_step", nat.ptr(p), nat.ptr(g), nat.ptr(buf), nat.c_int64(n),
+                 nat.c_double(1e-2), nat.c_double(0.9), nat.c_double(1e-3), nat.c_int(step),
+                 nat.stream_ptr())
+        torch.cuda.synchronize()
+        assert float((p - ref_p.detach()).abs().max()) < 1e-6
 
 
 def test_fare_training_loop_reduces_loss():
@@ -98,3 +117,118 @@ def test_fare_training_loop_reduces_loss():
     _log("fare_loop", losses=losses)
     assert all(l == l for l in losses)
     assert losses[-1] < 0.7 * losses[0]
+
+
+def _pair(name, seed=1, seed_orig=None):
+    from robustvlm_b200 import model as rm
+    o = ovit.build(name, seed=seed)
+    oo = ovit.build(name, seed=seed if seed_orig is None else seed_orig)
+    vt, vto = rm.VisionTransformer(name), rm.VisionTransformer(name)
+    vt.load_state_dict(o.state_dict())
+    vto.load_state_dict(oo.state_dict())
+    return (rm.ClipVisionModel(vt.cuda(), None, None), rm.ClipVisionModel(vto.cuda(), None, None).eval(),
+            o, oo)
+
+
+def test_trainer_follows_reference_loop():
+    """attack = 'none' (no attack noise): the trainer against the reference's own step sequence
+    (train/adversarial_training_clip.py:340-366) replayed on CPU with the oracle tower,
+    torch.optim.AdamW (torch defaults, :197) and cosine_lr called AFTER the step (:366).  The lr
+    sequence must be identical (first step at the constructor lr); the loss trajectory must agree
+    within 3 % (bf16 engine vs fp32 autograd)."""
+    from robustvlm_b200.train import AdversarialTrainer, cosine_lr
+    name, B, steps, lr, wd, warm = "tiny-32", 8, 6, 2e-4, 1e-4, 3
+    m, mo, o, oo = _pair(name, seed=1, seed_orig=2)
+    tr = AdversarialTrainer(m, mo, lr=lr, wd=wd, steps=40, warmup=warm, attack="none", loss="l2")
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand(B, 3, 224, 224, generator=g)
+    ref_m, ref_o = ovit.ClipVisionModel(o).train(), ovit.ClipVisionModel(oo).eval()
+    opt = torch.optim.AdamW(o.parameters(), lr=lr, weight_decay=wd)
+    lr_at = cosine_lr(lr, warm, 40)
+    ours, ref, lrs_o, lrs_r = [], [], [], []
+    for s in range(steps):
+        log = tr.train_step(data.cuda(), None)
+        ours.append(float(log["loss"]))
+        lrs_o.append(log["lr"])
+        with torch.no_grad():
+            eo = ref_o(data, output_normalize=False)
+        loss = oa.compute_loss("l2", ref_m(data, output_normalize=False), None, eo, 100.0, None)
+        lrs_r.append(opt.param_groups[0]["lr"])
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        opt.param_groups[0]["lr"] = lr_at(s + 1)
+        ref.append(float(loss))
+    _log("trainer_vs_reference_loop", ours=ours, ref=ref, lrs=lrs_o)
+    assert lrs_o == lrs_r and lrs_o[0] == lr
+    assert ref[-1] < 0.9 * ref[0]
+    for a, b in zip(ours, ref):
+        assert abs(a - b) <= 0.03 * abs(b), (ours, ref)
+
+
+@pytest.mark.parametrize("variant", ["clean_weight", "trades", "apgd_tecoa", "sgd"])
+def test_trainer_variants(variant):
+    """--clean_weight / --trades / --attack apgd with the TeCoA loss / --opt sgd run, reduce
+    their loss and report the reference's log fields (:368-385)."""
+    from robustvlm_b200.train import AdversarialTrainer
+    name, B = "tiny-32", 8
+    m, mo, o, oo = _pair(name, seed=1, seed_orig=2)
+    g = torch.Generator().manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(o.cfg.out_dim, 10, generator=g), dim=0).cuda()
+    kw = dict(lr=3e-4, wd=1e-4, steps=40, warmup=2, iterations=2, text_embedding=text)
+    if variant == "clean_weight":
+        kw.update(clean_weight=0.5, loss_clean="l2")
+    elif variant == "trades":
+        kw.update(trades=True)
+    elif variant == "apgd_tecoa":
+        kw.update(attack="apgd", loss="ce", inner_loss="ce", output_normalize=True, lr=1e-3)
+    else:
+        kw.update(opt="sgd", lr=1e-4)
+    tr = AdversarialTrainer(m, mo, **kw)
+    data = torch.rand(B, 3, 224, 224, generator=g).cuda()
+    y = torch.randint(0, 10, (B,), generator=g).cuda()
+    logs = [tr.train_step(data, y) for _ in range(8)]
+    tot = [float(l["loss_total"]) for l in logs]
+    _log("trainer_variant", variant=variant, loss_total=tot, acc=logs[-1]["acc"],
+         racc=logs[-1]["racc"], cos=float(logs[-1]["cos_sim"]))
+    assert all(t == t for t in tot)
+    if variant in ("clean_weight", "apgd_tecoa"):   # Adam at these rates makes clear progress;
+        assert tot[-1] < tot[0]                     # TRADES' target moves, SGD's rate is untuned
+    assert 0.0 <= logs[-1]["acc"] <= 100.0 and 0.0 <= logs[-1]["racc"] <= 100.0
+    assert -1.0 <= float(logs[-1]["cos_sim_clean"]) <= 1.0 + 1e-6
+    if variant == "clean_weight":
+        l0 = logs[0]                                                            # :361
+        mix = 0.5 * float(l0["loss_clean"]) + 0.5 * float(l0["loss"])
+        assert abs(float(l0["loss_total"]) - mix) <= 1e-5 * abs(mix)
+    ev = tr.evaluate(data, y, n_iter=5)
+    assert set(ev) == {"eval/racc", "eval/acc", "eval/cos-sim"} and ev["eval/racc"] <= ev["eval/acc"]
+
+
+def test_trainer_checkpoint_resume(tmp_path):
+    """Save in the reference's formats, resume in a fresh trainer (`--pretrained`,
+    `--optimizer_state`, `--start_step`, :93-103,207-208,219): the resumed run reproduces the
+    uninterrupted one bit for bit (attack = 'none' keeps the step deterministic), and
+    torch.optim.AdamW accepts the optimizer file."""
+    from robustvlm_b200.train import AdversarialTrainer
+    name, B = "tiny-32", 4
+    g = torch.Generator().manual_seed(0)
+    data = torch.rand(B, 3, 224, 224, generator=g).cuda()
+    kw = dict(lr=2e-4, wd=1e-4, steps=40, warmup=3, attack="none")
+    m, mo, o, oo = _pair(name, seed=1, seed_orig=2)
+    a = AdversarialTrainer(m, mo, **kw)
+    for _ in range(3):
+        a.train_step(data, None)
+    a.save(str(tmp_path), "step_3")
+    tail_a = [float(a.train_step(data, None)["loss"]) for _ in range(3)]
+    m2, mo2, _, _ = _pair(name, seed=5, seed_orig=2)
+    b = AdversarialTrainer(m2, mo2, start_step=3, **kw)
+    b.load_model_state_dict(str(tmp_path / "checkpoints" / "step_3.pt"))
+    opt_sd = torch.load(str(tmp_path / "checkpoints" / "step_3_opt.pt"))
+    b.load_optimizer_state_dict(opt_sd)
+    tail_b = [float(b.train_step(data, None)["loss"]) for _ in range(3)]
+    assert tail_a == tail_b
+    assert torch.equal(a.flat_p, b.flat_p) and torch.equal(a.flat_m, b.flat_m)
+    ref_opt = torch.optim.AdamW(ovit.build(name, seed=1).parameters(), lr=1.0)
+    ref_opt.load_state_dict(opt_sd)
+    assert ref_opt.param_groups[0]["lr"] == a.lr_at(3) and len(ref_opt.state_dict()["state"]) == len(
+        a.layout)

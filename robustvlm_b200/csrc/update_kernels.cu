@@ -41,11 +41,36 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
   return t;  // valid in warp 0
 }
 
+// Sum of the RED_BLOCKS partial sums of sample b: one value per lane, xor-shuffle tree (a fixed
+// order, so every pass of every launch forms bitwise the same norm).  Must be called by full
+// warps before any divergence.
 __device__ __forceinline__ float sample_sum(const float* partial, int b) {
-  float s = 0.f;
-#pragma unroll 8
-  for (int i = 0; i < RED_BLOCKS; ++i) s += partial[b * RED_BLOCKS + i];
-  return s;
+  static_assert(RED_BLOCKS == 32, "one partial sum per lane");
+  float v = partial[b * RED_BLOCKS + (threadIdx.x & 31)];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffff, v, o);
+  return v;
+}
+
+// Element loops of the multi-pass kernels: float4 accesses when n % 4 == 0 (every image shape),
+// scalar otherwise.  `body(idx, k)` sees k = 4 or 1 consecutive elements starting at base + idx.
+template <int V> struct Pack { float v[V]; };
+template <int V> __device__ __forceinline__ Pack<V> ldp(const float* p, long long idx) {
+  Pack<V> r;
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + idx);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+    r.v[0] = p[idx];
+  }
+  return r;
+}
+template <int V> __device__ __forceinline__ void stp(float* p, long long idx, const Pack<V>& r) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p + idx) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else {
+    p[idx] = r.v[0];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -94,25 +119,33 @@ __global__ void pgd_update_linf_kernel(float* __restrict__ delta, float* __restr
 // PGD ell_2: four passes, three deterministic per-sample reductions.
 // ---------------------------------------------------------------------------
 // pass 1: partial[b][blk] = sum g^2 (NaN -> 0)
+template <int V>
 __global__ void l2_sumsq_kernel(const float* __restrict__ a, const float* __restrict__ bsub,
                                 long long n, float* __restrict__ partial, int scrub_nan,
-                                const float* __restrict__ mask = nullptr) {
+                                const float* __restrict__ mask) {
   __shared__ float sh[32];
   const long long base = (long long)blockIdx.y * n;
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float v = a[base + i];
-    if (bsub) v = __fsub_rn(v, bsub[base + i]);
-    if (mask) v = __fmul_rn(mask[base + i], v);
-    if (scrub_nan && v != v) v = 0.f;
-    s = __fadd_rn(s, __fmul_rn(v, v));
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    Pack<V> va = ldp<V>(a, base + i), vb, vm;
+    if (bsub) vb = ldp<V>(bsub, base + i);
+    if (mask) vm = ldp<V>(mask, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float v = va.v[j];
+      if (bsub) v = __fsub_rn(v, vb.v[j]);
+      if (mask) v = __fmul_rn(vm.v[j], v);
+      if (scrub_nan && v != v) v = 0.f;
+      s = __fadd_rn(s, __fmul_rn(v, v));
+    }
   }
   const float t = block_sum(s, sh);
   if (threadIdx.x == 0) partial[blockIdx.y * RED_BLOCKS + blockIdx.x] = t;
 }
 
 // pass 2: m = momentum*v + g / max(||g||, 1e-12)  -> vel (unnormalised); partial = sum m^2
+template <int V>
 __global__ void pgd_l2_momentum_kernel(float* __restrict__ vel, const float* __restrict__ grad,
                                        const float* __restrict__ mask, long long n, float momentum,
                                        const float* __restrict__ gpart,
@@ -122,20 +155,27 @@ __global__ void pgd_l2_momentum_kernel(float* __restrict__ vel, const float* __r
   const long long base = (long long)b * n;
   const float gn = fmaxf(sqrtf(sample_sum(gpart, b)), 1e-12f);
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float g = grad[base + i];
-    if (mask) g = __fmul_rn(mask[base + i], g);
-    if (g != g) g = 0.f;
-    const float m = __fadd_rn(__fmul_rn(momentum, vel[base + i]), __fdiv_rn(g, gn));
-    vel[base + i] = m;
-    s = __fadd_rn(s, __fmul_rn(m, m));
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    Pack<V> g = ldp<V>(grad, base + i), v = ldp<V>(vel, base + i), vm;
+    if (mask) vm = ldp<V>(mask, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float gj = g.v[j];
+      if (mask) gj = __fmul_rn(vm.v[j], gj);
+      if (gj != gj) gj = 0.f;
+      const float m = __fadd_rn(__fmul_rn(momentum, v.v[j]), __fdiv_rn(gj, gn));
+      v.v[j] = m;
+      s = __fadd_rn(s, __fmul_rn(m, m));
+    }
+    stp<V>(vel, base + i, v);
   }
   const float t = block_sum(s, sh);
   if (threadIdx.x == 0) mpart[b * RED_BLOCKS + blockIdx.x] = t;
 }
 
 // pass 3: v = m / max(||m||,1e-12); delta += dir*step*v; partial = sum delta^2
+template <int V>
 __global__ void pgd_l2_step_kernel(float* __restrict__ delta, float* __restrict__ vel, long long n,
                                    float stepsize, float dir, const float* __restrict__ mpart,
                                    float* __restrict__ dpart) {
@@ -144,19 +184,26 @@ __global__ void pgd_l2_step_kernel(float* __restrict__ delta, float* __restrict_
   const long long base = (long long)b * n;
   const float mn = fmaxf(sqrtf(sample_sum(mpart, b)), 1e-12f);
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float v = __fdiv_rn(vel[base + i], mn);
-    vel[base + i] = v;
-    const float d = __fadd_rn(delta[base + i], __fmul_rn(__fmul_rn(stepsize, v), dir));
-    delta[base + i] = d;
-    s = __fadd_rn(s, __fmul_rn(d, d));
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    Pack<V> v = ldp<V>(vel, base + i), d = ldp<V>(delta, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float vj = __fdiv_rn(v.v[j], mn);
+      v.v[j] = vj;
+      const float dj = __fadd_rn(d.v[j], __fmul_rn(__fmul_rn(stepsize, vj), dir));
+      d.v[j] = dj;
+      s = __fadd_rn(s, __fmul_rn(dj, dj));
+    }
+    stp<V>(vel, base + i, v);
+    stp<V>(delta, base + i, d);
   }
   const float t = block_sum(s, sh);
   if (threadIdx.x == 0) dpart[b * RED_BLOCKS + blockIdx.x] = t;
 }
 
 // pass 4: renorm (torch.renorm: rows with norm > eps scaled by eps/(norm+1e-7)), image clamp
+template <int V>
 __global__ void pgd_l2_project_kernel(float* __restrict__ delta, const float* __restrict__ x,
                                       int image_space, long long n, float eps,
                                       const float* __restrict__ dpart) {
@@ -164,21 +211,27 @@ __global__ void pgd_l2_project_kernel(float* __restrict__ delta, const float* __
   const long long base = (long long)b * n;
   const float dn = sqrtf(sample_sum(dpart, b));
   const float scale = dn > eps ? __fdiv_rn(eps, __fadd_rn(dn, 1e-7f)) : 1.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    float d = __fmul_rn(delta[base + i], scale);
-    if (image_space) {
-      const float xv = x[base + i];
-      const float xa = fminf(fmaxf(__fadd_rn(xv, d), 0.f), 1.f);
-      d = __fsub_rn(xa, xv);
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    Pack<V> d = ldp<V>(delta, base + i), xv;
+    if (image_space) xv = ldp<V>(x, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float dj = __fmul_rn(d.v[j], scale);
+      if (image_space) {
+        const float xa = fminf(fmaxf(__fadd_rn(xv.v[j], dj), 0.f), 1.f);
+        dj = __fsub_rn(xa, xv.v[j]);
+      }
+      d.v[j] = dj;
     }
-    delta[base + i] = d;
+    stp<V>(delta, base + i, d);
   }
 }
 
 // ---------------------------------------------------------------------------
 // APGD step, ell_inf: fused single pass.
 // ---------------------------------------------------------------------------
+template <int V>
 __global__ void apgd_step_linf_kernel(float* __restrict__ x_adv, float* __restrict__ x_adv_old,
                                       const float* __restrict__ x, const float* __restrict__ grad,
                                       const float* __restrict__ step_size, long long n, float eps,
@@ -187,21 +240,27 @@ __global__ void apgd_step_linf_kernel(float* __restrict__ x_adv, float* __restri
   const long long base = (long long)b * n;
   const float s = step_size[b];
   const float one_minus_a = (float)(1.0 - (double)a);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float xa = x_adv[base + i], xo = x_adv_old[base + i], xc = x[base + i];
-    const float g = grad[base + i];
-    const float grad2 = __fsub_rn(xa, xo);
-    const float lo = __fsub_rn(xc, eps), hi = __fadd_rn(xc, eps);
-    float sg = fsign(g);
-    if (g != g) sg = g;  // torch.sign(nan) = nan (the reference does not scrub in APGD)
-    float z = __fadd_rn(xa, __fmul_rn(s, sg));
-    z = fminf(fmaxf(fminf(fmaxf(z, lo), hi), 0.f), 1.f);
-    float z2 = __fadd_rn(__fadd_rn(xa, __fmul_rn(__fsub_rn(z, xa), a)),
-                         __fmul_rn(grad2, one_minus_a));
-    z2 = fminf(fmaxf(fminf(fmaxf(z2, lo), hi), 0.f), 1.f);
-    x_adv_old[base + i] = xa;
-    x_adv[base + i] = z2;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    Pack<V> pa = ldp<V>(x_adv, base + i), po = ldp<V>(x_adv_old, base + i);
+    const Pack<V> pc = ldp<V>(x, base + i), pg = ldp<V>(grad, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float xa = pa.v[j], xo = po.v[j], xc = pc.v[j], g = pg.v[j];
+      const float grad2 = __fsub_rn(xa, xo);
+      const float lo = __fsub_rn(xc, eps), hi = __fadd_rn(xc, eps);
+      float sg = fsign(g);
+      if (g != g) sg = g;  // torch.sign(nan) = nan (the reference does not scrub in APGD)
+      float z = __fadd_rn(xa, __fmul_rn(s, sg));
+      z = fminf(fmaxf(fminf(fmaxf(z, lo), hi), 0.f), 1.f);
+      float z2 = __fadd_rn(__fadd_rn(xa, __fmul_rn(__fsub_rn(z, xa), a)),
+                           __fmul_rn(grad2, one_minus_a));
+      z2 = fminf(fmaxf(fminf(fmaxf(z2, lo), hi), 0.f), 1.f);
+      po.v[j] = xa;
+      pa.v[j] = z2;
+    }
+    stp<V>(x_adv_old, base + i, po);
+    stp<V>(x_adv, base + i, pa);
   }
 }
 
@@ -227,74 +286,94 @@ struct ApgdL2Args {
   float* p_w;         // partial sums of (w-x)^2
 };
 
-__device__ __forceinline__ float apgd_l2_u(const ApgdL2Args& A, long long idx, float s, float gn) {
-  return __fadd_rn(A.x_adv[idx], __fdiv_rn(__fmul_rn(s, A.grad[idx]), __fadd_rn(gn, 1e-12f)));
+__device__ __forceinline__ float apgd_l2_u(float xa, float g, float s, float gden) {
+  return __fadd_rn(xa, __fdiv_rn(__fmul_rn(s, g), gden));
 }
-__device__ __forceinline__ float apgd_l2_proj(float xc, float u, float un, float eps) {
-  const float t = __fmul_rn(__fdiv_rn(__fsub_rn(u, xc), __fadd_rn(un, 1e-12f)), fminf(eps, un));
+__device__ __forceinline__ float apgd_l2_proj(float xc, float u, float uden, float umin) {
+  const float t = __fmul_rn(__fdiv_rn(__fsub_rn(u, xc), uden), umin);
   return fminf(fmaxf(__fadd_rn(xc, t), 0.f), 1.f);
 }
+__device__ __forceinline__ float apgd_l2_w(float xa, float xo, float xc, float g, float s,
+                                           float gden, float uden, float umin, float a,
+                                           float one_minus_a) {
+  const float u = apgd_l2_u(xa, g, s, gden);
+  const float z = apgd_l2_proj(xc, u, uden, umin);
+  const float grad2 = __fsub_rn(xa, xo);
+  return __fadd_rn(__fadd_rn(xa, __fmul_rn(__fsub_rn(z, xa), a)), __fmul_rn(grad2, one_minus_a));
+}
 
+template <int V>
 __global__ void apgd_l2_pass_u(ApgdL2Args A) {
   __shared__ float sh[32];
   const int b = blockIdx.y;
   const long long base = (long long)b * A.n;
-  const float gn = sqrtf(sample_sum(A.p_g, b));
+  const float gden = __fadd_rn(sqrtf(sample_sum(A.p_g, b)), 1e-12f);
   const float s = A.step_size[b];
   float acc = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A.n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float u = apgd_l2_u(A, base + i, s, gn);
-    const float d = __fsub_rn(u, A.x[base + i]);
-    acc = __fadd_rn(acc, __fmul_rn(d, d));
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < A.n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    const Pack<V> pa = ldp<V>(A.x_adv, base + i), pg = ldp<V>(A.grad, base + i),
+                  pc = ldp<V>(A.x, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float d = __fsub_rn(apgd_l2_u(pa.v[j], pg.v[j], s, gden), pc.v[j]);
+      acc = __fadd_rn(acc, __fmul_rn(d, d));
+    }
   }
   const float t = block_sum(acc, sh);
   if (threadIdx.x == 0) A.p_u[b * RED_BLOCKS + blockIdx.x] = t;
 }
 
-__device__ __forceinline__ float apgd_l2_w(const ApgdL2Args& A, long long idx, float s, float gn,
-                                           float un, float one_minus_a) {
-  const float xa = A.x_adv[idx], xc = A.x[idx];
-  const float u = apgd_l2_u(A, idx, s, gn);
-  const float z = apgd_l2_proj(xc, u, un, A.eps);
-  const float grad2 = __fsub_rn(xa, A.x_adv_old[idx]);
-  return __fadd_rn(__fadd_rn(xa, __fmul_rn(__fsub_rn(z, xa), A.a)),
-                   __fmul_rn(grad2, one_minus_a));
-}
-
+template <int V>
 __global__ void apgd_l2_pass_w(ApgdL2Args A) {
   __shared__ float sh[32];
   const int b = blockIdx.y;
   const long long base = (long long)b * A.n;
-  const float gn = sqrtf(sample_sum(A.p_g, b));
+  const float gden = __fadd_rn(sqrtf(sample_sum(A.p_g, b)), 1e-12f);
   const float un = sqrtf(sample_sum(A.p_u, b));
+  const float uden = __fadd_rn(un, 1e-12f), umin = fminf(A.eps, un);
   const float s = A.step_size[b];
   const float oma = (float)(1.0 - (double)A.a);
   float acc = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A.n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float w = apgd_l2_w(A, base + i, s, gn, un, oma);
-    const float d = __fsub_rn(w, A.x[base + i]);
-    acc = __fadd_rn(acc, __fmul_rn(d, d));
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < A.n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    const Pack<V> pa = ldp<V>(A.x_adv, base + i), po = ldp<V>(A.x_adv_old, base + i),
+                  pg = ldp<V>(A.grad, base + i), pc = ldp<V>(A.x, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float w = apgd_l2_w(pa.v[j], po.v[j], pc.v[j], pg.v[j], s, gden, uden, umin, A.a, oma);
+      const float d = __fsub_rn(w, pc.v[j]);
+      acc = __fadd_rn(acc, __fmul_rn(d, d));
+    }
   }
   const float t = block_sum(acc, sh);
   if (threadIdx.x == 0) A.p_w[b * RED_BLOCKS + blockIdx.x] = t;
 }
 
+template <int V>
 __global__ void apgd_l2_pass_final(ApgdL2Args A) {
   const int b = blockIdx.y;
   const long long base = (long long)b * A.n;
-  const float gn = sqrtf(sample_sum(A.p_g, b));
+  const float gden = __fadd_rn(sqrtf(sample_sum(A.p_g, b)), 1e-12f);
   const float un = sqrtf(sample_sum(A.p_u, b));
   const float wn = sqrtf(sample_sum(A.p_w, b));
+  const float uden = __fadd_rn(un, 1e-12f), umin = fminf(A.eps, un);
+  const float wden = __fadd_rn(wn, 1e-12f), wmin = fminf(A.eps, wn);
   const float s = A.step_size[b];
   const float oma = (float)(1.0 - (double)A.a);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < A.n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const float xa = A.x_adv[base + i];
-    const float w = apgd_l2_w(A, base + i, s, gn, un, oma);
-    A.x_adv_old[base + i] = xa;
-    A.x_adv[base + i] = apgd_l2_proj(A.x[base + i], w, wn, A.eps);
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * V; i < A.n;
+       i += (long long)gridDim.x * blockDim.x * V) {
+    Pack<V> pa = ldp<V>(A.x_adv, base + i), po = ldp<V>(A.x_adv_old, base + i);
+    const Pack<V> pg = ldp<V>(A.grad, base + i), pc = ldp<V>(A.x, base + i);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float xa = pa.v[j];
+      const float w = apgd_l2_w(xa, po.v[j], pc.v[j], pg.v[j], s, gden, uden, umin, A.a, oma);
+      po.v[j] = xa;
+      pa.v[j] = apgd_l2_proj(pc.v[j], w, wden, wmin);
+    }
+    stp<V>(A.x_adv_old, base + i, po);
+    stp<V>(A.x_adv, base + i, pa);
   }
 }
 
@@ -459,11 +538,18 @@ extern "C" int rvlm_pgd_update_l2_masked(float* delta, float* velocity, const fl
   float* pm = workspace + (size_t)B * RED_BLOCKS;
   float* pd = workspace + (size_t)2 * B * RED_BLOCKS;
   const dim3 grid(RED_BLOCKS, B);
-  l2_sumsq_kernel<<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, pg, 1, mask);
-  pgd_l2_momentum_kernel<<<grid, UPD_THREADS, 0, st>>>(velocity, grad, mask, n, momentum, pg, pm);
-  pgd_l2_step_kernel<<<grid, UPD_THREADS, 0, st>>>(delta, velocity, n, stepsize,
-                                                   maximize ? 1.f : -1.f, pm, pd);
-  pgd_l2_project_kernel<<<grid, UPD_THREADS, 0, st>>>(delta, x, image_space, n, eps, pd);
+  const float dir = maximize ? 1.f : -1.f;
+  if ((n & 3) == 0) {
+    l2_sumsq_kernel<4><<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, pg, 1, mask);
+    pgd_l2_momentum_kernel<4><<<grid, UPD_THREADS, 0, st>>>(velocity, grad, mask, n, momentum, pg, pm);
+    pgd_l2_step_kernel<4><<<grid, UPD_THREADS, 0, st>>>(delta, velocity, n, stepsize, dir, pm, pd);
+    pgd_l2_project_kernel<4><<<grid, UPD_THREADS, 0, st>>>(delta, x, image_space, n, eps, pd);
+  } else {
+    l2_sumsq_kernel<1><<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, pg, 1, mask);
+    pgd_l2_momentum_kernel<1><<<grid, UPD_THREADS, 0, st>>>(velocity, grad, mask, n, momentum, pg, pm);
+    pgd_l2_step_kernel<1><<<grid, UPD_THREADS, 0, st>>>(delta, velocity, n, stepsize, dir, pm, pd);
+    pgd_l2_project_kernel<1><<<grid, UPD_THREADS, 0, st>>>(delta, x, image_space, n, eps, pd);
+  }
   return cuda_rc(4);
 }
 
@@ -471,8 +557,12 @@ extern "C" int rvlm_apgd_step_linf(float* x_adv, float* x_adv_old, const float* 
                                    const float* grad, const float* step_size, int B, long long n,
                                    float eps, float a, void* stream) {
   if (B <= 0 || n <= 0) return RVLM_ERR_INVAL;
-  apgd_step_linf_kernel<<<upd_grid(n, B), UPD_THREADS, 0, (cudaStream_t)stream>>>(
-      x_adv, x_adv_old, x, grad, step_size, n, eps, a);
+  if ((n & 3) == 0)
+    apgd_step_linf_kernel<4><<<upd_grid(n >> 2, B), UPD_THREADS, 0, (cudaStream_t)stream>>>(
+        x_adv, x_adv_old, x, grad, step_size, n, eps, a);
+  else
+    apgd_step_linf_kernel<1><<<upd_grid(n, B), UPD_THREADS, 0, (cudaStream_t)stream>>>(
+        x_adv, x_adv_old, x, grad, step_size, n, eps, a);
   return cuda_rc();
 }
 
@@ -484,10 +574,17 @@ extern "C" int rvlm_apgd_step_l2(float* x_adv, float* x_adv_old, const float* x,
   ApgdL2Args A{x_adv, x_adv_old, x, grad, step_size, n, eps, a, workspace,
                workspace + (size_t)B * RED_BLOCKS, workspace + (size_t)2 * B * RED_BLOCKS};
   const dim3 grid(RED_BLOCKS, B);
-  l2_sumsq_kernel<<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, workspace, 0);
-  apgd_l2_pass_u<<<grid, UPD_THREADS, 0, st>>>(A);
-  apgd_l2_pass_w<<<grid, UPD_THREADS, 0, st>>>(A);
-  apgd_l2_pass_final<<<grid, UPD_THREADS, 0, st>>>(A);
+  if ((n & 3) == 0) {
+    l2_sumsq_kernel<4><<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, workspace, 0, nullptr);
+    apgd_l2_pass_u<4><<<grid, UPD_THREADS, 0, st>>>(A);
+    apgd_l2_pass_w<4><<<grid, UPD_THREADS, 0, st>>>(A);
+    apgd_l2_pass_final<4><<<grid, UPD_THREADS, 0, st>>>(A);
+  } else {
+    l2_sumsq_kernel<1><<<grid, UPD_THREADS, 0, st>>>(grad, nullptr, n, workspace, 0, nullptr);
+    apgd_l2_pass_u<1><<<grid, UPD_THREADS, 0, st>>>(A);
+    apgd_l2_pass_w<1><<<grid, UPD_THREADS, 0, st>>>(A);
+    apgd_l2_pass_final<1><<<grid, UPD_THREADS, 0, st>>>(A);
+  }
   return cuda_rc(4);
 }
 

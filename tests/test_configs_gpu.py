@@ -64,7 +64,8 @@ def test_config1_vitb32_one_step_pgd():
              nat.ptr(x.cuda()), c_int(B), c_int64(3 * 224 * 224), c_float(step), c_float(eps),
              c_int(1), c_float(0.9), nat.stream_ptr())
     torch.cuda.synchronize()
-    assert torch.equal(delta.cpu(), ref - x)
+    assert torch.equal((x.cuda() + delta).cpu(), ref)          # x + delta as returned (:68)
+    assert float(delta.abs().max()) <= eps
     # (b) end to end through the fused engine
     out = attacks.pgd(ours, rm.ComputeLossWrapper(e_orig.cuda(), None, "mean", "l2", 100.0), x.cuda(),
                       None, "linf", eps, 1, step, False, perturbation=d0.clone().cuda(),

@@ -178,9 +178,10 @@ def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_las
             grad.copy_(g_new)
         counter3 += 1
         is_ck = counter3 == k
+        loss_c, pred_c = loss.contiguous(), pred.to(torch.int32).contiguous()   # held across the call
         nat.call("rvlm_apgd_bookkeep", nat.ptr(x_adv), nat.ptr(grad), nat.ptr(x_best),
-                 nat.ptr(grad_best), nat.ptr(x_best_adv), nat.ptr(loss.contiguous()),
-                 nat.ptr(pred.to(torch.int32).contiguous()), nat.ptr(loss_steps),
+                 nat.ptr(grad_best), nat.ptr(x_best_adv), nat.ptr(loss_c),
+                 nat.ptr(pred_c), nat.ptr(loss_steps),
                  nat.ptr(loss_best), nat.ptr(loss_best_last), nat.ptr(reduced_last),
                  nat.ptr(step_size), nat.ptr(acc), nat.ptr(flags), c_int(B), c_int64(n),
                  c_int(n_iter), c_int(i), c_int(k if is_ck else 0), c_float(float(k * thr_decr)),

@@ -60,11 +60,12 @@ def test_config1_vitb32_one_step_pgd():
     (g_ref,) = torch.autograd.grad(wrap(ref_m(xa, output_normalize=False), None), xa)
     # (a) the update arithmetic alone, given the reference's gradient: bit-exact
     delta, vel = d0.clone().cuda(), torch.zeros_like(d0).cuda()
-    nat.call("rvlm_pgd_update_linf", nat.ptr(delta), nat.ptr(vel), nat.ptr(g_ref.cuda().contiguous()),
-             nat.ptr(x.cuda()), c_int(B), c_int64(3 * 224 * 224), c_float(step), c_float(eps),
-             c_int(1), c_float(0.9), nat.stream_ptr())
+    g_dev, x_dev = g_ref.cuda().contiguous(), x.cuda()         # held: the call takes raw pointers
+    nat.call("rvlm_pgd_update_linf", nat.ptr(delta), nat.ptr(vel), nat.ptr(g_dev), nat.ptr(x_dev),
+             c_int(B), c_int64(3 * 224 * 224), c_float(step), c_float(eps), c_int(1), c_float(0.9),
+             nat.stream_ptr())
     torch.cuda.synchronize()
-    assert torch.equal((x.cuda() + delta).cpu(), ref)          # x + delta as returned (:68)
+    assert torch.equal((x_dev + delta).cpu(), ref)             # x + delta as returned (:68)
     assert float(delta.abs().max()) <= eps
     # (b) end to end through the fused engine
     out = attacks.pgd(ours, rm.ComputeLossWrapper(e_orig.cuda(), None, "mean", "l2", 100.0), x.cuda(),

@@ -240,8 +240,10 @@ def workload_config(args, B):
                          "SURVEY.md 8d); FLOP figures stay the full algorithmic ones"}
 
 
-def cpu_baseline_sample(model_name, seconds=20.0):
-    """Bounded CPU sample of the same workload (oracle port), rank 0, N = 1 only."""
+def cpu_baseline_sample(model_name, seconds=20.0, keep=None):
+    """Bounded CPU sample of the same workload (oracle port), rank 0, N = 1 only.  `keep`, if a
+    dict, receives the sample's inputs / output so the GPU path can be compared on them (the
+    second half of BASELINE.json's metric: delta max-abs-err vs the reference)."""
     Bs = 8
     oa, model, wrap, x, d0, cores, avail = _cpu_arm_setup(model_name, Bs)
     t0 = time.perf_counter()
@@ -250,9 +252,12 @@ def cpu_baseline_sample(model_name, seconds=20.0):
     t1 = time.perf_counter() - t0
     n_it = int(max(1, min(ITERS, seconds // max(t1, 1e-3))))
     t0 = time.perf_counter()
-    oa.pgd(model, wrap, x, None, "linf", EPS, n_it, STEPSIZE, False, perturbation=d0.clone(),
-           mode="max")
+    x_adv = oa.pgd(model, wrap, x, None, "linf", EPS, n_it, STEPSIZE, False,
+                   perturbation=d0.clone(), mode="max")
     t = (time.perf_counter() - t0) / n_it * ITERS
+    if keep is not None:
+        keep.update(x=x, d0=d0, x_adv=x_adv, n_it=n_it, e_orig=wrap.embedding_orig,
+                    state_dict=model.model.state_dict())
     return {"value": Bs / t, "unit": "img/s", "cores": cores, "kind": "port",
             "sample": f"{Bs} images x {n_it} of {ITERS} PGD iterations (scaled), {model_name} fp32 "
                       f"oracle port of train/pgd_train.py::pgd, {cores} threads (calibrated; "
@@ -260,6 +265,34 @@ def cpu_baseline_sample(model_name, seconds=20.0):
 
 
 # ------------------------------------------------------------------------------------
+def delta_vs_reference(vt, m, keep, dev):
+    """BASELINE.json's second metric: delta = x_adv - x of the CUDA path against the CPU arm's
+    (the oracle port of train/pgd_train.py::pgd, fp32) on the SAME weights, images, start and
+    iteration count as the cpu_baseline sample.  A different fp32 summation order alone flips
+    sign(g) where g ~ 0, and one flipped sign moves that entry by
+    2*stepsize per iteration, so the max-abs error is quantised in steps of 2/255 * n_it; the
+    informative figures are the fraction of identical entries and the loss reached."""
+    import torch
+    from robustvlm_b200 import attacks, model as rmodel
+    vt.load_state_dict(keep["state_dict"])                 # same weights as the CPU arm
+    x, d0, ref = keep["x"].to(dev), keep["d0"].to(dev), keep["x_adv"]
+    wrap = rmodel.ComputeLossWrapper(keep["e_orig"].to(dev), None, "mean", "l2", 100.0)
+    out = attacks.pgd(m, wrap, x, None, "linf", EPS, keep["n_it"], STEPSIZE, False,
+                      perturbation=d0, mode="max")
+    with torch.no_grad():
+        emb = m(keep["x"].to(dev), output_normalize=False).cpu()
+        l_ours = float(wrap(m(out, output_normalize=False), None))
+        l_ref = float(wrap(m(ref.to(dev), output_normalize=False), None))
+    d_o, d_r = out.cpu() - keep["x"], ref - keep["x"]
+    return {"max_abs_err": float((d_o - d_r).abs().max()),
+            "mean_abs_err": float((d_o - d_r).abs().mean()),
+            "identical_frac": float((d_o == d_r).float().mean()),
+            "images": int(x.shape[0]), "iterations": int(keep["n_it"]),
+            "fare_loss_ours": l_ours, "fare_loss_ref_delta": l_ref,
+            "linf_ours": float(d_o.abs().max()), "eps": EPS,
+            "emb_norm": float(emb.norm(dim=1).mean())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -380,7 +413,9 @@ def run_ours(args):
                          "whole_step_algorithmic_tflops": algo_tf / (ms / 1e3)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_sample(args.model)
+            keep = {}
+            line["cpu_baseline"] = cpu_baseline_sample(args.model, keep=keep)
+            line["delta_vs_ref"] = delta_vs_reference(vt, m, keep, dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -534,8 +534,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint8_t* s_q = s_v + full_bytes;                 // [2][16384]
   uint8_t* s_p = s_q + 2 * 16384;                  // [2][nblk * 16384]
   uint16_t* s_tail = reinterpret_cast<uint16_t*>(s_p + 2 * P.nblk * 16384);  // [2][2][64]
-  uint16_t* s_qtail = s_tail + 256;                // [64] the peeled query row
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qtail + 64);
+  uint16_t* s_qtail = s_tail + 256;                // [2][64] the peeled query row, per group
+  float* s_part = reinterpret_cast<float*>(s_qtail + 128);   // [2][68] group 0's half of that row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 136);
   uint64_t* bar_k = bars + 0;
   uint64_t* bar_v = bars + 1;
   uint64_t* bar_q = bars + 2;       // [2]
@@ -543,14 +544,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint64_t* bar_p = bars + 6;       // [2] 128 arrivals
   uint64_t* bar_o = bars + 8;       // [2]
   uint64_t* bar_ofree = bars + 10;  // [2] 128 arrivals
-  uint64_t* bar_tail = bars + 12;   // 128 arrivals: peeled query row done with K / V
+  uint64_t* bar_tail = bars + 12;   // 256 arrivals: both halves of the peeled query row done with K / V
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bar_k, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_tail, 128);
+    mbar_init(bar_tail, 256);
     for (int g = 0; g < 2; ++g) {
       mbar_init(&bar_q[g], 1);
       mbar_init(&bar_s[g], 1);
@@ -651,22 +652,28 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         }
-        if (P.tail && g == ng - 1) {
+        if (P.tail) {
           // ---- the peeled QUERY row (token 256) on the CUDA cores, in the shadow of the S
-          // MMAs: scores against all 257 keys, softmax, P V.  Scratch = this group's P buffer.
-          float* sc = reinterpret_cast<float*>(my_p);   // [272] scores / probabilities
-          float* red = sc + 288;                        // [8] warp partials
-          float* oh = red + 8;                          // [2][64] output halves
+          // MMAs, SPLIT between the two row groups (T = 257 always runs both): group g scores
+          // keys [g*128, g*128+128) (the last group also key 256), forms its own softmax
+          // partials (max, sum) and partial P V; group 0 hands {o[64], max, sum} to group 1
+          // through a double-buffered 68-float slot (bar.arrive / bar.sync on barrier 3), and
+          // group 1 merges the two halves flash-style and writes the row.  Scratch = this
+          // group's P buffer.
+          float* sc = reinterpret_cast<float*>(my_p);   // [129] this group's scores / probabilities
+          float* red = sc + 136;                        // [8] warp partials
+          float* oh = red + 8;                          // [2][64] output halves (two key quarters)
+          float* part = s_part + (it & 1) * 68;         // group 0 -> group 1
+          uint16_t* qt = s_qtail + g * 64;              // this group's copy of the peeled query
           if (r < 8)
-            *reinterpret_cast<uint4*>(s_qtail + r * 8) = *reinterpret_cast<const uint4*>(
+            *reinterpret_cast<uint4*>(qt + r * 8) = *reinterpret_cast<const uint4*>(
                 P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 + r * 8);
           mbar_wait(bar_k, ph, 43);
-          mbar_wait(bar_v, ph, 44);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           float qv[64];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            const uint4 qu = *reinterpret_cast<const uint4*>(s_qtail + c * 8);
+            const uint4 qu = *reinterpret_cast<const uint4*>(qt + c * 8);
             const uint32_t* qa = &qu.x;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -675,34 +682,37 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               qv[c * 8 + 2 * i + 1] = x.y;
             }
           }
-          float lmax = -INFINITY;
-          for (int kv = r; kv < T; kv += 128) {
+          float lmax;
+          {
+            const int kv = g * 128 + r;
             float acc = 0.f;
-            if (kv < 256) {
-              const uint8_t* krow = s_k + kv * 128;
+            const uint8_t* krow = s_k + kv * 128;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint4 ku = *reinterpret_cast<const uint4*>(krow + ((c ^ (kv & 7)) << 4));
-                const uint32_t* ka = &ku.x;
+            for (int c = 0; c < 8; ++c) {
+              const uint4 ku = *reinterpret_cast<const uint4*>(krow + ((c ^ (kv & 7)) << 4));
+              const uint32_t* ka = &ku.x;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 y = unpackc<FMT>(ka[i]);
-                  acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
-                }
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const uint4 ku = *reinterpret_cast<const uint4*>(kt + c * 8);
-                const uint32_t* ka = &ku.x;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float2 y = unpackc<FMT>(ka[i]);
-                  acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
-                }
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = unpackc<FMT>(ka[i]);
+                acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
               }
             }
-            sc[kv] = acc;
+            sc[r] = acc;
+            lmax = acc;
+          }
+          if (g == 1 && r == 127) {   // key 256 (this group's k_tail copy)
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 ku = *reinterpret_cast<const uint4*>(kt + c * 8);
+              const uint32_t* ka = &ku.x;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = unpackc<FMT>(ka[i]);
+                acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
+              }
+            }
+            sc[128] = acc;
             lmax = fmaxf(lmax, acc);
           }
 #pragma unroll
@@ -710,43 +720,68 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           if (lane == 0) red[warp & 3] = lmax;
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           const float tmc = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * c2;
-          float lsum = 0.f;
-          for (int kv = r; kv < T; kv += 128) {
-            const float e = fast_ex2(fmaf(sc[kv], c2, -tmc));
-            sc[kv] = e;
+          float lsum;
+          {
+            const float e = fast_ex2(fmaf(sc[r], c2, -tmc));
+            sc[r] = e;
+            lsum = e;
+          }
+          if (g == 1 && r == 127) {
+            const float e = fast_ex2(fmaf(sc[128], c2, -tmc));
+            sc[128] = e;
             lsum += e;
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffff, lsum, o);
           if (lane == 0) red[4 + (warp & 3)] = lsum;
+          mbar_wait(bar_v, ph, 44);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           const float tsum = (red[4] + red[5]) + (red[6] + red[7]);
-          {  // o[d] over this thread's half of the keys
+          {  // o[d] over one quarter of the keys (this thread's half of the group's keys)
             const int d = r & 63, hf = r >> 6;
-            const int k0 = hf * 128, k1 = hf ? 256 : 128;
-            float acc = 0.f;
-            for (int kv = k0; kv < k1; ++kv) {
-              const uint16_t hv = *reinterpret_cast<const uint16_t*>(
-                  s_v + kv * 128 + (((d >> 3) ^ (kv & 7)) << 4) + (d & 7) * 2);
-              const float v = ld1<FMT>(&hv);
-              acc = fmaf(sc[kv], v, acc);
+            const int j0 = hf * 64;
+            const uint8_t* vbase = s_v + (size_t)(g * 128) * 128 + (d & 7) * 2;
+            float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+            for (int j = j0; j < j0 + 64; j += 2) {
+              const uint16_t h0 = *reinterpret_cast<const uint16_t*>(
+                  vbase + j * 128 + (((d >> 3) ^ (j & 7)) << 4));
+              const uint16_t h1 = *reinterpret_cast<const uint16_t*>(
+                  vbase + (j + 1) * 128 + (((d >> 3) ^ ((j + 1) & 7)) << 4));
+              acc0 = fmaf(sc[j], ld1<FMT>(&h0), acc0);
+              acc1 = fmaf(sc[j + 1], ld1<FMT>(&h1), acc1);
             }
-            if (hf == 1) {
+            float acc = acc0 + acc1;
+            if (g == 1 && hf == 1) {
               const uint16_t hv = vt[d];
-              const float v = ld1<FMT>(&hv);
-              acc = fmaf(sc[256], v, acc);
+              acc = fmaf(sc[128], ld1<FMT>(&hv), acc);
             }
             oh[hf * 64 + d] = acc;
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-          if (r < 32) {
-            const float inv = 1.f / tsum;
-            const float o0 = (oh[2 * r] + oh[64 + 2 * r]) * inv;
-            const float o1 = (oh[2 * r + 1] + oh[64 + 2 * r + 1]) * inv;
-            reinterpret_cast<uint32_t*>(P.o_out + ((size_t)b * T + 256) * W + h * 64)[r] =
-                packc<FMT>(o0, o1);
-            if (r == 0)
-              P.lse_out[((size_t)b * P.H + h) * T + 256] = (tmc + log2f(tsum)) * 0.6931471805599453f;
+          if (g == 0) {
+            if (r < 64) part[r] = oh[r] + oh[64 + r];
+            if (r == 64) part[64] = tmc;
+            if (r == 65) part[65] = tsum;
+            __threadfence_block();
+            asm volatile("bar.arrive 3, 256;" ::: "memory");
+          } else {
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (r < 32) {
+              const float m0 = part[64], l0 = part[65];
+              const float mm = fmaxf(m0, tmc);
+              const float a0 = fast_ex2(m0 - mm), a1 = fast_ex2(tmc - mm);
+              const float ltot = fmaf(l0, a0, tsum * a1);
+              const float inv = 1.f / ltot;
+              const float o0 = fmaf(part[2 * r], a0, (oh[2 * r] + oh[64 + 2 * r]) * a1) * inv;
+              const float o1 =
+                  fmaf(part[2 * r + 1], a0, (oh[2 * r + 1] + oh[64 + 2 * r + 1]) * a1) * inv;
+              reinterpret_cast<uint32_t*>(P.o_out + ((size_t)b * T + 256) * W + h * 64)[r] =
+                  packc<FMT>(o0, o1);
+              if (r == 0)
+                P.lse_out[((size_t)b * P.H + h) * T + 256] =
+                    (mm + log2f(ltot)) * 0.6931471805599453f;
+            }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");  // scratch free again
           mbar_arrive(bar_tail);
@@ -2153,7 +2188,7 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
   const size_t smem = (size_t)2 * P.kvm * 128 + 2 * 16384 + (size_t)2 * P.nblk * 16384 + 512 +
-                      128 + 128 + 1024;
+                      256 + 544 + 128 + 1024;   // + q_tail[2][64] + part[2][68] + barriers + align
   auto kern = fmt ? attn_fwd2_kernel<1> : attn_fwd2_kernel<0>;
   static size_t set[2] = {0, 0};
   if (smem > set[fmt ? 1 : 0]) {

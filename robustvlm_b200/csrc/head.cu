@@ -13,14 +13,20 @@
 // into row b*T of the [B*T, W] gradient buffers (all other rows are zero: only the
 // CLS token reaches the loss).
 //
-// Tiny work (B rows): one CTA per sample, fp32 SIMT.
+// Tiny work (B rows): one CTA of 1024 threads per sample, fp32 SIMT.  The four matrix-vector
+// products (proj, text and their transposes; 3 MB each, streamed from L2 by every CTA) are
+// latency-bound, so they are organised for memory-level parallelism: the forward products split
+// the reduction dimension over four 256-thread slices with up to four independent accumulators
+// per thread (partial sums merged through shared memory in a fixed order), the transposed ones
+// run one warp per output with four independent partial sums per lane.
 #include "engine_internal.cuh"
 #include "../../include/rvlm.h"
 
 namespace rvlm {
 
 void count_launch(int n);
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 1024;
+constexpr int HEAD_SLICES = HEAD_THREADS / 256;   // reduction slices of the forward products
 
 __device__ __forceinline__ float blk_sum(float v, float* red) {
 #pragma unroll
@@ -66,6 +72,64 @@ __device__ __forceinline__ int blk_argmax(const float* v, int n, float* red, int
   return fi;
 }
 
+// out[j] = sum_i v[i] * Mx[i * ldm + j], j < n_out, i < n_in  (Mx row-major [n_in, n_out]).
+// Thread t: columns (t & 255) + 256 k, rows of slice t >> 8.  `part` = [HEAD_SLICES][n_out] scratch.
+__device__ __forceinline__ void matvec_fwd(const float* __restrict__ v, const float* __restrict__ Mx,
+                                           int n_in, int n_out, float scale, float* part,
+                                           float* out) {
+  const int col0 = threadIdx.x & 255, slice = threadIdx.x >> 8;
+  const int per = (n_in + HEAD_SLICES - 1) / HEAD_SLICES;
+  const int i0 = slice * per, i1 = min(n_in, i0 + per);
+  for (int cb = 0; cb < n_out; cb += 1024) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ok[k] = cb + col0 + 256 * k < n_out;
+#pragma unroll 4
+    for (int i = i0; i < i1; ++i) {
+      const float vi = v[i];
+      const float* row = Mx + (size_t)i * n_out + cb + col0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ok[k]) acc[k] = fmaf(vi, __ldg(row + 256 * k), acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ok[k]) part[slice * n_out + cb + col0 + 256 * k] = acc[k];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_out; j += HEAD_THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < HEAD_SLICES; ++sl) t += part[sl * n_out + j];
+    out[j] = t * scale;
+  }
+  __syncthreads();
+}
+
+// out[i] = scale * sum_j Mx[i * n_out + j] * v[j]: one warp per row i, four partial sums per lane.
+template <typename F>
+__device__ __forceinline__ void matvec_bwd(const float* __restrict__ v, const float* __restrict__ Mx,
+                                           int n_in, int n_out, F&& emit) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < n_in; i += HEAD_THREADS / 32) {
+    const float* row = Mx + (size_t)i * n_out;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = lane;
+    for (; j + 96 < n_out; j += 128) {
+      a0 = fmaf(__ldg(row + j), v[j], a0);
+      a1 = fmaf(__ldg(row + j + 32), v[j + 32], a1);
+      a2 = fmaf(__ldg(row + j + 64), v[j + 64], a2);
+      a3 = fmaf(__ldg(row + j + 96), v[j + 96], a3);
+    }
+    for (; j < n_out; j += 32) a0 = fmaf(__ldg(row + j), v[j], a0);
+    float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
+    if (lane == 0) emit(i, acc);
+  }
+}
+
 __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
   extern __shared__ float sm[];
   const int W = A.W, D = A.D, C = A.C;
@@ -74,6 +138,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
   float* e = pooled + W;        // [D] embedding (normalised if requested)
   float* de = e + D;            // [D]
   float* lg = de + D;           // [C] logits / dlogits
+  float* part = lg + (C > 0 ? C : 1);   // [HEAD_SLICES][max(D, C)] partial sums
   __shared__ float red[32];
   __shared__ int redi[32];
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -92,12 +157,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
   }
   __syncthreads();
   // ---- projection
-  for (int d = tid; d < D; d += HEAD_THREADS) {
-    float acc = 0.f;
-    for (int w = 0; w < W; ++w) acc += pooled[w] * __ldg(A.proj + (size_t)w * D + d);
-    e[d] = acc;
-  }
-  __syncthreads();
+  matvec_fwd(pooled, A.proj, W, D, 1.f, part, e);
   float nrm = 1.f;
   if (A.normalize) {
     float ss = 0.f;
@@ -124,12 +184,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
     // upstream gradient w.r.t. the (normalised) embedding supplied by the caller
     for (int d = tid; d < D; d += HEAD_THREADS) de[d] = A.emb_orig[(size_t)b * D + d];
   } else if (A.mode == 2) {
-    for (int c = tid; c < C; c += HEAD_THREADS) {
-      float acc = 0.f;
-      for (int d = 0; d < D; ++d) acc += e[d] * __ldg(A.text + (size_t)d * C + c);
-      lg[c] = acc * A.logit_scale;
-    }
-    __syncthreads();
+    matvec_fwd(e, A.text, D, C, A.logit_scale, part, lg);
     if (A.logits_out)
       for (int c = tid; c < C; c += HEAD_THREADS) A.logits_out[(size_t)b * C + c] = lg[c];
     if (A.pred_on_logits) pred = (blk_argmax(lg, C, red, redi) == (int)yb) ? 1 : 0;
@@ -146,14 +201,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
       lg[c] = expf(lg[c] - lz) - ((long long)c == yb ? 1.f : 0.f);
     __syncthreads();
     // d e = logit_scale * text @ dlogits
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int d = warp; d < D; d += HEAD_THREADS / 32) {
-      float acc = 0.f;
-      for (int c = lane; c < C; c += 32) acc += __ldg(A.text + (size_t)d * C + c) * lg[c];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
-      if (lane == 0) de[d] = acc * A.logit_scale;
-    }
+    matvec_bwd(lg, A.text, D, C, [&](int d, float acc) { de[d] = acc * A.logit_scale; });
   }
   __syncthreads();
   if ((A.mode == 1 || A.mode == 2) && !(A.mode == 2 && A.pred_on_logits))
@@ -182,19 +230,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
     __syncthreads();
   }
   // ---- d pooled = proj @ d emb  (reuse `pooled` as g = dpooled * gamma)
-  {
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int w = warp; w < W; w += HEAD_THREADS / 32) {
-      float acc = 0.f;
-      for (int d = lane; d < D; d += 32) acc += __ldg(A.proj + (size_t)w * D + d) * de[d];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffff, acc, o);
-      if (lane == 0) {
-        if (A.t_dpooled) A.t_dpooled[(size_t)b * W + w] = acc * A.grad_scale;
-        pooled[w] = acc * A.ln_g[w] * A.grad_scale;
-      }
-    }
-  }
+  matvec_bwd(de, A.proj, W, D, [&](int w, float acc) {
+    if (A.t_dpooled) A.t_dpooled[(size_t)b * W + w] = acc * A.grad_scale;
+    pooled[w] = acc * A.ln_g[w] * A.grad_scale;
+  });
   __syncthreads();
   // ---- ln_post backward
   float s1 = 0.f, s2 = 0.f;
@@ -226,7 +265,9 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
 }
 
 int launch_head(const HeadArgs& A, int B, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * A.W + 2 * A.D + (A.C > 0 ? A.C : 1)) * sizeof(float);
+  const int mx = A.D > A.C ? A.D : A.C;
+  const size_t smem = (size_t)(2 * A.W + 2 * A.D + (A.C > 0 ? A.C : 1) + HEAD_SLICES * mx) *
+                      sizeof(float);
   static size_t set = 0;
   if (smem > set && smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -66,7 +66,7 @@ def test_config1_vitb32_one_step_pgd():
              nat.stream_ptr())
     torch.cuda.synchronize()
     assert torch.equal((x_dev + delta).cpu(), ref)             # x + delta as returned (:68)
-    assert float(delta.abs().max()) <= eps
+    assert float(delta.abs().max()) <= float(torch.tensor(eps, dtype=torch.float32))   # fp32 eps
     # (b) end to end through the fused engine
     out = attacks.pgd(ours, rm.ComputeLossWrapper(e_orig.cuda(), None, "mean", "l2", 100.0), x.cuda(),
                       None, "linf", eps, 1, step, False, perturbation=d0.clone().cuda(),

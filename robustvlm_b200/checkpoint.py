@@ -119,9 +119,12 @@ def save_periodic(model_state, opt_state_fn, output_dir, step_total, total_steps
 
 def load_visual_state_dict(path_or_sd, prefix_candidates=("visual.", "module.visual.", "model.")):
     """A vision-tower state dict from a FARE / TeCoA checkpoint (the tower alone, as the
-    reference saves it) or from a full CLIP state dict (keys under `visual.`)."""
+    reference saves it), from the `{'vision_encoder_state_dict': ...}` wrapper of the original TeCoA
+    files, or from a full CLIP state dict (keys under `visual.`)."""
     sd = torch.load(path_or_sd, map_location="cpu") if isinstance(path_or_sd, (str, os.PathLike)) \
         else path_or_sd
+    if "vision_encoder_state_dict" in sd:        # the original TeCoA release, CLIP_eval/eval_utils.py:45-48
+        sd = sd["vision_encoder_state_dict"]
     if "conv1.weight" in sd:
         return dict(sd)
     for pre in prefix_candidates:

@@ -105,6 +105,7 @@ def test_saving_rules_and_loading(tmp_path):
     full = {"visual." + k: v for k, v in sd.items()}
     full["logit_scale"] = torch.tensor(4.6)
     assert list(ck.load_visual_state_dict(full)) == list(sd)                    # a whole CLIP
+    assert list(ck.load_visual_state_dict({"vision_encoder_state_dict": dict(sd)})) == list(sd)
     vt = rm.VisionTransformer("tiny-32")
     vt.load_state_dict(back)                                                    # strict
     with pytest.raises(KeyError):

@@ -48,9 +48,13 @@ def allreduce_mean_(flat_grad: torch.Tensor, local_count: int, global_count: int
     the gradient of the mean loss over the GLOBAL batch (the loss is a batch mean,
     train/adversarial_training_clip.py:517,528) even when shards are uneven."""
     if dist.is_initialized() and dist.get_world_size() > 1:
-        flat_grad.mul_(float(local_count))
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
-        flat_grad.div_(float(global_count))
+        world = dist.get_world_size()
+        if local_count * world == global_count and dist.get_backend() == "nccl":
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)      # even shards: one pass, in NCCL
+        else:
+            flat_grad.mul_(float(local_count))
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+            flat_grad.div_(float(global_count))
     return flat_grad
 
 

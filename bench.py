@@ -209,7 +209,8 @@ def run_reference(args):
     sample = (f"{Bs} images x {n_it} of {ITERS} PGD iterations per step, scaled to {ITERS}; "
               f"{name} fp32, torch {torch.__version__}, {cores} threads (calibrated; "
               f"{avail} CPUs available)")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s", "n_gpus": 0,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s",
+            "n_gpus": args.gpus, "device": "cpu (host cores of the box; this arm leaves the GPUs idle)",
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_call * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, Bs),

@@ -22,16 +22,17 @@ def set_mask(data, mask_out):
     """`_set_mask` (vlm_eval/attacks/pgd.py:75-87 == apgd.py:34-46): dim 1 indexes the frames
     of one sample (context images ..., query image last)."""
     mask = torch.ones_like(data)
-    if mask_out == "context":
-        mask[:, :-1, ...] = 0
-    elif mask_out == "query":
-        mask[:, -1, ...] = 0
+    if mask_out is None:
+        return mask
+    if isinstance(mask_out, str):
+        frames = {"context": slice(None, -1), "query": -1}.get(mask_out)
+        if frames is None:
+            raise NotImplementedError(f"Unknown mask_out: {mask_out}")
     elif isinstance(mask_out, int):
-        mask[:, mask_out, ...] = 0
-    elif mask_out is None:
-        pass
+        frames = mask_out
     else:
         raise NotImplementedError(f"Unknown mask_out: {mask_out}")
+    mask[:, frames] = 0
     return mask
 
 

@@ -2160,6 +2160,401 @@ static int launch_attn(const AttnPlan& pl, cudaStream_t st) {
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
+// =====================================================================================
+// Forward, version 3 (T == 257 only): ONE 128-row tile per work item, TWO CTAs per SM.
+//
+// fwd2 keeps two row groups of one (image, head) in lock step on one set of K / V / S
+// buffers, so every group serialises S-MMA -> softmax -> PV-MMA -> epilogue and ~25 % of its
+// time is spent waiting on MMA / TMA latency (profiles/r01_attn_v3_lines.txt).  Here a CTA is
+// one row group (4 worker warps + the control warp, 160 threads) with its OWN K, V and
+// 256-column S accumulator, and two such CTAs share an SM (2 x 98 KB smem, 2 x 256 TMEM
+// columns): while one waits, the other computes.  To fit, the Q tile and the 16-bit P tile
+// share one 32 KB buffer -- P is produced and consumed in two 128-column halves (the PV MMAs
+// of the first half run under the exp pass of the second) -- and the peeled 257th query row is
+// done by the CTA that holds tile 1, scratch in the upper half of that buffer while the S MMA
+// still reads Q from the lower half.  Work items (image, head, tile) are dealt so that
+// neighbouring CTAs hold the two tiles of one (image, head) at the same time (K / V hit in
+// L2) and every CTA alternates between tile 0 and tile 1 (balanced peeled-row work).
+// =====================================================================================
+constexpr int AT3_THREADS = 160;   // 4 worker warps + 1 control warp
+constexpr int AT3_CTRL_WARP = 4;
+
+struct AttnFwd3Params {
+  int B, H, W;
+  const uint16_t* qkv;
+  uint16_t* o_out;
+  float* lse_out;
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(AT3_THREADS, 2)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x 256
+                 AttnFwd3Params P) {
+  constexpr int T = 257;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int W = P.W;
+  uint8_t* s_k = smem;                    // [256][64] K, K-major SW128
+  uint8_t* s_v = s_k + 32768;             // [256][64] V (consumed MN-major)
+  uint8_t* s_c = s_v + 32768;             // 32 KB: Q tile (first 16 KB) until S is done, then a P half
+  uint16_t* s_tail = reinterpret_cast<uint16_t*>(s_c + 32768);   // [2 (item parity)]{k_tail[64], v_tail[64]}
+  uint16_t* s_qtail = s_tail + 256;       // [64] the peeled query row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_qtail + 64);
+  uint64_t* bar_k = bars + 0;
+  uint64_t* bar_v = bars + 1;
+  uint64_t* bar_q = bars + 2;
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_p0 = bars + 4;      // 128 arrivals: P columns [0, 128) written
+  uint64_t* bar_pfree = bars + 5;   // first-half PV MMAs done: the P buffer may be overwritten
+  uint64_t* bar_p1 = bars + 6;      // 128 arrivals: P columns [128, 256) written
+  uint64_t* bar_o = bars + 7;
+  uint64_t* bar_ofree = bars + 8;   // 128 arrivals: O read out, TMEM free for the next S
+  uint64_t* bar_tail = bars + 9;    // 128 arrivals: peeled query row done with K / V
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p0, 128);
+    mbar_init(bar_pfree, 1);
+    mbar_init(bar_p1, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_ofree, 128);
+    mbar_init(bar_tail, 128);
+    fence_barrier_init();
+  }
+  if (warp == AT3_CTRL_WARP) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_work = P.B * P.H * 2;
+  const uint32_t f = (uint32_t)FMT;
+  // k-th work item of this CTA: neighbours hold the two tiles of one (image, head); the tile
+  // alternates with k
+  auto work = [&](int k, int& item, int& tile) -> bool {
+    const int idx = (int)blockIdx.x + k * (int)gridDim.x;
+    if (idx >= n_work) return false;
+    item = idx >> 1;
+    tile = (idx ^ k) & 1;
+    return true;
+  };
+
+  if (warp == AT3_CTRL_WARP) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issuer =====================
+      auto load_k = [&](int item) {
+        mbar_arrive_expect_tx(bar_k, 32768);
+        tma_load_3d(s_k, &tmFull, bar_k, W + (item % P.H) * 64, 0, item / P.H);
+      };
+      auto load_v = [&](int item) {
+        mbar_arrive_expect_tx(bar_v, 32768);
+        tma_load_3d(s_v, &tmFull, bar_v, 2 * W + (item % P.H) * 64, 0, item / P.H);
+      };
+      auto load_q = [&](int item, int tile) {
+        mbar_arrive_expect_tx(bar_q, 16384);
+        tma_load_3d(s_c, &tmTile, bar_q, (item % P.H) * 64, tile * 128, item / P.H);
+      };
+      const uint32_t idS = idesc_ab(f, f, 128, 256, 0, 0);
+      const uint32_t idO = idesc_ab(f, f, 128, 64, 0, 1);
+      const uint32_t ca = smem_u32(s_c), ka = smem_u32(s_k), va = smem_u32(s_v);
+      int item, tile, nitem, ntile, n_tail = 0;
+      if (work(0, item, tile)) {
+        load_k(item);
+        load_v(item);
+        load_q(item, tile);
+      }
+      for (int k = 0; work(k, item, tile); ++k) {
+        const uint32_t ph = k & 1;
+        const bool more = work(k + 1, nitem, ntile);
+        mbar_wait(bar_k, ph, 130);
+        mbar_wait(bar_q, ph, 131);
+        if (k > 0) mbar_wait(bar_ofree, ph ^ 1, 132);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_f16(tmem, make_smem_desc_sw128(ca + s * 32, 16, 1024),
+                   make_smem_desc_sw128(ka + s * 32, 16, 1024), idS, s > 0);
+        umma_commit(bar_s);
+        mbar_wait(bar_s, ph, 133);                                   // K consumed by the MMAs
+        if (tile == 1) { mbar_wait(bar_tail, n_tail & 1, 137); ++n_tail; }   // ... and by the peeled row
+        if (more) load_k(nitem);
+        mbar_wait(bar_v, ph, 134);
+        mbar_wait(bar_p0, ph, 135);                                  // P[:, 0:128) written (Q consumed)
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          umma_f16(tmem, make_smem_desc_sw128(ca + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(va + s * 2048, 8192, 1024), idO, s > 0);
+        umma_commit(bar_pfree);
+        mbar_wait(bar_p1, ph, 136);                                  // P[:, 128:256) written
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          umma_f16(tmem, make_smem_desc_sw128(ca + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(va + (8 + s) * 2048, 8192, 1024), idO, 1);
+        umma_commit(bar_o);
+        mbar_wait(bar_o, ph, 138);                                   // V and P consumed
+        if (more) {
+          load_v(nitem);
+          load_q(nitem, ntile);
+        }
+      }
+    }
+  } else {
+    // ===================== row workers: thread = one row of the tile =====================
+    const int r = threadIdx.x;                        // 0 .. 127
+    const uint32_t ts = tmem + ((uint32_t)(warp * 32) << 16);
+    const float c2 = 0.125f * 1.4426950408889634f;
+    int item, tile;
+    for (int k = 0; work(k, item, tile); ++k) {
+      const uint32_t ph = k & 1;
+      // double-buffered by item parity: a warp that runs ahead into item k + 1 must not
+      // overwrite the rows a slower warp still reads in the epilogue of item k
+      uint16_t* tl = s_tail + ph * 128;
+      const uint16_t* kt = tl;                        // k_tail[64]
+      const uint16_t* vt = tl + 64;                   // v_tail[64]
+      const int b = item / P.H, h = item % P.H;
+      const int row = tile * 128 + r;
+      if (r < 16) {  // the peeled key / value row (index 256)
+        const uint16_t* src = P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 +
+                              (r < 8 ? W : 2 * W) + (r & 7) * 8;
+        *reinterpret_cast<uint4*>(tl + r * 8) = *reinterpret_cast<const uint4*>(src);
+      }
+      if (tile == 1 && r >= 16 && r < 24)
+        *reinterpret_cast<uint4*>(s_qtail + (r - 16) * 8) = *reinterpret_cast<const uint4*>(
+            P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 + (r - 16) * 8);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tile == 1) {
+        // ---- the peeled QUERY row (token 256) on the CUDA cores, in the shadow of the S MMA:
+        // scores against all 257 keys, softmax, P V.  Scratch = upper half of the Q / P buffer.
+        float* sc = reinterpret_cast<float*>(s_c + 16384);   // [257] scores / probabilities
+        float* red = sc + 264;                               // [8] warp partials
+        float* oh = red + 8;                                 // [2][64] output halves
+        mbar_wait(bar_k, ph, 143);
+        float qv[64];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 qu = *reinterpret_cast<const uint4*>(s_qtail + c * 8);
+          const uint32_t* qa = &qu.x;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = unpackc<FMT>(qa[i]);
+            qv[c * 8 + 2 * i] = x.x;
+            qv[c * 8 + 2 * i + 1] = x.y;
+          }
+        }
+        float lmax = -INFINITY;
+        for (int kv = r; kv < T; kv += 128) {
+          float acc = 0.f;
+          const uint8_t* krow = s_k + kv * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 ku = kv < 256
+                                 ? *reinterpret_cast<const uint4*>(krow + ((c ^ (kv & 7)) << 4))
+                                 : *reinterpret_cast<const uint4*>(kt + c * 8);
+            const uint32_t* kaa = &ku.x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 y = unpackc<FMT>(kaa[i]);
+              acc = fmaf(qv[c * 8 + 2 * i], y.x, fmaf(qv[c * 8 + 2 * i + 1], y.y, acc));
+            }
+          }
+          sc[kv] = acc;
+          lmax = fmaxf(lmax, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffff, lmax, o));
+        if (lane == 0) red[warp] = lmax;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float tmc = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * c2;
+        float lsum = 0.f;
+        for (int kv = r; kv < T; kv += 128) {
+          const float e = fast_ex2(fmaf(sc[kv], c2, -tmc));
+          sc[kv] = e;
+          lsum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffff, lsum, o);
+        if (lane == 0) red[4 + warp] = lsum;
+        mbar_wait(bar_v, ph, 144);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const float tsum = (red[4] + red[5]) + (red[6] + red[7]);
+        {  // o[d] over this thread's half of the keys
+          const int d = r & 63, hf = r >> 6;
+          const uint8_t* vbase = s_v + (size_t)(hf * 128) * 128 + (d & 7) * 2;
+          const float* scb = sc + hf * 128;
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+          for (int j = 0; j < 128; j += 2) {
+            const uint16_t h0 = *reinterpret_cast<const uint16_t*>(
+                vbase + j * 128 + (((d >> 3) ^ (j & 7)) << 4));
+            const uint16_t h1 = *reinterpret_cast<const uint16_t*>(
+                vbase + (j + 1) * 128 + (((d >> 3) ^ ((j + 1) & 7)) << 4));
+            acc0 = fmaf(scb[j], ld1<FMT>(&h0), acc0);
+            acc1 = fmaf(scb[j + 1], ld1<FMT>(&h1), acc1);
+          }
+          float acc = acc0 + acc1;
+          if (hf == 1) {
+            const uint16_t hv = vt[d];
+            acc = fmaf(sc[256], ld1<FMT>(&hv), acc);
+          }
+          oh[hf * 64 + d] = acc;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (r < 32) {
+          const float inv = 1.f / tsum;
+          const float o0 = (oh[2 * r] + oh[64 + 2 * r]) * inv;
+          const float o1 = (oh[2 * r + 1] + oh[64 + 2 * r + 1]) * inv;
+          reinterpret_cast<uint32_t*>(P.o_out + ((size_t)b * T + 256) * W + h * 64)[r] =
+              packc<FMT>(o0, o1);
+          if (r == 0)
+            P.lse_out[((size_t)b * P.H + h) * T + 256] = (tmc + log2f(tsum)) * 0.6931471805599453f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // scratch free again
+        mbar_arrive(bar_tail);
+      }
+      mbar_wait(bar_q, ph, 142);   // makes the TMA-written Q tile visible
+      float s_t = 0.f;
+      {  // score against the peeled key: q_row . k_tail from swizzled smem
+        const uint8_t* qrow = s_c + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 qu = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+          const uint4 ku = *reinterpret_cast<const uint4*>(kt + c * 8);
+          const uint32_t* qa = &qu.x;
+          const uint32_t* kaa = &ku.x;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = unpackc<FMT>(qa[i]), y = unpackc<FMT>(kaa[i]);
+            s_t = fmaf(x.x, y.x, fmaf(x.y, y.y, s_t));
+          }
+        }
+      }
+      mbar_wait(bar_s, ph, 140);
+      tc_fence_after();
+      float mx;
+      {
+        float m0 = s_t, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        auto pmax = [&](const uint32_t (&v)[16]) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(v[i]));
+            m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+          }
+        };
+        uint32_t va[16], vb[16];
+        tmem_ld16(ts, va);
+#pragma unroll 1
+        for (int q = 0; q < 16; q += 2) {
+          tmem_ld_wait();
+          tmem_ld16(ts + (q + 1) * 16, vb);
+          pmax(va);
+          tmem_ld_wait();
+          if (q + 2 < 16) tmem_ld16(ts + (q + 2) * 16, va);
+          pmax(vb);
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      const float mc = mx * c2;
+      const float p_t = fast_ex2(fmaf(s_t, c2, -mc));
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      uint8_t* prow = s_c + r * 128;
+      const uint32_t rx = (uint32_t)(r & 7) << 4;
+      auto pexp = [&](const uint32_t (&v)[16], int q) {   // q: 16-column piece 0..7 of this half
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = fast_ex2(fmaf(__uint_as_float(v[i]), c2, -mc));
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          sum0 += e[i]; sum1 += e[i + 1]; sum2 += e[i + 2]; sum3 += e[i + 3];
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 2; ++q8) {
+          const int cc = q * 16 + q8 * 8;   // column within the 128-column half
+          *reinterpret_cast<uint4*>(prow + (cc >> 6) * 16384 +
+                                    (((uint32_t)((cc & 63) >> 3) << 4) ^ rx)) =
+              make_uint4(packc<FMT>(e[q8 * 8 + 0], e[q8 * 8 + 1]),
+                         packc<FMT>(e[q8 * 8 + 2], e[q8 * 8 + 3]),
+                         packc<FMT>(e[q8 * 8 + 4], e[q8 * 8 + 5]),
+                         packc<FMT>(e[q8 * 8 + 6], e[q8 * 8 + 7]));
+        }
+      };
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) mbar_wait(bar_pfree, ph, 145);   // first-half PV MMAs done with the buffer
+        const uint32_t tb = ts + half * 128;
+        uint32_t va[16], vb[16];
+        tmem_ld16(tb, va);
+#pragma unroll 1
+        for (int q = 0; q < 8; q += 2) {
+          tmem_ld_wait();
+          tmem_ld16(tb + (q + 1) * 16, vb);
+          pexp(va, q);
+          tmem_ld_wait();
+          if (q + 2 < 8) tmem_ld16(tb + (q + 2) * 16, va);
+          pexp(vb, q + 1);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(half == 0 ? bar_p0 : bar_p1);
+      }
+      const float rsum = (sum0 + sum1) + (sum2 + sum3) + p_t;
+      mbar_wait(bar_o, ph, 141);
+      tc_fence_after();
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(ts, v0);
+        tmem_ld32(ts + 32, v1);
+        tmem_ld_wait();
+        const float inv = 1.f / rsum;
+        const size_t grow = (size_t)b * T + row;
+        uint4* dst = reinterpret_cast<uint4*>(P.o_out + grow * W + h * 64);
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) {
+          const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
+          const uint4 vu = *reinterpret_cast<const uint4*>(vt + q8 * 8);
+          const uint32_t* vaa = &vu.x;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 y = unpackc<FMT>(vaa[i]);
+            o[2 * i] = fmaf(p_t, y.x, o[2 * i]);
+            o[2 * i + 1] = fmaf(p_t, y.y, o[2 * i + 1]);
+          }
+          uint4 u;
+          u.x = packc<FMT>(o[0] * inv, o[1] * inv);
+          u.y = packc<FMT>(o[2] * inv, o[3] * inv);
+          u.z = packc<FMT>(o[4] * inv, o[5] * inv);
+          u.w = packc<FMT>(o[6] * inv, o[7] * inv);
+          dst[q8] = u;
+        }
+        P.lse_out[((size_t)b * P.H + h) * T + row] = (mc + log2f(rsum)) * 0.6931471805599453f;
+      }
+      tc_fence_before();
+      mbar_arrive(bar_ofree);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT3_CTRL_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 }  // namespace rvlm
 
 using namespace rvlm;
@@ -2187,6 +2582,31 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   if (rc) return rc;
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
+  static const int use_fwd3 = [] {
+    const char* e = getenv("RVLM_ATTN_FWD3");
+    return (e && e[0] == '1') ? 1 : 0;
+  }();
+  if (T == 257 && use_fwd3) {   // one tile per CTA, two CTAs per SM
+    AttnFwd3Params P3{B, H, H * 64, P.qkv, P.o_out, P.lse_out};
+    const size_t smem3 = 3 * 32768 + 512 + 128 + 128 + 1024;
+    auto kern3 = fmt ? attn_fwd3_kernel<1> : attn_fwd3_kernel<0>;
+    static bool set3[2] = {false, false};
+    if (!set3[fmt ? 1 : 0]) {
+      cudaError_t e = cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem3);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kern3, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return -(int)e - 1000;
+      set3[fmt ? 1 : 0] = true;
+    }
+    int grid3 = 2 * sm_count();
+    if (2 * B * H < grid3) grid3 = 2 * B * H;
+    kern3<<<grid3, AT3_THREADS, smem3, (cudaStream_t)stream>>>(tmTile, tmFull, P3);
+    count_launch(1);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e - 1000;
+  }
   const size_t smem = (size_t)2 * P.kvm * 128 + 2 * 16384 + (size_t)2 * P.nblk * 16384 + 512 +
                       256 + 544 + 128 + 1024;   // + q_tail[2][64] + part[2][68] + barriers + align
   auto kern = fmt ? attn_fwd2_kernel<1> : attn_fwd2_kernel<0>;

@@ -2323,14 +2323,21 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       const uint16_t* vt = tl + 64;                   // v_tail[64]
       const int b = item / P.H, h = item % P.H;
       const int row = tile * 128 + r;
-      if (r < 16) {  // the peeled key / value row (index 256)
-        const uint16_t* src = P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 +
-                              (r < 8 ? W : 2 * W) + (r & 7) * 8;
-        *reinterpret_cast<uint4*>(tl + r * 8) = *reinterpret_cast<const uint4*>(src);
+      // token 256 of this (image, head): threads 0-7 its key row, 8-15 its value row, 16-23 its
+      // query row (tile 1 only).  Item 0 loads them here; later items find them prefetched by
+      // the previous iteration (issued after the max pass, stored after the epilogue).
+      auto tail_src = [&](int bb, int hh) -> const uint16_t* {
+        return P.qkv + ((size_t)bb * T + 256) * 3 * W + hh * 64 +
+               (r < 8 ? W : (r < 16 ? 2 * W : 0)) + (r & 7) * 8;
+      };
+      if (k == 0 && r < 24) {
+        const uint4 t4 = *reinterpret_cast<const uint4*>(tail_src(b, h));
+        if (r < 16) *reinterpret_cast<uint4*>(tl + r * 8) = t4;
+        else if (tile == 1) *reinterpret_cast<uint4*>(s_qtail + (r - 16) * 8) = t4;
       }
-      if (tile == 1 && r >= 16 && r < 24)
-        *reinterpret_cast<uint4*>(s_qtail + (r - 16) * 8) = *reinterpret_cast<const uint4*>(
-            P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 + (r - 16) * 8);
+      int nitem = 0, ntile = 0;
+      const bool more = work(k + 1, nitem, ntile);
+      uint4 pre = make_uint4(0u, 0u, 0u, 0u);
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (tile == 1) {
         // ---- the peeled QUERY row (token 256) on the CUDA cores, in the shadow of the S MMA:
@@ -2465,6 +2472,8 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
+      if (more && r < 24 && (r < 16 || ntile == 1))       // next item's token-256 rows, in flight
+        pre = *reinterpret_cast<const uint4*>(tail_src(nitem / P.H, nitem % P.H));   // under the exp pass
       const float mc = mx * c2;
       const float p_t = fast_ex2(fmaf(s_t, c2, -mc));
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
@@ -2544,6 +2553,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       }
       tc_fence_before();
       mbar_arrive(bar_ofree);
+      if (more && r < 24) {   // published by the barrier at the top of the next item
+        if (r < 16) *reinterpret_cast<uint4*>(s_tail + (ph ^ 1) * 128 + r * 8) = pre;
+        else if (ntile == 1) *reinterpret_cast<uint4*>(s_qtail + (r - 16) * 8) = pre;
+      }
     }
   }
 
@@ -2583,8 +2596,8 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
   static const int use_fwd3 = [] {
-    const char* e = getenv("RVLM_ATTN_FWD3");
-    return (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("RVLM_ATTN_FWD3");   // default on; RVLM_ATTN_FWD3=0 selects fwd2
+    return (e && e[0] == '0') ? 0 : 1;
   }();
   if (T == 257 && use_fwd3) {   // one tile per CTA, two CTAs per SM
     AttnFwd3Params P3{B, H, H * 64, P.qkv, P.o_out, P.lse_out};

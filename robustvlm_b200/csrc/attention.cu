@@ -644,6 +644,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         const bool valid = row < P.tm;
         const bool warp_valid = (g * 128 + (warp & 3) * 32) < P.tm;
         if (P.tail) {
+          // NOTE: single-buffered -- a warp that runs ahead into the next item rewrites these
+          // rows while a slower warp of the group may still read v_tail in its epilogue; the
+          // global-load latency in front of the store has always covered the skew (results are
+          // bit-stable run to run), but attn_fwd3 double-buffers them by item parity instead.
           if (r < 16) {  // this group's copy of the peeled key / value row (index 256)
             const uint16_t* src = P.qkv + ((size_t)b * T + 256) * 3 * W + h * 64 +
                                   (r < 8 ? W : 2 * W) + (r & 7) * 8;
@@ -2595,10 +2599,8 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   if (rc) return rc;
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
-  static const int use_fwd3 = [] {
-    const char* e = getenv("RVLM_ATTN_FWD3");   // default on; RVLM_ATTN_FWD3=0 selects fwd2
-    return (e && e[0] == '0') ? 0 : 1;
-  }();
+  const char* env3 = getenv("RVLM_ATTN_FWD3");   // default on; RVLM_ATTN_FWD3=0 selects fwd2
+  const bool use_fwd3 = !(env3 && env3[0] == '0');   // (read per call: the tests toggle it)
   if (T == 257 && use_fwd3) {   // one tile per CTA, two CTAs per SM
     AttnFwd3Params P3{B, H, H * 64, P.qkv, P.o_out, P.lse_out};
     const size_t smem3 = 3 * 32768 + 512 + 128 + 128 + 1024;

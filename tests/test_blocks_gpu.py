@@ -146,10 +146,17 @@ def _attn_ref(qkv, B, T, H):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc", "tc3"])
-@pytest.mark.parametrize("B,T,H", [(2, 50, 2), (3, 257, 4), (1, 257, 16), (2, 256, 4), (40, 257, 8)])
+@pytest.mark.parametrize("impl", ["simt", "tc", "tc3", "tc_fwd2"])
+@pytest.mark.parametrize("B,T,H", [(2, 50, 2), (3, 257, 4), (1, 257, 16), (2, 256, 4), (40, 257, 8),
+                                   (37, 257, 16)])
 def test_attention_fwd_bwd(impl, B, T, H, monkeypatch):
     nat = _nat()
+    # forward: T = 257 runs attn_fwd3 (one tile per CTA, two CTAs per SM) unless RVLM_ATTN_FWD3=0
+    monkeypatch.setenv("RVLM_ATTN_FWD3", "0" if impl == "tc_fwd2" else "1")
+    if impl == "tc_fwd2":
+        if T != 257:
+            pytest.skip("fwd2 is already the forward for T != 257")
+        impl = "tc"
     if impl == "tc3":   # the fused dQ/dK/dV backward kernel (T in {256, 257})
         if T < 256:
             pytest.skip("fused backward covers T in {256, 257}")

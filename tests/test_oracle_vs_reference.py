@@ -82,3 +82,42 @@ def test_model_wrappers(ns, setup):
     with torch.no_grad():
         for flag in (False, True):
             assert torch.equal(m(x, output_normalize=flag), r(x, output_normalize=flag))
+
+
+@pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 1.5)])
+def test_apgd_attack_variants(ns, setup, norm, eps):
+    """Less-travelled branches of autoattack/autopgd_base.py: EOT averaging (:267-286,371-386),
+    perturb(best_loss=True) (:482-502), y=None (:470-473), use_rs=False (:219-220), an explicit
+    x_init through attack_single_run (:221-224)."""
+    m, x, d0, y, text, eo = setup
+    cm = vit.ClassificationModel(m.model, text, 100.0)
+    with torch.no_grad():
+        yc = cm(x).argmax(1)
+    kw = dict(n_iter=9, norm=norm, n_restarts=2, eps=eps, seed=3, alpha=2.0)
+    A, R = oa.APGDAttack(cm, eot_iter=2, **kw), ns.APGDAttack(cm, eot_iter=2, **kw)
+    assert torch.equal(A.perturb(x, yc), R.perturb(x, yc))
+    A, R = oa.APGDAttack(cm, loss="dlr", **kw), ns.APGDAttack(cm, loss="dlr", **kw)
+    torch.manual_seed(11)
+    a = A.perturb(x, yc, best_loss=True)
+    torch.manual_seed(11)
+    b = R.perturb(x, yc, best_loss=True)
+    assert torch.equal(a, b)
+    assert torch.equal(A.perturb(x), R.perturb(x))                       # y = None -> predictions
+    A, R = oa.APGDAttack(cm, use_rs=False, **kw), ns.APGDAttack(cm, use_rs=False, **kw)
+    assert torch.equal(A.perturb(x, yc), R.perturb(x, yc))
+    x0 = (x + d0).clamp(0, 1)
+    ra, rr = A.attack_single_run(x, yc, x_init=x0), R.attack_single_run(x, yc, x_init=x0)
+    for u, v in zip(ra, rr):
+        assert torch.equal(u, v)
+
+
+def test_apgd_train_initial_stepsize(ns, setup):
+    """`initial_stepsize` (train/apgd_train.py:168-169), as the in-training evaluation passes it
+    when clean_weight > 0 (train/adversarial_training_clip.py:407)."""
+    m, x, d0, y, text, eo = setup
+    for norm, eps in (("linf", 4 / 255), ("l2", 1.5)):
+        a = oa.apgd_train(m, x, y, norm, eps, n_iter=12, initial_stepsize=0.05 * eps,
+                          loss_fn=oa.ComputeLossWrapper(eo, text, "none", "ce", 100.0))
+        b = ns.apgd_train(m, x, y, norm, eps, n_iter=12, initial_stepsize=0.05 * eps,
+                          loss_fn=ns.ComputeLossWrapper(eo, text, "none", "ce", 100.0))
+        assert torch.equal(a, b)

@@ -14,8 +14,6 @@ the L1/L0 branches are secondary / dead code).
 """
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn.functional as F
 

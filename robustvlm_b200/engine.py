@@ -8,7 +8,7 @@ caller-side workspace tensor.  torch is used for device memory and streams only.
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, Structure, byref, c_float, c_int, c_longlong, c_size_t, c_void_p
+from ctypes import POINTER, Structure, byref, c_float, c_int, c_size_t, c_void_p
 
 import torch
 

@@ -21,6 +21,8 @@
  *     allocation (workspaces are sized by query calls and owned by the caller);
  *   - all calls are asynchronous on `stream` unless stated otherwise;
  *   - fmt: 0 = fp16, 1 = bf16 (16-bit operand / activation format).
+ *   - the per-function cudaFuncSetAttribute opt-ins are cached per device; a handle must be
+ *     used with the device it was created on current.
  */
 #ifndef RVLM_H_
 #define RVLM_H_
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RVLM_ABI_VERSION 1
+#define RVLM_ABI_VERSION 2
 
 #define RVLM_ERR_INVAL (-22)
 #define RVLM_ERR_ALIGN (-23)
@@ -43,6 +45,10 @@ extern "C" {
 
 #define RVLM_FMT_F16 0
 #define RVLM_FMT_BF16 1
+/* forward operands as fp16 hi + lo pairs, three tcgen05 MMAs per product (hi*hi + lo*hi + hi*lo):
+ * the fp32-class forward for FARE's cancellation site (train/adversarial_training_clip.py:509-521,
+ * SURVEY.md Appendix E).  Valid for rvlm_vit_config.fmt_fwd only. */
+#define RVLM_FMT_F16X2 2
 
 int rvlm_abi_version(void);
 const char* rvlm_strerror(int code);
@@ -80,6 +86,12 @@ int rvlm_gemm16_out16(const void* A, int lda, const void* B, int ldb, void* C, i
 int rvlm_gemm16_out32(const void* A, int lda, const void* B, int ldb, float* C, int ldc,
                       const float* bias, const float* resid, int ldr, int M, int N, int K, int fmt,
                       int flags, void* stream);
+/* Split operands: A = A_hi + A_lo, B = B_hi + B_lo (fp16 pairs, lo = fp16(x - hi)); the product
+ * is formed as hi*hi + lo*hi + hi*lo by three tcgen05 MMAs into one fp32 TMEM accumulator
+ * (2-CTA kernel, K-major operands; the forward GEMM of RVLM_FMT_F16X2). */
+int rvlm_gemm16_split_out32(const void* A_hi, const void* A_lo, int lda, const void* B_hi,
+                            const void* B_lo, int ldb, float* C, int ldc, const float* bias,
+                            const float* resid, int ldr, int M, int N, int K, void* stream);
 /* H = A*B^T + bias (pre-activation, may be NULL), Act = QuickGELU(H); both 16-bit [M,N] pitch ld */
 int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* H, void* Act, int ld,
                      const float* bias, int M, int N, int K, int fmt, void* stream);
@@ -174,6 +186,11 @@ int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H,
 int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16, float* lse_tmp,
                   void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o, int fmt_g,
                   void* stream);
+/* Split-operand forward (the attention part of RVLM_FMT_F16X2): q | k | v and o as fp16 hi + lo
+ * pairs in separate buffers of the same layout; softmax(q k^T / 8) v with every product formed as
+ * hi*hi + lo*hi + hi*lo.  o_lo and lse may be NULL.  T <= 272. */
+int rvlm_attn_fwd_split(const void* qkv_hi, const void* qkv_lo, void* o_hi, void* o_lo, float* lse,
+                        int B, int T, int H, void* stream);
 /* Class-token row only (the last block of the tower needs nothing else):
  * forward writes o16[b*T, :] for every image b; backward takes the class-token output
  * gradient do_cls16 [B, W] and writes the dense dqkv16 [B*T, 3W] (dQ rows t > 0 are zero).
@@ -203,7 +220,8 @@ typedef void* rvlm_vit_handle;
 typedef struct {
   int image, patch, width, layers, heads, mlp, out_dim;
   float mean[3], std[3]; /* Normalize() inside the model (:116,254) */
-  int fmt_fwd;           /* 16-bit format of forward operands  (RVLM_FMT_F16 recommended) */
+  int fmt_fwd;           /* format of forward operands: RVLM_FMT_F16 (fast), RVLM_FMT_F16X2 (fp32-class)
+                            or RVLM_FMT_BF16 (the outer training step) */
   int fmt_bwd;           /* 16-bit format of gradient operands (RVLM_FMT_BF16 recommended) */
   int flags;
 } rvlm_vit_config;
@@ -340,14 +358,6 @@ int rvlm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
  * weight decay, momentum buffer initialised with the first gradient (step == 1), no dampening. */
 int rvlm_sgd_step(float* param, const float* grad, float* momentum_buf, long long n, double lr,
                   double momentum, double weight_decay, int step, void* stream);
-
-/* Self-test of tcgen05.mma with the A operand in TMEM: C[128,64] = A[128,64] * B[64,64]^T
- * (16-bit A, B row-major; fp32 C). */
-int rvlm_selftest_ts_mma(const void* A, const void* B, float* C, int fmt, void* stream);
-
-/* Test hook: pointer of an internal workspace buffer (see vit_engine.cu). */
-int rvlm_vit_debug_buffer(rvlm_vit_handle h, void* workspace, int B, int with_backward, int which,
-                          int layer, void** ptr_out);
 
 #ifdef __cplusplus
 }

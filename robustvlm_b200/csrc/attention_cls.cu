@@ -87,20 +87,30 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// qkv_lo / o_lo non-null: split-operand forward (fp16 hi + lo pairs; x = hi + lo in fp32)
 __global__ void __launch_bounds__(CLS_THREADS)
-attn_cls_fwd_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ o, int T, int H,
-                    int fmt) {
+attn_cls_fwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict__ qkv_lo,
+                    uint16_t* __restrict__ o, uint16_t* __restrict__ o_lo, int T, int H, int fmt) {
   __shared__ float sc[CLS_TMAX];
   __shared__ float red[4];
   __shared__ float oh[2][64];
   const int W = H * 64, tid = threadIdx.x;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const uint16_t* base = qkv + (size_t)b * T * 3 * W + h * 64;
+  const size_t boff = (size_t)b * T * 3 * W + h * 64;
+  const uint16_t* base = qkv + boff;
   float q[64];
   load_vec64(base, fmt, q);
+  if (qkv_lo) {
+    float ql[64];
+    load_vec64(qkv_lo + boff, 0, ql);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) q[i] += ql[i];
+  }
   float lmax = -INFINITY;
   for (int kv = tid; kv < T; kv += CLS_THREADS) {
-    const float s = dot_row64(base + (size_t)kv * 3 * W + W, fmt, q) * 0.125f;
+    float s = dot_row64(base + (size_t)kv * 3 * W + W, fmt, q);
+    if (qkv_lo) s += dot_row64(qkv_lo + boff + (size_t)kv * 3 * W + W, 0, q);
+    s *= 0.125f;
     sc[kv] = s;
     lmax = fmaxf(lmax, s);
   }
@@ -123,13 +133,23 @@ attn_cls_fwd_kernel(const uint16_t* __restrict__ qkv, uint16_t* __restrict__ o, 
     a1 = fmaf(sc[kv + 1], ld1f(vp + (size_t)(kv + 1) * 3 * W, fmt), a1);
   }
   if (kv < k1) a0 = fmaf(sc[kv], ld1f(vp + (size_t)kv * 3 * W, fmt), a0);
+  if (qkv_lo) {
+    const uint16_t* vl = qkv_lo + boff + 2 * W + d;
+    for (kv = k0; kv < k1; ++kv) a1 = fmaf(sc[kv], ld1f(vl + (size_t)kv * 3 * W, 0), a1);
+  }
   oh[hf][d] = a0 + a1;
   __syncthreads();
   if (tid < 32) {
     const float inv = 1.f / sum;
-    reinterpret_cast<uint32_t*>(o + (size_t)b * T * W + h * 64)[tid] =
-        pack2((oh[0][2 * tid] + oh[1][2 * tid]) * inv,
-              (oh[0][2 * tid + 1] + oh[1][2 * tid + 1]) * inv, fmt);
+    const float o0 = (oh[0][2 * tid] + oh[1][2 * tid]) * inv;
+    const float o1 = (oh[0][2 * tid + 1] + oh[1][2 * tid + 1]) * inv;
+    const uint32_t hi = pack2(o0, o1, fmt);
+    reinterpret_cast<uint32_t*>(o + (size_t)b * T * W + h * 64)[tid] = hi;
+    if (o_lo) {
+      const float2 hf2 = unpack2(hi, 0);
+      reinterpret_cast<uint32_t*>(o_lo + (size_t)b * T * W + h * 64)[tid] =
+          pack2(o0 - hf2.x, o1 - hf2.y, 0);
+    }
   }
 }
 
@@ -200,10 +220,14 @@ attn_cls_bwd_kernel(const uint16_t* __restrict__ qkv, const uint16_t* __restrict
 }  // namespace
 
 // o16[b*T, :] (class-token rows only; the other rows of o16 are left untouched)
-int attn_cls_fwd(const void* qkv16, void* o16, int B, int T, int H, int fmt, cudaStream_t st) {
+int attn_cls_fwd(const void* qkv16, void* o16, int B, int T, int H, int fmt, cudaStream_t st,
+                 const void* qkv16lo, void* o16lo) {
   if (B <= 0 || T <= 0 || T > CLS_TMAX || H <= 0) return RVLM_ERR_INVAL;
+  if ((qkv16lo || o16lo) && fmt != 0) return RVLM_ERR_INVAL;
   attn_cls_fwd_kernel<<<B * H, CLS_THREADS, 0, st>>>(reinterpret_cast<const uint16_t*>(qkv16),
-                                                    reinterpret_cast<uint16_t*>(o16), T, H, fmt);
+                                                    reinterpret_cast<const uint16_t*>(qkv16lo),
+                                                    reinterpret_cast<uint16_t*>(o16),
+                                                    reinterpret_cast<uint16_t*>(o16lo), T, H, fmt);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
@@ -227,7 +251,7 @@ int attn_cls_bwd(const void* qkv16, const void* do_cls, void* dqkv16, int B, int
 extern "C" int rvlm_attn_cls_fwd(const void* qkv16, void* o16, int B, int T, int H, int fmt,
                                  void* stream) {
   if (!qkv16 || !o16) return RVLM_ERR_INVAL;
-  return rvlm::attn_cls_fwd(qkv16, o16, B, T, H, fmt, (cudaStream_t)stream);
+  return rvlm::attn_cls_fwd(qkv16, o16, B, T, H, fmt, (cudaStream_t)stream, nullptr, nullptr);
 }
 extern "C" int rvlm_attn_cls_bwd(const void* qkv16, const void* do_cls16, void* dqkv16, int B, int T,
                                  int H, int fmt, void* stream) {

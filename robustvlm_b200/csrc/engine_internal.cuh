@@ -73,7 +73,7 @@ int launch_patchify(const float* img, float* pm, int B, const PatchGeom& g, cuda
 int launch_unpatchify(const float* pm, float* img, int B, const PatchGeom& g, cudaStream_t st);
 // A16[r, k] = 16-bit((x[r,k] + delta[r,k] - mean_c) / std_c); delta may be null
 int launch_patch_operand(const float* xp, const float* dp, uint16_t* a16, int lda, long long rows,
-                         const PatchGeom& g, int fmt, cudaStream_t st);
+                         const PatchGeom& g, int fmt, cudaStream_t st, uint16_t* a16lo = nullptr);
 // tok[b, 0, :] = cls + pos[0]
 int launch_cls_rows(float* tok, const float* cls, const float* pos, int B, int T, int W,
                     cudaStream_t st);
@@ -127,6 +127,7 @@ struct EpiPatchPgdLinf {
   float* dp;         // [rows, kp] delta (in place)
   float* vp;         // [rows, kp] velocity (in place)
   uint16_t* a16;     // [rows, lda] next forward operand
+  uint16_t* a16lo;   // may be null: its fp16 lo half (split-operand forward)
   int kp, pp, lda, fmt;
   float stepsize, eps, dir, momentum;
   float mean[3], inv_std[3];
@@ -173,10 +174,18 @@ struct EpiPatchPgdLinf {
     pk.x = pack2(nx[0], nx[1], fmt);
     pk.y = pack2(nx[2], nx[3], fmt);
     *reinterpret_cast<uint2*>(a16 + (size_t)row * lda + col) = pk;
+    if (a16lo) {
+      const float2 h0 = unpack2(pk.x, 0), h1 = unpack2(pk.y, 0);
+      uint2 lo;
+      lo.x = pack2(nx[0] - h0.x, nx[1] - h0.y, 0);
+      lo.y = pack2(nx[2] - h1.x, nx[3] - h1.y, 0);
+      *reinterpret_cast<uint2*>(a16lo + (size_t)row * lda + col) = lo;
+    }
   }
 };
 
 // ---- misc elementwise (convert.cu) ----------------------------------------
+// fmt 0 / 1 = fp16 / bf16; fmt 2 = the fp16 lo half of a split operand, fp16(v - float(fp16(v)))
 int launch_convert16(const float* src, uint16_t* dst, long long n, int fmt, cudaStream_t st);
 // dst[c, r] (pitch ldd) = 16-bit(src[r, c]) for src [R, C] row-major
 int launch_transpose_convert16(const float* src, uint16_t* dst, int R, int C, int ldd, int fmt,

@@ -36,6 +36,12 @@ __device__ __forceinline__ float4 unpack4(const uint2& u, int fmt) {
   const float2 a = unpack2(u.x, fmt), b = unpack2(u.y, fmt);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+// fp16 hi + lo pair of four values: hi = fp16(v), lo = fp16(v - hi)  (split-operand forward)
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  hi = pack4(v, 0);
+  const float4 h = unpack4(hi, 0);
+  lo = pack4(make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w), 0);
+}
 // per-column operand of an epilogue (the bias of 4 consecutive columns), loaded once per chunk
 __device__ __forceinline__ float4 load_bias(const float* bias, int col) {
   return bias ? __ldg(reinterpret_cast<const float4*>(bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -72,6 +78,7 @@ struct EpiStore16Dual {
   int ldc;
   const float* bias;
   int fmt, fmt2;
+  uint16_t* Clo;  // may be null: fp16 lo half of C (split-operand forward; fmt == 0)
   using Aux = NoAux;
   using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
@@ -79,7 +86,14 @@ struct EpiStore16Dual {
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
                                              const Col& b) const {
     const float4 v = add4(acc, b);
-    *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(v, fmt);
+    if (Clo) {
+      uint2 hi, lo;
+      split4(v, hi, lo);
+      *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = hi;
+      *reinterpret_cast<uint2*>(Clo + (size_t)row * ldc + col) = lo;
+    } else {
+      *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(v, fmt);
+    }
     if (C2) *reinterpret_cast<uint2*>(C2 + (size_t)row * ldc + col) = pack4(v, fmt2);
   }
 };
@@ -121,6 +135,7 @@ struct EpiGelu {
   int ld;
   const float* bias;
   int fmt;
+  uint16_t* Alo;  // may be null: fp16 lo half of A (split-operand forward; fmt == 0)
   using Aux = NoAux;
   using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
@@ -131,7 +146,14 @@ struct EpiGelu {
     const float4 a = make_float4(quick_gelu(h.x), quick_gelu(h.y), quick_gelu(h.z),
                                  quick_gelu(h.w));
     if (H) *reinterpret_cast<uint2*>(H + (size_t)row * ld + col) = pack4(h, fmt);
-    *reinterpret_cast<uint2*>(A + (size_t)row * ld + col) = pack4(a, fmt);
+    if (Alo) {
+      uint2 hi, lo;
+      split4(a, hi, lo);
+      *reinterpret_cast<uint2*>(A + (size_t)row * ld + col) = hi;
+      *reinterpret_cast<uint2*>(Alo + (size_t)row * ld + col) = lo;
+    } else {
+      *reinterpret_cast<uint2*>(A + (size_t)row * ld + col) = pack4(a, fmt);
+    }
   }
 };
 

@@ -323,28 +323,37 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
       : "memory");
 }
 
+// SPLIT: both operands are given as fp16 hi + lo pairs (x = hi + lo to ~22 bits) and every
+// product is formed as hi*hi + lo*hi + hi*lo, three MMAs into the same TMEM accumulator -- the
+// fp32-class forward FARE's cancellation site needs (the dropped lo*lo
+// term is ~2^-22 relative).  A stage then holds four 16 KB tiles and the ring is 3 deep; per
+// stage the tensor pipe has three times the work, so the fill latency is covered as before.
+template <bool SPLIT>
 struct Gemm2Smem {
-  static constexpr int kStages = 6;
+  static constexpr int kStages = SPLIT ? 3 : 6;
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;   // 128 x 64
   static constexpr int kBBytes = 128 * GEMM_BK * 2;       // half of the 256-row B tile
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * 32 * 4;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
-template <class Epi>
+template <class Epi, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   int M, int N, int K, int fmt, Epi epi) {
-  using S = Gemm2Smem;
+                   const __grid_constant__ CUtensorMap tmAlo,
+                   const __grid_constant__ CUtensorMap tmBlo, int M, int N, int K, int fmt,
+                   Epi epi) {
+  using S = Gemm2Smem<SPLIT>;
   constexpr int kStages = S::kStages;
   constexpr int BN = 256;
   extern __shared__ uint8_t smem_raw[];
   // (pointer arithmetic on the __shared__ array, not an integer round trip: keeps the
   // address space visible to the compiler -> LDS / STS instead of generic LD / ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  // stage layout: [A hi | B hi] (+ [A lo | B lo] when SPLIT), 16 KB each
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint8_t* smem_b = smem + S::kABytes;
   float* staging = reinterpret_cast<float*>(smem + kStages * S::kStageBytes);
   uint64_t* bars =
       reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes + S::kStagingBytes);
@@ -366,6 +375,10 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (SPLIT) {
+      tma_prefetch_desc(&tmAlo);
+      tma_prefetch_desc(&tmBlo);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -403,10 +416,16 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // simply count against the leader's expect_tx (a transiently negative tx-count is
         // legal while the leader's arrival is still pending).  No cross-CTA hop in the loop.
         if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::kStageBytes);
-        tma_load_2d_pair(smem_a + stage * S::kABytes, &tmA, &full_bar[stage], kb * GEMM_BK,
-                         m_blk * 256 + (int)rank * 128);
-        tma_load_2d_pair(smem_b + stage * S::kBBytes, &tmB, &full_bar[stage], kb * GEMM_BK,
-                         n_blk * BN + (int)rank * 128);
+        uint8_t* sa = smem_a + stage * S::kStageBytes;
+        uint8_t* sb = smem_b + stage * S::kStageBytes;
+        tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * GEMM_BK, m_blk * 256 + (int)rank * 128);
+        tma_load_2d_pair(sb, &tmB, &full_bar[stage], kb * GEMM_BK, n_blk * BN + (int)rank * 128);
+        if (SPLIT) {
+          tma_load_2d_pair(sa + 32768, &tmAlo, &full_bar[stage], kb * GEMM_BK,
+                           m_blk * 256 + (int)rank * 128);
+          tma_load_2d_pair(sb + 32768, &tmBlo, &full_bar[stage], kb * GEMM_BK,
+                           n_blk * BN + (int)rank * 128);
+        }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -425,13 +444,20 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int kb = 0; kb < num_k; ++kb) {
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem_a + stage * S::kABytes);
-        const uint32_t b_addr = smem_u32(smem_b + stage * S::kBBytes);
+        const uint32_t a_addr = smem_u32(smem_a + stage * S::kStageBytes);
+        const uint32_t b_addr = smem_u32(smem_b + stage * S::kStageBytes);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k)
-          umma_f16_2cta(tmem_d, make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
-                        make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_f16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (SPLIT) {
+            umma_f16_2cta(tmem_d, make_smem_desc_sw128(a_addr + 32768 + k * 32, 16, 1024), db,
+                          idesc, 1u);
+            umma_f16_2cta(tmem_d, da, make_smem_desc_sw128(b_addr + 32768 + k * 32, 16, 1024),
+                          idesc, 1u);
+          }
+        }
         umma_commit_2cta(&empty_bar[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -493,8 +519,29 @@ void count_launch(int n = 1);
 struct GemmProfScope {
   cudaStream_t st;
   int slot;
-  GemmProfScope(cudaStream_t s, double flops);
+  // flops: algorithmic 2MNK of the product; mma_factor: tensor-pipe passes per product (3 for
+  // split operands) -- reported separately so the roofline can state both
+  GemmProfScope(cudaStream_t s, double flops, double mma_factor = 1.0);
   ~GemmProfScope();
+};
+
+// "Has this been done on the current device?" for the per-function cudaFuncSetAttribute
+// opt-ins: the attribute is per device, so the cache is too (a process may drive several GPUs).
+struct DeviceOnce {
+  unsigned long long mask[2] = {0ull, 0ull};
+  static int dev() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 127;
+  }
+  bool done() const {
+    const int d = dev();
+    return (__atomic_load_n(&mask[d >> 6], __ATOMIC_ACQUIRE) >> (d & 63)) & 1ull;
+  }
+  void mark() {
+    const int d = dev();
+    __atomic_fetch_or(&mask[d >> 6], 1ull << (d & 63), __ATOMIC_RELEASE);
+  }
 };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -510,12 +557,12 @@ int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   else       rc = make_tmap_2d(&tmB, B, K, N, ldb, GEMM_BK);
   if (rc) return rc;
   auto kern = gemm16_kernel<BN, A_MN, B_MN, Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GemmSmem<BN>::kTotal);
     if (e != cudaSuccess) return -(int)e - 1000;
-    attr_set = true;
+    attr_set.mark();
   }
   const int num_tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   int grid = sm_count();
@@ -533,30 +580,43 @@ int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, 
 
 bool gemm_use_2cta();
 
-template <class Epi>
+// Alo / Blo non-null: split operands (fp16 hi + lo), three MMAs per product.
+template <class Epi, bool SPLIT = false>
 int launch_gemm16_2cta(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int fmt,
-                       const Epi& epi, cudaStream_t stream) {
+                       const Epi& epi, cudaStream_t stream, const void* Alo = nullptr,
+                       const void* Blo = nullptr) {
   if (N % 32 != 0 || M <= 0 || K <= 0) return -22;
-  CUtensorMap tmA, tmB;
+  if (SPLIT && (!Alo || !Blo || fmt != 0)) return -22;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo;
   int rc = make_tmap_2d(&tmA, A, M, K, lda, GEMM_BM);
   if (rc) return rc;
   rc = make_tmap_2d(&tmB, B, N, K, ldb, 128);
   if (rc) return rc;
-  auto kern = gemm16_2cta_kernel<Epi>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (SPLIT) {
+    rc = make_tmap_2d(&tmAlo, Alo, M, K, lda, GEMM_BM);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tmBlo, Blo, N, K, ldb, 128);
+    if (rc) return rc;
+  } else {
+    tmAlo = tmA;
+    tmBlo = tmB;
+  }
+  auto kern = gemm16_2cta_kernel<Epi, SPLIT>;
+  using S = Gemm2Smem<SPLIT>;
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Gemm2Smem::kTotal);
+                                         S::kTotal);
     if (e != cudaSuccess) return -(int)e - 1000;
-    attr_set = true;
+    attr_set.mark();
   }
   const int num_tiles = ((M + 255) / 256) * ((N + 255) / 256);
   int grid = sm_count() & ~1;
   if (2 * num_tiles < grid) grid = 2 * num_tiles;
   cudaError_t e;
   {
-    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K);
-    kern<<<grid, GEMM_THREADS, Gemm2Smem::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
+    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K, SPLIT ? 3.0 : 1.0);
+    kern<<<grid, GEMM_THREADS, S::kTotal, stream>>>(tmA, tmB, tmAlo, tmBlo, M, N, K, fmt, epi);
     e = cudaGetLastError();
   }
   count_launch();
@@ -569,6 +629,14 @@ int launch_gemm_kmajor(const void* A, int lda, const void* B, int ldb, int M, in
                        int fmt, const Epi& epi, cudaStream_t stream) {
   if (gemm_use_2cta()) return launch_gemm16_2cta(A, lda, B, ldb, M, N, K, fmt, epi, stream);
   return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, stream);
+}
+// Forward GEMM of the engine: split operands when the lo halves are given (2-CTA kernel only)
+template <class Epi>
+int launch_gemm_fwd(const void* A, const void* Alo, int lda, const void* B, const void* Blo,
+                    int ldb, int M, int N, int K, int fmt, const Epi& epi, cudaStream_t stream) {
+  if (Alo && Blo)
+    return launch_gemm16_2cta<Epi, true>(A, lda, B, ldb, M, N, K, fmt, epi, stream, Alo, Blo);
+  return launch_gemm_kmajor(A, lda, B, ldb, M, N, K, fmt, epi, stream);
 }
 
 }  // namespace rvlm

@@ -53,7 +53,7 @@ extern "C" int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, 
                                 void* stream) {
   if ((reinterpret_cast<uintptr_t>(Act) & 15) || (reinterpret_cast<uintptr_t>(H) & 15) || (ld & 7))
     return RVLM_ERR_ALIGN;
-  EpiGelu epi{reinterpret_cast<uint16_t*>(H), reinterpret_cast<uint16_t*>(Act), ld, bias, fmt};
+  EpiGelu epi{reinterpret_cast<uint16_t*>(H), reinterpret_cast<uint16_t*>(Act), ld, bias, fmt, nullptr};
   return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, (cudaStream_t)stream);
 }
 
@@ -65,4 +65,16 @@ extern "C" int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int l
   EpiGeluBwd epi{reinterpret_cast<uint16_t*>(out), ld, reinterpret_cast<const uint16_t*>(H), fmt_h,
                  fmt};
   return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, (cudaStream_t)stream);
+}
+
+extern "C" int rvlm_gemm16_split_out32(const void* A_hi, const void* A_lo, int lda, const void* B_hi,
+                                       const void* B_lo, int ldb, float* C, int ldc,
+                                       const float* bias, const float* resid, int ldr, int M,
+                                       int N, int K, void* stream) {
+  if (!A_hi || !A_lo || !B_hi || !B_lo) return RVLM_ERR_INVAL;
+  if ((reinterpret_cast<uintptr_t>(C) & 15) || (ldc & 3)) return RVLM_ERR_ALIGN;
+  if (resid && ((reinterpret_cast<uintptr_t>(resid) & 15) || (ldr & 3))) return RVLM_ERR_ALIGN;
+  EpiStore32 epi{C, ldc, bias, resid, ldr};
+  return launch_gemm_fwd(A_hi, A_lo, lda, B_hi, B_lo, ldb, M, N, K, RVLM_FMT_F16, epi,
+                         (cudaStream_t)stream);
 }

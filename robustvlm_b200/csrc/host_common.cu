@@ -54,12 +54,12 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
+struct ProfRec { cudaEvent_t e0, e1; double flops, mma; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
 
-GemmProfScope::GemmProfScope(cudaStream_t s, double flops) : st(s), slot(-1) {
+GemmProfScope::GemmProfScope(cudaStream_t s, double flops, double mma_factor) : st(s), slot(-1) {
   if (!g_prof_on) return;
   if (g_prof_used == g_prof.size()) {
     ProfRec r{};
@@ -68,6 +68,7 @@ GemmProfScope::GemmProfScope(cudaStream_t s, double flops) : st(s), slot(-1) {
   }
   slot = (int)g_prof_used++;
   g_prof[slot].flops = flops;
+  g_prof[slot].mma = flops * mma_factor;
   cudaEventRecord(g_prof[slot].e0, st);
 }
 GemmProfScope::~GemmProfScope() {

@@ -34,8 +34,8 @@ template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ beta, uint16_t* __restrict__ y16,
-              float* __restrict__ y32, float2* __restrict__ stats, int M, int fmt,
-              LnStrides sd) {
+              uint16_t* __restrict__ y16lo, float* __restrict__ y32,
+              float2* __restrict__ stats, int M, int fmt, LnStrides sd) {
   constexpr int W = NV * 128;
   const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -72,6 +72,13 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
       p.x = pack2(o.x, o.y, fmt);
       p.y = pack2(o.z, o.w, fmt);
       reinterpret_cast<uint2*>(y16 + (size_t)row * sd.y)[i * 32 + lane] = p;
+      if (y16lo) {   // split-operand forward: lo = fp16(y - hi)   (fmt == fp16)
+        const float2 a = unpack2(p.x, 0), b = unpack2(p.y, 0);
+        uint2 q;
+        q.x = pack2(o.x - a.x, o.y - a.y, 0);
+        q.y = pack2(o.z - b.x, o.w - b.y, 0);
+        reinterpret_cast<uint2*>(y16lo + (size_t)row * sd.y)[i * 32 + lane] = q;
+      }
     }
   }
 }
@@ -163,17 +170,19 @@ namespace rvlm {
 // strided entry points (engine-internal); pitches in elements, 0 = dense (W)
 int ln_fwd_strided(const float* x, long long ldx, const float* gamma, const float* beta, void* y16,
                    float* y32, long long ldy, float* stats, int M, int W, int fmt,
-                   cudaStream_t st) {
+                   cudaStream_t st, void* y16lo_ = nullptr) {
   if (M <= 0) return RVLM_ERR_INVAL;
+  if (y16lo_ && fmt != 0) return RVLM_ERR_INVAL;
   const dim3 grid((M + LN_WARPS - 1) / LN_WARPS), block(LN_WARPS * 32);
   uint16_t* y = reinterpret_cast<uint16_t*>(y16);
+  uint16_t* ylo = reinterpret_cast<uint16_t*>(y16lo_);
   float2* s = reinterpret_cast<float2*>(stats);
   const LnStrides sd{ldx ? ldx : W, ldy ? ldy : W, 0, 0};
   switch (W) {
-    case 128: ln_fwd_kernel<1><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
-    case 256: ln_fwd_kernel<2><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
-    case 768: ln_fwd_kernel<6><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
-    case 1024: ln_fwd_kernel<8><<<grid, block, 0, st>>>(x, gamma, beta, y, y32, s, M, fmt, sd); break;
+    case 128: ln_fwd_kernel<1><<<grid, block, 0, st>>>(x, gamma, beta, y, ylo, y32, s, M, fmt, sd); break;
+    case 256: ln_fwd_kernel<2><<<grid, block, 0, st>>>(x, gamma, beta, y, ylo, y32, s, M, fmt, sd); break;
+    case 768: ln_fwd_kernel<6><<<grid, block, 0, st>>>(x, gamma, beta, y, ylo, y32, s, M, fmt, sd); break;
+    case 1024: ln_fwd_kernel<8><<<grid, block, 0, st>>>(x, gamma, beta, y, ylo, y32, s, M, fmt, sd); break;
     default: return RVLM_ERR_UNSUPPORTED;
   }
   count_launch(1);

@@ -36,7 +36,8 @@ __global__ void patch_layout_kernel(const float* __restrict__ src, const float* 
 }
 
 __global__ void patch_operand_kernel(const float* __restrict__ xp, const float* __restrict__ dp,
-                                     uint16_t* __restrict__ a16, int lda, long long rows, int kp,
+                                     uint16_t* __restrict__ a16, uint16_t* __restrict__ a16lo,
+                                     int lda, long long rows, int kp,
                                      int pp, float m0, float m1, float m2, float s0, float s1,
                                      float s2, int fmt) {
   const int k4 = kp >> 2;
@@ -64,6 +65,13 @@ __global__ void patch_operand_kernel(const float* __restrict__ xp, const float* 
     pk.x = pack2(o[0], o[1], fmt);
     pk.y = pack2(o[2], o[3], fmt);
     *reinterpret_cast<uint2*>(a16 + r * lda + k) = pk;
+    if (a16lo) {   // split-operand forward (fmt == fp16): lo = fp16(v - hi)
+      const float2 h0 = unpack2(pk.x, 0), h1 = unpack2(pk.y, 0);
+      uint2 lo;
+      lo.x = pack2(o[0] - h0.x, o[1] - h0.y, 0);
+      lo.y = pack2(o[2] - h1.x, o[3] - h1.y, 0);
+      *reinterpret_cast<uint2*>(a16lo + r * lda + k) = lo;
+    }
   }
 }
 
@@ -108,9 +116,9 @@ int launch_unpatchify_add(const float* xp, const float* dp, float* img, int B, c
   return rc();
 }
 int launch_patch_operand(const float* xp, const float* dp, uint16_t* a16, int lda, long long rows,
-                         const PatchGeom& g, int fmt, cudaStream_t st) {
+                         const PatchGeom& g, int fmt, cudaStream_t st, uint16_t* a16lo) {
   const long long n = rows * (g.kp >> 2);
-  patch_operand_kernel<<<nblk(n, 256), 256, 0, st>>>(xp, dp, a16, lda, rows, g.kp,
+  patch_operand_kernel<<<nblk(n, 256), 256, 0, st>>>(xp, dp, a16, a16lo, lda, rows, g.kp,
                                                      g.patch * g.patch, g.mean[0], g.mean[1],
                                                      g.mean[2], g.inv_std[0], g.inv_std[1],
                                                      g.inv_std[2], fmt);
@@ -125,6 +133,14 @@ int launch_cls_rows(float* tok, const float* cls, const float* pos, int B, int T
 // ---------------------------------------------------------------------------
 // weight conversion (fp32 open_clip layout -> 16-bit GEMM operands)
 // ---------------------------------------------------------------------------
+// fmt: 0 = fp16, 1 = bf16, 2 = the fp16 LO half of a split operand: fp16(v - float(fp16(v)))
+__device__ __forceinline__ uint16_t cvt16(float v, int fmt) {
+  if (fmt == 1) { __nv_bfloat16 h = __float2bfloat16_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __half h = __float2half_rn(v);
+  if (fmt == 2) h = __float2half_rn(v - __half2float(h));
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
 __global__ void convert16_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
                                  int R, int C, int ldd, int fmt) {
   const long long total = (long long)R * C;
@@ -132,11 +148,7 @@ __global__ void convert16_kernel(const float* __restrict__ src, uint16_t* __rest
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / C;
     const int c = (int)(i - r * C);
-    const float v = src[i];
-    uint16_t o;
-    if (fmt) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
-    else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
-    dst[r * ldd + c] = o;
+    dst[r * ldd + c] = cvt16(src[i], fmt);
   }
 }
 
@@ -153,11 +165,7 @@ __global__ void transpose_convert16_kernel(const float* __restrict__ src,
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = bx + j, r = by + threadIdx.x;  // dst row = c, dst col = r
     if (c < C && r < R) {
-      const float v = tile[threadIdx.x][j];
-      uint16_t o;
-      if (fmt) { __nv_bfloat16 h = __float2bfloat16_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
-      else { __half h = __float2half_rn(v); o = *reinterpret_cast<uint16_t*>(&h); }
-      dst[(size_t)c * ldd + r] = o;
+      dst[(size_t)c * ldd + r] = cvt16(tile[threadIdx.x][j], fmt);
     }
   }
 }

@@ -3,7 +3,7 @@
 //   A[i, k] (16-bit) lives in TMEM lane i, 32-bit column k/2, low half = even k.
 // D[128, 64] = A[128, 64] * B[64, 64]^T, A written by tcgen05.st from the row-owner threads.
 #include "gemm.cuh"
-#include "../../include/rvlm.h"
+#include "rvlm_debug.h"
 
 namespace rvlm {
 

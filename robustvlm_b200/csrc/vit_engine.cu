@@ -14,7 +14,7 @@
 #include "gemm.cuh"
 #include "epilogues.cuh"
 #include "engine_internal.cuh"
-#include "../../include/rvlm.h"
+#include "rvlm_debug.h"
 
 #include <cstdlib>
 #include <vector>
@@ -36,10 +36,11 @@ extern "C" int rvlm_layernorm_bwd16(const void*, const float*, const float*, con
                                     const float*, float*, void*, int, int, int, int, void*);
 
 namespace rvlm {
-int attn_cls_fwd(const void*, void*, int, int, int, int, cudaStream_t);
+int attn_cls_fwd(const void*, void*, int, int, int, int, cudaStream_t, const void*, void*);
+int attn_fwd_split(const void*, const void*, void*, void*, float*, int, int, int, cudaStream_t);
 int attn_cls_bwd(const void*, const void*, void*, int, int, int, int, cudaStream_t);
 int ln_fwd_strided(const float*, long long, const float*, const float*, void*, float*, long long,
-                   float*, int, int, int, cudaStream_t);
+                   float*, int, int, int, cudaStream_t, void* y16lo = nullptr);
 int ln_bwd16_strided(const void*, long long, const float*, long long, const float*, const float*,
                      const float*, long long, float*, void*, long long, int, int, int,
                      cudaStream_t);
@@ -52,6 +53,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct LayerDev {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *bqkv, *bo, *bfc, *bpr;
   uint16_t *wqkv, *wo, *wfc, *wpr;      // forward operands [N, K], fmt_fwd
+  uint16_t *wqkv_lo, *wo_lo, *wfc_lo, *wpr_lo;   // their fp16 lo halves (split forward), else null
   uint16_t *wqkvT, *woT, *wfcT, *wprT;  // dgrad operands   [K_fwd, N_fwd] = [N', K'], fmt_bwd
 };
 
@@ -63,7 +65,10 @@ struct Engine {
   size_t slab_bytes = 0;
   float *cls, *pos, *lnpre_g, *lnpre_b, *lnpost_g, *lnpost_b, *proj;
   uint16_t *conv_w, *conv_wT;
+  uint16_t* conv_w_lo = nullptr;
   std::vector<LayerDev> layers;
+  int ff = 0;        // 16-bit format of the forward operands (fp16 when split)
+  int split = 0;     // cfg.fmt_fwd == RVLM_FMT_F16X2: forward operands are fp16 hi + lo pairs
   int attn_simt = 0;
   int cls_last = 1;  // last block: class-token row only (flag RVLM_VIT_FULL_LAST_BLOCK / env RVLM_CLS_LAST=0 disable)
   int ln_dz16 = 1;   // attack-path dgrad GEMMs hand LayerNorm' a 16-bit gradient (RVLM_LN_DZ16=0: fp32)
@@ -83,6 +88,8 @@ struct Ws {
   uint16_t* qkvf16;             // [M, 3W] transient forward-format q|k|v
   float* lse;     // [L] x [B, H, T]
   uint16_t *y16, *act16;
+  // split forward: the fp16 lo halves of the transient forward operands
+  uint16_t *a16lo, *y16lo, *act16lo, *qkvf16lo, *o16lo;
   // outer training step (stash == 2): per-layer GEMM inputs kept for the weight gradients
   uint16_t *ty16, *tz16, *tact16;   // [L] x [M, W], [M, W], [M, F]
   float *red;                        // column-reduction scratch
@@ -139,6 +146,13 @@ Ws carve(const Engine& E, uint8_t* base, int B, int stash) {
   w.loss = take<float>(p, used, B);
   w.pred = take<int>(p, used, B);
   w.upd = take<float>(p, used, (size_t)B * 32 * 3);
+  if (E.split) {
+    w.a16lo = take<uint16_t>(p, used, R * E.kld);
+    w.y16lo = take<uint16_t>(p, used, M * W);
+    w.act16lo = take<uint16_t>(p, used, M * F);
+    w.qkvf16lo = take<uint16_t>(p, used, M * 3 * W);
+    w.o16lo = take<uint16_t>(p, used, M * W);
+  }
   if (stash == 2) {
     w.ty16 = take<uint16_t>(p, used, L * M * W);
     w.tz16 = take<uint16_t>(p, used, L * M * W);
@@ -174,13 +188,16 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e - 1000
 // Precondition: w.a16 holds the normalised 16-bit patch operand of the batch.
 int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
   const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
-  const int ff = E.cfg.fmt_fwd;
+  const int ff = E.ff;
   const size_t MW = (size_t)M * W;
   void* stv = (void*)st;
+  // split forward: every GEMM operand has an fp16 lo half (null pointers otherwise)
+  const bool sp = E.split != 0;
   RV(launch_cls_rows(w.tok32, E.cls, E.pos, B, E.T, W, st));
   {
     EpiPatchFwd epi{w.tok32, E.pos, E.np, E.T, W};
-    RV((launch_gemm_kmajor(w.a16, E.kld, E.conv_w, E.kld, R, W, E.kp, ff, epi, st)));
+    RV((launch_gemm_fwd(w.a16, w.a16lo, E.kld, E.conv_w, E.conv_w_lo, E.kld, R, W, E.kp, ff, epi,
+                        st)));
   }
   RV(rvlm_layernorm_fwd(w.tok32, E.lnpre_g, E.lnpre_b, nullptr, w.x32, w.stats_pre, M, W, ff, stv));
   for (int l = 0; l < E.L; ++l) {
@@ -199,45 +216,55 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     uint16_t* y1 = train ? w.ty16 + (size_t)l * MW : w.y16;
     uint16_t* z1 = train ? w.tz16 + (size_t)l * MW : w.y16;
     uint16_t* act = train ? w.tact16 + (size_t)l * M * F : w.act16;
-    RV(rvlm_layernorm_fwd(x_in, Lw.ln1_g, Lw.ln1_b, y1, nullptr, st1, M, W, ff, stv));
+    uint16_t* y1lo = sp ? w.y16lo : nullptr;
+    RV(ln_fwd_strided(x_in, 0, Lw.ln1_g, Lw.ln1_b, y1, nullptr, 0, st1, M, W, ff, st, y1lo));
     {  // q|k|v in the forward format (transient) + the backward's copy in the gradient format
-      EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd};
-      RV((launch_gemm_kmajor(y1, W, Lw.wqkv, W, M, 3 * W, W, ff, epi, st)));
+      EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd,
+                         sp ? w.qkvf16lo : nullptr};
+      RV((launch_gemm_fwd(y1, y1lo, W, Lw.wqkv, Lw.wqkv_lo, W, M, 3 * W, W, ff, epi, st)));
     }
     if (l == E.L - 1 && E.cls_last && !train) {
       // ---- last block, class-token rows only (row pitch T*W inside the [B*T, W] streams; the
       // per-row operands of the MLP live compactly in the first B rows of their buffers)
       const long long TW = (long long)E.T * W;
-      RV(attn_cls_fwd(w.qkvf16, o, B, E.T, E.H, ff, st));
+      RV(attn_cls_fwd(w.qkvf16, o, B, E.T, E.H, ff, st, sp ? w.qkvf16lo : nullptr,
+                      sp ? w.o16lo : nullptr));
       {
         EpiStore32 epi{xm, (int)TW, Lw.bo, x_in, (int)TW};
-        RV((launch_gemm_kmajor(o, (int)TW, Lw.wo, W, B, W, W, ff, epi, st)));
+        RV((launch_gemm_fwd(o, sp ? w.o16lo : nullptr, (int)TW, Lw.wo, Lw.wo_lo, W, B, W, W, ff, epi,
+                            st)));
       }
-      RV(ln_fwd_strided(xm, TW, Lw.ln2_g, Lw.ln2_b, w.y16, nullptr, 0, st2, B, W, ff, st));
+      RV(ln_fwd_strided(xm, TW, Lw.ln2_g, Lw.ln2_b, w.y16, nullptr, 0, st2, B, W, ff, st,
+                        sp ? w.y16lo : nullptr));
       {
-        EpiGelu epi{w.stash ? h : nullptr, w.act16, F, Lw.bfc, ff};
-        RV((launch_gemm_kmajor(w.y16, W, Lw.wfc, W, B, F, W, ff, epi, st)));
+        EpiGelu epi{w.stash ? h : nullptr, w.act16, F, Lw.bfc, ff, sp ? w.act16lo : nullptr};
+        RV((launch_gemm_fwd(w.y16, sp ? w.y16lo : nullptr, W, Lw.wfc, Lw.wfc_lo, W, B, F, W, ff, epi,
+                            st)));
       }
       {
         EpiStore32 epi{x_out, (int)TW, Lw.bpr, xm, (int)TW};
-        RV((launch_gemm_kmajor(w.act16, F, Lw.wpr, F, B, W, F, ff, epi, st)));
+        RV((launch_gemm_fwd(w.act16, sp ? w.act16lo : nullptr, F, Lw.wpr, Lw.wpr_lo, F, B, W, F, ff,
+                            epi, st)));
       }
       break;
     }
-    if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
+    if (sp) RV(attn_fwd_split(w.qkvf16, w.qkvf16lo, o, w.o16lo, lse, B, E.T, E.H, st));
+    else if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     else RV(rvlm_attn_fwd(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
     {
       EpiStore32 epi{xm, W, Lw.bo, x_in, W};
-      RV((launch_gemm_kmajor(o, W, Lw.wo, W, M, W, W, ff, epi, st)));
+      RV((launch_gemm_fwd(o, sp ? w.o16lo : nullptr, W, Lw.wo, Lw.wo_lo, W, M, W, W, ff, epi, st)));
     }
-    RV(rvlm_layernorm_fwd(xm, Lw.ln2_g, Lw.ln2_b, z1, nullptr, st2, M, W, ff, stv));
+    uint16_t* z1lo = sp ? w.y16lo : nullptr;
+    RV(ln_fwd_strided(xm, 0, Lw.ln2_g, Lw.ln2_b, z1, nullptr, 0, st2, M, W, ff, st, z1lo));
     {
-      EpiGelu epi{w.stash ? h : nullptr, act, F, Lw.bfc, ff};
-      RV((launch_gemm_kmajor(z1, W, Lw.wfc, W, M, F, W, ff, epi, st)));
+      EpiGelu epi{w.stash ? h : nullptr, act, F, Lw.bfc, ff, sp ? w.act16lo : nullptr};
+      RV((launch_gemm_fwd(z1, z1lo, W, Lw.wfc, Lw.wfc_lo, W, M, F, W, ff, epi, st)));
     }
     {
       EpiStore32 epi{x_out, W, Lw.bpr, xm, W};
-      RV((launch_gemm_kmajor(act, F, Lw.wpr, F, M, W, F, ff, epi, st)));
+      RV((launch_gemm_fwd(act, sp ? w.act16lo : nullptr, F, Lw.wpr, Lw.wpr_lo, F, M, W, F, ff, epi,
+                          st)));
     }
   }
   return 0;
@@ -288,7 +315,7 @@ int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, in
 // ---- backward (dgrad only) down to the token gradient of the patch rows -----------
 int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
   const int M = B * E.T, W = E.W, F = E.F;
-  const int ff = E.cfg.fmt_fwd, fg = E.cfg.fmt_bwd;
+  const int ff = E.ff, fg = E.cfg.fmt_bwd;
   const size_t MW = (size_t)M * W;
   void* stv = (void*)st;
   for (int l = E.L - 1; l >= 0; --l) {
@@ -378,7 +405,7 @@ int wgrad(const uint16_t* dY, int Nw, const uint16_t* X, int Kw, int Mtok, int f
 int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads* g,
                        cudaStream_t st) {
   const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
-  const int ff = E.cfg.fmt_fwd, fg = E.cfg.fmt_bwd;
+  const int ff = E.ff, fg = E.cfg.fmt_bwd;
   const size_t MW = (size_t)M * W;
   void* stv = (void*)st;
   RV(launch_head_param_grads(w.t_pooled, w.t_demb, w.t_dpooled, w.t_xhat, B, W, E.D, g->proj,
@@ -460,8 +487,9 @@ int run_patch_grad(const Engine& E, const Ws& w, int B, cudaStream_t st) {
 
 int run_patch_pgd_linf(const Engine& E, const Ws& w, int B, float stepsize, float eps,
                        int maximize, float momentum, cudaStream_t st) {
-  EpiPatchPgdLinf epi{w.xp, w.dp, w.vp, w.a16, E.kp, E.cfg.patch * E.cfg.patch, E.kld,
-                      E.cfg.fmt_fwd, stepsize, eps, maximize ? 1.f : -1.f, momentum,
+  EpiPatchPgdLinf epi{w.xp, w.dp, w.vp, w.a16, E.split ? w.a16lo : nullptr, E.kp,
+                      E.cfg.patch * E.cfg.patch, E.kld,
+                      E.ff, stepsize, eps, maximize ? 1.f : -1.f, momentum,
                       {E.geom.mean[0], E.geom.mean[1], E.geom.mean[2]},
                       {E.geom.inv_std[0], E.geom.inv_std[1], E.geom.inv_std[2]}};
   return launch_gemm_kmajor(w.dtok16, E.W, E.conv_wT, E.W, B * E.np, E.kp32, E.W,
@@ -469,7 +497,7 @@ int run_patch_pgd_linf(const Engine& E, const Ws& w, int B, float stepsize, floa
 }
 
 int load_weights(Engine& E, const rvlm_vit_weights* wt, cudaStream_t st) {
-  const int W = E.W, F = E.F, D = E.D, ff = E.cfg.fmt_fwd, fg = E.cfg.fmt_bwd;
+  const int W = E.W, F = E.F, D = E.D, ff = E.ff, fg = E.cfg.fmt_bwd;
   auto cp = [&](float* dst, const float* src, size_t n) {
     return cuda_rc(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
   };
@@ -482,6 +510,7 @@ int load_weights(Engine& E, const rvlm_vit_weights* wt, cudaStream_t st) {
   RV(cp(E.proj, wt->proj, (size_t)W * D));
   // conv1.weight [W, 3, p, p] == [W, kp] row-major
   RV(launch_convert16_pitched(wt->conv1_weight, E.conv_w, W, E.kp, E.kld, ff, st));
+  if (E.split) RV(launch_convert16_pitched(wt->conv1_weight, E.conv_w_lo, W, E.kp, E.kld, 2, st));
   RV(launch_transpose_convert16(wt->conv1_weight, E.conv_wT, W, E.kp, W, fg, st));
   for (int l = 0; l < E.L; ++l) {
     LayerDev& Lw = E.layers[l];
@@ -497,6 +526,12 @@ int load_weights(Engine& E, const rvlm_vit_weights* wt, cudaStream_t st) {
     RV(launch_convert16(wt->attn_out_proj_weight[l], Lw.wo, (long long)W * W, ff, st));
     RV(launch_convert16(wt->mlp_c_fc_weight[l], Lw.wfc, (long long)F * W, ff, st));
     RV(launch_convert16(wt->mlp_c_proj_weight[l], Lw.wpr, (long long)W * F, ff, st));
+    if (E.split) {   // fp16 lo halves: fp16(w - float(fp16(w)))
+      RV(launch_convert16(wt->attn_in_proj_weight[l], Lw.wqkv_lo, (long long)3 * W * W, 2, st));
+      RV(launch_convert16(wt->attn_out_proj_weight[l], Lw.wo_lo, (long long)W * W, 2, st));
+      RV(launch_convert16(wt->mlp_c_fc_weight[l], Lw.wfc_lo, (long long)F * W, 2, st));
+      RV(launch_convert16(wt->mlp_c_proj_weight[l], Lw.wpr_lo, (long long)W * F, 2, st));
+    }
     RV(launch_transpose_convert16(wt->attn_in_proj_weight[l], Lw.wqkvT, 3 * W, W, 3 * W, fg, st));
     RV(launch_transpose_convert16(wt->attn_out_proj_weight[l], Lw.woT, W, W, W, fg, st));
     RV(launch_transpose_convert16(wt->mlp_c_fc_weight[l], Lw.wfcT, F, W, F, fg, st));
@@ -513,7 +548,7 @@ int prep_state(const Engine& E, const Ws& w, int B, const float* x_img, const fl
   else RV(cuda_rc(cudaMemsetAsync(w.dp, 0, n * sizeof(float), st)));
   if (zero_velocity) RV(cuda_rc(cudaMemsetAsync(w.vp, 0, n * sizeof(float), st)));
   RV(launch_patch_operand(w.xp, delta_img ? w.dp : nullptr, w.a16, E.kld, (long long)B * E.np,
-                          E.geom, E.cfg.fmt_fwd, st));
+                          E.geom, E.ff, st, E.split ? w.a16lo : nullptr));
   return 0;
 }
 
@@ -532,6 +567,13 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
   Engine* E = new (std::nothrow) Engine();
   if (!E) return RVLM_ERR_NOMEM;
   E->cfg = *cfg;
+  if (cfg->fmt_fwd != RVLM_FMT_F16 && cfg->fmt_fwd != RVLM_FMT_BF16 && cfg->fmt_fwd != RVLM_FMT_F16X2) {
+    delete E;
+    return RVLM_ERR_INVAL;
+  }
+  if (cfg->fmt_bwd != RVLM_FMT_F16 && cfg->fmt_bwd != RVLM_FMT_BF16) { delete E; return RVLM_ERR_INVAL; }
+  E->split = cfg->fmt_fwd == RVLM_FMT_F16X2 ? 1 : 0;
+  E->ff = E->split ? RVLM_FMT_F16 : cfg->fmt_fwd;
   E->W = cfg->width; E->D = cfg->out_dim; E->L = cfg->layers; E->H = cfg->heads; E->F = cfg->mlp;
   const int g = cfg->image / cfg->patch;
   E->np = g * g;
@@ -564,6 +606,7 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
     E->proj = take<float>(p, used, W * D);
     E->conv_w = take<uint16_t>(p, used, W * E->kld);
     E->conv_wT = take<uint16_t>(p, used, (size_t)E->kp32 * W);
+    if (E->split) E->conv_w_lo = take<uint16_t>(p, used, W * E->kld);
     E->layers.resize(L);
     for (size_t l = 0; l < L; ++l) {
       LayerDev& Lw = E->layers[l];
@@ -575,6 +618,11 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
       Lw.wfc = take<uint16_t>(p, used, F * W); Lw.wpr = take<uint16_t>(p, used, W * F);
       Lw.wqkvT = take<uint16_t>(p, used, 3 * W * W); Lw.woT = take<uint16_t>(p, used, W * W);
       Lw.wfcT = take<uint16_t>(p, used, F * W); Lw.wprT = take<uint16_t>(p, used, W * F);
+      Lw.wqkv_lo = Lw.wo_lo = Lw.wfc_lo = Lw.wpr_lo = nullptr;
+      if (E->split) {
+        Lw.wqkv_lo = take<uint16_t>(p, used, 3 * W * W); Lw.wo_lo = take<uint16_t>(p, used, W * W);
+        Lw.wfc_lo = take<uint16_t>(p, used, F * W); Lw.wpr_lo = take<uint16_t>(p, used, W * F);
+      }
     }
   };
   plan(nullptr);
@@ -675,7 +723,7 @@ extern "C" int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t w
   if (!h || !workspace || !x || !loss || !grads || B <= 0) return RVLM_ERR_INVAL;
   if (loss->mode != 1 && loss->mode != 2) return RVLM_ERR_INVAL;
   const Engine& E = *reinterpret_cast<Engine*>(h);
-  if (E.cfg.fmt_fwd != E.cfg.fmt_bwd) return RVLM_ERR_UNSUPPORTED;  // wgrad: one operand format
+  if (E.split || E.cfg.fmt_fwd != E.cfg.fmt_bwd) return RVLM_ERR_UNSUPPORTED;  // wgrad: one operand format
   Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 2);
   if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
   cudaStream_t st = (cudaStream_t)stream;
@@ -715,8 +763,8 @@ extern "C" int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace
       RV(run_patch_grad(E, w, B, st));
       RV(rvlm_pgd_update_l2(w.dp, w.vp, w.gp, w.xp, B, n, stepsize, eps, maximize, momentum, w.upd,
                             (void*)st));
-      RV(launch_patch_operand(w.xp, w.dp, w.a16, E.kld, (long long)B * E.np, E.geom,
-                              E.cfg.fmt_fwd, st));
+      RV(launch_patch_operand(w.xp, w.dp, w.a16, E.kld, (long long)B * E.np, E.geom, E.ff, st,
+                              E.split ? w.a16lo : nullptr));
     }
   }
   return launch_unpatchify_add(w.xp, w.dp, x_adv_out, B, E.geom, st);

@@ -17,7 +17,15 @@ from . import _native as nat
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # train/adversarial_training_clip.py:116
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
-FMT_F16, FMT_BF16 = 0, 1
+FMT_F16, FMT_BF16, FMT_F16X2 = 0, 1, 2
+# Engine precision modes: (forward operand format, gradient operand format).
+#   fast    fp16 forward operands (tf32-class), bf16 gradients            -- round-1 default
+#   fast16  fp16 forward operands, fp16 gradients rescaled per sample (11-bit mantissa)
+#   split   forward operands as fp16 hi + lo pairs, three tcgen05 MMAs per product
+#           (fp32-class forward for FARE's cancellation site), fp16 gradients
+#   bf16    bf16 / bf16 (the outer training step: weight-gradient GEMMs need one format)
+PRECISIONS = {"fast": (FMT_F16, FMT_BF16), "fast16": (FMT_F16, FMT_F16),
+              "split": (FMT_F16X2, FMT_F16), "bf16": (FMT_BF16, FMT_BF16)}
 LOSS_L2, LOSS_CE = 1, 2
 NORM_LINF, NORM_L2 = 0, 2
 FLAG_ATTN_SIMT = 1

@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .engine import CLIP_MEAN, CLIP_STD, FMT_BF16, FMT_F16, VitEngine
+from .engine import CLIP_MEAN, CLIP_STD, FMT_BF16, FMT_F16, PRECISIONS, VitEngine
 
 ARCHS = {  # `--clip_model_name` values (train/adversarial_training_clip.py:32,175-178)
     "ViT-L-14": dict(image=224, patch=14, width=1024, layers=24, heads=16, mlp=4096, out_dim=768),
@@ -65,8 +65,11 @@ class _Transformer(nn.Module):
 class VisionTransformer(nn.Module):
     """Holds the fp32 master parameters; all arithmetic happens in the CUDA engine."""
 
-    def __init__(self, arch="ViT-L-14", seed=None, fmt_fwd=FMT_F16, fmt_bwd=FMT_BF16, flags=0):
+    def __init__(self, arch="ViT-L-14", seed=None, fmt_fwd=FMT_F16, fmt_bwd=FMT_BF16, flags=0,
+                 precision=None):
         super().__init__()
+        if precision is not None:                    # a named mode of engine.PRECISIONS
+            fmt_fwd, fmt_bwd = PRECISIONS[precision]
         a = ARCHS[arch] if isinstance(arch, str) else dict(arch)
         self.arch = a
         w, m = a["width"], a["mlp"]

@@ -247,3 +247,66 @@ def test_ts_mma_operand_packing(fmt):
     err = (C - ref).abs().max().item()
     _log("ts_mma", fmt=fmt, err=err)
     assert err < 1e-2
+
+
+# ------------------------------------------------------------------------------------------
+# split-operand ("fp32-class") kernels: fp16 hi + lo pairs, hi*hi + lo*hi + hi*lo
+# ------------------------------------------------------------------------------------------
+def _split16(x):
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return hi.contiguous(), lo.contiguous()
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 768, 1024), (4112, 1024, 4096),
+                                   (300, 96, 192), (4, 512, 1024)])
+def test_gemm16_split(M, N, K):
+    """C = A B^T + bias + resid with both operands split: fp32-class result (the plain fp16
+    kernel is ~3e-4 relative on the same data)"""
+    nat = _nat()
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda") * K ** -0.5
+    bias = torch.randn(N, device="cuda")
+    resid = torch.randn(M, N, device="cuda")
+    ref = (A.double() @ B.double().t() + bias.double() + resid.double())
+    (Ah, Al), (Bh, Bl) = _split16(A), _split16(B)
+    C = torch.empty(M, N, device="cuda")
+    nat.call("rvlm_gemm16_split_out32", nat.ptr(Ah), nat.ptr(Al), nat.c_int(K), nat.ptr(Bh),
+             nat.ptr(Bl), nat.c_int(K), nat.ptr(C), nat.c_int(N), nat.ptr(bias), nat.ptr(resid),
+             nat.c_int(N), nat.c_int(M), nat.c_int(N), nat.c_int(K), nat.stream_ptr())
+    C1 = torch.empty(M, N, device="cuda")
+    nat.call("rvlm_gemm16_out32", nat.ptr(Ah), nat.c_int(K), nat.ptr(Bh), nat.c_int(K), nat.ptr(C1),
+             nat.c_int(N), nat.ptr(bias), nat.ptr(resid), nat.c_int(N), nat.c_int(M), nat.c_int(N),
+             nat.c_int(K), nat.c_int(0), nat.c_int(8), nat.stream_ptr())
+    torch.cuda.synchronize()
+    prod = (A.double() @ B.double().t())
+    err = float(((C.double() - ref).norm() / prod.norm()))
+    err1 = float(((C1.double() - ref).norm() / prod.norm()))
+    _log("gemm16_split", M=M, N=N, K=K, rel_err=err, rel_err_fp16=err1)
+    assert err < 2e-6 and err < 0.02 * err1
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 257, 4), (2, 50, 2), (37, 257, 1), (1, 256, 2), (2, 129, 2)])
+def test_attention_fwd_split(B, T, H):
+    """softmax(q k^T / 8) v with hi + lo operands vs torch in fp64"""
+    nat = _nat()
+    torch.manual_seed(B * 1000 + T + H)
+    W = 64 * H
+    qkv = torch.randn(B * T, 3 * W, device="cuda") * 1.5
+    qh, ql = _split16(qkv)
+    oh = torch.zeros(B * T, W, device="cuda", dtype=torch.half)
+    ol = torch.zeros_like(oh)
+    lse = torch.zeros(B, H, T, device="cuda")
+    nat.call("rvlm_attn_fwd_split", nat.ptr(qh), nat.ptr(ql), nat.ptr(oh), nat.ptr(ol), nat.ptr(lse),
+             nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.stream_ptr())
+    torch.cuda.synchronize()
+    x = (qh.double() + ql.double()).view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = (x[0] @ x[1].transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(s, -1) @ x[2]).permute(0, 2, 1, 3).reshape(B * T, W)
+    o = oh.double() + ol.double()
+    err = float((o - ref).norm() / ref.norm())
+    err_hi = float((oh.double() - ref).norm() / ref.norm())
+    lse_err = float((lse.double() - torch.logsumexp(s, -1)).abs().max())
+    _log("attn_fwd_split", B=B, T=T, H=H, rel_err=err, rel_err_hi_only=err_hi, lse_err=lse_err)
+    assert err < 5e-6 and lse_err < 1e-4

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, missing
     lib.rvlm_abi_version.restype = nat.c_int
-    assert lib.rvlm_abi_version() == 1
+    assert lib.rvlm_abi_version() == 2            # RVLM_ABI_VERSION (split-operand forward)
     assert lib.rvlm_strerror(0) == b"ok"
     assert b"aligned" in lib.rvlm_strerror(-23)
 

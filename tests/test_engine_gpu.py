@@ -136,3 +136,31 @@ def test_last_block_shortcut_equals_full(name, B):
     _log("cls_shortcut", model=name, emb_rel=e, cos_min=float(cos.min()))
     assert e < 2e-4
     assert float(cos.min()) > 0.9995
+
+
+@pytest.mark.parametrize("name", ["tiny-32", "tiny-14"])
+def test_split_forward_is_fp32_class(name):
+    """precision mode `split` (fp16 hi + lo operands, three MMAs per product, split attention):
+    the embedding agrees with the fp32 oracle to ~1e-5 where the fp16 forward gives ~2e-4, and
+    the FARE gradient at model_orig == model (the cancellation site) follows."""
+    from robustvlm_b200.engine import FMT_F16, FMT_F16X2, LossSpec, VitEngine
+    o = ovit.build(name, seed=3)
+    ref_m = ovit.ClipVisionModel(o).eval()
+    x, d0 = synth_batch(5, seed=4)
+    with torch.no_grad():
+        e_ref = ref_m(x + d0, output_normalize=False)
+        e_orig = ref_m(x, output_normalize=False)
+    xa = (x + d0).requires_grad_(True)
+    wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+    (g_ref,) = torch.autograd.grad(wrap(ref_m(xa, output_normalize=False), None), xa)
+    res = {}
+    for tag, ff in (("fp16", FMT_F16), ("split", FMT_F16X2)):
+        eng = VitEngine(o.state_dict(), fmt_fwd=ff, fmt_bwd=FMT_F16)
+        emb = eng.forward(x.cuda(), d0.cuda()).cpu()
+        out = eng.loss_grad(x.cuda(), LossSpec("l2", False, emb_orig=e_orig.cuda()), delta=d0.cuda())
+        agree, mis_big = sign_agreement(out["grad"], g_ref, tau=0.05)
+        res[tag] = (rel_err(emb, e_ref), 1.0 - agree, mis_big)
+        del eng
+    print(name, res)
+    assert res["split"][0] < 2e-5 and res["split"][0] < 0.2 * res["fp16"][0]
+    assert res["split"][1] < 0.5 * res["fp16"][1] + 1e-4 and res["split"][2] < 1e-3

@@ -292,15 +292,14 @@ int rvlm_vit_forward(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
 /* grad_out[B,3,H,W] = (d emb / d x)^T d_emb for the forward just run with
  * keep_for_backward = 1 (the vector-Jacobian product torch.autograd.grad(loss, x) needs for
  * an arbitrary loss on the embedding; d_emb: [B, out_dim] w.r.t. the returned, possibly
- * normalised, embedding).  Same per-sample positive-rescaling caveat as below when
- * fmt_bwd is fp16. */
+ * normalised, embedding).  The result carries the true scale also when fmt_bwd is fp16 (the
+ * internal per-sample rescaling is undone on output). */
 int rvlm_vit_backward_input(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, int B,
                             const float* d_emb, int output_normalize, float* grad_out,
                             void* stream);
 /* Per-sample loss, pred flag, embedding / logits, and d(sum_b loss_b)/d(x+delta) as
- * grad_out[B,3,H,W].  The gradient of each sample may be rescaled by a positive
- * per-sample constant (every consumer on this path applies sign() or an ell_2
- * normalisation per sample).  Outputs other than grad_out may be NULL. */
+ * grad_out[B,3,H,W] (true scale; with fp16 gradient operands each sample's gradient is carried
+ * at unit max-abs internally and rescaled on output).  Outputs other than grad_out may be NULL. */
 int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, const float* x,
                        const float* delta, int B, const rvlm_loss_config* loss, float* grad_out,
                        float* loss_out, int* pred_out, float* emb_out, float* logits_out,

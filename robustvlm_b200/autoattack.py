@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 import time
+import warnings
 
 import torch
 
@@ -88,8 +89,16 @@ class AutoAttack:
             raise ValueError(f"unknown version {version}")
         dropped = [a for a in wanted if a in _NOT_BUILT]
         self.attacks_to_run = [a for a in wanted if a in _APGD_FAMILY]
-        if dropped and self.verbose:
-            self.logger.log(f"{version}: {', '.join(dropped)} not built here (APGD family only)")
+        self.dropped_attacks = dropped
+        if dropped:
+            # never silent: robust accuracy from the APGD members alone is an UPPER bound of the
+            # reference's `{version}` AutoAttack number
+            msg = (f"AutoAttack version '{version}': {', '.join(dropped)} are not built here (APGD "
+                   f"family only, SURVEY.md §2); running {', '.join(self.attacks_to_run)} -- the "
+                   f"robust accuracy reported is an upper bound of the full '{version}' ensemble")
+            warnings.warn(msg, stacklevel=2)
+            if self.verbose:
+                self.logger.log(msg)
 
     def _run_one(self, attack, x, y):
         if attack == "apgd-ce":                                                    # :184-188
@@ -113,8 +122,10 @@ class AutoAttack:
         if state_path is not None:
             raise NotImplementedError("evaluation state files are not rebuilt")
         if self.verbose:
-            self.logger.log("using {} version including {}.".format(
-                self.version, ", ".join(self.attacks_to_run)))
+            self.logger.log("using {} version including {}{}.".format(
+                self.version, ", ".join(self.attacks_to_run),
+                " (APGD members only; not run: {})".format(", ".join(self.dropped_attacks))
+                if getattr(self, "dropped_attacks", None) else ""))
         n = x_orig.shape[0]
         with torch.no_grad():
             robust_flags = torch.zeros(n, dtype=torch.bool, device=x_orig.device)

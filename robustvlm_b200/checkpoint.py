@@ -92,11 +92,26 @@ def load_optimizer_state_dict(sd, layout, flat_a, flat_b=None):
     return step, dict(groups[0])
 
 
+def _atomic_save(obj, path):
+    """write to a temporary file in the same directory, then rename: a reader (or a crashed
+    writer) never sees a torn checkpoint"""
+    tmp = f"{path}.tmp.{os.getpid()}"
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
+
+
+def is_writer_rank() -> bool:
+    """One process per GPU here (the reference is single-process DataParallel,
+    train/adversarial_training_clip.py:184-190): only rank 0 touches the checkpoint directory."""
+    import torch.distributed as dist
+    return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+
 def save_pair(model_state, opt_state, ckpt_dir, stem):
     os.makedirs(ckpt_dir, exist_ok=True)
-    torch.save({k: v.detach().cpu() for k, v in model_state.items()},
-               os.path.join(ckpt_dir, f"{stem}.pt"))
-    torch.save(opt_state, os.path.join(ckpt_dir, f"{stem}_opt.pt"))
+    _atomic_save({k: v.detach().cpu() for k, v in model_state.items()},
+                 os.path.join(ckpt_dir, f"{stem}.pt"))
+    _atomic_save(opt_state, os.path.join(ckpt_dir, f"{stem}_opt.pt"))
 
 
 def save_periodic(model_state, opt_state_fn, output_dir, step_total, total_steps,
@@ -105,6 +120,8 @@ def save_periodic(model_state, opt_state_fn, output_dir, step_total, total_steps
     checkpoints, plus a rolling `fallback_N` every 200 steps.  Returns the stems written."""
     ckpt_dir = os.path.join(output_dir, "checkpoints")
     written = []
+    if not is_writer_rank():     # replicas hold identical parameters: rank 0 writes for all
+        return written
     if save_checkpoints and total_steps >= 10 and step_total % (total_steps // 10) == 0:
         save_pair(model_state, opt_state_fn(), ckpt_dir, f"step_{step_total}")
         written.append(f"step_{step_total}")
@@ -113,7 +130,10 @@ def save_periodic(model_state, opt_state_fn, output_dir, step_total, total_steps
         written.append(f"fallback_{step_total}")
         for f in os.listdir(ckpt_dir):          # :476-478 (substring test, as the reference)
             if f.startswith("fallback") and str(step_total) not in f:
-                os.remove(os.path.join(ckpt_dir, f))
+                try:
+                    os.remove(os.path.join(ckpt_dir, f))
+                except FileNotFoundError:       # removed concurrently: nothing left to do
+                    pass
     return written
 
 

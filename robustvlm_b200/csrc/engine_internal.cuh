@@ -28,6 +28,7 @@ struct HeadArgs {
   int fmt_g;
   float grad_scale;       // multiplies d loss_b / d emb
   int grad_unit;          // 1: rescale each sample's CLS-row gradient to unit max-abs
+  float* unit_out;        // [B] the factor applied (1 when grad_unit == 0); may be null
   // outer training step only (may be null): per-sample vectors for the head's parameter grads
   float* t_xhat;          // [B, W] normalised CLS row
   float* t_pooled;        // [B, W] ln_post output
@@ -70,7 +71,9 @@ struct PatchGeom {
 };
 // NCHW fp32 image batch <-> patch-major [B*np, kp] fp32
 int launch_patchify(const float* img, float* pm, int B, const PatchGeom& g, cudaStream_t st);
-int launch_unpatchify(const float* pm, float* img, int B, const PatchGeom& g, cudaStream_t st);
+// unit (nullable, [B]): img = pm / unit[b] (undoes the head's per-sample gradient rescaling)
+int launch_unpatchify(const float* pm, float* img, int B, const PatchGeom& g, cudaStream_t st,
+                      const float* unit = nullptr);
 // A16[r, k] = 16-bit((x[r,k] + delta[r,k] - mean_c) / std_c); delta may be null
 int launch_patch_operand(const float* xp, const float* dp, uint16_t* a16, int lda, long long rows,
                          const PatchGeom& g, int fmt, cudaStream_t st, uint16_t* a16lo = nullptr);

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
     mxabs = blk_max(mxabs, red);
     unit = (mxabs > 0.f && mxabs < INFINITY) ? 1.f / mxabs : 1.f;
   }
+  if (A.unit_out && tid == 0) A.unit_out[b] = unit;
   __syncthreads();
   float* d32 = A.dx32 + (size_t)b * A.T * W;
   uint16_t* d16 = A.dx16 ? A.dx16 + (size_t)b * A.T * W : nullptr;

@@ -13,7 +13,7 @@ namespace rvlm {
 template <bool TO_PATCH, bool ADD>
 __global__ void patch_layout_kernel(const float* __restrict__ src, const float* __restrict__ src2,
                                     float* __restrict__ dst, int B, int image, int p, int grid,
-                                    int kp) {
+                                    int kp, const float* __restrict__ unit = nullptr) {
   const long long total = (long long)B * 3 * image * image;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -30,6 +30,7 @@ __global__ void patch_layout_kernel(const float* __restrict__ src, const float* 
     } else {
       float v = src[pm];
       if (ADD) v = __fadd_rn(v, src2[pm]);
+      if (unit) v = v / unit[b];   // undo the per-sample rescaling of a 16-bit-gradient backward
       dst[i] = v;
     }
   }
@@ -102,10 +103,11 @@ int launch_patchify(const float* img, float* pm, int B, const PatchGeom& g, cuda
                                                                  g.patch, g.grid, g.kp);
   return rc();
 }
-int launch_unpatchify(const float* pm, float* img, int B, const PatchGeom& g, cudaStream_t st) {
+int launch_unpatchify(const float* pm, float* img, int B, const PatchGeom& g, cudaStream_t st,
+                      const float* unit) {
   const long long n = (long long)B * 3 * g.image * g.image;
   patch_layout_kernel<false, false><<<nblk(n, 256), 256, 0, st>>>(pm, nullptr, img, B, g.image,
-                                                                  g.patch, g.grid, g.kp);
+                                                                  g.patch, g.grid, g.kp, unit);
   return rc();
 }
 int launch_unpatchify_add(const float* xp, const float* dp, float* img, int B, const PatchGeom& g,

@@ -98,7 +98,7 @@ struct Ws {
   float *dx32, *dz32;
   uint16_t *dx16, *dh16, *do16, *dqkv16, *dtok16;
   // head
-  float *emb, *loss;
+  float *emb, *loss, *gunit;   // gunit [B]: per-sample factor the head applied to the gradient
   int* pred;
   float* upd;     // update-kernel reduction workspace
   size_t total;
@@ -144,6 +144,7 @@ Ws carve(const Engine& E, uint8_t* base, int B, int stash) {
   w.act16 = take<uint16_t>(p, used, M * F);
   w.emb = take<float>(p, used, (size_t)B * E.D);
   w.loss = take<float>(p, used, B);
+  w.gunit = take<float>(p, used, B);
   w.pred = take<int>(p, used, B);
   w.upd = take<float>(p, used, (size_t)B * 32 * 3);
   if (E.split) {
@@ -296,7 +297,10 @@ int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, in
   A.pred = w.pred;
   A.fmt_g = E.cfg.fmt_bwd;
   A.grad_scale = grad_scale;
+  // fp16 gradient operands: every sample's gradient is rescaled to unit max-abs at the head (range);
+  // consumers that need the true scale divide by w.gunit again (launch_unpatchify)
   A.grad_unit = (E.cfg.fmt_bwd == RVLM_FMT_F16 && w.stash != 2) ? 1 : 0;
+  A.unit_out = w.gunit;
   if (w.stash == 2) {
     A.t_xhat = w.t_xhat; A.t_pooled = w.t_pooled; A.t_dpooled = w.t_dpooled; A.t_demb = w.t_demb;
   }
@@ -686,7 +690,7 @@ extern "C" int rvlm_vit_backward_input(rvlm_vit_handle h, void* workspace,
   RV(run_head(E, w, B, &lc, 0, nullptr, nullptr, true, st));
   RV(run_backward(E, w, B, st));
   RV(run_patch_grad(E, w, B, st));
-  return launch_unpatchify(w.gp, grad_out, B, E.geom, st);
+  return launch_unpatchify(w.gp, grad_out, B, E.geom, st, w.gunit);   // true scale (a VJP)
 }
 
 extern "C" int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
@@ -711,7 +715,7 @@ extern "C" int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t wor
     if (!grad_out) return RVLM_ERR_INVAL;
     RV(run_backward(E, w, B, st));
     RV(run_patch_grad(E, w, B, st));
-    RV(launch_unpatchify(w.gp, grad_out, B, E.geom, st));
+    RV(launch_unpatchify(w.gp, grad_out, B, E.geom, st, w.gunit));   // true scale
   }
   return 0;
 }

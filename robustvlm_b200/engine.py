@@ -136,7 +136,8 @@ class VitEngine:
                               fmt_fwd, fmt_bwd, flags)
         self.handle = c_void_p(0)
         self._ws = None
-        self._ws_key = None
+        self._gen = 0          # bumped by every call that writes the workspace
+        self._kept = None      # (generation, B) of the forward whose activations it holds
         wc, keep = self._weights_struct(state_dict)
         with torch.cuda.device(self.device):
             nat.call("rvlm_vit_create", byref(self.cfg), byref(wc), nat.stream_ptr(),
@@ -185,12 +186,21 @@ class VitEngine:
         fn.restype = c_size_t
         return int(fn(self.handle, c_int(B), c_int(int(with_backward))))
 
-    def _workspace(self, B, with_backward):
+    def _workspace(self, B, with_backward, touch=True):
         need = self.workspace_bytes(B, with_backward)
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._kept = None
+        if touch:
+            self._gen += 1
+            self._kept = None
         return self._ws, need
+
+    def kept_stamp(self):
+        """identifies the activations a `forward(keep_for_backward=True)` left in the workspace;
+        None once any other call has overwritten them"""
+        return self._kept
 
     def max_batch(self, with_backward=True, budget_bytes=None):
         """Largest chunk size whose workspace fits the memory budget."""
@@ -215,11 +225,18 @@ class VitEngine:
         nat.call("rvlm_vit_forward", self.handle, nat.ptr(ws), c_size_t(nbytes), nat.ptr(x),
                  nat.ptr(delta), c_int(B), c_int(int(output_normalize)),
                  c_int(int(keep_for_backward)), nat.ptr(emb), nat.stream_ptr())
+        if keep_for_backward:
+            self._kept = (self._gen, B)
         return emb
 
     def backward_input(self, B, d_emb, output_normalize=False):
-        """VJP of the forward just run with keep_for_backward=True."""
-        ws, nbytes = self._workspace(B, True)
+        """VJP of the forward just run with keep_for_backward=True (raises if another call has
+        overwritten its activations since)."""
+        if self._kept is None or self._kept[1] != B:
+            raise nat.RvlmError("backward_input: no forward(keep_for_backward=True) of this batch "
+                                "size is resident in the workspace (another engine call ran in "
+                                "between)")
+        ws, nbytes = self._workspace(B, True, touch=False)
         d_emb = d_emb.detach().float().contiguous()
         img = self.arch["image"]
         grad = torch.empty(B, 3, img, img, device=self.device, dtype=torch.float32)

@@ -141,15 +141,28 @@ def _norm_constants(normalize):
 
 
 class _EngineVJP(torch.autograd.Function):
+    """The activations of the forward stay in the engine's workspace; `stamp` identifies them, and
+    the backward refuses to run if any other engine call has touched the workspace since (a second
+    forward before the backward, another attack, a larger batch): recompute instead of returning a
+    gradient of stale activations."""
+
     @staticmethod
     def forward(ctx, vision, eng, output_normalize):
         ctx.eng, ctx.norm, ctx.B = eng, output_normalize, vision.shape[0]
-        return eng.forward(vision.detach(), output_normalize=output_normalize,
-                           keep_for_backward=True)
+        out = eng.forward(vision.detach(), output_normalize=output_normalize,
+                          keep_for_backward=True)
+        ctx.stamp = eng.kept_stamp()
+        ctx.save_for_backward(vision)
+        return out
 
     @staticmethod
     def backward(ctx, d_emb):
-        return ctx.eng.backward_input(ctx.B, d_emb, ctx.norm), None, None
+        eng = ctx.eng
+        if eng.kept_stamp() != ctx.stamp:
+            # the workspace was reused in between: redo this node's forward, then differentiate
+            (vision,) = ctx.saved_tensors
+            eng.forward(vision.detach(), output_normalize=ctx.norm, keep_for_backward=True)
+        return eng.backward_input(ctx.B, d_emb, ctx.norm), None, None
 
 
 class ClipVisionModel(nn.Module):
@@ -181,7 +194,14 @@ class ClipVisionModel(nn.Module):
 
 
 class ClassificationModel(nn.Module):
-    """CLIP_eval/clip_robustbench.py:50-69: logits = normalize(phi(x)) @ T * logit_scale."""
+    """CLIP_eval/clip_robustbench.py:50-69: logits = normalize(phi(resizer(x))) @ T * logit_scale.
+
+    `model` is the vision tower (ours, or a ClipVisionModel around it).  `logit_scale` as in the
+    reference: True multiplies by `model.logit_scale.exp()` when the model carries the CLIP
+    parameter (a full CLIP module) and by 100 -- its value for every OpenAI checkpoint,
+    SURVEY.md §8a a11 -- when only the tower is given; False leaves the cosine logits; a number is
+    used as is.  `resizer` is applied to the images before the tower (:56,62); with a resizer the
+    fused attack path cannot be used (the gradient must flow through it) and autograd takes over."""
 
     def __init__(self, model, text_embedding, args=None, input_normalize=None, resizer=None,
                  logit_scale=True):
@@ -189,11 +209,18 @@ class ClassificationModel(nn.Module):
         self.visual = model if isinstance(model, ClipVisionModel) else ClipVisionModel(
             model, args, input_normalize)
         self.args = args
+        self.resizer = resizer
         self.register_buffer("text_embedding", text_embedding)  # [D, n_classes]
-        self.logit_scale_value = 100.0 if logit_scale is True else (
-            1.0 if logit_scale is False else float(logit_scale))
+        if logit_scale is True:
+            ls = getattr(model, "logit_scale", None)
+            self.logit_scale_value = float(ls.exp()) if torch.is_tensor(ls) else 100.0
+        else:
+            self.logit_scale_value = 1.0 if logit_scale is False else float(logit_scale)
 
     def forward(self, vision, output_normalize=True):
+        assert output_normalize                                               # :60
+        if self.resizer is not None:
+            vision = self.resizer(vision)
         emb = self.visual(vision, output_normalize=True)
         return (emb @ self.text_embedding) * self.logit_scale_value
 

@@ -121,8 +121,12 @@ class AdversarialTrainer:
         self._refresh()
 
     def save(self, output_dir, stem):
-        checkpoint.save_pair(self.vt.state_dict(), self.optimizer_state_dict(),
-                             f"{output_dir}/checkpoints", stem)
+        """`final.pt` / `final_opt.pt` (:238-239).  Rank 0 writes; every rank returns after it has."""
+        if checkpoint.is_writer_rank():
+            checkpoint.save_pair(self.vt.state_dict(), self.optimizer_state_dict(),
+                                 f"{output_dir}/checkpoints", stem)
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.barrier()
 
     def _refresh(self):
         sd = self.vt.state_dict()
@@ -219,7 +223,7 @@ class AdversarialTrainer:
         if output_dir is not None:                                                      # :467-479
             log["saved"] = checkpoint.save_periodic(
                 self.vt.state_dict(), self.optimizer_state_dict, output_dir, self.step_total,
-                self.steps, save_checkpoints)
+                self.steps, save_checkpoints)             # rank 0 only (checkpoint.is_writer_rank)
         return log
 
     def evaluate(self, data_eval, targets_eval, n_iter=50):

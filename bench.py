@@ -140,48 +140,66 @@ def _cpu_arm_setup(model_name, Bs):
     return oa, model, wrap, x, d0, best, n
 
 
-def run_reference_cuda(args):
-    """Informal extra baseline (NOT the reference arm the driver runs): the same oracle port of
-    the reference's pgd() around the restated ViT, executed by stock PyTorch on cuda:0 -- the
-    "reference's single-GPU PyTorch path" of BASELINE.json's target -- in fp32 and with TF32
-    matmuls allowed.  CUDA-event timing, 1 warm-up + `steps` timed calls, median."""
+def torch_cuda_baseline(model_name, Bs=64, calls=2, dev_index=0):
+    """The "reference's single-GPU PyTorch path" of BASELINE.json's >= 10x target, measured on the
+    same box: the oracle port of the reference's pgd() (train/pgd_train.py:5-68) around the
+    restated open_clip ViT, executed by STOCK PyTorch on the GPU (cuBLAS / SDPA), in fp32 (torch
+    defaults, what the reference runs) and with TF32 matmuls allowed (a stronger informal
+    baseline).  Bounded: `Bs` images, one warm-up + `calls` timed full 10-iteration calls per
+    precision, CUDA-event timing, median."""
     import torch
     from oracle import attacks as oa
     from oracle import vit as ovit
-    dev = torch.device("cuda", 0)
-    Bs = args.ref_batch
-    model = ovit.ClipVisionModel(ovit.build(args.model, seed=1)).eval().to(dev)
-    model_orig = ovit.ClipVisionModel(ovit.build(args.model, seed=2)).eval().to(dev)
+    dev = torch.device("cuda", dev_index)
+    model = ovit.ClipVisionModel(ovit.build(model_name, seed=1)).eval().to(dev)
+    model_orig = ovit.ClipVisionModel(ovit.build(model_name, seed=2)).eval().to(dev)
+    for p in list(model.parameters()) + list(model_orig.parameters()):
+        p.requires_grad_(False)
     x, d0 = synth(Bs, seed=0, device=dev)
     res = {}
-    for tf32 in (False, True):
-        torch.backends.cuda.matmul.allow_tf32 = tf32
-        torch.backends.cudnn.allow_tf32 = tf32
-        with torch.no_grad():
-            e_orig = model_orig(x, output_normalize=False)
-        wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                e_orig = model_orig(x, output_normalize=False)
+            wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
 
-        def one():
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            oa.pgd(model, wrap, x, None, "linf", EPS, ITERS, STEPSIZE, False,
-                   perturbation=d0.clone(), mode="max")
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / 1e3
-        one()
-        ts = sorted(one() for _ in range(max(1, args.steps)))
-        res["tf32" if tf32 else "fp32"] = Bs / ts[len(ts) // 2]
+            def one():
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                oa.pgd(model, wrap, x, None, "linf", EPS, ITERS, STEPSIZE, False,
+                       perturbation=d0.clone(), mode="max")
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / 1e3
+            one()
+            ts = sorted(one() for _ in range(max(1, calls)))
+            res["tf32" if tf32 else "fp32"] = Bs / ts[len(ts) // 2]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del model, model_orig
+    torch.cuda.empty_cache()
+    return {"fp32_img_s": res["fp32"], "tf32_img_s": res["tf32"], "batch": Bs, "calls": calls,
+            "what": "oracle port of train/pgd_train.py::pgd + restated open_clip ViT on stock "
+                    f"PyTorch {torch.__version__} CUDA (cuBLAS / SDPA), same box, same GPU"}
+
+
+def run_reference_cuda(args):
+    """`--impl reference --ref-device cuda`: the stock-PyTorch-on-GPU baseline as its own line."""
+    r = torch_cuda_baseline(args.model, args.ref_batch, max(1, args.steps))
     line = {"impl": "reference-torch-cuda", "metric": METRIC, "unit": "img/s", "n_gpus": 1,
-            "value": res["fp32"], "value_tf32": res["tf32"], "steps": args.steps, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, Bs),
-            "note": "oracle port of train/pgd_train.py::pgd + restated open_clip ViT on stock "
-                    f"PyTorch {torch.__version__} CUDA (cuBLAS/cuDNN), batch {Bs}; informal"}
+            "value": r["fp32_img_s"], "value_tf32": r["tf32_img_s"], "steps": args.steps,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.ref_batch),
+            "note": r["what"]}
     print(json.dumps(line), flush=True)
 
 
 def run_reference(args):
-    """CPU baseline arm: the oracle port of the reference's pgd() around the restated ViT."""
+    """CPU baseline arm: the oracle port of the reference's pgd() around the restated ViT, full
+    10-iteration calls (nothing extrapolated) on a bounded number of images per step so that
+    `--steps K --warmup W` ends within a few minutes."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -189,31 +207,37 @@ def run_reference(args):
     if args.ref_device == "cuda":
         return run_reference_cuda(args)
     name = args.model
-    Bs = 8
-    oa, model, wrap, x, d0, cores, avail = _cpu_arm_setup(name, Bs)
+    oa, model, wrap, x8, d8, cores, avail = _cpu_arm_setup(name, 8)
 
-    def one(n_it):
+    def one(Bs):
+        w = oa.ComputeLossWrapper(wrap.embedding_orig[:Bs], None, "mean", "l2", 100.0)
         t0 = time.perf_counter()
-        oa.pgd(model, wrap, x, None, "linf", EPS, n_it, STEPSIZE, False, perturbation=d0.clone(),
-               mode="max")
+        oa.pgd(model, w, x8[:Bs], None, "linf", EPS, ITERS, STEPSIZE, False,
+               perturbation=d8[:Bs].clone(), mode="max")
         return time.perf_counter() - t0
 
-    t1 = one(1)                                   # probe (also warms the thread pool)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_it = int(max(1, min(ITERS, budget // max(t1, 1e-3))))
+    # images per step: the largest of 8 / 4 / 2 whose K + W full calls fit ~200 s (probe: one call
+    # of 2 images; CPU GEMM efficiency is flat over these batch sizes)
+    t2 = one(2)
+    calls = max(1, args.steps + args.warmup)
+    Bs = 2
+    for cand in (8, 4):
+        if t2 * cand / 2 * calls <= 200.0:
+            Bs = cand
+            break
     for _ in range(args.warmup):
-        one(n_it)
-    times = [one(n_it) for _ in range(args.steps)]
-    per_call = sum(times) / len(times) / n_it * ITERS      # seconds for a 10-iteration call
+        one(Bs)
+    times = [one(Bs) for _ in range(args.steps)]
+    per_call = sum(times) / len(times)
     val = Bs / per_call
-    sample = (f"{Bs} images x {n_it} of {ITERS} PGD iterations per step, scaled to {ITERS}; "
-              f"{name} fp32, torch {torch.__version__}, {cores} threads (calibrated; "
-              f"{avail} CPUs available)")
+    sample = (f"{Bs} images per step, all {ITERS} PGD iterations of every call timed (no "
+              f"extrapolation); {name} fp32, torch {torch.__version__}, {cores} threads "
+              f"(calibrated; {avail} CPUs available)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s",
             "n_gpus": args.gpus, "device": "cpu (host cores of the box; this arm leaves the GPUs idle)",
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_call * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": workload_config(args, Bs),
+            "data": "synthetic", "config": workload_config(args, args.batch),
             "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0,
@@ -243,8 +267,9 @@ def workload_config(args, B):
 
 def cpu_baseline_sample(model_name, seconds=20.0, keep=None):
     """Bounded CPU sample of the same workload (oracle port), rank 0, N = 1 only.  `keep`, if a
-    dict, receives the sample's inputs / output so the GPU path can be compared on them (the
+    dict, receives the sample's inputs / outputs so the GPU path can be compared on them (the
     second half of BASELINE.json's metric: delta max-abs-err vs the reference)."""
+    import torch
     Bs = 8
     oa, model, wrap, x, d0, cores, avail = _cpu_arm_setup(model_name, Bs)
     t0 = time.perf_counter()
@@ -257,8 +282,14 @@ def cpu_baseline_sample(model_name, seconds=20.0, keep=None):
                    perturbation=d0.clone(), mode="max")
     t = (time.perf_counter() - t0) / n_it * ITERS
     if keep is not None:
+        # the reference's embedding and first-iteration gradient at x + delta0 (one more fwd + bwd)
+        for p_ in model.parameters():
+            p_.requires_grad_(False)
+        xa = (x + d0).requires_grad_(True)
+        e0 = model(xa, output_normalize=False)
+        (g0,) = torch.autograd.grad(wrap(e0, None), xa)
         keep.update(x=x, d0=d0, x_adv=x_adv, n_it=n_it, e_orig=wrap.embedding_orig,
-                    state_dict=model.model.state_dict())
+                    state_dict=model.model.state_dict(), e0=e0.detach(), g0=g0)
     return {"value": Bs / t, "unit": "img/s", "cores": cores, "kind": "port",
             "sample": f"{Bs} images x {n_it} of {ITERS} PGD iterations (scaled), {model_name} fp32 "
                       f"oracle port of train/pgd_train.py::pgd, {cores} threads (calibrated; "
@@ -266,32 +297,88 @@ def cpu_baseline_sample(model_name, seconds=20.0, keep=None):
 
 
 # ------------------------------------------------------------------------------------
-def delta_vs_reference(vt, m, keep, dev):
+def delta_vs_reference(m, keep, dev):
     """BASELINE.json's second metric: delta = x_adv - x of the CUDA path against the CPU arm's
     (the oracle port of train/pgd_train.py::pgd, fp32) on the SAME weights, images, start and
-    iteration count as the cpu_baseline sample.  A different fp32 summation order alone flips
-    sign(g) where g ~ 0, and one flipped sign moves that entry by
-    2*stepsize per iteration, so the max-abs error is quantised in steps of 2/255 * n_it; the
-    informative figures are the fraction of identical entries and the loss reached."""
+    iteration count as the cpu_baseline sample, plus the embedding error and the first
+    iteration's sign agreement.  A different fp32 summation order alone flips sign(g) where
+    g ~ 0, and one flipped sign moves that entry by 2*stepsize per
+    iteration, so the max-abs error is quantised in steps of 2/255 * n_it; the informative
+    figures are the fraction of identical entries, the mismatch among gradients that are not
+    near zero, and the loss reached."""
     import torch
     from robustvlm_b200 import attacks, model as rmodel
-    vt.load_state_dict(keep["state_dict"])                 # same weights as the CPU arm
+    from robustvlm_b200.engine import LossSpec
+    m.model.load_state_dict(keep["state_dict"])            # same weights as the CPU arm
     x, d0, ref = keep["x"].to(dev), keep["d0"].to(dev), keep["x_adv"]
     wrap = rmodel.ComputeLossWrapper(keep["e_orig"].to(dev), None, "mean", "l2", 100.0)
     out = attacks.pgd(m, wrap, x, None, "linf", EPS, keep["n_it"], STEPSIZE, False,
                       perturbation=d0, mode="max")
     with torch.no_grad():
-        emb = m(keep["x"].to(dev), output_normalize=False).cpu()
+        e0 = m(x + d0, output_normalize=False).cpu()
         l_ours = float(wrap(m(out, output_normalize=False), None))
         l_ref = float(wrap(m(ref.to(dev), output_normalize=False), None))
+    g = m.engine().loss_grad(x, LossSpec("l2", False, emb_orig=keep["e_orig"].to(dev)),
+                             delta=d0)["grad"].cpu()
+    g0 = keep["g0"]
+    mis = torch.sign(g) != torch.sign(g0)
+    big = g0.abs() > 0.05 * g0.abs().median()
     d_o, d_r = out.cpu() - keep["x"], ref - keep["x"]
     return {"max_abs_err": float((d_o - d_r).abs().max()),
             "mean_abs_err": float((d_o - d_r).abs().mean()),
             "identical_frac": float((d_o == d_r).float().mean()),
+            "emb_rel_err": float((e0 - keep["e0"]).norm() / keep["e0"].norm()),
+            "mismatch_frac": float(mis.float().mean()),
+            "mismatch_frac_big": float((mis & big).float().sum() / big.float().sum()),
             "images": int(x.shape[0]), "iterations": int(keep["n_it"]),
             "fare_loss_ours": l_ours, "fare_loss_ref_delta": l_ref,
-            "linf_ours": float(d_o.abs().max()), "eps": EPS,
-            "emb_norm": float(emb.norm(dim=1).mean())}
+            "linf_ours": float(d_o.abs().max()), "eps": EPS}
+
+
+def fare_train_step(args, dev, rank, world, timed_steps=3):
+    """Config 5's unit of work (BASELINE.json configs[4]): the WHOLE FARE step of
+    train/adversarial_training_clip.py:296-366 on this rank's shard -- model_orig forward, 10-step
+    PGD, clean forward, adversarial forward + full backward, all-reduce of the outer gradient
+    (per-block buckets overlapped with the backward, parallel.BucketedAllReduce), fused AdamW --
+    through robustvlm_b200.train.AdversarialTrainer.  Returns global images / s (max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from robustvlm_b200 import model as rmodel
+    from robustvlm_b200.train import AdversarialTrainer
+    B = args.batch
+    vt = rmodel.VisionTransformer(args.model, seed=1, precision=args.precision).to(dev)
+    vt_orig = rmodel.VisionTransformer(args.model, seed=1, precision=args.precision).to(dev)
+    m = rmodel.ClipVisionModel(vt, None, None).eval()
+    m_orig = rmodel.ClipVisionModel(vt_orig, None, None).eval()
+    tr = AdversarialTrainer(m, m_orig, lr=1e-5, wd=1e-4, steps=20000, warmup=1400, loss="l2",
+                            inner_loss="l2", norm="linf", eps=EPS, stepsize=STEPSIZE,
+                            iterations=ITERS, attack="pgd", output_normalize=False)
+    x, _ = synth(B, seed=500 + rank, device=dev)
+    tr.train_step(x, None, global_batch=B * world)          # warm-up (allocations, NCCL channels)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(timed_steps):
+        tr.train_step(x, None, global_batch=B * world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / timed_steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    peak = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    del tr, m, m_orig, vt, vt_orig
+    torch.cuda.empty_cache()
+    return {"value": B * world / (ms / 1e3), "unit": "img/s", "ms_per_step": ms,
+            "global_batch": B * world, "steps": timed_steps, "peak_mem_gib": peak,
+            "allreduce": ("none (1 GPU)" if world == 1 else
+                          "NCCL AVG of the 1.216 GB fp32 gradient in per-block buckets started "
+                          "behind per-block events and overlapped with the backward"),
+            "what": "whole FARE step: model_orig fwd + 10-step PGD + clean fwd + adv fwd/bwd + "
+                    "all-reduce + AdamW (BASELINE.json configs[4] per-GPU work)"}
 
 
 def run_ours(args):
@@ -308,34 +395,23 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    vt = rmodel.VisionTransformer(args.model, seed=1).to(dev)
-    vt_orig = rmodel.VisionTransformer(args.model, seed=2).to(dev)
-    m = rmodel.ClipVisionModel(vt, None, None).eval()
-    m_orig = rmodel.ClipVisionModel(vt_orig, None, None).eval()
     x_h, d0_h = synth(B, seed=100 + rank)
     x_h, d0_h = x_h.pin_memory(), d0_h.pin_memory()
     x, d0 = x_h.to(dev), d0_h.to(dev)
     chunk = min(args.chunk, B)
+    vt_orig = rmodel.VisionTransformer(args.model, seed=2, precision=args.precision).to(dev)
+    m_orig = rmodel.ClipVisionModel(vt_orig, None, None).eval()
     with torch.no_grad():
         e_orig = torch.cat([m_orig(x[i:i + chunk], output_normalize=False)
                             for i in range(0, B, chunk)])
-    vt_orig._engine = None           # release the frozen tower's workspace
+    del m_orig, vt_orig              # release the frozen tower's engine and workspace
     torch.cuda.empty_cache()
     wrap = rmodel.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
-
-    def step_resident():
-        return attacks.pgd(m, wrap, x, None, "linf", EPS, ITERS, STEPSIZE, False,
-                           perturbation=d0, mode="max", chunk=chunk)
-
     out_h = torch.empty_like(x_h).pin_memory()
 
-    def step_e2e():
-        xd = x_h.to(dev, non_blocking=True)
-        dd = d0_h.to(dev, non_blocking=True)
-        adv = attacks.pgd(m, wrap, xd, None, "linf", EPS, ITERS, STEPSIZE, False,
-                          perturbation=dd, mode="max", chunk=chunk)
-        out_h.copy_(adv, non_blocking=True)
-        return adv
+    def make(mode):
+        vt = rmodel.VisionTransformer(args.model, seed=1, precision=mode).to(dev)
+        return rmodel.ClipVisionModel(vt, None, None).eval()
 
     def barrier():
         torch.cuda.synchronize()
@@ -343,9 +419,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False):
+    def timed(fn, steps, profile=False, sample=True):
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = ClockSampler(local) if (rank == 0 and sample) else None
         if sampler:
             sampler.start()
         if profile:
@@ -377,6 +453,20 @@ def run_ours(args):
             ms = float(t.item())
         return ms, launches, prof, (sampler.summary() if sampler else None)
 
+    m = make(args.precision)
+
+    def step_resident(mm=None):
+        return attacks.pgd(mm or m, wrap, x, None, "linf", EPS, ITERS, STEPSIZE, False,
+                           perturbation=d0, mode="max", chunk=chunk)
+
+    def step_e2e():
+        xd = x_h.to(dev, non_blocking=True)
+        dd = d0_h.to(dev, non_blocking=True)
+        adv = attacks.pgd(m, wrap, xd, None, "linf", EPS, ITERS, STEPSIZE, False,
+                          perturbation=dd, mode="max", chunk=chunk)
+        out_h.copy_(adv, non_blocking=True)
+        return adv
+
     for _ in range(args.warmup):
         step_resident()
     ms, launches, prof, clocks = timed(step_resident, args.steps, profile=True)
@@ -387,6 +477,7 @@ def run_ours(args):
     n_img = B * world * args.steps
     value = n_img / (ms / 1e3)
     e2e = n_img / (ms_e2e / 1e3)
+    line = None
     if rank == 0:
         peak_tf, _, which = read_peaks()
         gemm_ms, gemm_fl, gemm_n = prof
@@ -396,7 +487,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 fwd operands / bf16 bwd operands, f32 accumulate + residual stream",
+            "dtype": PRECISION_DTYPE[args.precision],
             "data": "synthetic", "config": workload_config(args, B),
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(2 * x_h.numel() * 4),
                     "d2h_bytes_per_step": int(x_h.numel() * 4)},
@@ -405,21 +496,64 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                          "traffic": gemm_traffic()[0],
                          "traffic_algorithmic": gemm_traffic()[1],
-                         "traffic_source": "profiles/r01_gemm_traffic.json (ncu dram bytes per "
-                                           "launch, mean of the 4 forward GEMM variants)",
+                         "traffic_source": "profiles/r01_gemm_traffic.json (ncu --set full dram "
+                                           "bytes per launch, mean of the 4 forward GEMM variants; "
+                                           "a profiler cannot run inside the timed bench)",
                          "peak_source": f"{which} bf16_tflops_sustained",
-                         "kernel": "gemm16_2cta_kernel (tcgen05 cta_group::2, all epilogue variants)", "launches": gemm_n,
+                         "kernel": "gemm16_2cta_kernel (tcgen05 cta_group::2, all epilogue variants)",
+                         "launches": gemm_n,
                          "gemm_ms_per_step": gemm_ms / args.steps,
                          "gemm_share_of_step": gemm_ms / ms if ms else None,
                          "whole_step_algorithmic_tflops": algo_tf / (ms / 1e3)},
         }
-        if world == 1 and not args.no_cpu_baseline:
+    # ---- the other precision modes on the same workload (N = 1 only, bounded: 1 + 2 steps each)
+    modes = {}
+    if world == 1 and not args.no_modes:
+        models = {args.precision: m}
+        for mode in [k for k in ("fast16", "split", "fast") if k != args.precision]:
+            mm = make(mode)
+            step_resident(mm)
+            ms_m, _, _, _ = timed(lambda mm=mm: step_resident(mm), 2, sample=False)
+            modes[mode] = {"value": B * 2 / (ms_m / 1e3), "unit": "img/s",
+                           "ms_per_step": ms_m / 2, "dtype": PRECISION_DTYPE[mode]}
+            models[mode] = mm
+        modes[args.precision] = {"value": value, "unit": "img/s", "ms_per_step": ms / args.steps,
+                                 "dtype": PRECISION_DTYPE[args.precision], "default": True}
+        if not args.no_cpu_baseline:
             keep = {}
             line["cpu_baseline"] = cpu_baseline_sample(args.model, keep=keep)
-            line["delta_vs_ref"] = delta_vs_reference(vt, m, keep, dev)
+            for mode, mm in models.items():
+                modes[mode]["delta_vs_ref"] = delta_vs_reference(mm, keep, dev)
+            line["delta_vs_ref"] = modes[args.precision]["delta_vs_ref"]
+        line["modes"] = modes
+        del models
+    del m
+    torch.cuda.empty_cache()
+    if world == 1 and rank == 0 and not args.no_torch_baseline:
+        try:
+            tb = torch_cuda_baseline(args.model, args.ref_batch, 2, local)
+            tb["speedup_vs_fp32"] = value / tb["fp32_img_s"]
+            tb["speedup_vs_tf32"] = value / tb["tf32_img_s"]
+            line["torch_cuda_baseline"] = tb
+        except Exception as e:  # noqa: BLE001  (an OOM of the stock path must not lose the line)
+            line["torch_cuda_baseline"] = {"error": repr(e)[:200]}
+        torch.cuda.empty_cache()
+    if not args.no_train_step:
+        ts = fare_train_step(args, dev, rank, world)
+        if rank == 0:
+            line["train_step"] = ts
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+PRECISION_DTYPE = {
+    "fast": "f16 fwd operands / bf16 bwd operands, f32 accumulate + residual stream",
+    "fast16": "f16 fwd operands / f16 bwd operands (per-sample rescaled), f32 accumulate + residual stream",
+    "split": "f16 hi+lo fwd operands (3 MMAs per product, fp32-class) / f16 bwd operands, f32 accumulate",
+    "bf16": "bf16 operands, f32 accumulate",
+}
 
 
 def main():
@@ -432,6 +566,13 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--chunk", type=int, default=256, help="engine micro-batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fast16", choices=["fast", "fast16", "split"],
+                    help="engine precision mode of the headline value (robustvlm_b200.engine.PRECISIONS)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the other precision modes")
+    ap.add_argument("--no-torch-baseline", action="store_true",
+                    help="skip the stock-PyTorch-on-GPU baseline (N = 1)")
+    ap.add_argument("--no-train-step", action="store_true",
+                    help="skip the whole-FARE-step measurement (config 5's per-GPU work)")
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference only: 'cuda' times stock PyTorch on the GPU (informal)")
     ap.add_argument("--ref-batch", type=int, default=64)

@@ -347,6 +347,16 @@ int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t workspace_by
                          const float* x, int B, const rvlm_loss_config* loss, float loss_scale,
                          const rvlm_vit_grads* grads, float* loss_out, float* emb_out,
                          void* stream);
+/* The same with completion events for gradient bucketing: events = cudaEvent_t[layers + 1] (as
+ * void*), events[l] recorded on `stream` once every parameter gradient of block l is enqueued
+ * (blocks finish in the order layers-1 .. 0), events[layers] at the end (stem + head).  The
+ * caller starts the NCCL all-reduce of a block's gradients on another stream behind its event
+ * while the rest of the backward runs (replaces DataParallel's gradient gather,
+ * train/adversarial_training_clip.py:184-190,362). */
+int rvlm_vit_train_grads_ev(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                            const float* x, int B, const rvlm_loss_config* loss, float loss_scale,
+                            const rvlm_vit_grads* grads, float* loss_out, float* emb_out,
+                            void* const* events, int n_events, void* stream);
 /* torch.optim.AdamW semantics on a flat fp32 buffer (train/adversarial_training_clip.py:196-197,363):
  * decoupled weight decay, bias correction with the 1-based step count.
  * Hyper-parameters are doubles (what torch.optim holds); bias corrections formed in double. */

@@ -221,9 +221,12 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // ---------------------------------------------------------------------------
 // 16-bit conversions (runtime format: 0 = fp16, 1 = bf16)
 // ---------------------------------------------------------------------------
+// fp16 pair with SATURATION to +-65504 instead of +-inf: an activation / gradient outlier beyond
+// the fp16 range must not turn into inf -> NaN downstream (CLIP checkpoints have outlier channels)
 __device__ __forceinline__ uint32_t pack2_f16(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // {upper, lower}
+  return r;
 }
 __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

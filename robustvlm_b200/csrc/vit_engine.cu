@@ -406,8 +406,11 @@ int wgrad(const uint16_t* dY, int Nw, const uint16_t* X, int Kw, int Mtok, int f
 
 // Full backward of the outer training step: dgrad chain as in run_backward plus every
 // parameter gradient, written (overwritten) into `g` (open_clip layout, fp32).
+// `events` (nullable): cudaEvent_t[L + 1]; events[l] is recorded once every parameter gradient of
+// block l has been enqueued, events[L] at the very end (stem + head) -- the caller's hook for
+// starting the all-reduce of a block's gradient bucket while the backward continues.
 int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads* g,
-                       cudaStream_t st) {
+                       cudaStream_t st, void* const* events) {
   const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
   const int ff = E.ff, fg = E.cfg.fmt_bwd;
   const size_t MW = (size_t)M * W;
@@ -462,6 +465,7 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
                                            st)));
     }
     RV(launch_ln_param_grads(w.dz32, x_in, st1, M, W, w.red, g->ln_1_weight[l], g->ln_1_bias[l], st));
+    if (events) RV(cuda_rc(cudaEventRecord((cudaEvent_t)events[l], st)));
     RV(rvlm_layernorm_bwd(w.dz32, x_in, st1, Lw.ln1_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
   }
   // ln_pre: parameter grads, fp32 token gradient (positional / class embedding), 16-bit
@@ -479,6 +483,7 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
     EpiWgradPatch epi{g->conv1_weight, E.kp};
     RV((launch_gemm16<128, true, true>(w.dtok16, W, w.a16, E.kld, W, E.kp32, R, fg, epi, st)));
   }
+  if (events) RV(cuda_rc(cudaEventRecord((cudaEvent_t)events[E.L], st)));
   return 0;
 }
 
@@ -724,7 +729,17 @@ extern "C" int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t w
                                     const float* x, int B, const rvlm_loss_config* loss,
                                     float loss_scale, const rvlm_vit_grads* grads,
                                     float* loss_out, float* emb_out, void* stream) {
+  return rvlm_vit_train_grads_ev(h, workspace, workspace_bytes, x, B, loss, loss_scale, grads,
+                                 loss_out, emb_out, nullptr, 0, stream);
+}
+
+extern "C" int rvlm_vit_train_grads_ev(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,
+                                       const float* x, int B, const rvlm_loss_config* loss,
+                                       float loss_scale, const rvlm_vit_grads* grads,
+                                       float* loss_out, float* emb_out, void* const* events,
+                                       int n_events, void* stream) {
   if (!h || !workspace || !x || !loss || !grads || B <= 0) return RVLM_ERR_INVAL;
+  if (events && n_events != reinterpret_cast<Engine*>(h)->L + 1) return RVLM_ERR_INVAL;
   if (loss->mode != 1 && loss->mode != 2) return RVLM_ERR_INVAL;
   const Engine& E = *reinterpret_cast<Engine*>(h);
   if (E.split || E.cfg.fmt_fwd != E.cfg.fmt_bwd) return RVLM_ERR_UNSUPPORTED;  // wgrad: one operand format
@@ -736,7 +751,7 @@ extern "C" int rvlm_vit_train_grads(rvlm_vit_handle h, void* workspace, size_t w
   RV(run_head(E, w, B, loss, 0, emb_out, nullptr, true, st, loss_scale));
   if (loss_out)
     RV(cuda_rc(cudaMemcpyAsync(loss_out, w.loss, B * sizeof(float), cudaMemcpyDeviceToDevice, st)));
-  return run_backward_train(E, w, B, grads, st);
+  return run_backward_train(E, w, B, grads, st, events);
 }
 
 extern "C" int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace_bytes,

@@ -125,7 +125,7 @@ class LossSpec:
 
 class VitEngine:
     def __init__(self, state_dict: dict, *, image_size=224, mean=CLIP_MEAN, std=CLIP_STD,
-                 fmt_fwd=FMT_F16, fmt_bwd=FMT_BF16, flags=0, device="cuda"):
+                 fmt_fwd=FMT_F16, fmt_bwd=FMT_F16, flags=0, device="cuda"):
         if not torch.cuda.is_available():
             raise nat.RvlmError("VitEngine needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
@@ -289,10 +289,12 @@ class VitEngine:
                 tr[:, lo:hi] = trc
         return (out, tr) if trace else out
 
-    def train_grads(self, x, loss: LossSpec, grads: dict, loss_scale: float):
+    def train_grads(self, x, loss: LossSpec, grads: dict, loss_scale: float, events=None):
         """Outer training step: forward(x) + loss + full backward.  `grads` maps every
         state-dict key to a contiguous fp32 CUDA tensor of the parameter's shape; they are
-        overwritten with d(loss_scale * sum_b loss_b)/d(param).  Returns (loss[B], emb[B,D])."""
+        overwritten with d(loss_scale * sum_b loss_b)/d(param).  Returns (loss[B], emb[B,D]).
+        `events`: layers + 1 torch.cuda.Event objects; events[l] is recorded when block l's
+        parameter gradients are enqueued, events[-1] at the end (gradient bucketing)."""
         x = self._chk(x)
         B = x.shape[0]
         ws, nbytes = self._workspace(B, 2)
@@ -308,9 +310,16 @@ class VitEngine:
         lc = loss.to_c()
         out_loss = torch.empty(B, device=self.device, dtype=torch.float32)
         emb = torch.empty(B, self.arch["out_dim"], device=self.device, dtype=torch.float32)
-        nat.call("rvlm_vit_train_grads", self.handle, nat.ptr(ws), c_size_t(nbytes), nat.ptr(x),
-                 c_int(B), byref(lc), c_float(loss_scale), byref(gc), nat.ptr(out_loss),
-                 nat.ptr(emb), nat.stream_ptr())
+        if events is None:
+            nat.call("rvlm_vit_train_grads", self.handle, nat.ptr(ws), c_size_t(nbytes), nat.ptr(x),
+                     c_int(B), byref(lc), c_float(loss_scale), byref(gc), nat.ptr(out_loss),
+                     nat.ptr(emb), nat.stream_ptr())
+        else:
+            assert len(events) == L + 1
+            evs = (c_void_p * (L + 1))(*[e.cuda_event for e in events])
+            nat.call("rvlm_vit_train_grads_ev", self.handle, nat.ptr(ws), c_size_t(nbytes),
+                     nat.ptr(x), c_int(B), byref(lc), c_float(loss_scale), byref(gc),
+                     nat.ptr(out_loss), nat.ptr(emb), evs, c_int(L + 1), nat.stream_ptr())
         del keep
         return out_loss, emb
 

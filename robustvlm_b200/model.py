@@ -65,7 +65,7 @@ class _Transformer(nn.Module):
 class VisionTransformer(nn.Module):
     """Holds the fp32 master parameters; all arithmetic happens in the CUDA engine."""
 
-    def __init__(self, arch="ViT-L-14", seed=None, fmt_fwd=FMT_F16, fmt_bwd=FMT_BF16, flags=0,
+    def __init__(self, arch="ViT-L-14", seed=None, fmt_fwd=FMT_F16, fmt_bwd=FMT_F16, flags=0,
                  precision=None):
         super().__init__()
         if precision is not None:                    # a named mode of engine.PRECISIONS

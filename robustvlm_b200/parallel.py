@@ -58,6 +58,64 @@ def allreduce_mean_(flat_grad: torch.Tensor, local_count: int, global_count: int
     return flat_grad
 
 
+def grad_buckets(layout, n_layers: int):
+    """Contiguous [lo, hi) ranges of the flat gradient buffer: one per transformer block (its
+    parameters are adjacent in `model.parameters()` order) plus the rest (class / positional
+    embedding, proj, conv1, ln_pre in front; ln_post behind).  layout = checkpoint.param_layout."""
+    per = [[None, None] for _ in range(n_layers)]
+    total = 0
+    for name, _, off, n in layout:
+        total = max(total, off + n)
+        if name.startswith("transformer.resblocks."):
+            l = int(name.split(".")[2])
+            per[l][0] = off if per[l][0] is None else min(per[l][0], off)
+            per[l][1] = off + n if per[l][1] is None else max(per[l][1], off + n)
+    lo_all = min(p[0] for p in per)
+    hi_all = max(p[1] for p in per)
+    for a, b in zip(per, per[1:]):
+        assert a[1] == b[0], "block parameters are not contiguous in the flat buffer"
+    rest = [(0, lo_all), (hi_all, total)]
+    return [tuple(p) for p in per], [r for r in rest if r[1] > r[0]]
+
+
+class BucketedAllReduce:
+    """The outer-gradient all-reduce of the FARE / TeCoA step, bucketed per
+    transformer block and overlapped with the backward: the engine records an event when a
+    block's parameter gradients are enqueued (`rvlm_vit_train_grads_ev`); a side stream waits on
+    it and NCCL averages that block's slice of the flat buffer while the backward of the blocks
+    below is still running.  Even shards only (ReduceOp.AVG == the gradient of the global-batch
+    mean loss); the caller falls back to `allreduce_mean_` otherwise."""
+
+    def __init__(self, layout, n_layers, device):
+        self.blocks, self.rest = grad_buckets(layout, n_layers)
+        self.device = device
+        self.side = torch.cuda.Stream(device=device)
+        self.events = [torch.cuda.Event() for _ in range(n_layers + 1)]
+        for e in self.events:            # creates the cudaEvent_t handles the C engine records on
+            e.record(torch.cuda.current_stream(device))
+
+    def launch(self, flat_grad: torch.Tensor):
+        """enqueue every bucket's all-reduce behind its event; returns the work handles"""
+        works = []
+        op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        with torch.cuda.stream(self.side):
+            for l in range(len(self.blocks) - 1, -1, -1):
+                self.side.wait_event(self.events[l])
+                lo, hi = self.blocks[l]
+                works.append(dist.all_reduce(flat_grad[lo:hi], op=op, async_op=True))
+            self.side.wait_event(self.events[-1])
+            for lo, hi in self.rest:
+                works.append(dist.all_reduce(flat_grad[lo:hi], op=op, async_op=True))
+        return works
+
+    def finish(self, works, flat_grad):
+        for w in works:
+            w.wait()                     # the current stream waits for NCCL's
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        if dist.get_backend() != "nccl":
+            flat_grad.div_(float(dist.get_world_size()))
+
+
 def gather_batch(t: torch.Tensor) -> torch.Tensor:
     """All-gather shards along dim 0 (uneven shards allowed); used by tests / evaluation."""
     if not (dist.is_initialized() and dist.get_world_size() > 1):

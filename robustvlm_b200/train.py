@@ -92,6 +92,7 @@ class AdversarialTrainer:
         mean, std = model.engine().cfg.mean, model.engine().cfg.std
         self.train_engine = VitEngine(vt.state_dict(), mean=tuple(mean), std=tuple(std),
                                       fmt_fwd=FMT_BF16, fmt_bwd=FMT_BF16, device=self.dev)
+        self._bucketed = None            # parallel.BucketedAllReduce, built on first use
 
     # -- optimizer state / checkpoints (reference formats, checkpoint.py) ---------------
     def optimizer_state_dict(self):
@@ -192,8 +193,23 @@ class AdversarialTrainer:
         ref_emb = emb_clean.detach().clone() if c["trades"] else emb_orig               # :352-360
         spec = LossSpec(c["loss"], c["output_normalize"], emb_orig=ref_emb, text=self.text,
                         logit_scale=self.logit_scale, targets=targets)
-        loss_b, emb_adv = self.train_engine.train_grads(data_adv, spec, self.grads,
-                                                        (1.0 - cw) / B)                 # :349-362
+        dist = torch.distributed
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        # per-block gradient buckets all-reduced under the rest of the backward (even shards,
+        # a single backward); otherwise one blocking all-reduce after it
+        overlap = world > 1 and cw == 0.0 and B * world == global_batch and self.dev.type == "cuda"
+        works = None
+        if overlap:
+            if self._bucketed is None:
+                self._bucketed = parallel.BucketedAllReduce(self.layout, self.vt.arch["layers"],
+                                                            self.dev)
+            loss_b, emb_adv = self.train_engine.train_grads(data_adv, spec, self.grads,
+                                                            (1.0 - cw) / B,
+                                                            events=self._bucketed.events)
+            works = self._bucketed.launch(self.flat_g)
+        else:
+            loss_b, emb_adv = self.train_engine.train_grads(data_adv, spec, self.grads,
+                                                            (1.0 - cw) / B)             # :349-362
         loss = loss_b.mean()
         if cw > 0.0:
             nat.call("rvlm_add_f32", nat.ptr(self.flat_g), nat.ptr(self.flat_g),
@@ -203,7 +219,10 @@ class AdversarialTrainer:
             loss_total = cw * loss_clean + (1.0 - cw) * loss                            # :361
         else:
             loss_total = loss
-        parallel.allreduce_mean_(self.flat_g, B, global_batch)
+        if works is not None:
+            self._bucketed.finish(works, self.flat_g)
+        else:
+            parallel.allreduce_mean_(self.flat_g, B, global_batch)
         lr_used = self.lr
         self._optimizer_step()                                                          # :363
         self.step_total += 1                                                            # :365

@@ -164,3 +164,50 @@ def test_split_forward_is_fp32_class(name):
     print(name, res)
     assert res["split"][0] < 2e-5 and res["split"][0] < 0.2 * res["fp16"][0]
     assert res["split"][1] < 0.5 * res["fp16"][1] + 1e-4 and res["split"][2] < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["fast16", "split"])
+def test_fp16_operands_survive_outlier_channels(mode):
+    """fp16 forward AND fp16 gradient operands against CLIP-like activation outliers (trained
+    CLIP towers carry a few residual channels / c_fc rows that are 50-100x the rest; random-init
+    weights have none): a 6-layer tower with such channels planted.  No inf / NaN anywhere, the
+    embedding stays within 1e-3 of the fp32 oracle and the FARE gradient keeps its direction
+    (the fp16 packs saturate instead of overflowing; gradients travel rescaled per sample)."""
+    from robustvlm_b200.engine import PRECISIONS, LossSpec, VitEngine
+    cfg = ovit.VitConfig(224, 32, 256, 6, 4, 1024, 128)
+    o = ovit.build(cfg, seed=11)
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(5)
+        for blk in o.transformer.resblocks:
+            idx = torch.randperm(256, generator=g)[:3]
+            blk.ln_1.weight[idx] *= 60.0                   # outlier LayerNorm gains
+            blk.ln_2.weight[idx] *= 60.0
+            rows = torch.randperm(1024, generator=g)[:4]
+            blk.mlp.c_fc.weight[rows] *= 80.0              # outlier MLP rows (massive activations)
+            blk.mlp.c_proj.weight[:, rows] *= 0.05
+        o.class_embedding[7] += 40.0                       # a massive residual channel
+    ref_m = ovit.ClipVisionModel(o).eval()
+    for p in ref_m.parameters():
+        p.requires_grad_(False)
+    x, d0 = synth_batch(4, seed=9)
+    with torch.no_grad():
+        e_orig = ovit.ClipVisionModel(ovit.build(cfg, seed=12)).eval()(x, output_normalize=False)
+        e_ref = ref_m(x + d0, output_normalize=False)
+    xa = (x + d0).requires_grad_(True)
+    wrap = oa.ComputeLossWrapper(e_orig, None, "mean", "l2", 100.0)
+    (g_ref,) = torch.autograd.grad(wrap(ref_m(xa, output_normalize=False), None), xa)
+    ff, fb = PRECISIONS[mode]
+    eng = VitEngine(o.state_dict(), fmt_fwd=ff, fmt_bwd=fb)
+    emb = eng.forward(x.cuda(), d0.cuda()).cpu()
+    out = eng.loss_grad(x.cuda(), LossSpec("l2", False, emb_orig=e_orig.cuda()), delta=d0.cuda())
+    grad = out["grad"].cpu()
+    assert torch.isfinite(emb).all() and torch.isfinite(grad).all()
+    agree, mis_big = sign_agreement(grad, g_ref, tau=0.05)
+    cos = float(torch.nn.functional.cosine_similarity(grad.flatten(1), g_ref.flatten(1), dim=1).min())
+    # true scale: the fp16-gradient path undoes its per-sample rescaling on output
+    ratio = float(grad.flatten(1).norm(dim=1).div(g_ref.flatten(1).norm(dim=1)).sub(1).abs().max())
+    _log("outlier_stress", mode=mode, emb_rel_err=rel_err(emb, e_ref), sign_agree=agree,
+         mismatch_big=mis_big, cos_min=cos, norm_ratio_err=ratio,
+         act_scale=float(e_ref.abs().max()))
+    assert rel_err(emb, e_ref) < 1e-3
+    assert cos > 0.999 and mis_big < 5e-3 and ratio < 2e-2

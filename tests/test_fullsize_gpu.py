@@ -33,12 +33,19 @@ EPS_FARE, EPS_TECOA, STEP = 4 / 255, 2 / 255, 1 / 255
 #   emb rel err, [FARE-diff, FARE-same, CE] x (sign mismatch, mismatch among big), 10-step
 #   identical fraction FARE / TeCoA
 MODES = os.environ.get("RVLM_TEST_MODES", "fast,fast16,split").split(",")
+# measured on B200 (profiles/r02_test_metrics.jsonl), asserts at <= 2x:
+#   mode      emb rel   fare_diff            fare_same (cancellation)  ce                10-step identical
+#   fast      4.0e-4    1.84e-3 / 0          1.57e-2 / 5.9e-3          1.92e-3 / 0       0.98939 / 0.99643
+#   fast16    4.0e-4    2.8e-4  / 0          1.58e-2 / 5.9e-3          3.0e-4  / 0       0.99808 / 0.99923
+#   split     1.27e-5   2.6e-4  / 0          5.6e-4  / 0               2.6e-4  / 0       0.99820 / 0.99930
 LIMITS = {
-    #            emb     fare_diff        fare_same        ce              same10_fare same10_ce
-    "fast":   (1.0e-3, (2e-2, 1e-3), (8e-2, 4e-2), (2e-2, 1e-3), 0.97, 0.97),
-    "fast16": (1.0e-3, (1e-2, 1e-3), (8e-2, 4e-2), (1e-2, 1e-3), 0.98, 0.98),
-    "split":  (1.0e-4, (5e-3, 1e-3), (2e-2, 1e-3), (5e-3, 1e-3), 0.99, 0.99),
+    #          emb      fare_diff         fare_same         ce                same10 fare / ce   loss rel
+    "fast":   (8.5e-4, (3.7e-3, 1e-4), (3.2e-2, 1.2e-2), (3.9e-3, 1e-4), 0.979, 0.9929, 1e-5),
+    "fast16": (8.5e-4, (5.6e-4, 1e-4), (3.2e-2, 1.2e-2), (6.1e-4, 1e-4), 0.9961, 0.9984, 2e-6),
+    "split":  (2.6e-5, (5.2e-4, 1e-4), (1.2e-3, 1e-4), (5.2e-4, 1e-4), 0.9964, 0.9986, 2e-6),
 }
+# config 4 (APGD-CE ell_2, 20 iterations x 2 restarts): logits error / |logits|, ||adv - adv_ref|| / ||adv_ref - x||
+LIMITS4 = {"fast": (9e-4, 2.2e-2), "fast16": (9e-4, 2.2e-2), "split": (3e-5, 1.4e-3)}
 
 
 def _log(name, **kw):
@@ -175,11 +182,11 @@ def test_ten_step_pgd_vitl14(ref, mode, case):
          loss_ref=l_ref, max_abs_err=float((out - r).abs().max()),
          mean_abs_err=float((out - r).abs().mean()))
     assert float((out - x).abs().max()) <= eps + 1e-6 and out.min() >= 0 and out.max() <= 1
-    assert abs(l_ours - l_ref) <= 0.01 * abs(l_ref)
+    assert abs(l_ours - l_ref) <= LIMITS[mode][6] * abs(l_ref)     # north_star: within 1 %
     assert same >= LIMITS[mode][4 if case == "fare" else 5]
 
 
-@pytest.mark.parametrize("mode", [m for m in MODES if m != "fast16"])
+@pytest.mark.parametrize("mode", MODES)
 def test_config4_apgd_l2_vitl14(ref, mode):
     """APGD-CE ell_2 eps = 2.0 with restarts on the zero-shot classifier, against
     autoattack/autopgd_base.py:205-548 run by the oracle from the same CPU-RNG start."""
@@ -207,6 +214,8 @@ def test_config4_apgd_l2_vitl14(ref, mode):
          ce_ref=l_ref.tolist(), ce_ours=l_ours.tolist(), l2_ours=l2o.tolist(),
          l2_ref=(r - x).flatten(1).norm(dim=1).tolist(),
          adv_rel_diff=float((out - r).norm() / (r - x).norm().clamp_min(1e-12)))
-    assert float((lg - lg_ref).abs().max()) <= 2e-3 * float(lg_ref.abs().max())
+    assert float((lg - lg_ref).abs().max()) <= LIMITS4[mode][0] * float(lg_ref.abs().max())
     assert float(l2o.max()) <= 2.0 * (1 + 1e-4) and out.min() >= 0 and out.max() <= 1
     assert racc_ours == racc_ref
+    assert float((out - r).norm() / (r - x).norm().clamp_min(1e-12)) <= LIMITS4[mode][1]
+    assert float((l_ours - l_ref).abs().max()) <= 0.02 * float(l_ref.abs().max())

@@ -526,8 +526,11 @@ def run_ours(args):
                 modes[mode]["delta_vs_ref"] = delta_vs_reference(mm, keep, dev)
             line["delta_vs_ref"] = modes[args.precision]["delta_vs_ref"]
         line["modes"] = modes
-        del models
-    del m
+        models.clear()
+        mm = None
+    m = None                      # (the closures above keep the cell, not the engine)
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     if world == 1 and rank == 0 and not args.no_torch_baseline:
         try:
@@ -539,7 +542,10 @@ def run_ours(args):
             line["torch_cuda_baseline"] = {"error": repr(e)[:200]}
         torch.cuda.empty_cache()
     if not args.no_train_step:
-        ts = fare_train_step(args, dev, rank, world)
+        try:
+            ts = fare_train_step(args, dev, rank, world)
+        except Exception as e:  # noqa: BLE001  (never lose the headline line to an add-on)
+            ts = {"error": repr(e)[:300]}
         if rank == 0:
             line["train_step"] = ts
     if rank == 0:

@@ -257,6 +257,12 @@ typedef struct {
  * autoattack/autopgd_base.py:244). */
 #define RVLM_LOSS_L2 1 /* sum_d (emb - emb_orig)^2            (FARE)  */
 #define RVLM_LOSS_CE 2 /* CE(emb @ (logit_scale * text), y)   (TeCoA) */
+/* AutoAttack's APGD losses on the zero-shot logits z = emb @ (logit_scale * text), z_(k) the k-th
+ * largest (rvlm_vit_loss_grad only; n_classes >= 4, pred on the logits):
+ *   DLR          -(z_y - (argmax == y ? z_(2) : z_(1))) / (z_(1) - z_(3) + 1e-12)   autopgd_base.py:195-201
+ *   targeted DLR -(z_y - z_t) / (z_(1) - (z_(3) + z_(4)) / 2 + 1e-12)               autopgd_base.py:616-621 */
+#define RVLM_LOSS_DLR 4
+#define RVLM_LOSS_DLR_TARGETED 5
 typedef struct {
   int mode;
   int output_normalize;     /* F.normalize(emb, dim=-1) before the loss */
@@ -266,6 +272,7 @@ typedef struct {
   int n_classes;
   float logit_scale;
   const long long* targets; /* [B] int64, may be NULL for RVLM_LOSS_L2 */
+  const long long* y_target; /* [B] int64 target classes (RVLM_LOSS_DLR_TARGETED), else NULL */
 } rvlm_loss_config;
 
 #define RVLM_NORM_LINF 0

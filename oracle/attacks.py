@@ -215,8 +215,10 @@ class _ApgdBook:
     """Best-point / step-size bookkeeping shared by both APGD variants
     (train/apgd_train.py:318-355 == autopgd_base.py:400-446)."""
 
-    def __init__(self, n_iter, bs, ndims, loss0, device, thr_decr=0.75):
-        self.k, self.k_min, self.k_decr = apgd_schedule(n_iter)
+    def __init__(self, n_iter, bs, ndims, loss0, device, thr_decr=0.75, schedule_n_iter=None):
+        # the reference fixes the check-point schedule in the constructor (autopgd_base.py:157-159)
+        # and `decr_eps_pgd` later changes n_iter only: schedule_n_iter = the constructor's n_iter
+        self.k, self.k_min, self.k_decr = apgd_schedule(schedule_n_iter or n_iter)
         self.counter = 0
         self.thr = thr_decr
         self.ndims = ndims
@@ -316,11 +318,12 @@ class APGDAttack:
                  eot_iter=1, rho=0.75, topk=None, verbose=False, device=None, use_largereps=False,
                  is_tf_model=False, logger=None, alpha=None, use_rs=True):
         assert norm in ("Linf", "L2") and eps is not None
-        assert not is_tf_model and not use_largereps
+        assert not is_tf_model
         self.model, self.n_iter, self.eps, self.norm = predict, n_iter, eps, norm
         self.n_restarts, self.seed, self.loss, self.eot_iter = n_restarts, seed, loss, eot_iter
         self.thr_decr, self.verbose, self.device = rho, verbose, device
         self.use_rs, self.alpha = use_rs, alpha
+        self.use_largereps, self.n_iter_orig, self.eps_orig = use_largereps, n_iter, eps   # :143-145
 
     def normalize(self, x):
         """:180-193"""
@@ -378,7 +381,8 @@ class APGDAttack:
         alpha = 2.0 if self.alpha is None else self.alpha                  # :295-299
         step_size = alpha * self.eps * torch.ones([x.shape[0], *([1] * ndims)]).to(dev).detach()
         x_adv_old = x_adv.clone()
-        book = _ApgdBook(self.n_iter, x.shape[0], ndims, loss_indiv, dev, self.thr_decr)
+        book = _ApgdBook(self.n_iter, x.shape[0], ndims, loss_indiv, dev, self.thr_decr,
+                         schedule_n_iter=self.n_iter_orig)
         for i in range(self.n_iter):                                       # :326
             a = 0.75 if i > 0 else 1.0
             with torch.no_grad():
@@ -392,6 +396,35 @@ class APGDAttack:
                 x_adv, grad, x_best, grad_best, step_size = book.update(
                     i, loss_indiv, x_adv, grad, x_best, grad_best, step_size)
         return x_best, acc, book.loss_best, x_best_adv                     # :451
+
+    def decr_eps_pgd(self, x, y, epss, iters, use_rs=True):
+        """:550-582 (Linf branch)"""
+        assert len(epss) == len(iters)
+        assert self.norm in ("L1", "Linf")
+        self.use_rs = False
+        if not use_rs:
+            x_init = None
+        else:
+            x_init = x + torch.randn_like(x)
+            x_init = torch.clamp(x_init, 0.0, 1.0)
+            x_init = torch.min(torch.max(x_init, x - self.eps), x + self.eps)
+        for eps, niter in zip(epss, iters):
+            self.n_iter = niter + 0
+            self.eps = eps + 0.0
+            if x_init is not None:
+                x_init = torch.clamp(x_init, 0.0, 1.0)
+                x_init = torch.min(torch.max(x_init, x - self.eps), x + self.eps)
+            x_init, acc, loss, x_adv = self.attack_single_run(x, y, x_init=x_init)
+        return x_init, acc, loss, x_adv
+
+    def _largereps_schedule(self):
+        """:493-498"""
+        import math
+        epss = [3.0 * self.eps_orig, 2.0 * self.eps_orig, 1.0 * self.eps_orig]
+        iters = [math.ceil(c) for c in (0.3 * self.n_iter_orig, 0.3 * self.n_iter_orig,
+                                        0.4 * self.n_iter_orig)]
+        iters[-1] = self.n_iter_orig - sum(iters[:-1])
+        return epss, iters
 
     def perturb(self, x, y=None, best_loss=False, x_init=None):
         """:453-548"""
@@ -412,12 +445,18 @@ class APGDAttack:
                 adv_best = torch.where(_bview(m, x.dim() - 1), best_curr, adv_best)
                 loss_best = torch.where(m, loss_curr, loss_best)
             return adv_best
+        if self.use_largereps:
+            epss, iters = self._largereps_schedule()
         torch.random.manual_seed(self.seed)                                # :505
         for _ in range(self.n_restarts):                                   # :508
             idx = acc.nonzero().flatten()
             if idx.numel() == 0:
                 continue
-            _, acc_curr, _, adv_curr = self.attack_single_run(x[idx].clone(), y[idx].clone())
+            if not self.use_largereps:                                     # :517-520
+                res = self.attack_single_run(x[idx].clone(), y[idx].clone())
+            else:
+                res = self.decr_eps_pgd(x[idx].clone(), y[idx].clone(), epss, iters)
+            _, acc_curr, _, adv_curr = res
             fooled = (acc_curr == 0).nonzero().flatten()
             acc[idx[fooled]] = 0                                           # :521-525
             adv[idx[fooled]] = adv_curr[fooled].clone()

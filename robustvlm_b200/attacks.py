@@ -248,12 +248,14 @@ class APGDAttack:
                  eot_iter=1, rho=0.75, topk=None, verbose=False, device=None, use_largereps=False,
                  is_tf_model=False, logger=None, alpha=None, use_rs=True):
         assert norm in ("Linf", "L2", "L1") and eps is not None                    # :146-147
-        if norm == "L1" or use_largereps or is_tf_model:
+        if norm == "L1" or is_tf_model:
             raise NotImplementedError("only Linf / L2, PyTorch models (SURVEY.md §8a)")
+        if use_largereps and norm != "Linf":
+            raise NotImplementedError("use_largereps: Linf only (the reference asserts L1 / Linf, :552)")
         self.model, self.n_iter, self.eps, self.norm = predict, n_iter, eps, norm
         self.n_restarts, self.seed, self.loss, self.eot_iter = n_restarts, seed, loss, eot_iter
         self.thr_decr, self.topk, self.verbose, self.device = rho, topk, verbose, device
-        self.use_rs, self.use_largereps, self.alpha, self.logger = use_rs, False, alpha, logger
+        self.use_rs, self.use_largereps, self.alpha, self.logger = use_rs, use_largereps, alpha, logger
         self.n_iter_orig, self.eps_orig, self.y_target = n_iter, eps, None
 
     def normalize(self, x):
@@ -264,40 +266,82 @@ class APGDAttack:
             t = (x ** 2).view(x.shape[0], -1).sum(-1).sqrt()
         return x / (t.view(-1, *([1] * (x.dim() - 1))) + 1e-12)
 
+    def _fused_ok(self):
+        m = self.model
+        return (self.loss in ("ce", "dlr", "dlr-targeted") and isinstance(m, ClassificationModel)
+                and isinstance(m.visual.model, VisionTransformer) and m.resizer is None)
+
     def _fwd_bwd(self, y):
         m = self.model
-        if (self.loss == "ce" and self.eot_iter == 1 and isinstance(m, ClassificationModel)
-                and isinstance(m.visual.model, VisionTransformer)):
+        if self._fused_ok():
+            # model + loss + input gradient inside the engine: CE, DLR (:195-201) and targeted DLR
+            # (:616-621) are evaluated by the head kernel (top-4 logits on device), no autograd
             eng = m.visual.engine()
-            spec = LossSpec("ce", True, text=m.text_embedding, logit_scale=m.logit_scale_value,
-                            targets=y, pred_on_logits=True)
+            spec = LossSpec(self.loss, True, text=m.text_embedding,
+                            logit_scale=m.logit_scale_value, targets=y, pred_on_logits=True,
+                            y_target=self.y_target if self.loss == "dlr-targeted" else None)
 
             def fused(x_adv, need_grad):
                 r = eng.loss_grad(x_adv, spec, want_grad=need_grad)
                 return r["loss"], r["pred"].to(torch.int32), r["grad"]
-            return fused
-        if self.loss == "ce":
-            crit = torch.nn.CrossEntropyLoss(reduction="none")                     # :244
-        elif self.loss == "dlr":
-            crit = dlr_loss
-        elif self.loss == "dlr-targeted":
-            crit = self.dlr_loss_targeted                                          # :255-256
-        elif self.loss == "ce-targeted":
-            crit = self.ce_loss_targeted
+            base = fused
         else:
-            raise ValueError("unknowkn loss")
-        base = _autograd_fwd_bwd(m, crit, y)
+            if self.loss == "ce":
+                crit = torch.nn.CrossEntropyLoss(reduction="none")                 # :244
+            elif self.loss == "dlr":
+                crit = dlr_loss
+            elif self.loss == "dlr-targeted":
+                crit = self.dlr_loss_targeted                                      # :255-256
+            elif self.loss == "ce-targeted":
+                crit = self.ce_loss_targeted
+            else:
+                raise ValueError("unknowkn loss")
+            base = _autograd_fwd_bwd(m, crit, y)
         if self.eot_iter == 1:
             return base
 
         def eot(x_adv, need_grad):                                                 # :267-286
+            # the reference evaluates the model eot_iter times and averages the gradients (for
+            # randomised defences); the loss / prediction reported are those of the last pass
             acc_g, out = None, None
             for _ in range(self.eot_iter):
                 out = base(x_adv, need_grad)
                 if need_grad:
-                    acc_g = out[2] if acc_g is None else acc_g + out[2]
-            return out[0], out[1], (acc_g / float(self.eot_iter) if need_grad else None)
+                    acc_g = out[2].clone() if acc_g is None else acc_g.add_(out[2])
+            return out[0], out[1], (acc_g.div_(float(self.eot_iter)) if need_grad else None)
         return eot
+
+    def decr_eps_pgd(self, x, y, epss, iters, use_rs=True):
+        """:550-582 -- the `use_largereps` schedule: APGD runs at 3 eps, 2 eps, eps chained through
+        x_init.  Quirks kept: `self.use_rs` stays False afterwards; the check-point schedule is
+        the one of the ORIGINAL n_iter (set once in the constructor, :157-159)."""
+        assert len(epss) == len(iters)
+        assert self.norm in ("L1", "Linf")
+        self.use_rs = False
+        if not use_rs:
+            x_init = None
+        else:
+            x_init = x + torch.randn_like(x)
+            x_init = torch.clamp(x_init, 0.0, 1.0)
+            x_init = torch.min(torch.max(x_init, x - self.eps), x + self.eps)
+        res = None
+        for eps, niter in zip(epss, iters):
+            self.n_iter = niter + 0
+            self.eps = eps + 0.0
+            if x_init is not None:
+                x_init = torch.clamp(x_init, 0.0, 1.0)
+                x_init = torch.min(torch.max(x_init, x - self.eps), x + self.eps)
+            res = self.attack_single_run(x, y, x_init=x_init)
+            x_init = res[0]
+        return res
+
+    def _largereps_schedule(self):
+        """:493-498"""
+        epss = [3.0 * self.eps_orig, 2.0 * self.eps_orig, 1.0 * self.eps_orig]
+        iters = [math.ceil(c) for c in (0.3 * self.n_iter_orig, 0.3 * self.n_iter_orig,
+                                        0.4 * self.n_iter_orig)]
+        iters[-1] = self.n_iter_orig - sum(iters[:-1])
+        return epss, iters
 
     def attack_single_run(self, x, y, x_init=None):
         """:205-451 -> (x_best, acc, loss_best, x_best_adv)"""
@@ -315,7 +359,8 @@ class APGDAttack:
             x_adv = x_init.clone()
         alpha = 2.0 if self.alpha is None else self.alpha                          # :295-299
         return _apgd_core(self._fwd_bwd(y), x, x_adv, self.norm, float(self.eps), self.n_iter,
-                          alpha, self.thr_decr, skip_last_grad=False)
+                          alpha, self.thr_decr, skip_last_grad=False,
+                          schedule=apgd_schedule(self.n_iter_orig))                # :157-159
 
     def perturb(self, x, y=None, best_loss=False, x_init=None):
         """:453-548"""
@@ -341,12 +386,19 @@ class APGDAttack:
                 adv_best[m] = best_curr[m]
                 loss_best[m] = loss_curr[m]
             return adv_best
+        if self.use_largereps:                                                     # :493-498
+            epss, iters = self._largereps_schedule()
         torch.random.manual_seed(self.seed)                                        # :505
+        torch.cuda.random.manual_seed(self.seed)                                   # :506
         for _ in range(self.n_restarts):                                           # :508
             idx = acc.nonzero().flatten()          # the one host sync per restart (as :509)
             if idx.numel() == 0:
                 continue
-            _, acc_curr, _, adv_curr = self.attack_single_run(x[idx].clone(), y[idx].clone())
+            if not self.use_largereps:                                             # :517-520
+                res_curr = self.attack_single_run(x[idx].clone(), y[idx].clone())
+            else:
+                res_curr = self.decr_eps_pgd(x[idx].clone(), y[idx].clone(), epss, iters)
+            _, acc_curr, _, adv_curr = res_curr
             fooled = (acc_curr == 0).nonzero().flatten()
             acc[idx[fooled]] = False                                               # :521-525
             adv[idx[fooled]] = adv_curr[fooled].clone()
@@ -356,8 +408,9 @@ class APGDAttack:
 class APGDAttack_targeted(APGDAttack):
     """AutoPGD on the targeted DLR loss (autoattack/autopgd_base.py:584-707): for each target
     rank 2 .. n_target_classes+1 of the still-robust points' logits, n_restarts runs towards
-    that class.  The loss needs a per-row sort (top-4), so the gradient comes from autograd
-    through the engine's VJP; step / projection / bookkeeping are the CUDA update kernels."""
+    that class.  On our ClassificationModel the loss (top-4 logits) and its gradient are
+    evaluated by the head kernel (RVLM_LOSS_DLR_TARGETED); step / projection / bookkeeping are
+    the CUDA update kernels."""
 
     def __init__(self, predict, n_iter=100, norm="Linf", n_restarts=1, eps=None, seed=0,
                  eot_iter=1, rho=0.75, topk=None, n_target_classes=9, verbose=False, device=None,
@@ -395,7 +448,10 @@ class APGDAttack_targeted(APGDAttack):
         y = y_pred.detach().clone().long() if y is None else y.detach().clone().long().to(self.device)
         adv = x.clone()
         acc = y_pred == y
+        if self.use_largereps:                                                     # :666-671
+            epss, iters = self._largereps_schedule()
         torch.random.manual_seed(self.seed)                                        # :661
+        torch.cuda.random.manual_seed(self.seed)                                   # :662
         for target_class in range(2, self.n_target_classes + 2):                   # :678
             for _ in range(self.n_restarts):
                 idx = acc.nonzero().flatten()
@@ -405,7 +461,11 @@ class APGDAttack_targeted(APGDAttack):
                 with torch.no_grad():
                     output = self.model(x_to_fool)
                 self.y_target = output.sort(dim=1)[1][:, -target_class]            # :691
-                _, acc_curr, _, adv_curr = self.attack_single_run(x_to_fool, y_to_fool)
+                if not self.use_largereps:
+                    res_curr = self.attack_single_run(x_to_fool, y_to_fool)
+                else:
+                    res_curr = self.decr_eps_pgd(x_to_fool, y_to_fool, epss, iters)
+                _, acc_curr, _, adv_curr = res_curr
                 fooled = (acc_curr == 0).nonzero().flatten()
                 acc[idx[fooled]] = False
                 adv[idx[fooled]] = adv_curr[fooled].clone()

@@ -12,13 +12,15 @@ struct HeadArgs {
   const float* ln_b;
   const float* proj;      // [W, D]
   int mode;               // 0 none, 1 l2 (FARE), 2 ce (TeCoA / zero-shot classifier),
-                          // 3 external d(loss)/d(emb) passed in emb_orig
+                          // 3 external d(loss)/d(emb) passed in emb_orig,
+                          // 4 DLR, 5 targeted DLR on the class logits (AutoAttack's APGD losses)
   int normalize;          // F.normalize(emb) before the loss / output
   int pred_on_logits;     // 1: pred from class logits, 0: from the embedding
   const float* emb_orig;  // [B, D]      (mode 1)
   const float* text;      // [D, C]      (mode 2)
   float logit_scale;
   const long long* y;     // [B]         (may be null -> pred = 0)
+  const long long* y_target;  // [B]     (mode 5)
   float* emb_out;         // [B, D]      (may be null)
   float* logits_out;      // [B, C]      (may be null)
   float* loss;            // [B]         (may be null)

@@ -202,10 +202,67 @@ __global__ void __launch_bounds__(HEAD_THREADS) head_kernel(HeadArgs A) {
     __syncthreads();
     // d e = logit_scale * text @ dlogits
     matvec_bwd(lg, A.text, D, C, [&](int d, float acc) { de[d] = acc * A.logit_scale; });
+  } else if (A.mode == 4 || A.mode == 5) {
+    // DLR (autoattack/autopgd_base.py:195-201) and targeted DLR (:616-621) on the class logits:
+    //   dlr   = -(z_y - (argmax == y ? z_(2) : z_(1))) / (z_(1) - z_(3) + 1e-12)
+    //   dlr-t = -(z_y - z_t) / (z_(1) - (z_(3) + z_(4)) / 2 + 1e-12)
+    // z_(k) = k-th largest logit.  The gradient w.r.t. the logits has at most five non-zero
+    // entries, so d e = logit_scale * sum_j w_j text[:, idx_j].
+    matvec_fwd(e, A.text, D, C, A.logit_scale, part, lg);
+    if (A.logits_out)
+      for (int c = tid; c < C; c += HEAD_THREADS) A.logits_out[(size_t)b * C + c] = lg[c];
+    __syncthreads();
+    int ti[4];
+    float tv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {     // top-4 by repeated arg-max (first index on ties)
+      ti[k] = blk_argmax(lg, C, red, redi);
+      tv[k] = lg[ti[k]];
+      __syncthreads();
+      if (tid == 0) lg[ti[k]] = -INFINITY;
+      __syncthreads();
+    }
+    if (tid == 0)
+      for (int k = 0; k < 4; ++k) lg[ti[k]] = tv[k];
+    __syncthreads();
+    pred = (ti[0] == (int)yb) ? 1 : 0;
+    const int yi = (yb >= 0 && yb < C) ? (int)yb : 0;
+    int idx[5];
+    float wv[5];
+    if (A.mode == 4) {
+      const bool top = ti[0] == yi;
+      const int other = top ? ti[1] : ti[0];
+      const float Dn = tv[0] - tv[2] + 1e-12f;
+      const float N = lg[yi] - lg[other];
+      loss = -N / Dn;
+      idx[0] = yi;    wv[0] = -1.f / Dn;
+      idx[1] = other; wv[1] = 1.f / Dn;
+      idx[2] = ti[0]; wv[2] = N / (Dn * Dn);
+      idx[3] = ti[2]; wv[3] = -N / (Dn * Dn);
+      idx[4] = 0;     wv[4] = 0.f;
+    } else {
+      const long long tb = A.y_target ? A.y_target[b] : 0;
+      const int ti_ = (tb >= 0 && tb < C) ? (int)tb : 0;
+      const float Dn = tv[0] - 0.5f * (tv[2] + tv[3]) + 1e-12f;
+      const float N = lg[yi] - lg[ti_];
+      loss = -N / Dn;
+      idx[0] = yi;    wv[0] = -1.f / Dn;
+      idx[1] = ti_;   wv[1] = 1.f / Dn;
+      idx[2] = ti[0]; wv[2] = N / (Dn * Dn);
+      idx[3] = ti[2]; wv[3] = -0.5f * N / (Dn * Dn);
+      idx[4] = ti[3]; wv[4] = -0.5f * N / (Dn * Dn);
+    }
+    for (int d = tid; d < D; d += HEAD_THREADS) {
+      const float* trow = A.text + (size_t)d * C;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) acc = fmaf(wv[j], __ldg(trow + idx[j]), acc);
+      de[d] = acc * A.logit_scale;
+    }
   }
   __syncthreads();
   if ((A.mode == 1 || A.mode == 2) && !(A.mode == 2 && A.pred_on_logits))
-    pred = (blk_argmax(e, D, red, redi) == (int)yb) ? 1 : 0;
+    pred = (blk_argmax(e, D, red, redi) == (int)yb) ? 1 : 0;   // (DLR modes: always the logits)
   if (tid == 0) {
     if (A.loss) A.loss[b] = loss;
     if (A.pred) A.pred[b] = pred;

@@ -285,7 +285,8 @@ int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, in
   A.ln_g = E.lnpost_g; A.ln_b = E.lnpost_b; A.proj = E.proj;
   A.mode = lc ? lc->mode : 0;
   A.normalize = lc ? lc->output_normalize : normalize;
-  A.C = (lc && lc->mode == 2) ? lc->n_classes : 0;
+  A.C = (lc && (lc->mode == 2 || lc->mode == 4 || lc->mode == 5)) ? lc->n_classes : 0;
+  A.y_target = lc ? (const long long*)lc->y_target : nullptr;
   A.pred_on_logits = lc ? lc->pred_on_logits : 0;
   A.emb_orig = lc ? lc->emb_orig : nullptr;
   A.text = lc ? lc->text : nullptr;
@@ -704,7 +705,13 @@ extern "C" int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t wor
                                   int* pred_out, float* emb_out, float* logits_out, int want_grad,
                                   void* stream) {
   if (!h || !workspace || !x || !loss || B <= 0) return RVLM_ERR_INVAL;
-  if (loss->mode != 1 && loss->mode != 2) return RVLM_ERR_INVAL;
+  if (loss->mode != RVLM_LOSS_L2 && loss->mode != RVLM_LOSS_CE && loss->mode != RVLM_LOSS_DLR &&
+      loss->mode != RVLM_LOSS_DLR_TARGETED)
+    return RVLM_ERR_INVAL;
+  if (loss->mode == RVLM_LOSS_DLR_TARGETED && !loss->y_target) return RVLM_ERR_INVAL;
+  if ((loss->mode == RVLM_LOSS_DLR || loss->mode == RVLM_LOSS_DLR_TARGETED) &&
+      (!loss->text || !loss->targets || loss->n_classes < 4))
+    return RVLM_ERR_INVAL;
   const Engine& E = *reinterpret_cast<Engine*>(h);
   Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 1);
   if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;

@@ -26,7 +26,7 @@ FMT_F16, FMT_BF16, FMT_F16X2 = 0, 1, 2
 #   bf16    bf16 / bf16 (the outer training step: weight-gradient GEMMs need one format)
 PRECISIONS = {"fast": (FMT_F16, FMT_BF16), "fast16": (FMT_F16, FMT_F16),
               "split": (FMT_F16X2, FMT_F16), "bf16": (FMT_BF16, FMT_BF16)}
-LOSS_L2, LOSS_CE = 1, 2
+LOSS_L2, LOSS_CE, LOSS_DLR, LOSS_DLR_TARGETED = 1, 2, 4, 5
 NORM_LINF, NORM_L2 = 0, 2
 FLAG_ATTN_SIMT = 1
 
@@ -57,7 +57,7 @@ class VitGradsC(Structure):
 class LossConfigC(Structure):
     _fields_ = [("mode", c_int), ("output_normalize", c_int), ("pred_on_logits", c_int),
                 ("emb_orig", c_void_p), ("text", c_void_p), ("n_classes", c_int),
-                ("logit_scale", c_float), ("targets", c_void_p)]
+                ("logit_scale", c_float), ("targets", c_void_p), ("y_target", c_void_p)]
 
 
 _LAYER_KEYS = {
@@ -94,8 +94,10 @@ class LossSpec:
     train/adversarial_training_clip.py:260-274)."""
 
     def __init__(self, mode, output_normalize, emb_orig=None, text=None, logit_scale=100.0,
-                 targets=None, pred_on_logits=False):
-        self.mode = {"l2": LOSS_L2, "ce": LOSS_CE}.get(mode, mode)
+                 targets=None, pred_on_logits=False, y_target=None):
+        self.mode = {"l2": LOSS_L2, "ce": LOSS_CE, "dlr": LOSS_DLR,
+                     "dlr-targeted": LOSS_DLR_TARGETED}.get(mode, mode)
+        self.y_target = y_target
         self.output_normalize = bool(output_normalize)
         self.emb_orig, self.text, self.targets = emb_orig, text, targets
         self.logit_scale = float(logit_scale)
@@ -111,16 +113,19 @@ class LossSpec:
 
         eo = sl(self.emb_orig)
         tg = sl(self.targets)
+        yt = sl(self.y_target)
         if eo is not None:
             eo = eo.detach().float().contiguous()
         if tg is not None:
             tg = tg.detach().long().contiguous()
+        if yt is not None:
+            yt = yt.detach().long().contiguous()
         tx = self.text.detach().float().contiguous() if self.text is not None else None
-        self._keep = [eo, tg, tx]
+        self._keep = [eo, tg, tx, yt]
         return LossConfigC(self.mode, int(self.output_normalize), int(self.pred_on_logits),
                            nat.ptr(eo).value, nat.ptr(tx).value,
                            tx.shape[1] if tx is not None else 0, self.logit_scale,
-                           nat.ptr(tg).value)
+                           nat.ptr(tg).value, nat.ptr(yt).value)
 
 
 class VitEngine:
@@ -256,7 +261,7 @@ class VitEngine:
         emb = torch.empty(B, self.arch["out_dim"], device=self.device, dtype=torch.float32)
         grad = torch.empty_like(x) if want_grad else None
         logits = (torch.empty(B, lc.n_classes, device=self.device, dtype=torch.float32)
-                  if want_logits and lc.mode == LOSS_CE else None)
+                  if want_logits and lc.mode in (LOSS_CE, LOSS_DLR, LOSS_DLR_TARGETED) else None)
         nat.call("rvlm_vit_loss_grad", self.handle, nat.ptr(ws), c_size_t(nbytes), nat.ptr(x),
                  nat.ptr(delta), c_int(B), byref(lc), nat.ptr(grad), nat.ptr(out_loss),
                  nat.ptr(pred), nat.ptr(emb), nat.ptr(logits), c_int(int(want_grad)),

@@ -160,3 +160,80 @@ def test_apgd_attack_perturb(norm, eps):
     if norm == "Linf":
         assert float((out - x).abs().max()) <= eps + 1e-6
     assert racc_ours <= racc_ref + 0.34
+
+
+@pytest.mark.parametrize("loss", ["dlr", "dlr-targeted"])
+def test_dlr_losses_in_the_head_kernel(loss):
+    """DLR (autoattack/autopgd_base.py:195-201) and targeted DLR (:616-621): value and input
+    gradient from the head kernel (top-4 logits on device) vs autograd through the oracle."""
+    from robustvlm_b200.engine import LossSpec
+    B = 6
+    ours, ref_m = _pair(1)
+    x, d0 = _data(B, 23, 0.01)
+    torch.manual_seed(1)
+    text = torch.nn.functional.normalize(torch.randn(64, 10), dim=0)
+    cm_ref = ovit.ClassificationModel(ref_m.model, text, 100.0)
+    xa = (x + d0).clamp(0, 1).requires_grad_(True)
+    logits = cm_ref(xa)
+    y = logits.argmax(1)
+    y[::2] = (y[::2] + 3) % 10                     # half of the points start misclassified
+    yt = logits.sort(dim=1)[1][:, -3].detach()
+    R = oa.APGDAttack_targeted(cm_ref, eps=0.1)
+    R.y_target = yt
+    l_ref = oa.dlr_loss(logits, y) if loss == "dlr" else R.dlr_loss_targeted(logits, y)
+    (g_ref,) = torch.autograd.grad(l_ref.sum(), xa)
+    spec = LossSpec(loss, True, text=text.cuda(), logit_scale=100.0, targets=y.cuda(),
+                    pred_on_logits=True, y_target=yt.cuda() if loss == "dlr-targeted" else None)
+    r = ours.engine().loss_grad(xa.detach().cuda(), spec, want_logits=True)
+    l_err = float((r["loss"].cpu() - l_ref.detach()).abs().max())
+    cos = float(torch.nn.functional.cosine_similarity(r["grad"].cpu().flatten(1), g_ref.flatten(1),
+                                                      dim=1).min())
+    nrm = float(r["grad"].cpu().flatten(1).norm(dim=1).div(g_ref.flatten(1).norm(dim=1)).sub(1).abs().max())
+    _log("dlr_head", loss=loss, loss_err=l_err, cos_min=cos, norm_ratio_err=nrm,
+         logits_err=float((r["logits"].cpu() - logits.detach()).abs().max()))
+    assert torch.equal(r["pred"].cpu(), logits.argmax(1) == y)
+    assert l_err < 5e-3 and cos > 0.999 and nrm < 2e-2
+
+
+def test_apgd_fused_dlr_eot_and_largereps():
+    """APGDAttack with loss='dlr', eot_iter = 2 and `use_largereps` on the fused engine path
+    (no autograd), against the oracle run with the same noise."""
+    from robustvlm_b200 import attacks, model as rm
+    B = 6
+    ours, ref_m = _pair(1)
+    x, _ = _data(B, 29, 0.01)
+    torch.manual_seed(0)
+    text = torch.nn.functional.normalize(torch.randn(64, 10), dim=0)
+    cm_ref = ovit.ClassificationModel(ref_m.model, text, 100.0)
+    cm = rm.ClassificationModel(ours, text.cuda())
+    with torch.no_grad():
+        y = cm_ref(x).argmax(1)
+    real_randn_like = torch.randn_like
+    res = {}
+    for tag, kw in (("dlr_eot", dict(loss="dlr", eot_iter=2, norm="Linf", eps=4 / 255)),
+                    ("largereps", dict(loss="ce", use_largereps=True, norm="Linf", eps=2 / 255))):
+        R = oa.APGDAttack(cm_ref, n_iter=20, n_restarts=2, seed=0, alpha=2.0, **kw)
+        A = attacks.APGDAttack(cm, n_iter=20, n_restarts=2, seed=0, alpha=2.0, **kw)
+        outs = []
+        for atk, xx, yy in ((R, x, y), (A, x.cuda(), y.cuda())):
+            g = torch.Generator().manual_seed(77)      # decr_eps_pgd's randn_like: same noise for both
+            torch.randn_like = lambda t, g=g: torch.randn(t.shape, generator=g).to(t.device)
+            try:
+                real_grad = torch.autograd.grad
+                if atk is A:
+                    def boom(*a, **k):
+                        raise AssertionError("torch.autograd.grad called on the fused path")
+                    torch.autograd.grad = boom
+                outs.append(atk.perturb(xx, yy).cpu())
+            finally:
+                torch.randn_like = real_randn_like
+                torch.autograd.grad = real_grad
+        ref, out = outs
+        with torch.no_grad():
+            racc_ref = float((cm_ref(ref).argmax(1) == y).float().mean())
+            racc_ours = float((cm_ref(out).argmax(1) == y).float().mean())
+        res[tag] = (racc_ref, racc_ours, float((out - x).abs().max()), float((out - ref).abs().max()))
+        eps = kw["eps"]
+        assert out.min() >= 0 and out.max() <= 1 and float((out - x).abs().max()) <= eps + 1e-6
+        assert abs(racc_ours - racc_ref) <= 1.0 / B + 1e-6
+    _log("apgd_fused_dlr_eot_largereps", **{k: list(v) for k, v in res.items()})

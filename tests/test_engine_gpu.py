@@ -177,15 +177,25 @@ def test_fp16_operands_survive_outlier_channels(mode):
     cfg = ovit.VitConfig(224, 32, 256, 6, 4, 1024, 128)
     o = ovit.build(cfg, seed=11)
     with torch.no_grad():
+        # operand MAGNITUDE outliers with the function left well conditioned (as in a trained
+        # tower): a gain of 50-100 on a few LayerNorm channels is compensated in the weight
+        # columns that consume them, massive MLP hidden units are damped again by c_proj
         g = torch.Generator().manual_seed(5)
         for blk in o.transformer.resblocks:
             idx = torch.randperm(256, generator=g)[:3]
-            blk.ln_1.weight[idx] *= 60.0                   # outlier LayerNorm gains
-            blk.ln_2.weight[idx] *= 60.0
+            blk.ln_1.weight[idx] *= 60.0
+            blk.ln_1.bias[idx] *= 60.0
+            blk.attn.in_proj_weight[:, idx] /= 60.0
+            idx = torch.randperm(256, generator=g)[:3]
+            blk.ln_2.weight[idx] *= 100.0
+            blk.ln_2.bias[idx] *= 100.0
+            blk.mlp.c_fc.weight[:, idx] /= 100.0
             rows = torch.randperm(1024, generator=g)[:4]
-            blk.mlp.c_fc.weight[rows] *= 80.0              # outlier MLP rows (massive activations)
-            blk.mlp.c_proj.weight[:, rows] *= 0.05
+            blk.mlp.c_fc.weight[rows] *= 80.0              # massive hidden activations ...
+            blk.mlp.c_fc.bias[rows] *= 80.0
+            blk.mlp.c_proj.weight[:, rows] /= 80.0         # ... damped on the way out
         o.class_embedding[7] += 40.0                       # a massive residual channel
+        o.positional_embedding[:, 11] += 25.0
     ref_m = ovit.ClipVisionModel(o).eval()
     for p in ref_m.parameters():
         p.requires_grad_(False)
@@ -205,7 +215,8 @@ def test_fp16_operands_survive_outlier_channels(mode):
     agree, mis_big = sign_agreement(grad, g_ref, tau=0.05)
     cos = float(torch.nn.functional.cosine_similarity(grad.flatten(1), g_ref.flatten(1), dim=1).min())
     # true scale: the fp16-gradient path undoes its per-sample rescaling on output
-    ratio = float(grad.flatten(1).norm(dim=1).div(g_ref.flatten(1).norm(dim=1)).sub(1).abs().max())
+    # (loss_grad differentiates sum_b loss_b, the wrapper's "mean" divides by B)
+    ratio = float(grad.flatten(1).norm(dim=1).div(4 * g_ref.flatten(1).norm(dim=1)).sub(1).abs().max())
     _log("outlier_stress", mode=mode, emb_rel_err=rel_err(emb, e_ref), sign_agree=agree,
          mismatch_big=mis_big, cos_min=cos, norm_ratio_err=ratio,
          act_scale=float(e_ref.abs().max()))

@@ -117,6 +117,23 @@ def test_golden_apgd_eval(gold, models, norm, eps):
     assert int(fooled_o.sum()) >= int(fooled_r.sum()) - 1
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _no_autograd():
+    """fail if anything inside calls torch.autograd.grad: the fused path must not need it"""
+    real = torch.autograd.grad
+
+    def boom(*a, **k):
+        raise AssertionError("torch.autograd.grad called on the fused path")
+    torch.autograd.grad = boom
+    try:
+        yield
+    finally:
+        torch.autograd.grad = real
+
+
 @pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 1.0)])
 def test_golden_apgd_targeted(gold, models, norm, eps):
     """APGDAttack_targeted (autoattack/autopgd_base.py:584-707) vs the reference's output:
@@ -131,7 +148,8 @@ def test_golden_apgd_targeted(gold, models, norm, eps):
     atk = attacks.APGDAttack_targeted(cm, n_iter=k["n_iter"], norm=norm, n_restarts=k["n_restarts"],
                                       eps=eps, seed=k["seed"],
                                       n_target_classes=k["n_target_classes"], alpha=k["alpha"])
-    out = atk.perturb(x.cuda(), yc.cuda()).cpu()
+    with _no_autograd():            # targeted DLR + its gradient come from the head kernel
+        out = atk.perturb(x.cuda(), yc.cuda()).cpu()
     ref = gt[f"apgd_t_{norm}"]
     cm_ref = ovit.ClassificationModel(ref_m.model, text, 100.0)
     with torch.no_grad():
@@ -162,7 +180,8 @@ def test_golden_autoattack(gold, models):
                    seed=0)
     A.apgd.n_restarts = 1
     A.apgd_targeted.n_target_classes = gt["n_target_classes"]
-    x_adv, y_adv = A.run_standard_evaluation(x, y, bs=gt["bs"], return_labels=True)
+    with _no_autograd():            # apgd-ce and apgd-t both run on the fused engine path
+        x_adv, y_adv = A.run_standard_evaluation(x, y, bs=gt["bs"], return_labels=True)
     cm_ref = ovit.ClassificationModel(ref_m.model, gold["text"], 100.0)
     with torch.no_grad():
         pred = cm_ref(x_adv.cpu()).argmax(1)

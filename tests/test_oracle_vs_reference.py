@@ -121,3 +121,17 @@ def test_apgd_train_initial_stepsize(ns, setup):
         b = ns.apgd_train(m, x, y, norm, eps, n_iter=12, initial_stepsize=0.05 * eps,
                           loss_fn=ns.ComputeLossWrapper(eo, text, "none", "ce", 100.0))
         assert torch.equal(a, b)
+
+
+def test_apgd_use_largereps(ns, setup):
+    """`use_largereps` (autoattack/autopgd_base.py:493-498, 517-520, 550-582): the 3 eps / 2 eps / eps
+    schedule chained through x_init, with the constructor's check-point schedule."""
+    m, x, d0, y, text, eo = setup
+    cm = vit.ClassificationModel(m.model, text, 100.0)
+    with torch.no_grad():
+        yc = cm(x).argmax(1)
+    kw = dict(n_iter=20, norm="Linf", n_restarts=2, eps=2 / 255, seed=5, alpha=2.0,
+              use_largereps=True)
+    A, R = oa.APGDAttack(cm, **kw), ns.APGDAttack(cm, **kw)
+    assert torch.equal(A.perturb(x, yc), R.perturb(x, yc))       # CPU tensors: randn_like on the CPU RNG
+    assert (A.n_iter, A.eps, A.use_rs) == (R.n_iter, R.eps, R.use_rs)

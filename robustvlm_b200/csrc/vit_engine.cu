@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <vector>
 #include <new>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost a null-pointer test unless a tool is attached
 
 using namespace rvlm;
 
@@ -47,6 +48,13 @@ int ln_bwd16_strided(const void*, long long, const float*, long long, const floa
 }  // namespace rvlm
 
 namespace {
+
+// NVTX range around a phase of the step (visible in Nsight Systems / ncu --nvtx): forward, head +
+// loss, input-gradient backward, delta update, outer backward.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -188,6 +196,7 @@ inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : -(int)e - 1000
 // ---- forward --------------------------------------------------------------------
 // Precondition: w.a16 holds the normalised 16-bit patch operand of the batch.
 int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
+  NvtxRange nvtx_("rvlm.vit_forward");
   const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
   const int ff = E.ff;
   const size_t MW = (size_t)M * W;
@@ -279,6 +288,7 @@ const float* final_x(const Engine& E, const Ws& w, int B) {
 int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, int normalize,
              float* emb_out, float* logits_out, bool backward, cudaStream_t st,
              float grad_scale = 1.f) {
+  NvtxRange nvtx_("rvlm.head_loss");
   HeadArgs A{};
   A.xL = final_x(E, w, B);
   A.T = E.T; A.W = E.W; A.D = E.D;
@@ -319,6 +329,7 @@ int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, in
 
 // ---- backward (dgrad only) down to the token gradient of the patch rows -----------
 int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
+  NvtxRange nvtx_("rvlm.vit_backward_input");
   const int M = B * E.T, W = E.W, F = E.F;
   const int ff = E.ff, fg = E.cfg.fmt_bwd;
   const size_t MW = (size_t)M * W;
@@ -412,6 +423,7 @@ int wgrad(const uint16_t* dY, int Nw, const uint16_t* X, int Kw, int Mtok, int f
 // starting the all-reduce of a block's gradient bucket while the backward continues.
 int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads* g,
                        cudaStream_t st, void* const* events) {
+  NvtxRange nvtx_("rvlm.vit_backward_params");
   const int M = B * E.T, W = E.W, F = E.F, R = B * E.np;
   const int ff = E.ff, fg = E.cfg.fmt_bwd;
   const size_t MW = (size_t)M * W;
@@ -775,13 +787,16 @@ extern "C" int rvlm_pgd_run(rvlm_vit_handle h, void* workspace, size_t workspace
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)E.np * E.kp;
   RV(prep_state(E, w, B, x, delta0, true, st));
+  NvtxRange nvtx_run("rvlm.pgd_run");
   for (int it = 0; it < iterations; ++it) {
+    NvtxRange nvtx_it("rvlm.pgd_iteration");
     RV(run_forward(E, w, B, st));
     RV(run_head(E, w, B, loss, 0, nullptr, nullptr, true, st));
     if (loss_trace)
       RV(cuda_rc(cudaMemcpyAsync(loss_trace + (size_t)it * B, w.loss, B * sizeof(float),
                                  cudaMemcpyDeviceToDevice, st)));
     RV(run_backward(E, w, B, st));
+    NvtxRange nvtx_up("rvlm.delta_update");
     if (norm == RVLM_NORM_LINF) {
       // delta-update fused into the last backward kernel (also emits the next operand)
       RV(run_patch_pgd_linf(E, w, B, stepsize, eps, maximize, momentum, st));

@@ -88,16 +88,23 @@ class BucketedAllReduce:
 
     def __init__(self, layout, n_layers, device):
         self.blocks, self.rest = grad_buckets(layout, n_layers)
-        self.device = device
-        self.side = torch.cuda.Stream(device=device)
-        self.events = [torch.cuda.Event() for _ in range(n_layers + 1)]
-        for e in self.events:            # creates the cudaEvent_t handles the C engine records on
-            e.record(torch.cuda.current_stream(device))
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.side, self.events = None, None
+        if self.cuda:
+            self.side = torch.cuda.Stream(device=device)
+            self.events = [torch.cuda.Event() for _ in range(n_layers + 1)]
+            for e in self.events:        # creates the cudaEvent_t handles the C engine records on
+                e.record(torch.cuda.current_stream(device))
 
     def launch(self, flat_grad: torch.Tensor):
         """enqueue every bucket's all-reduce behind its event; returns the work handles"""
         works = []
         op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        if not self.cuda:                # host tensors (gloo tests): same buckets, no streams
+            for lo, hi in list(reversed(self.blocks)) + self.rest:
+                works.append(dist.all_reduce(flat_grad[lo:hi], op=op, async_op=True))
+            return works
         with torch.cuda.stream(self.side):
             for l in range(len(self.blocks) - 1, -1, -1):
                 self.side.wait_event(self.events[l])
@@ -111,7 +118,8 @@ class BucketedAllReduce:
     def finish(self, works, flat_grad):
         for w in works:
             w.wait()                     # the current stream waits for NCCL's
-        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
         if dist.get_backend() != "nccl":
             flat_grad.div_(float(dist.get_world_size()))
 

@@ -197,7 +197,8 @@ class AdversarialTrainer:
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         # per-block gradient buckets all-reduced under the rest of the backward (even shards,
         # a single backward); otherwise one blocking all-reduce after it
-        overlap = world > 1 and cw == 0.0 and B * world == global_batch and self.dev.type == "cuda"
+        overlap = (world > 1 and cw == 0.0 and B * world == global_batch
+                   and self.dev.type == "cuda" and self._bucketed is not False)
         works = None
         if overlap:
             if self._bucketed is None:

@@ -47,6 +47,18 @@ def _worker(rank, world, port, q):
     grads = torch.autograd.grad(loss, params)
     flat = torch.cat([g_.reshape(-1) for g_ in grads])
     parallel.allreduce_mean_(flat, xs.shape[0], B)
+    # the bucketed variant (per-block buckets + the rest) averages the same buffer identically
+    from robustvlm_b200 import checkpoint
+    rng = torch.Generator().manual_seed(100 + rank)
+    layout = checkpoint.param_layout(model.model)
+    n = sum(sz for *_, sz in layout)
+    fg = torch.randn(n, generator=rng)
+    whole = fg.clone()
+    dist.all_reduce(whole)
+    whole /= world
+    bk = parallel.BucketedAllReduce(layout, cfg.layers, "cpu")
+    bk.finish(bk.launch(fg), fg)
+    assert torch.equal(fg, whole), "bucketed all-reduce differs from the monolithic one"
     if rank == 0:
         q.put((adv, flat))
     dist.barrier()
@@ -82,6 +94,23 @@ def test_sharded_attack_and_gradient_allreduce():
     loss = oa.l2(model(adv, output_normalize=False), eo, "mean")
     full = torch.cat([g_.reshape(-1) for g_ in torch.autograd.grad(loss, params)])
     assert float((flat - full).norm() / full.norm()) < 1e-5
+
+
+def test_grad_buckets_partition_the_flat_buffer():
+    """one contiguous bucket per transformer block + the rest, covering [0, n) exactly once"""
+    from robustvlm_b200 import checkpoint, parallel
+    from robustvlm_b200.model import VisionTransformer
+    for arch, L in (("tiny-32", 2), ("ViT-B-32", 12)):
+        layout = checkpoint.param_layout(VisionTransformer(arch))
+        n = sum(sz for *_, sz in layout)
+        blocks, rest = parallel.grad_buckets(layout, L)
+        spans = sorted(blocks + rest)
+        assert len(blocks) == L and spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        for name, _, off, sz in layout:
+            if name.startswith("transformer.resblocks."):
+                lo, hi = blocks[int(name.split(".")[2])]
+                assert lo <= off and off + sz <= hi
 
 
 def test_shard_bounds_cover_everything():

@@ -78,8 +78,29 @@ def main():
     ref = p.clone()
     dist.broadcast(ref, src=0)
     res["replicas_identical_after_2_steps"] = bool(torch.equal(p, ref))
+    # ---- 4. even shards: the per-block bucketed all-reduce overlapped with the backward
+    # (parallel.BucketedAllReduce behind rvlm_vit_train_grads_ev's events) gives the same parameters,
+    # bit for bit, as one blocking all-reduce after the backward
+    Be = (B // world) * world
+    le, he = parallel.shard_bounds(Be, rank, world)
+    outs = []
+    for overlap in (True, False):
+        vt2 = rm.VisionTransformer(name, seed=1).to(dev)
+        m2 = rm.ClipVisionModel(vt2, None, None).eval()
+        tr2 = AdversarialTrainer(m2, mo, lr=1e-4, wd=1e-4, steps=20, warmup=2, attack="none")
+        if not overlap:
+            tr2._bucketed = False              # force the blocking path
+        for _ in range(2):
+            tr2.train_step(x[le:he], None, global_batch=Be)
+        outs.append(tr2.flat_p.clone())
+        used_overlap = tr2._bucketed not in (None, False)
+        if overlap:
+            res["bucketed_path_used"] = bool(used_overlap)
+    res["bucketed_equals_blocking"] = bool(torch.equal(outs[0], outs[1]))
     flags = torch.tensor([int(res["pgd_sharded_equals_whole"]), int(rel < 2e-2 and cos > 0.999),
-                          int(res["replicas_identical_after_2_steps"])], device=dev)
+                          int(res["replicas_identical_after_2_steps"]),
+                          int(res["bucketed_equals_blocking"] and res["bucketed_path_used"])],
+                         device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     ok = bool(flags.min().item() == 1)
     if rank == 0:

@@ -186,6 +186,13 @@ int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H,
 int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16, float* lse_tmp,
                   void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o, int fmt_g,
                   void* stream);
+/* The same given the forward's log-sum-exp (rvlm_attn_fwd's `lse`): valid when qkv16 holds the very
+ * bits the forward multiplied (same 16-bit format, forward not split), so P = exp(S - lse) is the
+ * forward's softmax exactly and nothing is recomputed (one TMEM sweep per tile less; the fused
+ * kernel for T in {256, 257}; other T fall back to rvlm_attn_bwd with `lse` as scratch). */
+int rvlm_attn_bwd_lse(const void* qkv16, const void* o16, const void* do16, float* lse,
+                      void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o, int fmt_g,
+                      void* stream);
 /* Split-operand forward (the attention part of RVLM_FMT_F16X2): q | k | v and o as fp16 hi + lo
  * pairs in separate buffers of the same layout; softmax(q k^T / 8) v with every product formed as
  * hi*hi + lo*hi + hi*lo.  o_lo and lse may be NULL.  T <= 272. */

@@ -2115,6 +2115,483 @@ static int launch_bwd3(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
+// =====================================================================================
+// Backward, version 4 (T in {256, 257}; the forward's log-sum-exp is given): the fused dQ / dK /
+// dV kernel of version 3 re-cut around what actually bounds it.  Version 3 runs 8 worker warps
+// (two threads per row) through THREE TMEM sweeps per tile (row max, exp, dS) with three
+// cross-thread exchanges (max, row sum, D), rescales the dO tile in shared memory and waits on
+// five MMA hand-offs; its tensor pipe is 13 % busy, its issue slots 32 %, and each warp issues
+// one instruction every ~7 cycles: it is bound by per-warp latency, then by TMEM reads
+// (64 B / clk / SM: every sweep of a 128 x 256 fp32 tile is 2048 cycles).  Here
+//   * the softmax statistics are NOT recomputed: P = exp2(S c - lse_fwd) with the forward's
+//     log-sum-exp, which is exact because the backward's q | k copy holds the same bits the
+//     forward multiplied (the engine selects this kernel only when fmt_fwd == fmt_bwd and the
+//     forward is not split) -- one TMEM sweep less, no max / sum exchanges, no dO rescaling
+//     (dP = dO V^T is formed from the TMA-loaded tile as is, D = o . dO is the true one);
+//   * 16 worker warps, four threads per row with 64 columns each: twice the warps to hide the
+//     TMEM-load / shared-memory / MUFU latencies, 32 packed probabilities per thread in
+//     registers (<= 120 registers at 544 threads);
+//   * the peeled 257th query row needs no block reductions either (its lse is known).
+// TMEM, shared-memory tiles and the MMA sequence are those of version 3.
+// =====================================================================================
+constexpr int AT4_THREADS = 544;   // 16 worker warps + 1 control warp
+constexpr int AT4_CTRL_WARP = 16;
+
+template <int FMT, bool TAIL>
+__global__ void __launch_bounds__(AT4_THREADS, 1)
+attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
+                 const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x 256
+                 const __grid_constant__ CUtensorMap tmDoTile, // dO,  box 64 x 128
+                 AttnBwd2Params P, const float* __restrict__ lse_fwd) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int KVM = 256, NBLK = 4;
+  const int T = P.T, W = P.W;
+  constexpr int full_bytes = KVM * 128;
+  uint8_t* s_k = smem;
+  uint8_t* s_v = s_k + full_bytes;
+  uint8_t* s_tile0 = s_v + full_bytes;       // [2][16384] Q_i
+  uint8_t* s_tile1 = s_tile0 + 2 * 16384;    // [2][16384] dO_i
+  uint8_t* s_p = s_tile1 + 2 * 16384;        // [4][16384] P, then dS
+  float* s_p256 = reinterpret_cast<float*>(s_p + NBLK * 16384);  // [272] P[256, kv]  (peeled row)
+  float* s_ds256 = s_p256 + 272;                                 // [272] dS[256, kv]
+  float* s_dd = s_ds256 + 272;    // [4][128] quarter sums of o . dO
+  float* s_tt = s_dd + 512;       // [256] per-row peeled-column terms: p_t | ds_t
+  float* s_part = s_tt + 256;     // [2][8][64] partial sums of the peeled kv row / query row
+  // [2][5][64] k_256 v_256 q_256 dO_256 o_256 of the current / the next item
+  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_part + 1024);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 2 * 320);
+  uint64_t* bar_full = bars + 0;
+  uint64_t* bar_tile = bars + 1;      // [2]
+  uint64_t* bar_s = bars + 3;
+  uint64_t* bar_dp = bars + 4;
+  uint64_t* bar_p = bars + 5;         // 512 arrivals, two uses per tile
+  uint64_t* bar_acc = bars + 6;       // dQ complete
+  uint64_t* bar_acc_free = bars + 7;  // 512 arrivals: dQ accumulator drained
+  uint64_t* bar_kv_free = bars + 8;   // 512 arrivals: dK / dV accumulators drained
+  uint64_t* bar_trow = bars + 9;      // 512 arrivals: peeled row done with K / V
+  uint64_t* bar_kdone = bars + 10;    // last tensor-core read of K / V of this item retired
+  uint64_t* bar_dk = bars + 11;       // dK MMAs of a tile retired (Q_i / dS no longer read)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(&bar_tile[0], 1);
+    mbar_init(&bar_tile[1], 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_dp, 1);
+    mbar_init(bar_p, 512);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_acc_free, 512);
+    mbar_init(bar_kv_free, 512);
+    mbar_init(bar_trow, 512);
+    mbar_init(bar_kdone, 1);
+    mbar_init(bar_dk, 1);
+    fence_barrier_init();
+  }
+  if (warp == AT4_CTRL_WARP) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int n_items = P.B * P.H;
+  const int colQ = 0, colK = W, colV = 2 * W;
+  constexpr uint32_t TR = 0, TDV = 256, TDK = 384;
+  const int ntile = P.ntile;   // 2
+
+  if (warp == AT4_CTRL_WARP) {
+    if (lane == 0) {
+      // ===================== TMA + MMA issuer (as version 3) =====================
+      auto load_full = [&](int item) {
+        const int b = item / P.H, h = item % P.H;
+        mbar_arrive_expect_tx(bar_full, 2 * full_bytes);
+        tma_load_3d(s_k, &tmFull, bar_full, colK + h * 64, 0, b);
+        tma_load_3d(s_v, &tmFull, bar_full, colV + h * 64, 0, b);
+      };
+      auto load_tile = [&](int item, int j, uint32_t gg) {
+        const int b = item / P.H, h = item % P.H, buf = gg & 1;
+        mbar_arrive_expect_tx(&bar_tile[buf], 32768);
+        tma_load_3d(s_tile0 + buf * 16384, &tmTile, &bar_tile[buf], colQ + h * 64, j * 128, b);
+        tma_load_3d(s_tile1 + buf * 16384, &tmDoTile, &bar_tile[buf], h * 64, j * 128, b);
+      };
+      const uint32_t idS = idesc_ab(FMT, FMT, 128, KVM, 0, 0);
+      const uint32_t idT = idesc_ab(FMT, FMT, 128, 64, 1, 1);   // A and B both MN-major
+      uint32_t g = 0;
+      int it = 0;
+      if ((int)blockIdx.x < n_items) {
+        load_full(blockIdx.x);
+        load_tile(blockIdx.x, 0, 0);
+      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int next = item + gridDim.x;
+        mbar_wait(bar_full, it & 1, 170);
+        for (int j = 0; j < ntile; ++j, ++g) {
+          const int buf = g & 1;
+          if (g > 0) {
+            mbar_wait(bar_acc_free, (g - 1) & 1, 173);
+            mbar_wait(bar_dk, (g - 1) & 1, 178);
+          }
+          if (j + 1 < ntile) load_tile(item, j + 1, g + 1);
+          else if (next < n_items) load_tile(next, 0, g + 1);
+          mbar_wait(&bar_tile[buf], (g >> 1) & 1, 172);
+          tc_fence_after();
+          const uint32_t t0 = smem_u32(s_tile0 + buf * 16384), t1 = smem_u32(s_tile1 + buf * 16384);
+          const uint32_t ka = smem_u32(s_k), va = smem_u32(s_v), pa = smem_u32(s_p);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // S = Q_i K^T
+            umma_f16(tmem + TR, make_smem_desc_sw128(t0 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_s);
+          mbar_wait(bar_p, (2 * g) & 1, 174);        // P written, S consumed
+          if (j == 0 && it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 171);   // dK / dV drained
+          tc_fence_after();
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)             // dV_jj += P^T dO_i
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              umma_f16(tmem + TDV + jj * 64,
+                       make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
+                       make_smem_desc_sw128(t1 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                // dP = dO_i V^T into the (consumed) S region
+            umma_f16(tmem + TR, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(va + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_dp);
+          mbar_wait(bar_p, (2 * g + 1) & 1, 175);    // dS written over P
+          tc_fence_after();
+          issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
+          umma_commit(bar_acc);
+          if (j + 1 == ntile) umma_commit(bar_kdone);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)             // dK_jj += dS^T Q_i
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              umma_f16(tmem + TDK + jj * 64,
+                       make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
+                       make_smem_desc_sw128(t0 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
+          umma_commit(bar_dk);
+        }
+        mbar_wait(bar_kdone, it & 1, 176);
+        if (TAIL) mbar_wait(bar_trow, it & 1, 177);
+        if (next < n_items) load_full(next);
+      }
+    }
+  } else {
+    // ===================== row workers: thread = (row r, column quarter cq) =====================
+    const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7;
+    const uint32_t ts = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const float c2 = 0.125f * 1.4426950408889634f;
+    const float LOG2E = 1.4426950408889634f;
+    const uint32_t rx = (uint32_t)(r & 7) << 4;
+    uint8_t* prow = s_p + cq * 16384 + r * 128;   // this thread's 64 columns = one 16 KB block
+    auto tail_src = [&](int item_) -> const uint4* {
+      const int b_ = item_ / P.H, h_ = item_ % P.H;
+      const int which = tid >> 3, c = tid & 7;
+      const size_t rowq = ((size_t)b_ * T + 256) * 3 * W + h_ * 64 + c * 8;
+      const size_t rowd = ((size_t)b_ * T + 256) * W + h_ * 64 + c * 8;
+      const uint16_t* src = which == 0 ? P.qkv + rowq + colK : which == 1 ? P.qkv + rowq + colV
+                          : which == 2 ? P.qkv + rowq + colQ : which == 3 ? P.d_o + rowd
+                                                                          : P.o + rowd;
+      return reinterpret_cast<const uint4*>(src);
+    };
+    if (TAIL && tid < 40 && (int)blockIdx.x < n_items)
+      *reinterpret_cast<uint4*>(s_tv + tid * 8) = *tail_src(blockIdx.x);
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    uint32_t g = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int b = item / P.H, h = item % P.H;
+      const float* lse_row = lse_fwd + ((size_t)b * P.H + h) * T;
+      const uint16_t* tvb = s_tv + (it & 1) * 320;
+      const uint16_t* tv0 = tvb;              // k_256
+      const uint16_t* tv1 = tvb + 64;         // v_256
+      const uint16_t* tv2 = tvb + 128;        // q_256
+      const uint16_t* tv3 = tvb + 192;        // dO_256
+      const uint16_t* tv4 = tvb + 256;        // o_256 (forward format)
+      float tdv = 0.f, tdk = 0.f;   // this thread's share of dv_256[d], dk_256[d] (d = tid & 63)
+      if (TAIL) {
+        // ============ the peeled QUERY row (token 256) on the CUDA cores ============
+        const float l2 = __ldg(lse_row + 256) * LOG2E;
+        const float D = dot_rows16(tv4, P.fmt_o, tv3, FMT);
+        mbar_wait(bar_full, it & 1, 180);
+        if (tid < 256) {
+          const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
+          s_p256[tid] = fast_ex2(fmaf(sv, c2, -l2));
+          if (tid == 0) s_p256[256] = fast_ex2(fmaf(dot_vec<FMT>(tv0, tv2), c2, -l2));
+        } else {
+          s_ds256[tid - 256] = dot_swz_row<FMT>(s_v, tid - 256, tv3);     // dP[256, kv]
+          if (tid == 256) s_ds256[256] = dot_vec<FMT>(tv1, tv3);
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        if (tid < 256) s_ds256[tid] = s_p256[tid] * (s_ds256[tid] - D) * 0.125f;
+        if (tid == 256) s_ds256[256] = s_p256[256] * (s_ds256[256] - D) * 0.125f;
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        {
+          const int d = tid & 63, qt = tid >> 6;       // 8 groups of 32 keys
+          float acc = 0.f;
+          for (int kv = qt * 32; kv < qt * 32 + 32; ++kv)
+            acc = fmaf(s_ds256[kv], swz_at<FMT>(s_k, kv, d), acc);
+          if (qt == 7) acc = fmaf(s_ds256[256], ld1<FMT>(tv0 + d), acc);
+          s_part[qt * 64 + d] = acc;
+          if (qt == 0) {   // the (q = 256, kv = 256) corner of dk_256 / dv_256
+            tdv = s_p256[256] * ld1<FMT>(tv3 + d);
+            tdk = s_ds256[256] * ld1<FMT>(tv2 + d);
+          }
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        if (tid < 32) {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            a0 += s_part[q * 64 + 2 * tid];
+            a1 += s_part[q * 64 + 2 * tid + 1];
+          }
+          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64)[tid] =
+              packc<FMT>(a0, a1);
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        mbar_arrive(bar_trow);
+      }
+      for (int j = 0; j < ntile; ++j, ++g) {
+        const int buf = g & 1;
+        const int row = j * 128 + r;
+        const size_t grow = (size_t)b * T + row;
+        uint8_t* tq = s_tile0 + buf * 16384;
+        uint8_t* tdo = s_tile1 + buf * 16384;
+        const float l2 = __ldg(lse_row + row) * LOG2E;
+        // this thread's quarter of the o row (D_r = o_r . dO_r), requested early
+        uint4 g_o[2];
+        {
+          const uint4* po = reinterpret_cast<const uint4*>(P.o + grow * W + h * 64 + cq * 16);
+          g_o[0] = po[0];
+          g_o[1] = po[1];
+        }
+        mbar_wait(&bar_tile[buf], (g >> 1) & 1, 181);
+        float a_t = 0.f, b_t = 0.f;
+        if (TAIL && cq == 3) {
+          a_t = dot_swz_row<FMT>(tq, r, tv0);    // q_r . k_256
+          b_t = dot_swz_row<FMT>(tdo, r, tv1);   // dO_r . v_256
+        }
+        {
+          float dd = 0.f;
+          const uint8_t* drow = tdo + r * 128;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const uint4 ud =
+                *reinterpret_cast<const uint4*>(drow + (((cq * 2 + i) ^ (r & 7)) << 4));
+            const uint32_t* pa = &g_o[i].x;
+            const uint32_t* pb = &ud.x;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 x = unpack2(pa[u], P.fmt_o), y = unpackc<FMT>(pb[u]);
+              dd = fmaf(x.x, y.x, fmaf(x.y, y.y, dd));
+            }
+          }
+          s_dd[cq * 128 + r] = dd;
+        }
+        // ---------------- pass 1: P = exp2(S c - lse) ----------------
+        mbar_wait(bar_s, g & 1, 182);
+        tc_fence_after();
+        const uint32_t tcol = ts + TR + cq * 64;
+        uint32_t pk[32];
+        float p_t = 0.f;
+        {
+          uint32_t v[2][16];
+          tmem_ld16(tcol, v[0]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            tmem_ld_wait();
+            if (q + 1 < 4) tmem_ld16(tcol + (q + 1) * 16, v[(q + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              const float e0 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i]), c2, -l2));
+              const float e1 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + 1]), c2, -l2));
+              pk[q * 8 + i / 2] = packc<FMT>(e0, e1);
+            }
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8)
+              *reinterpret_cast<uint4*>(prow + ((((uint32_t)(q * 2 + q8)) << 4) ^ rx)) =
+                  make_uint4(pk[q * 8 + q8 * 4], pk[q * 8 + q8 * 4 + 1], pk[q * 8 + q8 * 4 + 2],
+                             pk[q * 8 + q8 * 4 + 3]);
+          }
+          if (TAIL && cq == 3) p_t = fast_ex2(fmaf(a_t, c2, -l2));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        asm volatile("bar.sync 2, 512;" ::: "memory");     // publishes s_dd (under the dV / dP MMAs)
+        const float Dr = (s_dd[r] + s_dd[128 + r]) + (s_dd[256 + r] + s_dd[384 + r]);
+        // ---------------- pass 2: dS = P (dP - D) / 8 ----------------
+        mbar_wait(bar_dp, g & 1, 183);
+        tc_fence_after();
+        {
+          const float nDsc = -Dr * 0.125f;
+          uint32_t v[2][16];
+          tmem_ld16(tcol, v[0]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            tmem_ld_wait();
+            if (q + 1 < 4) tmem_ld16(tcol + (q + 1) * 16, v[(q + 1) & 1]);
+#pragma unroll
+            for (int q8 = 0; q8 < 2; ++q8) {
+              float d[8];
+#pragma unroll
+              for (int u = 0; u < 8; u += 2) {
+                const int i = q8 * 8 + u;
+                const float2 pp = unpackc<FMT>(pk[q * 8 + i / 2]);
+                d[u] = pp.x * fmaf(__uint_as_float(v[q & 1][i]), 0.125f, nDsc);
+                d[u + 1] = pp.y * fmaf(__uint_as_float(v[q & 1][i + 1]), 0.125f, nDsc);
+              }
+              *reinterpret_cast<uint4*>(prow + ((((uint32_t)(q * 2 + q8)) << 4) ^ rx)) =
+                  make_uint4(packc<FMT>(d[0], d[1]), packc<FMT>(d[2], d[3]),
+                             packc<FMT>(d[4], d[5]), packc<FMT>(d[6], d[7]));
+            }
+          }
+          if (TAIL && cq == 3) {
+            s_tt[r] = p_t;
+            s_tt[128 + r] = p_t * (b_t - Dr) * 0.125f;
+          }
+        }
+        if (TAIL) {
+          // peeled KEY row (kv = 256): dv_256 += sum_q p_t[q] dO_q ; dk_256 += sum_q ds_t[q] Q_q
+          asm volatile("bar.sync 2, 512;" ::: "memory");
+          const int d = tid & 63, qt = tid >> 6;      // 8 groups of 16 rows
+          for (int q = qt * 16; q < qt * 16 + 16; ++q) {
+            tdv = fmaf(s_tt[q], swz_at<FMT>(tdo, q, d), tdv);
+            tdk = fmaf(s_tt[128 + q], swz_at<FMT>(tq, q, d), tdk);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(bar_p);
+        // ---------------- dQ epilogue: 16 columns per thread ----------------
+        mbar_wait(bar_acc, g & 1, 184);
+        tc_fence_after();
+        {
+          const float dst = TAIL ? s_tt[128 + r] : 0.f;
+          uint32_t v0[16];
+          tmem_ld16(ts + TR + cq * 16, v0);
+          tmem_ld_wait();
+          uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + grow * 3 * W + colQ + h * 64 + cq * 16);
+#pragma unroll
+          for (int q8 = 0; q8 < 2; ++q8) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v0[q8 * 8 + i]);
+            if (TAIL) {
+              const uint4 tu = *reinterpret_cast<const uint4*>(tv0 + cq * 16 + q8 * 8);
+              const uint32_t* ta = &tu.x;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = unpackc<FMT>(ta[i]);
+                o[2 * i] = fmaf(dst, y.x, o[2 * i]);
+                o[2 * i + 1] = fmaf(dst, y.y, o[2 * i + 1]);
+              }
+            }
+            dst4[q8] = make_uint4(packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
+                                  packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(bar_acc_free);
+      }
+      // ---------------- dK / dV epilogue: cq 0,1 -> dV tiles 0,1 ; cq 2,3 -> dK tiles 0,1 --------
+      uint4 tv_next = make_uint4(0u, 0u, 0u, 0u);
+      const bool tv_fetch = TAIL && tid < 40 && item + (int)gridDim.x < n_items;
+      if (tv_fetch) tv_next = *tail_src(item + gridDim.x);
+      mbar_wait(bar_dk, (g - 1) & 1, 185);   // the last tile's dK MMAs (dV retired earlier)
+      tc_fence_after();
+      {
+        const int isk = cq >> 1, jj = cq & 1;
+        const uint32_t base = (isk ? TDK : TDV) + jj * 64;
+        const uint16_t* tvx = isk ? tv2 : tv3;            // rank-1 term of the peeled query row
+        const int kv = jj * 128 + r;
+        uint32_t v0[32], v1[32];
+        tmem_ld32(ts + base, v0);
+        tmem_ld32(ts + base + 32, v1);
+        tmem_ld_wait();
+        const float w = TAIL ? (isk ? s_ds256[kv] : s_p256[kv]) : 0.f;
+        uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + ((size_t)b * T + kv) * 3 * W +
+                                               (isk ? colK : colV) + h * 64);
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) {
+          const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
+          if (TAIL) {
+            const uint4 tu = *reinterpret_cast<const uint4*>(tvx + q8 * 8);
+            const uint32_t* ta = &tu.x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 y = unpackc<FMT>(ta[i]);
+              o[2 * i] = fmaf(w, y.x, o[2 * i]);
+              o[2 * i + 1] = fmaf(w, y.y, o[2 * i + 1]);
+            }
+          }
+          dst4[q8] = make_uint4(packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
+                                packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_kv_free);
+      if (TAIL) {
+        // dk_256 / dv_256: reduce the eight row-group partials
+        const int d = tid & 63, qt = tid >> 6;
+        s_part[qt * 64 + d] = tdv;
+        s_part[512 + qt * 64 + d] = tdk;
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        if (tid < 64) {
+          const int which = tid >> 5, l2i = tid & 31;   // 0: dv, 1: dk
+          const float* pp = s_part + which * 512;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            a0 += pp[q * 64 + 2 * l2i];
+            a1 += pp[q * 64 + 2 * l2i + 1];
+          }
+          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W +
+                                      (which ? colK : colV) + h * 64)[l2i] = packc<FMT>(a0, a1);
+        }
+      }
+      if (tv_fetch) *reinterpret_cast<uint4*>(s_tv + ((it + 1) & 1) * 320 + tid * 8) = tv_next;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AT4_CTRL_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int FMT, bool TAIL>
+static int launch_bwd4(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                       const AttnBwd2Params& P, const float* lse_fwd, cudaStream_t st) {
+  auto kern = attn_bwd4_kernel<FMT, TAIL>;
+  const size_t smem = (size_t)2 * 256 * 128 + 4 * 16384 + (size_t)4 * 16384 +
+                      (272 * 2 + 512 + 256 + 1024) * 4 + 2 * 640 + 128 + 1024;
+  static DeviceOnce attr;
+  if (!attr.done()) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return -(int)e - 1000;
+    attr.mark();
+  }
+  int grid = sm_count();
+  if (P.B * P.H < grid) grid = P.B * P.H;
+  kern<<<grid, AT4_THREADS, smem, st>>>(a, b, c, P, lse_fwd);
+  count_launch(1);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
 struct AttnPlan {
   AttnParams P;
   size_t smem;
@@ -2638,6 +3115,46 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
+}
+
+extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16,
+                             float* lse_tmp, void* dqkv16, int B, int T, int H, int fmt_qkv,
+                             int fmt_o, int fmt_g, void* stream);
+
+// Backward given the forward's log-sum-exp (rvlm_attn_fwd's `lse`), valid when qkv16 holds the
+// very bits the forward multiplied (same format, not split): version 4 for T in {256, 257},
+// otherwise the statistics are recomputed by rvlm_attn_bwd (lse is then used as its scratch).
+extern "C" int rvlm_attn_bwd_lse(const void* qkv16, const void* o16, const void* do16, float* lse,
+                                 void* dqkv16, int B, int T, int H, int fmt_qkv, int fmt_o,
+                                 int fmt_g, void* stream) {
+  if (fmt_qkv != fmt_g) return RVLM_ERR_UNSUPPORTED;
+  if (!lse) return RVLM_ERR_INVAL;
+  const char* e4 = getenv("RVLM_ATTN_BWD4");   // default on; RVLM_ATTN_BWD4=0 selects version 3
+  const bool use_v4 = !(e4 && e4[0] == '0');   // (read per call: the tests cover both)
+  if (!use_v4 || (T != 257 && T != 256))
+    return rvlm_attn_bwd(qkv16, o16, do16, lse, dqkv16, B, T, H, fmt_qkv, fmt_o, fmt_g, stream);
+  AttnBwd2Params P{};
+  P.B = B; P.T = T; P.H = H; P.W = H * 64;
+  P.tm = 256; P.kvm = 256; P.nblk = 4; P.ntile = 2;
+  P.tail = T > 256 ? 1 : 0;
+  P.fmt_o = fmt_o;
+  P.qkv = reinterpret_cast<const uint16_t*>(qkv16);
+  P.o = reinterpret_cast<const uint16_t*>(o16);
+  P.d_o = reinterpret_cast<const uint16_t*>(do16);
+  P.lse_tmp = nullptr;
+  P.dqkv = reinterpret_cast<uint16_t*>(dqkv16);
+  CUtensorMap tmTile, tmFull, tmDoTile;
+  const uint64_t W3 = 3ull * P.W, Wd = P.W;
+  int rc = make_tmap_3d(&tmTile, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 128);
+  if (!rc) rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, 256);
+  if (!rc) rc = make_tmap_3d(&tmDoTile, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T == 257)
+    return fmt_g ? launch_bwd4<1, true>(tmTile, tmFull, tmDoTile, P, lse, st)
+                 : launch_bwd4<0, true>(tmTile, tmFull, tmDoTile, P, lse, st);
+  return fmt_g ? launch_bwd4<1, false>(tmTile, tmFull, tmDoTile, P, lse, st)
+               : launch_bwd4<0, false>(tmTile, tmFull, tmDoTile, P, lse, st);
 }
 
 extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do16,

@@ -29,6 +29,8 @@ extern "C" int rvlm_attn_bwd_simt(const void*, const void*, const void*, float*,
 extern "C" int rvlm_attn_fwd(const void*, void*, float*, int, int, int, int, void*);
 extern "C" int rvlm_attn_bwd(const void*, const void*, const void*, float*, void*, int, int, int,
                              int, int, int, void*);
+extern "C" int rvlm_attn_bwd_lse(const void*, const void*, const void*, float*, void*, int, int,
+                                 int, int, int, int, void*);
 extern "C" int rvlm_layernorm_fwd(const float*, const float*, const float*, void*, float*, float*,
                                   int, int, int, void*);
 extern "C" int rvlm_layernorm_bwd(const float*, const float*, const float*, const float*,
@@ -77,6 +79,10 @@ struct Engine {
   std::vector<LayerDev> layers;
   int ff = 0;        // 16-bit format of the forward operands (fp16 when split)
   int split = 0;     // cfg.fmt_fwd == RVLM_FMT_F16X2: forward operands are fp16 hi + lo pairs
+  // forward and backward multiply the same q | k | v bits (one 16-bit format, forward not split):
+  // ONE q|k|v copy serves both, and the backward takes the forward's softmax statistics as they
+  // are (rvlm_attn_bwd_lse) instead of recomputing them
+  int same_qkv = 0;
   int attn_simt = 0;
   int cls_last = 1;  // last block: class-token row only (flag RVLM_VIT_FULL_LAST_BLOCK / env RVLM_CLS_LAST=0 disable)
   int ln_dz16 = 1;   // attack-path dgrad GEMMs hand LayerNorm' a 16-bit gradient (RVLM_LN_DZ16=0: fp32)
@@ -227,9 +233,13 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     uint16_t* z1 = train ? w.tz16 + (size_t)l * MW : w.y16;
     uint16_t* act = train ? w.tact16 + (size_t)l * M * F : w.act16;
     uint16_t* y1lo = sp ? w.y16lo : nullptr;
+    uint16_t* qf = w.qkvf16;   // q|k|v the forward attention reads
     RV(ln_fwd_strided(x_in, 0, Lw.ln1_g, Lw.ln1_b, y1, nullptr, 0, st1, M, W, ff, st, y1lo));
     {  // q|k|v in the forward format (transient) + the backward's copy in the gradient format
-      EpiStore16Dual epi{w.qkvf16, w.stash ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd,
+      // (same_qkv: the kept copy IS the forward operand -- one store of 2 * 3W bytes per row less)
+      const bool one = E.same_qkv && w.stash;
+      qf = one ? qkv : w.qkvf16;
+      EpiStore16Dual epi{qf, (w.stash && !one) ? qkv : nullptr, 3 * W, Lw.bqkv, ff, E.cfg.fmt_bwd,
                          sp ? w.qkvf16lo : nullptr};
       RV((launch_gemm_fwd(y1, y1lo, W, Lw.wqkv, Lw.wqkv_lo, W, M, 3 * W, W, ff, epi, st)));
     }
@@ -237,7 +247,7 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       // ---- last block, class-token rows only (row pitch T*W inside the [B*T, W] streams; the
       // per-row operands of the MLP live compactly in the first B rows of their buffers)
       const long long TW = (long long)E.T * W;
-      RV(attn_cls_fwd(w.qkvf16, o, B, E.T, E.H, ff, st, sp ? w.qkvf16lo : nullptr,
+      RV(attn_cls_fwd(qf, o, B, E.T, E.H, ff, st, sp ? w.qkvf16lo : nullptr,
                       sp ? w.o16lo : nullptr));
       {
         EpiStore32 epi{xm, (int)TW, Lw.bo, x_in, (int)TW};
@@ -258,9 +268,9 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       }
       break;
     }
-    if (sp) RV(attn_fwd_split(w.qkvf16, w.qkvf16lo, o, w.o16lo, lse, B, E.T, E.H, st));
-    else if (E.attn_simt) RV(rvlm_attn_fwd_simt(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
-    else RV(rvlm_attn_fwd(w.qkvf16, o, lse, B, E.T, E.H, ff, stv));
+    if (sp) RV(attn_fwd_split(qf, w.qkvf16lo, o, w.o16lo, lse, B, E.T, E.H, st));
+    else if (E.attn_simt) RV(rvlm_attn_fwd_simt(qf, o, lse, B, E.T, E.H, ff, stv));
+    else RV(rvlm_attn_fwd(qf, o, lse, B, E.T, E.H, ff, stv));
     {
       EpiStore32 epi{xm, W, Lw.bo, x_in, W};
       RV((launch_gemm_fwd(o, sp ? w.o16lo : nullptr, W, Lw.wo, Lw.wo_lo, W, M, W, W, ff, epi, st)));
@@ -391,6 +401,8 @@ int run_backward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     }
     if (E.attn_simt)
       RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
+    else if (E.same_qkv)   // `lse` holds the forward's statistics of exactly these q | k bits
+      RV(rvlm_attn_bwd_lse(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     if (E.ln_dz16) {  // d ln_1 output
       EpiStore16 epi{w.do16, W, nullptr, fg};
@@ -468,6 +480,8 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
     }
     if (E.attn_simt)
       RV(rvlm_attn_bwd_simt(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
+    else if (E.same_qkv)
+      RV(rvlm_attn_bwd_lse(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     else RV(rvlm_attn_bwd(qkv, o, w.do16, lse, w.dqkv16, B, E.T, E.H, fg, ff, fg, stv));
     // attn.in_proj: dY = dqkv
     RV(wgrad(w.dqkv16, 3 * W, y1, W, M, fg, g->attn_in_proj_weight[l], st));
@@ -596,6 +610,7 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
   if (cfg->fmt_bwd != RVLM_FMT_F16 && cfg->fmt_bwd != RVLM_FMT_BF16) { delete E; return RVLM_ERR_INVAL; }
   E->split = cfg->fmt_fwd == RVLM_FMT_F16X2 ? 1 : 0;
   E->ff = E->split ? RVLM_FMT_F16 : cfg->fmt_fwd;
+  E->same_qkv = (!E->split && cfg->fmt_fwd == cfg->fmt_bwd) ? 1 : 0;
   E->W = cfg->width; E->D = cfg->out_dim; E->L = cfg->layers; E->H = cfg->heads; E->F = cfg->mlp;
   const int g = cfg->image / cfg->patch;
   E->np = g * g;

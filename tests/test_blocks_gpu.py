@@ -312,3 +312,46 @@ def test_attention_fwd_split(B, T, H):
     lse_err = float((lse.double() - torch.logsumexp(s, -1)).abs().max())
     _log("attn_fwd_split", B=B, T=T, H=H, rel_err=err, rel_err_hi_only=err_hi, lse_err=lse_err)
     assert err < 5e-6 and lse_err < 1e-4
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+@pytest.mark.parametrize("B,T,H", [(3, 257, 4), (1, 257, 16), (2, 256, 4), (40, 257, 8), (37, 257, 16)])
+def test_attention_bwd_with_forward_lse(B, T, H, fmt):
+    """rvlm_attn_bwd_lse (version 4: no statistics recomputed, 16 worker warps) on the same q | k | v
+    bits the forward used, vs autograd through the fp32 reference and vs the self-normalising
+    version 3 on identical inputs."""
+    nat = _nat()
+    torch.manual_seed(B * T + H + fmt)
+    W = H * 64
+    dt = _dt(fmt)
+    qkv = (torch.randn(B * T, 3 * W, device="cuda") * 1.5).to(dt)
+    o = torch.empty(B * T, W, device="cuda", dtype=dt)
+    lse = torch.empty(B, H, T, device="cuda")
+    nat.call("rvlm_attn_fwd", nat.ptr(qkv), nat.ptr(o), nat.ptr(lse), nat.c_int(B), nat.c_int(T),
+             nat.c_int(H), nat.c_int(fmt), nat.stream_ptr())
+    d_o = (torch.randn(B * T, W, device="cuda") * 0.1).to(dt)
+    qf = qkv.float().requires_grad_(True)
+    o_ref, _ = _attn_ref(qf, B, T, H)
+    (dqkv_ref,) = torch.autograd.grad(o_ref, qf, d_o.float())
+    out = {}
+    for tag, fn, env in (("v4", "rvlm_attn_bwd_lse", "1"), ("v3", "rvlm_attn_bwd_lse", "0")):
+        os.environ["RVLM_ATTN_BWD4"] = env
+        dqkv = torch.full((B * T, 3 * W), float("nan"), device="cuda", dtype=dt)
+        lse_in = lse.clone()
+        try:
+            nat.call(fn, nat.ptr(qkv), nat.ptr(o), nat.ptr(d_o), nat.ptr(lse_in), nat.ptr(dqkv),
+                     nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.c_int(fmt), nat.c_int(fmt),
+                     nat.c_int(fmt), nat.stream_ptr())
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("RVLM_ATTN_BWD4", None)
+        out[tag] = dqkv.float()
+    scale = dqkv_ref.abs().max().item()
+    e4 = (out["v4"] - dqkv_ref).abs().max().item()
+    e3 = (out["v3"] - dqkv_ref).abs().max().item()
+    rel4 = float((out["v4"] - dqkv_ref).norm() / dqkv_ref.norm())
+    rel3 = float((out["v3"] - dqkv_ref).norm() / dqkv_ref.norm())
+    _log("attn_bwd4", B=B, T=T, H=H, fmt=fmt, err_v4=e4, err_v3=e3, rel_v4=rel4, rel_v3=rel3,
+         scale=scale)
+    assert torch.isfinite(out["v4"]).all()
+    assert e4 <= (3e-2 if fmt else 6e-3) * scale and rel4 <= 1.3 * rel3 + 1e-4

@@ -51,6 +51,32 @@ def main():
            "err_o": float((o[: nb * T].float() - o_ref).abs().max()),
            "err_o_last": float((o[-T:].float() - o_ref2).abs().max()),
            "err_lse": float((lse[:nb] - lse_ref).abs().max())}
+    # backward at the same shape: version 4 (forward lse, 16 worker warps), version 3 (self-normalising)
+    d_o = (torch.randn(B * T, W, device="cuda") * 0.1).to(dt)
+    dqkv = torch.empty(B * T, 3 * W, device="cuda", dtype=dt)
+
+    def bwd(fn, env):
+        os.environ["RVLM_ATTN_BWD4"] = env
+        lse_in = lse.clone()
+        c = lambda: nat.call(fn, nat.ptr(qkv), nat.ptr(o), nat.ptr(d_o), nat.ptr(lse_in),  # noqa: E731
+                             nat.ptr(dqkv), nat.c_int(B), nat.c_int(T), nat.c_int(H),
+                             nat.c_int(args.fmt), nat.c_int(args.fmt), nat.c_int(args.fmt),
+                             nat.stream_ptr())
+        for _ in range(3):
+            c()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.reps):
+            c()
+        b.record()
+        torch.cuda.synchronize()
+        os.environ.pop("RVLM_ATTN_BWD4", None)
+        return a.elapsed_time(b) * 1e3 / args.reps, dqkv.float().clone()
+    us4, g4 = bwd("rvlm_attn_bwd_lse", "1")
+    us3, g3 = bwd("rvlm_attn_bwd_lse", "0")
+    res.update(bwd4_us=us4, bwd3_us=us3, bwd4_vs_bwd3_rel=float((g4 - g3).norm() / g3.norm()),
+               bwd4_tflops=10.0 * B * H * T * T * 64 / (us4 * 1e-6) / 1e12)
     print(json.dumps(res), flush=True)
 
 

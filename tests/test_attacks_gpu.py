@@ -80,9 +80,10 @@ def test_pgd_fare(path, norm, eps, step):
     same = float(((out - x) == (ref - x)).float().mean())
     _log("pgd_fare", path=path, norm=norm, same=same, loss_ours=l_ours, loss_ref=l_ref,
          max_abs_err=float((out - ref).abs().max()))
-    assert abs(l_ours - l_ref) <= 0.05 * abs(l_ref)
+    # measured (profiles/r02_test_metrics.jsonl): loss within 7e-7 relative, 99.937 % of delta identical
+    assert abs(l_ours - l_ref) <= 1e-5 * abs(l_ref)
     if norm == "linf":
-        assert same > 0.9
+        assert same > 0.9987
 
 
 def test_pgd_tecoa_ce():
@@ -103,7 +104,7 @@ def test_pgd_tecoa_ce():
     l_ref = _loss_after(ref_m, wrap_ref, ref, y, True)
     same = float(((out - x) == (ref - x)).float().mean())
     _log("pgd_tecoa", same=same, loss_ours=l_ours, loss_ref=l_ref)
-    assert same > 0.9 and abs(l_ours - l_ref) <= 0.05 * abs(l_ref)
+    assert same > 0.9987 and abs(l_ours - l_ref) <= 1e-5 * abs(l_ref)    # measured 0.99938, 1.5e-6
 
 
 @pytest.mark.parametrize("norm,eps", [("linf", 4 / 255), ("l2", 2.0)])
@@ -129,7 +130,7 @@ def test_apgd_train(norm, eps):
         assert float((out - x).abs().max()) <= eps + 1e-6
     else:
         assert float((out - x).flatten(1).norm(dim=1).max()) <= eps * (1 + 1e-4)
-    assert l_ours >= 0.9 * l_ref
+    assert abs(l_ours - l_ref) <= 2e-5 * abs(l_ref)                       # measured 7.5e-6 / 4.8e-6
 
 
 @pytest.mark.parametrize("norm,eps", [("Linf", 4 / 255), ("L2", 2.0)])
@@ -145,7 +146,9 @@ def test_apgd_attack_perturb(norm, eps):
     with torch.no_grad():
         logits_ref = cm_ref(x)
         logits = cm(x.cuda()).cpu()
-    assert float((logits - logits_ref).abs().max()) < 0.05 * float(logits_ref.abs().max())
+    _log("apgd_attack_logits", norm=norm, err=float((logits - logits_ref).abs().max()),
+         scale=float(logits_ref.abs().max()))
+    assert float((logits - logits_ref).abs().max()) < 1e-3 * float(logits_ref.abs().max())
     y = logits_ref.argmax(1)
     R = oa.APGDAttack(cm_ref, n_iter=20, norm=norm, n_restarts=2, eps=eps, seed=0, alpha=2.0)
     A = attacks.APGDAttack(cm, n_iter=20, norm=norm, n_restarts=2, eps=eps, seed=0, alpha=2.0)
@@ -159,7 +162,7 @@ def test_apgd_attack_perturb(norm, eps):
     assert out.min() >= 0 and out.max() <= 1
     if norm == "Linf":
         assert float((out - x).abs().max()) <= eps + 1e-6
-    assert racc_ours <= racc_ref + 0.34
+    assert abs(racc_ours - racc_ref) < 1e-6            # the same points end up fooled
 
 
 @pytest.mark.parametrize("loss", ["dlr", "dlr-targeted"])

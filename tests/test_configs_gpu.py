@@ -29,24 +29,31 @@ def _log(name, **kw):
     print(name, kw)
 
 
-def _ours(o):
+def _ours(o, precision=None):
     from robustvlm_b200 import model as rm
     cfg = o.cfg if hasattr(o, "cfg") else None
     vt = rm.VisionTransformer(dict(image=cfg.image_size, patch=cfg.patch, width=cfg.width,
                                    layers=cfg.layers, heads=cfg.heads, mlp=cfg.mlp,
-                                   out_dim=cfg.out_dim))
+                                   out_dim=cfg.out_dim), precision=precision)
     vt.load_state_dict(o.state_dict())
     return rm.ClipVisionModel(vt.cuda(), None, None).eval()
 
 
-def test_config1_vitb32_one_step_pgd():
+# config 1 is FARE's cancellation site (the frozen copy equals the model): the forward precision
+# decides it.  Measured (profiles/r02_test_metrics.jsonl): fast16 1.07 % of delta entries differ,
+# 0.25 % of those with |g| > 0.05 median; split (fp32-class forward): see LIMITS1.
+LIMITS1 = {"fast16": (2.2e-2, 5e-3), "split": (2e-3, 5e-4)}
+
+
+@pytest.mark.parametrize("mode", ["fast16", "split"])
+def test_config1_vitb32_one_step_pgd(mode):
     from robustvlm_b200 import _native as nat
     from robustvlm_b200 import attacks, model as rm
     from robustvlm_b200._native import c_float, c_int, c_int64
     torch.manual_seed(0)                                  # train/adversarial_training_clip.py:532
     o = ovit.build("ViT-B-32", seed=0)
     ref_m = ovit.ClipVisionModel(o).eval()
-    ours = _ours(o)
+    ours = _ours(o, mode)
     B, eps, step = 4, 4 / 255, 1 / 255
     g = torch.Generator().manual_seed(0)
     x = torch.rand(B, 3, 224, 224, generator=g)
@@ -75,10 +82,10 @@ def test_config1_vitb32_one_step_pgd():
     med = g_ref.abs().median()
     big = g_ref.abs() > 0.05 * med
     frac, frac_big = float(mism.float().mean()), float((mism & big).float().sum() / big.sum())
-    _log("config1_vitb32", mismatch=int(mism.sum()), n=mism.numel(), frac=frac, frac_big=frac_big,
+    _log("config1_vitb32", mode=mode, mismatch=int(mism.sum()), n=mism.numel(), frac=frac, frac_big=frac_big,
          max_abs_delta_err=float(((out - x) - (ref - x)).abs().max()))
     assert float((out - x).abs().max()) <= eps + 1e-6 and out.min() >= 0 and out.max() <= 1
-    assert frac < 0.04 and frac_big < 0.01
+    assert frac < LIMITS1[mode][0] and frac_big < LIMITS1[mode][1]
 
 
 @pytest.fixture(scope="module")

@@ -60,7 +60,7 @@ def test_golden_pgd_fare_linf(gold, models):
         l_r = float(w(ref_m(ref, output_normalize=False), y))
     _log("golden_pgd_fare_linf", same=same, loss_ours=l_o, loss_ref=l_r)
     assert float((out - x).abs().max()) <= 4 / 255 + 1e-6 and out.min() >= 0 and out.max() <= 1
-    assert same > 0.97 and abs(l_o - l_r) <= 0.02 * abs(l_r)
+    assert same > 0.9979 and abs(l_o - l_r) <= 1e-5 * abs(l_r)           # measured 0.99897, 5e-7
 
 
 def test_golden_pgd_fare_l2_and_tecoa_min(gold, models):
@@ -79,7 +79,7 @@ def test_golden_pgd_fare_l2_and_tecoa_min(gold, models):
     ref2 = gold["pgd_tecoa_linf_min"]
     same = float(((out2 - x) == (ref2 - x)).float().mean())
     _log("golden_pgd_tecoa_min", same=same)
-    assert same > 0.97
+    assert same > 0.9987                                                  # measured 0.99935
 
 
 @pytest.mark.parametrize("norm,eps", [("linf", 4 / 255), ("l2", 1.0)])

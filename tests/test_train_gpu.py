@@ -44,8 +44,10 @@ def test_param_grads_match_autograd(name, loss):
     spec = LossSpec(loss, normalize, emb_orig=e_orig.cuda(), text=text.cuda(), targets=y.cuda())
     loss_b, _ = eng.train_grads(x.cuda(), spec, grads, 1.0 / B)
     torch.cuda.synchronize()
-    assert abs(float(loss_b.mean()) - float(lval)) <= 0.05 * abs(float(lval))
+    loss_rel = abs(float(loss_b.mean()) - float(lval.detach())) / abs(float(lval.detach()))
+    assert loss_rel <= 5e-3                                  # bf16 forward of the outer step
     worst = ("", 1.0)
+    worst_ratio = 0.0
     for k, r in ref.items():
         gk = grads[k].cpu()
         assert torch.isfinite(gk).all(), k
@@ -53,9 +55,11 @@ def test_param_grads_match_autograd(name, loss):
         ratio = float(gk.norm() / r.norm().clamp_min(1e-30))
         if float(cos) < worst[1]:
             worst = (k, float(cos))
-        assert float(cos) > 0.97, (k, float(cos))
-        assert 0.9 < ratio < 1.1, (k, ratio)
-    _log("param_grads", model=name, loss=loss, worst_key=worst[0], worst_cos=worst[1])
+        worst_ratio = max(worst_ratio, abs(ratio - 1.0))
+        assert float(cos) > 0.99996, (k, float(cos))         # measured worst 0.99998
+        assert 0.98 < ratio < 1.02, (k, ratio)
+    _log("param_grads", model=name, loss=loss, worst_key=worst[0], worst_cos=worst[1],
+         worst_norm_ratio_err=worst_ratio, loss_rel_err=loss_rel)
 
 
 def test_adamw_matches_torch():
@@ -163,7 +167,7 @@ def test_trainer_follows_reference_loop():
     assert lrs_o == lrs_r and lrs_o[0] == lr
     assert ref[-1] < 0.9 * ref[0]
     for a, b in zip(ours, ref):
-        assert abs(a - b) <= 0.03 * abs(b), (ours, ref)
+        assert abs(a - b) <= 2e-3 * abs(b), (ours, ref)      # measured <= 8.1e-4 over six steps
 
 
 @pytest.mark.parametrize("variant", ["clean_weight", "trades", "apgd_tecoa", "sgd"])

@@ -2303,6 +2303,19 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
     asm volatile("bar.sync 1, 512;" ::: "memory");
     uint32_t g = 0;
     int it = 0;
+    // this thread's quarter of the o row of the NEXT tile (D_r = o_r . dO_r), always requested
+    // one tile ahead so that its HBM / L2 latency never shows
+    auto o_src = [&](int item_, int j_) -> const uint4* {
+      const int b_ = item_ / P.H, h_ = item_ % P.H;
+      return reinterpret_cast<const uint4*>(P.o + ((size_t)b_ * T + j_ * 128 + r) * W + h_ * 64 +
+                                            cq * 16);
+    };
+    uint4 o_nx0 = make_uint4(0u, 0u, 0u, 0u), o_nx1 = o_nx0;
+    if ((int)blockIdx.x < n_items) {
+      const uint4* po = o_src(blockIdx.x, 0);
+      o_nx0 = po[0];
+      o_nx1 = po[1];
+    }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / P.H, h = item % P.H;
       const float* lse_row = lse_fwd + ((size_t)b * P.H + h) * T;
@@ -2318,17 +2331,17 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         const float l2 = __ldg(lse_row + 256) * LOG2E;
         const float D = dot_rows16(tv4, P.fmt_o, tv3, FMT);
         mbar_wait(bar_full, it & 1, 180);
-        if (tid < 256) {
+        if (tid < 256) {   // key tid: probability and dS of row 256 (both dot products, no exchange)
           const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
-          s_p256[tid] = fast_ex2(fmaf(sv, c2, -l2));
-          if (tid == 0) s_p256[256] = fast_ex2(fmaf(dot_vec<FMT>(tv0, tv2), c2, -l2));
-        } else {
-          s_ds256[tid - 256] = dot_swz_row<FMT>(s_v, tid - 256, tv3);     // dP[256, kv]
-          if (tid == 256) s_ds256[256] = dot_vec<FMT>(tv1, tv3);
+          const float dpv = dot_swz_row<FMT>(s_v, tid, tv3);
+          const float pv = fast_ex2(fmaf(sv, c2, -l2));
+          s_p256[tid] = pv;
+          s_ds256[tid] = pv * (dpv - D) * 0.125f;
+        } else if (tid == 256) {   // key 256
+          const float pv = fast_ex2(fmaf(dot_vec<FMT>(tv0, tv2), c2, -l2));
+          s_p256[256] = pv;
+          s_ds256[256] = pv * (dot_vec<FMT>(tv1, tv3) - D) * 0.125f;
         }
-        asm volatile("bar.sync 3, 512;" ::: "memory");
-        if (tid < 256) s_ds256[tid] = s_p256[tid] * (s_ds256[tid] - D) * 0.125f;
-        if (tid == 256) s_ds256[256] = s_p256[256] * (s_ds256[256] - D) * 0.125f;
         asm volatile("bar.sync 3, 512;" ::: "memory");
         {
           const int d = tid & 63, qt = tid >> 6;       // 8 groups of 32 keys
@@ -2353,8 +2366,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64)[tid] =
               packc<FMT>(a0, a1);
         }
-        asm volatile("bar.sync 3, 512;" ::: "memory");
-        mbar_arrive(bar_trow);
+        mbar_arrive(bar_trow);   // (each thread after its own last read of K / V)
       }
       for (int j = 0; j < ntile; ++j, ++g) {
         const int buf = g & 1;
@@ -2363,12 +2375,14 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         uint8_t* tq = s_tile0 + buf * 16384;
         uint8_t* tdo = s_tile1 + buf * 16384;
         const float l2 = __ldg(lse_row + row) * LOG2E;
-        // this thread's quarter of the o row (D_r = o_r . dO_r), requested early
-        uint4 g_o[2];
-        {
-          const uint4* po = reinterpret_cast<const uint4*>(P.o + grow * W + h * 64 + cq * 16);
-          g_o[0] = po[0];
-          g_o[1] = po[1];
+        uint4 g_o[2] = {o_nx0, o_nx1};
+        {   // request the next tile's quarter now
+          const int nitem = (j + 1 < ntile) ? item : item + (int)gridDim.x;
+          if (nitem < n_items) {
+            const uint4* po = o_src(nitem, (j + 1 < ntile) ? j + 1 : 0);
+            o_nx0 = po[0];
+            o_nx1 = po[1];
+          }
         }
         mbar_wait(&bar_tile[buf], (g >> 1) & 1, 181);
         float a_t = 0.f, b_t = 0.f;
@@ -2503,6 +2517,11 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       uint4 tv_next = make_uint4(0u, 0u, 0u, 0u);
       const bool tv_fetch = TAIL && tid < 40 && item + (int)gridDim.x < n_items;
       if (tv_fetch) tv_next = *tail_src(item + gridDim.x);
+      if (TAIL) {   // dk_256 / dv_256 partials of the eight row groups (reduced after the barrier)
+        const int d = tid & 63, qt = tid >> 6;
+        s_part[qt * 64 + d] = tdv;
+        s_part[512 + qt * 64 + d] = tdk;
+      }
       mbar_wait(bar_dk, (g - 1) & 1, 185);   // the last tile's dK MMAs (dV retired earlier)
       tc_fence_after();
       {
@@ -2515,51 +2534,54 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         tmem_ld32(ts + base + 32, v1);
         tmem_ld_wait();
         const float w = TAIL ? (isk ? s_ds256[kv] : s_p256[kv]) : 0.f;
-        uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + ((size_t)b * T + kv) * 3 * W +
-                                               (isk ? colK : colV) + h * 64);
+        uint16_t* dstp = P.dqkv + ((size_t)b * T + kv) * 3 * W + (isk ? colK : colV) + h * 64;
 #pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8) {
-          const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
-          float o[8];
+        for (int q16 = 0; q16 < 4; ++q16) {   // 16 columns = one 32-byte sector per store
+          uint32_t pkd[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
-          if (TAIL) {
-            const uint4 tu = *reinterpret_cast<const uint4*>(tvx + q8 * 8);
-            const uint32_t* ta = &tu.x;
+          for (int q8 = 0; q8 < 2; ++q8) {
+            const int c8 = q16 * 2 + q8;
+            const uint32_t* sv = c8 < 4 ? &v0[c8 * 8] : &v1[(c8 - 4) * 8];
+            float o[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 y = unpackc<FMT>(ta[i]);
-              o[2 * i] = fmaf(w, y.x, o[2 * i]);
-              o[2 * i + 1] = fmaf(w, y.y, o[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
+            if (TAIL) {
+              const uint4 tu = *reinterpret_cast<const uint4*>(tvx + c8 * 8);
+              const uint32_t* ta = &tu.x;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 y = unpackc<FMT>(ta[i]);
+                o[2 * i] = fmaf(w, y.x, o[2 * i]);
+                o[2 * i + 1] = fmaf(w, y.y, o[2 * i + 1]);
+              }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pkd[q8 * 4 + i] = packc<FMT>(o[2 * i], o[2 * i + 1]);
           }
-          dst4[q8] = make_uint4(packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
-                                packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dstp + q16 * 16),
+                       "r"(pkd[0]), "r"(pkd[1]), "r"(pkd[2]), "r"(pkd[3]), "r"(pkd[4]), "r"(pkd[5]),
+                       "r"(pkd[6]), "r"(pkd[7])
+                       : "memory");
         }
       }
       tc_fence_before();
       mbar_arrive(bar_kv_free);
-      if (TAIL) {
-        // dk_256 / dv_256: reduce the eight row-group partials
-        const int d = tid & 63, qt = tid >> 6;
-        s_part[qt * 64 + d] = tdv;
-        s_part[512 + qt * 64 + d] = tdk;
-        asm volatile("bar.sync 3, 512;" ::: "memory");
-        if (tid < 64) {
-          const int which = tid >> 5, l2i = tid & 31;   // 0: dv, 1: dk
-          const float* pp = s_part + which * 512;
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            a0 += pp[q * 64 + 2 * l2i];
-            a1 += pp[q * 64 + 2 * l2i + 1];
-          }
-          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W +
-                                      (which ? colK : colV) + h * 64)[l2i] = packc<FMT>(a0, a1);
-        }
-      }
       if (tv_fetch) *reinterpret_cast<uint4*>(s_tv + ((it + 1) & 1) * 320 + tid * 8) = tv_next;
+      // one barrier per item: publishes the partials and the next item's peeled vectors, and orders
+      // this item's reads of s_p256 / s_ds256 before the next item's writes
       asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (TAIL && tid < 64) {
+        const int which = tid >> 5, l2i = tid & 31;   // 0: dv, 1: dk
+        const float* pp = s_part + which * 512;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a0 += pp[q * 64 + 2 * l2i];
+          a1 += pp[q * 64 + 2 * l2i + 1];
+        }
+        reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W +
+                                    (which ? colK : colV) + h * 64)[l2i] = packc<FMT>(a0, a1);
+      }
     }
   }
 
@@ -2589,485 +2611,6 @@ static int launch_bwd4(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   kern<<<grid, AT4_THREADS, smem, st>>>(a, b, c, P, lse_fwd);
   count_launch(1);
   cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? 0 : -(int)e - 1000;
-}
-
-// =====================================================================================
-// Backward, version 5 (T in {256, 257}; the forward's log-sum-exp is given): version 4 split
-// over the KEY dimension so that TWO CTAs share an SM.  ncu on version 4 (profiles/
-// r02_attn_bwd4_ncu.txt): tensor pipe 13 %, issue slots 33 %, the rest of the time every warp of
-// the one resident CTA waits on the same hand-off (dV + dP MMAs 8 %, dQ MMA 6 %, TMA 3 %, o-row
-// loads 7 %, barriers 10 %): one serial chain per SM.  Here a work item is (image, head, key half
-// jj): the CTA keeps K_jj, V_jj (128 keys) and the dK_jj / dV_jj accumulators, walks the two
-// 128-row query tiles and ADDS its partial dQ_i = dS_i[:, half] K_jj into the (zeroed) output with
-// 16-byte vector reductions (two addends per element: the result does not depend on their
-// order).  Per CTA: 104 KB of shared memory, 256 TMEM columns ([0,128) S / dP / dQ, [128,192) dV,
-// [192,256) dK), 8 worker warps (two threads per row, 64 columns each) -- so two CTAs are
-// resident per SM and one computes while the other waits.  Neighbouring CTAs hold the two key
-// halves of one (image, head) at the same time (Q / dO tiles hit in L2).
-// =====================================================================================
-constexpr int AT5_THREADS = 288;   // 8 worker warps + 1 control warp
-constexpr int AT5_CTRL_WARP = 8;
-
-template <int FMT>
-__device__ __forceinline__ void red_add16x8(uint16_t* dst, uint32_t a, uint32_t b, uint32_t c,
-                                            uint32_t d) {
-  if (FMT)
-    asm volatile("red.global.v4.bf16x2.add.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(a),
-                 "r"(b), "r"(c), "r"(d)
-                 : "memory");
-  else
-    asm volatile("red.global.v4.f16x2.add.noftz [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(a),
-                 "r"(b), "r"(c), "r"(d)
-                 : "memory");
-}
-
-template <int FMT, bool TAIL>
-__global__ void __launch_bounds__(AT5_THREADS, 2)
-attn_bwd5_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
-                 const __grid_constant__ CUtensorMap tmDoTile, // dO,  box 64 x 128
-                 AttnBwd2Params P, const float* __restrict__ lse_fwd) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int T = P.T, W = P.W;
-  uint8_t* s_k = smem;                 // [128][64] K_jj
-  uint8_t* s_v = s_k + 16384;          // [128][64] V_jj
-  uint8_t* s_q = s_v + 16384;          // [128][64] Q_i
-  uint8_t* s_do = s_q + 16384;         // [128][64] dO_i
-  uint8_t* s_p = s_do + 16384;         // [2][16384] P, then dS  (128 q rows x 128 keys)
-  float* s_p256 = reinterpret_cast<float*>(s_p + 2 * 16384);   // [144] P[256, kv] of this key half (+ key 256)
-  float* s_ds256 = s_p256 + 144;                               // [144] dS[256, kv]
-  float* s_dd = s_ds256 + 144;    // [2][128] half sums of o . dO
-  float* s_tt = s_dd + 256;       // [256] per-row peeled-column terms: p_t | ds_t   (jj == 1)
-  float* s_part = s_tt + 256;     // [2][4][64] partial sums
-  // [2][5][64] k_256 v_256 q_256 dO_256 o_256 of the current / the next item
-  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_part + 512);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 2 * 320);
-  uint64_t* bar_full = bars + 0;
-  uint64_t* bar_tile = bars + 1;
-  uint64_t* bar_s = bars + 2;
-  uint64_t* bar_dp = bars + 3;
-  uint64_t* bar_p = bars + 4;         // 256 arrivals, two uses per tile
-  uint64_t* bar_acc = bars + 5;       // dQ partial complete
-  uint64_t* bar_acc_free = bars + 6;  // 256 arrivals: dQ accumulator drained, Q / dO tile consumed
-  uint64_t* bar_kv_free = bars + 7;   // 256 arrivals: dK / dV accumulators drained
-  uint64_t* bar_trow = bars + 8;      // 256 arrivals: peeled row done with K / V
-  uint64_t* bar_kdone = bars + 9;     // last tensor-core read of K / V of this item retired
-  uint64_t* bar_dk = bars + 10;       // dK MMAs of a tile retired (Q_i / dS no longer read)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    mbar_init(bar_full, 1);
-    mbar_init(bar_tile, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_dp, 1);
-    mbar_init(bar_p, 256);
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_acc_free, 256);
-    mbar_init(bar_kv_free, 256);
-    mbar_init(bar_trow, 256);
-    mbar_init(bar_kdone, 1);
-    mbar_init(bar_dk, 1);
-    fence_barrier_init();
-  }
-  if (warp == AT5_CTRL_WARP) {
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const int n_work = P.B * P.H * 2;
-  const int colQ = 0, colK = W, colV = 2 * W;
-  constexpr uint32_t TR = 0, TDV = 128, TDK = 192;
-  constexpr int ntile = 2;
-
-  if (warp == AT5_CTRL_WARP) {
-    if (lane == 0) {
-      // ===================== TMA + MMA issuer =====================
-      // key half of the it-th work item of this CTA: alternates (the CTA holding key half 1 also
-      // owns the peeled key), and neighbouring CTAs always hold complementary halves
-      auto load_full = [&](int idx, int it_) {
-        const int item = idx >> 1, jj = (idx ^ it_) & 1;
-        const int b = item / P.H, h = item % P.H;
-        mbar_arrive_expect_tx(bar_full, 32768);
-        tma_load_3d(s_k, &tmTile, bar_full, colK + h * 64, jj * 128, b);
-        tma_load_3d(s_v, &tmTile, bar_full, colV + h * 64, jj * 128, b);
-      };
-      auto load_tile = [&](int idx, int j) {
-        const int item = idx >> 1;
-        const int b = item / P.H, h = item % P.H;
-        mbar_arrive_expect_tx(bar_tile, 32768);
-        tma_load_3d(s_q, &tmTile, bar_tile, colQ + h * 64, j * 128, b);
-        tma_load_3d(s_do, &tmDoTile, bar_tile, h * 64, j * 128, b);
-      };
-      const uint32_t idS = idesc_ab(FMT, FMT, 128, 128, 0, 0);
-      const uint32_t idT = idesc_ab(FMT, FMT, 128, 64, 1, 1);   // A and B both MN-major
-      const uint32_t t0 = smem_u32(s_q), t1 = smem_u32(s_do);
-      const uint32_t ka = smem_u32(s_k), va = smem_u32(s_v), pa = smem_u32(s_p);
-      uint32_t g = 0;
-      int it = 0;
-      if ((int)blockIdx.x < n_work) load_full(blockIdx.x, 0);
-      for (int idx = blockIdx.x; idx < n_work; idx += gridDim.x, ++it) {
-        const int next = idx + gridDim.x;
-        for (int j = 0; j < ntile; ++j, ++g) {
-          // the single Q / dO buffer: tile g-1 fully consumed (dQ drained, its dK MMAs retired)
-          if (g > 0) {
-            mbar_wait(bar_acc_free, (g - 1) & 1, 273);
-            mbar_wait(bar_dk, (g - 1) & 1, 278);
-          }
-          load_tile(idx, j);
-          if (j == 0) mbar_wait(bar_full, it & 1, 270);
-          mbar_wait(bar_tile, g & 1, 272);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // S = Q_i K_jj^T
-            umma_f16(tmem + TR, make_smem_desc_sw128(t0 + k * 32, 16, 1024),
-                     make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
-          umma_commit(bar_s);
-          mbar_wait(bar_p, (2 * g) & 1, 274);        // P written, S consumed
-          if (j == 0 && it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 271);   // dK / dV drained
-          tc_fence_after();
-#pragma unroll
-          for (int s = 0; s < 8; ++s)                // dV_jj += P^T dO_i
-            umma_f16(tmem + TDV, make_smem_desc_sw128(pa + s * 2048, 16384, 1024),
-                     make_smem_desc_sw128(t1 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)                // dP = dO_i V_jj^T into the (consumed) S region
-            umma_f16(tmem + TR, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
-                     make_smem_desc_sw128(va + k * 32, 16, 1024), idS, k > 0);
-          umma_commit(bar_dp);
-          mbar_wait(bar_p, (2 * g + 1) & 1, 275);    // dS written over P
-          tc_fence_after();
-          issue_mma2(tmem + TR, pa, ka, 128, FMT, FMT);   // dQ_i partial = dS K_jj  (acc in [0,64))
-          umma_commit(bar_acc);
-          if (j + 1 == ntile) umma_commit(bar_kdone);
-#pragma unroll
-          for (int s = 0; s < 8; ++s)                // dK_jj += dS^T Q_i
-            umma_f16(tmem + TDK, make_smem_desc_sw128(pa + s * 2048, 16384, 1024),
-                     make_smem_desc_sw128(t0 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
-          umma_commit(bar_dk);
-        }
-        mbar_wait(bar_kdone, it & 1, 276);
-        if (TAIL) mbar_wait(bar_trow, it & 1, 277);
-        if (next < n_work) load_full(next, it + 1);
-      }
-    }
-  } else {
-    // ===================== row workers: thread = (row r, column half cq) =====================
-    const int tid = threadIdx.x, r = tid & 127, cq = tid >> 7;
-    const uint32_t ts = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const float c2 = 0.125f * 1.4426950408889634f;
-    const float LOG2E = 1.4426950408889634f;
-    const uint32_t rx = (uint32_t)(r & 7) << 4;
-    uint8_t* prow = s_p + cq * 16384 + r * 128;   // this thread's 64 keys = one 16 KB block
-    auto tail_src = [&](int idx_) -> const uint4* {
-      const int item_ = idx_ >> 1;
-      const int b_ = item_ / P.H, h_ = item_ % P.H;
-      const int which = tid >> 3, c = tid & 7;
-      const size_t rowq = ((size_t)b_ * T + 256) * 3 * W + h_ * 64 + c * 8;
-      const size_t rowd = ((size_t)b_ * T + 256) * W + h_ * 64 + c * 8;
-      const uint16_t* src = which == 0 ? P.qkv + rowq + colK : which == 1 ? P.qkv + rowq + colV
-                          : which == 2 ? P.qkv + rowq + colQ : which == 3 ? P.d_o + rowd
-                                                                          : P.o + rowd;
-      return reinterpret_cast<const uint4*>(src);
-    };
-    if (TAIL && tid < 40 && (int)blockIdx.x < n_work)
-      *reinterpret_cast<uint4*>(s_tv + tid * 8) = *tail_src(blockIdx.x);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    uint32_t g = 0;
-    int it = 0;
-    for (int idx = blockIdx.x; idx < n_work; idx += gridDim.x, ++it) {
-      const int item = idx >> 1, jj = (idx ^ it) & 1;
-      const int b = item / P.H, h = item % P.H;
-      const bool last_half = jj == 1;            // owns the peeled key (token 256)
-      const float* lse_row = lse_fwd + ((size_t)b * P.H + h) * T;
-      const uint16_t* tvb = s_tv + (it & 1) * 320;
-      const uint16_t* tv0 = tvb;              // k_256
-      const uint16_t* tv1 = tvb + 64;         // v_256
-      const uint16_t* tv2 = tvb + 128;        // q_256
-      const uint16_t* tv3 = tvb + 192;        // dO_256
-      const uint16_t* tv4 = tvb + 256;        // o_256 (forward format)
-      float tdv = 0.f, tdk = 0.f;   // (jj == 1) this thread's share of dv_256[d], dk_256[d]
-      if (TAIL) {
-        // ===== the peeled QUERY row (token 256) against this CTA's 128 keys (+ key 256 if jj == 1)
-        const float l2 = __ldg(lse_row + 256) * LOG2E;
-        const float D = dot_rows16(tv4, P.fmt_o, tv3, FMT);
-        mbar_wait(bar_full, it & 1, 280);
-        if (tid < 128) {
-          const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
-          s_p256[tid] = fast_ex2(fmaf(sv, c2, -l2));
-          if (tid == 0) s_p256[128] = last_half ? fast_ex2(fmaf(dot_vec<FMT>(tv0, tv2), c2, -l2)) : 0.f;
-        } else {
-          s_ds256[tid - 128] = dot_swz_row<FMT>(s_v, tid - 128, tv3);     // dP[256, kv]
-          if (tid == 128) s_ds256[128] = last_half ? dot_vec<FMT>(tv1, tv3) : 0.f;
-        }
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (tid < 128) s_ds256[tid] = s_p256[tid] * (s_ds256[tid] - D) * 0.125f;
-        if (tid == 128) s_ds256[128] = s_p256[128] * (s_ds256[128] - D) * 0.125f;
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        {
-          const int d = tid & 63, qt = tid >> 6;       // 4 groups of 32 keys
-          float acc = 0.f;
-          for (int kv = qt * 32; kv < qt * 32 + 32; ++kv)
-            acc = fmaf(s_ds256[kv], swz_at<FMT>(s_k, kv, d), acc);
-          if (qt == 3 && last_half) acc = fmaf(s_ds256[128], ld1<FMT>(tv0 + d), acc);
-          s_part[qt * 64 + d] = acc;
-          if (qt == 0 && last_half) {   // the (q = 256, kv = 256) corner of dk_256 / dv_256
-            tdv = s_p256[128] * ld1<FMT>(tv3 + d);
-            tdk = s_ds256[128] * ld1<FMT>(tv2 + d);
-          }
-        }
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (tid < 8) {   // dq_256: this key half's partial, 8 columns per thread
-          float a[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            a[i] = (s_part[tid * 8 + i] + s_part[64 + tid * 8 + i]) +
-                   (s_part[128 + tid * 8 + i] + s_part[192 + tid * 8 + i]);
-          red_add16x8<FMT>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64 + tid * 8,
-                           packc<FMT>(a[0], a[1]), packc<FMT>(a[2], a[3]), packc<FMT>(a[4], a[5]),
-                           packc<FMT>(a[6], a[7]));
-        }
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        mbar_arrive(bar_trow);
-      }
-      for (int j = 0; j < ntile; ++j, ++g) {
-        const int row = j * 128 + r;
-        const size_t grow = (size_t)b * T + row;
-        const float l2 = __ldg(lse_row + row) * LOG2E;
-        // this thread's half of the o row (D_r = o_r . dO_r), requested early
-        uint4 g_o[4];
-        {
-          const uint4* po = reinterpret_cast<const uint4*>(P.o + grow * W + h * 64 + cq * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) g_o[i] = po[i];
-        }
-        mbar_wait(bar_tile, g & 1, 281);
-        float a_t = 0.f, b_t = 0.f;
-        if (TAIL && last_half && cq == 1) {
-          a_t = dot_swz_row<FMT>(s_q, r, tv0);    // q_r . k_256
-          b_t = dot_swz_row<FMT>(s_do, r, tv1);   // dO_r . v_256
-        }
-        {
-          float dd = 0.f;
-          const uint8_t* drow = s_do + r * 128;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint4 ud =
-                *reinterpret_cast<const uint4*>(drow + (((cq * 4 + i) ^ (r & 7)) << 4));
-            const uint32_t* pa = &g_o[i].x;
-            const uint32_t* pb = &ud.x;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 x = unpack2(pa[u], P.fmt_o), y = unpackc<FMT>(pb[u]);
-              dd = fmaf(x.x, y.x, fmaf(x.y, y.y, dd));
-            }
-          }
-          s_dd[cq * 128 + r] = dd;
-        }
-        // ---------------- pass 1: P = exp2(S c - lse) ----------------
-        mbar_wait(bar_s, g & 1, 282);
-        tc_fence_after();
-        const uint32_t tcol = ts + TR + cq * 64;
-        uint32_t pk[32];
-        float p_t = 0.f;
-        {
-          uint32_t v[2][16];
-          tmem_ld16(tcol, v[0]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            tmem_ld_wait();
-            if (q + 1 < 4) tmem_ld16(tcol + (q + 1) * 16, v[(q + 1) & 1]);
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              const float e0 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i]), c2, -l2));
-              const float e1 = fast_ex2(fmaf(__uint_as_float(v[q & 1][i + 1]), c2, -l2));
-              pk[q * 8 + i / 2] = packc<FMT>(e0, e1);
-            }
-#pragma unroll
-            for (int q8 = 0; q8 < 2; ++q8)
-              *reinterpret_cast<uint4*>(prow + ((((uint32_t)(q * 2 + q8)) << 4) ^ rx)) =
-                  make_uint4(pk[q * 8 + q8 * 4], pk[q * 8 + q8 * 4 + 1], pk[q * 8 + q8 * 4 + 2],
-                             pk[q * 8 + q8 * 4 + 3]);
-          }
-          if (TAIL && last_half && cq == 1) p_t = fast_ex2(fmaf(a_t, c2, -l2));
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_p);
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // publishes s_dd (under the dV / dP MMAs)
-        const float Dr = s_dd[r] + s_dd[128 + r];
-        // ---------------- pass 2: dS = P (dP - D) / 8 ----------------
-        mbar_wait(bar_dp, g & 1, 283);
-        tc_fence_after();
-        {
-          const float nDsc = -Dr * 0.125f;
-          uint32_t v[2][16];
-          tmem_ld16(tcol, v[0]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            tmem_ld_wait();
-            if (q + 1 < 4) tmem_ld16(tcol + (q + 1) * 16, v[(q + 1) & 1]);
-#pragma unroll
-            for (int q8 = 0; q8 < 2; ++q8) {
-              float d[8];
-#pragma unroll
-              for (int u = 0; u < 8; u += 2) {
-                const int i = q8 * 8 + u;
-                const float2 pp = unpackc<FMT>(pk[q * 8 + i / 2]);
-                d[u] = pp.x * fmaf(__uint_as_float(v[q & 1][i]), 0.125f, nDsc);
-                d[u + 1] = pp.y * fmaf(__uint_as_float(v[q & 1][i + 1]), 0.125f, nDsc);
-              }
-              *reinterpret_cast<uint4*>(prow + ((((uint32_t)(q * 2 + q8)) << 4) ^ rx)) =
-                  make_uint4(packc<FMT>(d[0], d[1]), packc<FMT>(d[2], d[3]),
-                             packc<FMT>(d[4], d[5]), packc<FMT>(d[6], d[7]));
-            }
-          }
-          if (TAIL && last_half && cq == 1) {
-            s_tt[r] = p_t;
-            s_tt[128 + r] = p_t * (b_t - Dr) * 0.125f;
-          }
-        }
-        if (TAIL && last_half) {
-          // peeled KEY row (kv = 256): dv_256 += sum_q p_t[q] dO_q ; dk_256 += sum_q ds_t[q] Q_q
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          const int d = tid & 63, qt = tid >> 6;      // 4 groups of 32 rows
-          for (int q = qt * 32; q < qt * 32 + 32; ++q) {
-            tdv = fmaf(s_tt[q], swz_at<FMT>(s_do, q, d), tdv);
-            tdk = fmaf(s_tt[128 + q], swz_at<FMT>(s_q, q, d), tdk);
-          }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        mbar_arrive(bar_p);
-        // ---------------- dQ epilogue: 32 columns per thread, added into the output --------
-        mbar_wait(bar_acc, g & 1, 284);
-        tc_fence_after();
-        {
-          const float dst = (TAIL && last_half) ? s_tt[128 + r] : 0.f;
-          uint32_t v0[32];
-          tmem_ld32(ts + TR + cq * 32, v0);
-          tmem_ld_wait();
-          uint16_t* dstp = P.dqkv + grow * 3 * W + colQ + h * 64 + cq * 32;
-#pragma unroll
-          for (int q8 = 0; q8 < 4; ++q8) {
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(v0[q8 * 8 + i]);
-            if (TAIL && last_half) {
-              const uint4 tu = *reinterpret_cast<const uint4*>(tv0 + cq * 32 + q8 * 8);
-              const uint32_t* ta = &tu.x;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 y = unpackc<FMT>(ta[i]);
-                o[2 * i] = fmaf(dst, y.x, o[2 * i]);
-                o[2 * i + 1] = fmaf(dst, y.y, o[2 * i + 1]);
-              }
-            }
-            red_add16x8<FMT>(dstp + q8 * 8, packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
-                             packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(bar_acc_free);
-      }
-      // ---------------- dK_jj / dV_jj epilogue: cq 0 -> dV, cq 1 -> dK ----------------
-      uint4 tv_next = make_uint4(0u, 0u, 0u, 0u);
-      const bool tv_fetch = TAIL && tid < 40 && idx + (int)gridDim.x < n_work;
-      if (tv_fetch) tv_next = *tail_src(idx + gridDim.x);
-      mbar_wait(bar_dk, (g - 1) & 1, 285);   // the last tile's dK MMAs (dV retired earlier)
-      tc_fence_after();
-      {
-        const int isk = cq;
-        const uint32_t base = isk ? TDK : TDV;
-        const uint16_t* tvx = isk ? tv2 : tv3;            // rank-1 term of the peeled query row
-        const int kv = jj * 128 + r;
-        uint32_t v0[32], v1[32];
-        tmem_ld32(ts + base, v0);
-        tmem_ld32(ts + base + 32, v1);
-        tmem_ld_wait();
-        const float w = TAIL ? (isk ? s_ds256[r] : s_p256[r]) : 0.f;
-        uint4* dst4 = reinterpret_cast<uint4*>(P.dqkv + ((size_t)b * T + kv) * 3 * W +
-                                               (isk ? colK : colV) + h * 64);
-#pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8) {
-          const uint32_t* sv = q8 < 4 ? &v0[q8 * 8] : &v1[(q8 - 4) * 8];
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(sv[i]);
-          if (TAIL) {
-            const uint4 tu = *reinterpret_cast<const uint4*>(tvx + q8 * 8);
-            const uint32_t* ta = &tu.x;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 y = unpackc<FMT>(ta[i]);
-              o[2 * i] = fmaf(w, y.x, o[2 * i]);
-              o[2 * i + 1] = fmaf(w, y.y, o[2 * i + 1]);
-            }
-          }
-          dst4[q8] = make_uint4(packc<FMT>(o[0], o[1]), packc<FMT>(o[2], o[3]),
-                                packc<FMT>(o[4], o[5]), packc<FMT>(o[6], o[7]));
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_kv_free);
-      if (TAIL && last_half) {
-        // dk_256 / dv_256: reduce the four row-group partials
-        const int d = tid & 63, qt = tid >> 6;
-        s_part[qt * 64 + d] = tdv;
-        s_part[256 + qt * 64 + d] = tdk;
-        asm volatile("bar.sync 3, 256;" ::: "memory");
-        if (tid < 64) {
-          const int which = tid >> 5, l2i = tid & 31;   // 0: dv, 1: dk
-          const float* pp = s_part + which * 256;
-          const float a0 = (pp[2 * l2i] + pp[64 + 2 * l2i]) + (pp[128 + 2 * l2i] + pp[192 + 2 * l2i]);
-          const float a1 = (pp[2 * l2i + 1] + pp[64 + 2 * l2i + 1]) +
-                           (pp[128 + 2 * l2i + 1] + pp[192 + 2 * l2i + 1]);
-          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W +
-                                      (which ? colK : colV) + h * 64)[l2i] = packc<FMT>(a0, a1);
-        }
-      }
-      if (tv_fetch) *reinterpret_cast<uint4*>(s_tv + ((it + 1) & 1) * 320 + tid * 8) = tv_next;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == AT5_CTRL_WARP) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
-
-template <int FMT, bool TAIL>
-static int launch_bwd5(const CUtensorMap& a, const CUtensorMap& c, const AttnBwd2Params& P,
-                       const float* lse_fwd, cudaStream_t st) {
-  auto kern = attn_bwd5_kernel<FMT, TAIL>;
-  const size_t smem = (size_t)4 * 16384 + 2 * 16384 + (144 * 2 + 256 + 256 + 512) * 4 + 2 * 640 +
-                      128 + 1024;
-  static DeviceOnce attr;
-  if (!attr.done()) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                               cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return -(int)e - 1000;
-    attr.mark();
-  }
-  // the partial dQ of the two key halves are ADDED into the output: zero its q third first
-  cudaError_t e = cudaMemset2DAsync(P.dqkv, (size_t)3 * P.W * 2, 0, (size_t)P.W * 2,
-                                    (size_t)P.B * P.T, st);
-  if (e != cudaSuccess) return -(int)e - 1000;
-  int grid = 2 * sm_count();
-  if (2 * P.B * P.H < grid) grid = 2 * P.B * P.H;
-  kern<<<grid, AT5_THREADS, smem, st>>>(a, c, P, lse_fwd);
-  count_launch(1);
-  e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
 }
 
@@ -3608,11 +3151,8 @@ extern "C" int rvlm_attn_bwd_lse(const void* qkv16, const void* o16, const void*
                                  int fmt_g, void* stream) {
   if (fmt_qkv != fmt_g) return RVLM_ERR_UNSUPPORTED;
   if (!lse) return RVLM_ERR_INVAL;
-  // RVLM_ATTN_BWD4: "0" selects version 3 (statistics recomputed), "1" version 4 (one CTA per SM),
-  // unset / anything else version 5 (key-split, two CTAs per SM).  Read per call: the tests cover all.
-  const char* e4 = getenv("RVLM_ATTN_BWD4");
-  const bool use_v4 = !(e4 && e4[0] == '0');
-  const bool use_v5 = !(e4 && (e4[0] == '0' || e4[0] == '1'));
+  const char* e4 = getenv("RVLM_ATTN_BWD4");   // default on; RVLM_ATTN_BWD4=0 selects version 3
+  const bool use_v4 = !(e4 && e4[0] == '0');   // (read per call: the tests cover both)
   if (!use_v4 || (T != 257 && T != 256))
     return rvlm_attn_bwd(qkv16, o16, do16, lse, dqkv16, B, T, H, fmt_qkv, fmt_o, fmt_g, stream);
   AttnBwd2Params P{};
@@ -3632,13 +3172,6 @@ extern "C" int rvlm_attn_bwd_lse(const void* qkv16, const void* o16, const void*
   if (!rc) rc = make_tmap_3d(&tmDoTile, do16, Wd, T, B, Wd, (uint64_t)T * Wd, 64, 128);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_v5) {
-    if (T == 257)
-      return fmt_g ? launch_bwd5<1, true>(tmTile, tmDoTile, P, lse, st)
-                   : launch_bwd5<0, true>(tmTile, tmDoTile, P, lse, st);
-    return fmt_g ? launch_bwd5<1, false>(tmTile, tmDoTile, P, lse, st)
-                 : launch_bwd5<0, false>(tmTile, tmDoTile, P, lse, st);
-  }
   if (T == 257)
     return fmt_g ? launch_bwd4<1, true>(tmTile, tmFull, tmDoTile, P, lse, st)
                  : launch_bwd4<0, true>(tmTile, tmFull, tmDoTile, P, lse, st);

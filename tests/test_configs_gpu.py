@@ -41,8 +41,8 @@ def _ours(o, precision=None):
 
 # config 1 is FARE's cancellation site (the frozen copy equals the model): the forward precision
 # decides it.  Measured (profiles/r02_test_metrics.jsonl): fast16 1.07 % of delta entries differ,
-# 0.25 % of those with |g| > 0.05 median; split (fp32-class forward): see LIMITS1.
-LIMITS1 = {"fast16": (2.2e-2, 5e-3), "split": (2e-3, 5e-4)}
+# 0.25 % of those with |g| > 0.05 median; split (fp32-class forward) 0.031 %, none of them big.
+LIMITS1 = {"fast16": (2.2e-2, 5e-3), "split": (6.3e-4, 1e-4)}
 
 
 @pytest.mark.parametrize("mode", ["fast16", "split"])

@@ -7,7 +7,7 @@
 //   o16   [B*T, W],  lse [B, H, T] (natural log of the softmax denominator, scaled scores)
 // Semantics: softmax(q k^T / sqrt(64)) v per head, no mask, no dropout
 // (nn.MultiheadAttention inside open_clip's ResidualAttentionBlock).
-#include "ptx.cuh"
+#include "gemm.cuh"
 #include "../../include/rvlm.h"
 
 namespace rvlm {
@@ -240,12 +240,11 @@ extern "C" int rvlm_attn_fwd_simt_rows(const void* qkv16, void* o16, float* lse,
                                        int H, int fmt, int t_begin, int t_end, void* stream) {
   const int threads = 128, nw = threads / 32;
   const size_t smem = (size_t)2 * T * ROWP * 2 + (size_t)nw * T * 4 + (size_t)nw * HD * 4;
-  static size_t set = 0;
-  if (smem > set) {
+  static DeviceMax set;
+  if (set.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_simt_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;
-    set = smem;
   }
   attn_fwd_simt_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint16_t*>(qkv16), reinterpret_cast<uint16_t*>(o16), lse, T, H, fmt,
@@ -262,12 +261,11 @@ extern "C" int rvlm_attn_bwd_simt(const void* qkv16, const void* o16, const void
   const int threads = 256, nw = threads / 32;
   const size_t smem = (size_t)4 * T * ROWP * 2 + (size_t)2 * T * 4 + (size_t)nw * 2 * T * 4 +
                       (size_t)nw * 128 * 4;
-  static size_t set = 0;
-  if (smem > set) {
+  static DeviceMax set;
+  if (set.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_simt_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;
-    set = smem;
   }
   attn_bwd_simt_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(
       reinterpret_cast<const uint16_t*>(qkv16), reinterpret_cast<const uint16_t*>(o16),

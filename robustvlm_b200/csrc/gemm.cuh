@@ -544,6 +544,17 @@ struct DeviceOnce {
   }
 };
 
+// the same for opt-ins whose size varies with the call: remembers the largest value set per device
+struct DeviceMax {
+  size_t v[128] = {};
+  bool need(size_t bytes) {
+    const int d = DeviceOnce::dev();
+    if (bytes <= v[d]) return false;
+    v[d] = bytes;
+    return true;
+  }
+};
+
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int fmt,
                   const Epi& epi, cudaStream_t stream, int max_ctas = 0) {

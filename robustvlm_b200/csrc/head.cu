@@ -19,6 +19,7 @@
 // the reduction dimension over four 256-thread slices with up to four independent accumulators
 // per thread (partial sums merged through shared memory in a fixed order), the transposed ones
 // run one warp per output with four independent partial sums per lane.
+#include "gemm.cuh"
 #include "engine_internal.cuh"
 #include "../../include/rvlm.h"
 
@@ -326,12 +327,11 @@ int launch_head(const HeadArgs& A, int B, cudaStream_t st) {
   const int mx = A.D > A.C ? A.D : A.C;
   const size_t smem = (size_t)(2 * A.W + 2 * A.D + (A.C > 0 ? A.C : 1) + HEAD_SLICES * mx) *
                       sizeof(float);
-  static size_t set = 0;
-  if (smem > set && smem > 48 * 1024) {
+  static DeviceMax set;
+  if (smem > 48 * 1024 && set.need(smem)) {
     cudaError_t e = cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return -(int)e - 1000;
-    set = smem;
   }
   head_kernel<<<B, HEAD_THREADS, smem, st>>>(A);
   count_launch(1);

@@ -67,5 +67,46 @@ def report(path):
             f"{h.split('issue_stalled_')[1].split('_per')[0]}={v:.2f}" for h, v in top))
 
 
+def table(path, hbm_peak_gbs=6532.2):
+    """one line per distinct kernel (mean over its captured launches): time, DRAM bytes, achieved
+    GB/s and its fraction of the measured HBM peak (MEASURED_PEAKS.json hbm_gbs), tensor-pipe
+    utilisation, issue-slot utilisation"""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+
+    def val(d, k):
+        try:
+            v = float(d[k].replace(",", ""))
+        except (KeyError, ValueError):
+            return float("nan")
+        u = units[hdr.index(k)]
+        return v * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3,
+                    "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+    agg = collections.OrderedDict()
+    for row in rows[2:]:
+        d = dict(zip(hdr, row))
+        name = re.sub(r"\(.*", "", d["Kernel Name"]).replace("void ", "").replace("rvlm::", "")
+        name = re.sub(r"<unnamed>::", "", name)
+        key = (name, d.get("Grid Size", ""))
+        a = agg.setdefault(key, [0, 0.0, 0.0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += val(d, "gpu__time_duration.sum")
+        a[2] += val(d, "dram__bytes_read.sum")
+        a[3] += val(d, "dram__bytes_write.sum")
+        a[4] += val(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+        a[5] += val(d, "smsp__issue_active.avg.pct_of_peak_sustained_active")
+    print(f"# {path}: per-kernel means; HBM peak = {hbm_peak_gbs} GB/s (MEASURED_PEAKS.json); ncu "
+          "--clock-control none, kernels serialised (cold L2)")
+    print(f"{'n':>3} {'time_us':>9} {'rd_MB':>8} {'wr_MB':>8} {'GB/s':>7} {'of_HBM':>6} {'tensor%':>7} "
+          f"{'issue%':>6}  kernel  grid")
+    for (name, grid), (n, t, rd, wr, tp, ia) in agg.items():
+        t, rd, wr, tp, ia = t / n, rd / n, wr / n, tp / n, ia / n
+        gbs = (rd + wr) / (t * 1e-6) / 1e9 if t > 0 else float("nan")
+        print(f"{n:3d} {t:9.1f} {rd / 1e6:8.1f} {wr / 1e6:8.1f} {gbs:7.0f} {gbs / hbm_peak_gbs:6.2f} "
+              f"{tp:7.1f} {ia:6.1f}  {name[:110]}  {grid}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "report": report, "table": table}[sys.argv[1]](sys.argv[2])

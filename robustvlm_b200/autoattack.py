@@ -7,14 +7,19 @@ evaluation runs (`CLIP_eval/clip_robustbench.py:289-300`, version='custom',
 attacks_to_run=['apgd-ce', 'apgd-t']).  FAB and Square are out of scope and
 raise NotImplementedError when asked for; the 'standard' / 'plus' presets therefore keep
 their APGD members and drop the rest, with a note on the logger.
-The evaluation state file, randomised-defence checks and TF adapters of the reference are
-control plane and not rebuilt.
+The evaluation state file (`EvaluationState`, autoattack/state.py: resume an interrupted
+evaluation) is kept in the reference's JSON layout; randomised-defence checks and TF adapters
+of the reference are control plane and not rebuilt.
 """
 from __future__ import annotations
 
+import ast
+import json
 import math
 import time
 import warnings
+from datetime import datetime
+from pathlib import Path
 
 import torch
 
@@ -22,6 +27,87 @@ from .attacks import APGDAttack, APGDAttack_targeted
 
 _APGD_FAMILY = ("apgd-ce", "apgd-dlr", "apgd-t")
 _NOT_BUILT = ("fab", "fab-t", "square")
+
+
+class EvaluationState:
+    """autoattack/state.py:11-89 -- which attacks have run and which points are still robust, saved
+    as JSON so `run_standard_evaluation(state_path=...)` can resume.  Same keys as the reference's
+    file.  (The reference writes `_attacks_to_run` through `json.dump(default=str)`, i.e. as the
+    repr of a set, and then compares that string with a set on resume -- `autoattack.py:89-91`
+    always raises; here the set is written as a sorted list and both forms are read.)"""
+
+    SAVE_TIMEOUT = 60
+
+    def __init__(self, attacks_to_run, path=None):
+        self._attacks_to_run = set(attacks_to_run)
+        self.path = Path(path) if path is not None else None
+        self._run_attacks = set()
+        self._robust_flags = None
+        self._last_saved = datetime(1, 1, 1)
+        self._clean_accuracy = float("nan")
+
+    def to_disk(self, force=False):
+        since = (datetime.now() - self._last_saved).total_seconds()
+        if self.path is None or (since < self.SAVE_TIMEOUT and not force):
+            return
+        self._last_saved = datetime.now()
+        d = {"_attacks_to_run": sorted(self._attacks_to_run), "path": str(self.path),
+             "_run_attacks": sorted(self._run_attacks),
+             "_robust_flags": (self._robust_flags.cpu().tolist()
+                               if self._robust_flags is not None else None),
+             "_last_saved": self._last_saved.isoformat(), "_SAVE_TIMEOUT": self.SAVE_TIMEOUT,
+             "_clean_accuracy": self._clean_accuracy}
+        tmp = self.path.with_suffix(self.path.suffix + ".tmp")
+        with tmp.open("w") as f:
+            json.dump(d, f)
+        tmp.replace(self.path)
+
+    @classmethod
+    def from_disk(cls, path):
+        path = Path(path)
+        with path.open("r") as f:
+            d = json.load(f)
+        atr = d["_attacks_to_run"]
+        if isinstance(atr, str):                 # a file written by the reference itself
+            atr = ast.literal_eval(atr)
+        st = cls(atr, path=d.get("path", path))
+        if Path(d.get("path", path)) != path:
+            warnings.warn(UserWarning("The given path is different from the one found in the state file."))
+        st._run_attacks = set(d["_run_attacks"])
+        if d.get("_robust_flags") is not None:
+            st._robust_flags = torch.tensor(d["_robust_flags"], dtype=torch.bool)
+        st._last_saved = datetime.fromisoformat(d["_last_saved"])
+        st._clean_accuracy = float(d.get("_clean_accuracy", float("nan")))
+        return st
+
+    @property
+    def robust_flags(self):
+        return self._robust_flags
+
+    @robust_flags.setter
+    def robust_flags(self, flags):
+        self._robust_flags = flags
+        self.to_disk(force=True)
+
+    @property
+    def run_attacks(self):
+        return self._run_attacks
+
+    def add_run_attack(self, attack):
+        self._run_attacks.add(attack)
+        self.to_disk()
+
+    @property
+    def attacks_to_run(self):
+        return self._attacks_to_run
+
+    @property
+    def clean_accuracy(self):
+        return self._clean_accuracy
+
+    @clean_accuracy.setter
+    def clean_accuracy(self, accuracy):
+        self._clean_accuracy = accuracy
 
 
 class _Logger:
@@ -119,30 +205,56 @@ class AutoAttack:
     def run_standard_evaluation(self, x_orig, y_orig, bs=250, return_labels=False, state_path=None):
         """:82-261 -- clean pass, then every attack on the still-robust points in batches of
         `bs`; returns the adversarial images (and the predictions on them)."""
-        if state_path is not None:
-            raise NotImplementedError("evaluation state files are not rebuilt")
+        state_path = Path(state_path) if state_path is not None else None
+        if state_path is not None and state_path.exists():                         # :88-98
+            state = EvaluationState.from_disk(state_path)
+            if set(self.attacks_to_run) != state.attacks_to_run:
+                raise ValueError("The state was created with a different set of attacks "
+                                 "to run. You are probably using the wrong state file.")
+            if self.verbose:
+                self.logger.log("Restored state from {}".format(state_path))
+                self.logger.log("Since the state has been restored, **only** the adversarial "
+                                "examples from the current run are going to be returned.")
+        else:
+            state = EvaluationState(set(self.attacks_to_run), path=state_path)     # :99-103
+            state.to_disk()
+        attacks_to_run = [a for a in self.attacks_to_run if a not in state.run_attacks]   # :105
         if self.verbose:
             self.logger.log("using {} version including {}{}.".format(
-                self.version, ", ".join(self.attacks_to_run),
+                self.version, ", ".join(attacks_to_run),
                 " (APGD members only; not run: {})".format(", ".join(self.dropped_attacks))
                 if getattr(self, "dropped_attacks", None) else ""))
+            if state.run_attacks:
+                self.logger.log("{} was/were already run.".format(", ".join(sorted(state.run_attacks))))
         n = x_orig.shape[0]
         with torch.no_grad():
-            robust_flags = torch.zeros(n, dtype=torch.bool, device=x_orig.device)
-            y_adv = torch.empty_like(y_orig)
-            for s in range(0, n, bs):                                              # :127-138
-                x = x_orig[s:s + bs].clone().to(self.device)
-                y = y_orig[s:s + bs].clone().to(self.device)
-                out = self.get_logits(x).max(dim=1)[1]
-                y_adv[s:s + bs] = out.to(y_adv.device)
-                robust_flags[s:s + bs] = y.eq(out).to(robust_flags.device)
-            robust_accuracy = robust_flags.sum().item() / n
-            self.robust_accuracy_dict = {"clean": robust_accuracy}
-            if self.verbose:
-                self.logger.log("initial accuracy: {:.2%}".format(robust_accuracy))
+            # (the reference leaves y_adv undefined on resume, :125-155; here it starts from the labels)
+            y_adv = y_orig.clone()
+            if state.robust_flags is None:
+                robust_flags = torch.zeros(n, dtype=torch.bool, device=x_orig.device)
+                for s in range(0, n, bs):                                          # :127-138
+                    x = x_orig[s:s + bs].clone().to(self.device)
+                    y = y_orig[s:s + bs].clone().to(self.device)
+                    out = self.get_logits(x).max(dim=1)[1]
+                    y_adv[s:s + bs] = out.to(y_adv.device)
+                    robust_flags[s:s + bs] = y.eq(out).to(robust_flags.device)
+                state.robust_flags = robust_flags
+                robust_accuracy = robust_flags.sum().item() / n
+                self.robust_accuracy_dict = {"clean": robust_accuracy}
+                state.clean_accuracy = robust_accuracy
+                if self.verbose:
+                    self.logger.log("initial accuracy: {:.2%}".format(robust_accuracy))
+            else:                                                                  # :147-153
+                robust_flags = state.robust_flags.to(x_orig.device)
+                robust_accuracy = robust_flags.sum().item() / n
+                self.robust_accuracy_dict = {"clean": state.clean_accuracy}
+                if self.verbose:
+                    self.logger.log("initial clean accuracy: {:.2%}".format(state.clean_accuracy))
+                    self.logger.log("robust accuracy at the time of restoring the state: "
+                                    "{:.2%}".format(robust_accuracy))
             x_adv = x_orig.clone().detach()
             startt = time.time()
-            for attack in self.attacks_to_run:                                     # :157
+            for attack in attacks_to_run:                                          # :157
                 num_robust = robust_flags.sum().item()
                 if num_robust == 0:
                     break
@@ -157,6 +269,7 @@ class AutoAttack:
                     false_batch = ~y.eq(out).to(robust_flags.device)               # :222-226
                     nr = idc[false_batch]
                     robust_flags[nr] = False
+                    state.robust_flags = robust_flags                              # :225
                     x_adv[nr] = adv_curr[false_batch].detach().to(x_adv.device)
                     y_adv[nr] = out[false_batch].detach().to(y_adv.device)
                     if self.verbose:
@@ -164,9 +277,11 @@ class AutoAttack:
                             attack, bi + 1, n_batches, int(false_batch.sum()), x.shape[0]))
                 robust_accuracy = robust_flags.sum().item() / n
                 self.robust_accuracy_dict[attack] = robust_accuracy
+                state.add_run_attack(attack)                                       # :236
                 if self.verbose:
                     self.logger.log("robust accuracy after {}: {:.2%} (total time {:.1f} s)".format(
                         attack.upper(), robust_accuracy, time.time() - startt))
+            state.to_disk(force=True)                                              # :243
             if self.verbose:                                                       # :246-256
                 d = (x_adv - x_orig).reshape(n, -1)
                 res = d.abs().max(1)[0] if self.norm == "Linf" else (d ** 2).sum(-1).sqrt()

@@ -132,3 +132,26 @@ def test_cosine_lr_known_values():
     assert lr(0) == pytest.approx(1e-5 / 1400) and lr(1399) == pytest.approx(1e-5)
     assert lr(1400) == pytest.approx(1e-5) and lr(20000) == pytest.approx(0.0, abs=1e-20)
     assert lr(10700) == pytest.approx(0.5e-5)
+
+
+def test_evaluation_state_round_trip(tmp_path):
+    """autoattack/state.py: the evaluation state survives a save / load, in the reference's keys,
+    and a file written the reference's way (the set as its repr) is read too"""
+    import json
+    from robustvlm_b200.autoattack import EvaluationState
+    p = tmp_path / "state.json"
+    st = EvaluationState({"apgd-ce", "apgd-t"}, path=p)
+    st.to_disk()
+    st.robust_flags = torch.tensor([True, False, True, True])
+    st.clean_accuracy = 0.75
+    st.add_run_attack("apgd-ce")
+    st.to_disk(force=True)
+    d = json.load(open(p))
+    assert set(d) == {"_attacks_to_run", "path", "_run_attacks", "_robust_flags", "_last_saved",
+                      "_SAVE_TIMEOUT", "_clean_accuracy"}
+    back = EvaluationState.from_disk(p)
+    assert back.attacks_to_run == {"apgd-ce", "apgd-t"} and back.run_attacks == {"apgd-ce"}
+    assert back.robust_flags.tolist() == [True, False, True, True] and back.clean_accuracy == 0.75
+    d["_attacks_to_run"] = str({"apgd-ce", "apgd-t"})          # what json.dump(default=str) writes
+    json.dump(d, open(p, "w"))
+    assert EvaluationState.from_disk(p).attacks_to_run == {"apgd-ce", "apgd-t"}

@@ -199,6 +199,45 @@ def test_golden_autoattack(gold, models):
                    verbose=False).run_standard_evaluation(x[:2], y[:2], bs=2)
 
 
+def test_autoattack_state_resume(gold, models, tmp_path):
+    """run_standard_evaluation(state_path=...) (autoattack/autoattack.py:88-105,225,236): an
+    evaluation interrupted after apgd-ce resumes with apgd-t only and ends at the robust flags of
+    the uninterrupted run."""
+    from robustvlm_b200 import model as rm
+    from robustvlm_b200.autoattack import AutoAttack, EvaluationState
+    gt = torch.load(GOLD.replace("reference_vectors.pt", "reference_vectors_targeted.pt"),
+                    weights_only=False)["aa"]
+    ours, _ = models
+    cm = rm.ClassificationModel(ours, gold["text"].cuda())
+    x, y, eps = gt["x"].cuda(), gt["y"].cuda(), gt["eps"]
+
+    def make(attacks):
+        A = AutoAttack(cm, norm="Linf", eps=eps, version="custom", attacks_to_run=attacks, alpha=2.0,
+                       verbose=False, device="cuda", iterations_apgd=gt["iterations_apgd"], seed=0)
+        A.apgd.n_restarts = 1
+        A.apgd_targeted.n_target_classes = gt["n_target_classes"]
+        return A
+    full = make(["apgd-ce", "apgd-t"])
+    _, y_full = full.run_standard_evaluation(x, y, bs=gt["bs"], return_labels=True)
+    # "interrupted": the state of a run that finished apgd-ce only
+    p = tmp_path / "aa_state.json"
+    first = make(["apgd-ce"])
+    first.run_standard_evaluation(x, y, bs=gt["bs"], state_path=tmp_path / "ce_only.json")
+    st_ce = EvaluationState.from_disk(tmp_path / "ce_only.json")
+    st = EvaluationState({"apgd-ce", "apgd-t"}, path=p)
+    st._run_attacks = {"apgd-ce"}
+    st._clean_accuracy = st_ce.clean_accuracy
+    st.robust_flags = st_ce.robust_flags          # (the setter writes the file)
+    resumed = make(["apgd-ce", "apgd-t"])
+    resumed.run_standard_evaluation(x, y, bs=gt["bs"], state_path=p)
+    end = EvaluationState.from_disk(p)
+    assert end.run_attacks == {"apgd-ce", "apgd-t"}
+    assert list(resumed.robust_accuracy_dict) == ["clean", "apgd-t"]          # apgd-ce was not re-run
+    assert torch.equal(end.robust_flags, (y_full == y).cpu())
+    with pytest.raises(ValueError):                                           # :89-91
+        make(["apgd-ce"]).run_standard_evaluation(x, y, bs=gt["bs"], state_path=p)
+
+
 def test_fullsize_vitl14_properties():
     """BASELINE.json configs[1] at reduced batch: size-independent properties of the fused
     10-step PGD on ViT-L/14 -- constraints, determinism, invariance to micro-batching (the

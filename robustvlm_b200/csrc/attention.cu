@@ -608,9 +608,9 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   float* s_ds256 = s_p256 + 272;                                 // [272] dS[256, kv]
   float* s_dd = s_ds256 + 272;    // [4][128] quarter sums of o . dO
   float* s_tt = s_dd + 512;       // [256] per-row peeled-column terms: p_t | ds_t
-  float* s_part = s_tt + 256;     // [2][8][64] partial sums of the peeled kv row / query row
+  float* s_part = s_tt + 256;     // [3][8][64] partial sums: dv_256 | dk_256 | dq_256
   // [2][5][64] k_256 v_256 q_256 dO_256 o_256 of the current / the next item
-  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_part + 1024);
+  uint16_t* s_tv = reinterpret_cast<uint16_t*>(s_part + 1536);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tv + 2 * 320);
   uint64_t* bar_full = bars + 0;
   uint64_t* bar_tile = bars + 1;      // [2]
@@ -762,10 +762,12 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                                             cq * 16);
     };
     uint4 o_nx0 = make_uint4(0u, 0u, 0u, 0u), o_nx1 = o_nx0;
+    float lse_nx = 0.f;   // the row's forward log-sum-exp, prefetched with the o quarter
     if ((int)blockIdx.x < n_items) {
       const uint4* po = o_src(blockIdx.x, 0);
       o_nx0 = po[0];
       o_nx1 = po[1];
+      lse_nx = __ldg(lse_fwd + (size_t)blockIdx.x * T + r);
     }
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int b = item / P.H, h = item % P.H;
@@ -777,62 +779,25 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       const uint16_t* tv3 = tvb + 192;        // dO_256
       const uint16_t* tv4 = tvb + 256;        // o_256 (forward format)
       float tdv = 0.f, tdk = 0.f;   // this thread's share of dv_256[d], dk_256[d] (d = tid & 63)
-      if (TAIL) {
-        // ============ the peeled QUERY row (token 256) on the CUDA cores ============
-        const float l2 = __ldg(lse_row + 256) * LOG2E;
-        const float D = dot_rows16(tv4, P.fmt_o, tv3, FMT);
-        mbar_wait(bar_full, it & 1, 180);
-        if (tid < 256) {   // key tid: probability and dS of row 256 (both dot products, no exchange)
-          const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
-          const float dpv = dot_swz_row<FMT>(s_v, tid, tv3);
-          const float pv = fast_ex2(fmaf(sv, c2, -l2));
-          s_p256[tid] = pv;
-          s_ds256[tid] = pv * (dpv - D) * 0.125f;
-        } else if (tid == 256) {   // key 256
-          const float pv = fast_ex2(fmaf(dot_vec<FMT>(tv0, tv2), c2, -l2));
-          s_p256[256] = pv;
-          s_ds256[256] = pv * (dot_vec<FMT>(tv1, tv3) - D) * 0.125f;
-        }
-        asm volatile("bar.sync 3, 512;" ::: "memory");
-        {
-          const int d = tid & 63, qt = tid >> 6;       // 8 groups of 32 keys
-          float acc = 0.f;
-          for (int kv = qt * 32; kv < qt * 32 + 32; ++kv)
-            acc = fmaf(s_ds256[kv], swz_at<FMT>(s_k, kv, d), acc);
-          if (qt == 7) acc = fmaf(s_ds256[256], ld1<FMT>(tv0 + d), acc);
-          s_part[qt * 64 + d] = acc;
-          if (qt == 0) {   // the (q = 256, kv = 256) corner of dk_256 / dv_256
-            tdv = s_p256[256] * ld1<FMT>(tv3 + d);
-            tdk = s_ds256[256] * ld1<FMT>(tv2 + d);
-          }
-        }
-        asm volatile("bar.sync 3, 512;" ::: "memory");
-        if (tid < 32) {
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            a0 += s_part[q * 64 + 2 * tid];
-            a1 += s_part[q * 64 + 2 * tid + 1];
-          }
-          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64)[tid] =
-              packc<FMT>(a0, a1);
-        }
-        mbar_arrive(bar_trow);   // (each thread after its own last read of K / V)
-      }
+      // (the peeled query row is done AFTER the tiles: K / V stay resident until then, and the
+      // next item's K / V load -- issued once it is through -- hides under the dK / dV epilogue)
+      const float l256 = TAIL ? __ldg(lse_row + 256) * LOG2E : 0.f;
       for (int j = 0; j < ntile; ++j, ++g) {
         const int buf = g & 1;
         const int row = j * 128 + r;
         const size_t grow = (size_t)b * T + row;
         uint8_t* tq = s_tile0 + buf * 16384;
         uint8_t* tdo = s_tile1 + buf * 16384;
-        const float l2 = __ldg(lse_row + row) * LOG2E;
+        const float l2 = lse_nx * LOG2E;
         uint4 g_o[2] = {o_nx0, o_nx1};
-        {   // request the next tile's quarter now
+        {   // request the next tile's quarter (and log-sum-exp) now
           const int nitem = (j + 1 < ntile) ? item : item + (int)gridDim.x;
           if (nitem < n_items) {
-            const uint4* po = o_src(nitem, (j + 1 < ntile) ? j + 1 : 0);
+            const int nj = (j + 1 < ntile) ? j + 1 : 0;
+            const uint4* po = o_src(nitem, nj);
             o_nx0 = po[0];
             o_nx1 = po[1];
+            lse_nx = __ldg(lse_fwd + (size_t)nitem * T + nj * 128 + r);
           }
         }
         mbar_wait(&bar_tile[buf], (g >> 1) & 1, 181);
@@ -964,6 +929,48 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         tc_fence_before();
         mbar_arrive(bar_acc_free);
       }
+      if (TAIL) {
+        // ============ the peeled QUERY row (token 256) on the CUDA cores ============
+        const float l2 = l256;
+        const float D = dot_rows16(tv4, P.fmt_o, tv3, FMT);
+        mbar_wait(bar_full, it & 1, 180);
+        if (tid < 256) {   // key tid: probability and dS of row 256 (both dot products, no exchange)
+          const float sv = dot_swz_row<FMT>(s_k, tid, tv2);
+          const float dpv = dot_swz_row<FMT>(s_v, tid, tv3);
+          const float pv = fast_ex2(fmaf(sv, c2, -l2));
+          s_p256[tid] = pv;
+          s_ds256[tid] = pv * (dpv - D) * 0.125f;
+        } else if (tid == 256) {   // key 256
+          const float pv = fast_ex2(fmaf(dot_vec<FMT>(tv0, tv2), c2, -l2));
+          s_p256[256] = pv;
+          s_ds256[256] = pv * (dot_vec<FMT>(tv1, tv3) - D) * 0.125f;
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        {
+          const int d = tid & 63, qt = tid >> 6;       // 8 groups of 32 keys
+          float acc = 0.f;
+          for (int kv = qt * 32; kv < qt * 32 + 32; ++kv)
+            acc = fmaf(s_ds256[kv], swz_at<FMT>(s_k, kv, d), acc);
+          if (qt == 7) acc = fmaf(s_ds256[256], ld1<FMT>(tv0 + d), acc);
+          s_part[1024 + qt * 64 + d] = acc;
+          if (qt == 0) {   // the (q = 256, kv = 256) corner of dk_256 / dv_256
+            tdv = fmaf(s_p256[256], ld1<FMT>(tv3 + d), tdv);
+            tdk = fmaf(s_ds256[256], ld1<FMT>(tv2 + d), tdk);
+          }
+        }
+        asm volatile("bar.sync 3, 512;" ::: "memory");
+        if (tid < 32) {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            a0 += s_part[1024 + q * 64 + 2 * tid];
+            a1 += s_part[1024 + q * 64 + 2 * tid + 1];
+          }
+          reinterpret_cast<uint32_t*>(P.dqkv + ((size_t)b * T + 256) * 3 * W + colQ + h * 64)[tid] =
+              packc<FMT>(a0, a1);
+        }
+        mbar_arrive(bar_trow);   // (each thread after its own last read of K / V)
+      }
       // ---------------- dK / dV epilogue: cq 0,1 -> dV tiles 0,1 ; cq 2,3 -> dK tiles 0,1 --------
       uint4 tv_next = make_uint4(0u, 0u, 0u, 0u);
       const bool tv_fetch = TAIL && tid < 40 && item + (int)gridDim.x < n_items;
@@ -1049,7 +1056,7 @@ static int launch_bwd4(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
                        const AttnBwd2Params& P, const float* lse_fwd, cudaStream_t st) {
   auto kern = attn_bwd4_kernel<FMT, TAIL>;
   const size_t smem = (size_t)2 * 256 * 128 + 4 * 16384 + (size_t)4 * 16384 +
-                      (272 * 2 + 512 + 256 + 1024) * 4 + 2 * 640 + 128 + 1024;
+                      (272 * 2 + 512 + 256 + 1536) * 4 + 2 * 640 + 128 + 1024;
   static DeviceOnce attr;
   if (!attr.done()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

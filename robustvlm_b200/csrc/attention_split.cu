@@ -182,11 +182,14 @@ attn_fwd_split_kernel(const __grid_constant__ CUtensorMap tmQhi,   // box 64 x 1
       const int tile = idx % P.ntile, item = idx / P.ntile;
       const int b = item / P.H, h = item % P.H;
       const int row = tile * 128 + r;
+      // a warp whose 32 rows all lie beyond T (the last tile of T = 257 has ONE valid row) keeps
+      // the barrier protocol but skips the sweeps: its P rows are never read back
+      const bool wvalid = tile * 128 + warp * 32 < T;
       mbar_wait(bar_s, ph, 210);
       tc_fence_after();
       // ---- row max over the valid columns
       float mx = -INFINITY;
-      for (int q = 0; q < kvp; q += 16) {
+      for (int q = 0; wvalid && q < kvp; q += 16) {
         uint32_t v[16];
         tmem_ld16(ts + q, v);
         tmem_ld_wait();
@@ -200,7 +203,7 @@ attn_fwd_split_kernel(const __grid_constant__ CUtensorMap tmQhi,   // box 64 x 1
       for (int c = 0; c < P.nchunk; ++c, ++nchunks_done) {
         if (nchunks_done > 0) mbar_wait(bar_pv, (nchunks_done - 1) & 1, 211);   // P buffer free
         const int cols = min(128, kvp - c * 128);
-        for (int q = 0; q < cols; q += 16) {
+        for (int q = 0; wvalid && q < cols; q += 16) {
           uint32_t v[16];
           tmem_ld16(ts + c * 128 + q, v);
           tmem_ld_wait();
@@ -234,7 +237,7 @@ attn_fwd_split_kernel(const __grid_constant__ CUtensorMap tmQhi,   // box 64 x 1
       // ---- epilogue: O / rowsum -> hi / lo
       mbar_wait(bar_pv, (nchunks_done - 1) & 1, 212);
       tc_fence_after();
-      {
+      if (wvalid) {
         uint32_t v0[32], v1[32];
         tmem_ld32(ts + TO, v0);
         tmem_ld32(ts + TO + 32, v1);

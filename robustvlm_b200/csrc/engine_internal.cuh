@@ -136,20 +136,41 @@ struct EpiPatchPgdLinf {
   int kp, pp, lda, fmt;
   float stepsize, eps, dir, momentum;
   float mean[3], inv_std[3];
-  // x / delta / velocity are read inside operator() (3 float4 per piece x 8 pieces held
-  // early would not fit the register budget; this GEMM runs once per PGD step)
-  struct Aux {};
+  // delta and velocity (read-modify-write) are requested EARLY through the Aux mechanism -- inside
+  // operator() their loads could not be hoisted above the previous piece's stores to the same
+  // arrays, and eight dependent load -> store round trips per chunk made this GEMM 516 us
+  // (profiles/r02_kernels_ncu.txt) against 86 us for the plain patch dgrad; x is read-only (ld.nc)
+  // (inside rvlm_pgd_run the velocity is 0 at the start and sign(...) afterwards, i.e. always in
+  // {-1, 0, +1}: it is carried through the Aux registers as four 2-bit codes)
+  struct Aux { float4 d; uint32_t vs; };
   struct Col {};
-  __device__ __forceinline__ Aux load(int, int) const { return {}; }
+  __device__ __forceinline__ Aux load(int row, int col) const {
+    Aux a;
+    a.d = make_float4(0.f, 0.f, 0.f, 0.f);
+    a.vs = 0u;
+    if (col < kp) {
+      const size_t off = (size_t)row * kp + col;
+      a.d = *reinterpret_cast<const float4*>(dp + off);
+      const float4 v = *reinterpret_cast<const float4*>(vp + off);
+      a.vs = (v.x > 0.f ? 1u : (v.x < 0.f ? 2u : 0u)) | (v.y > 0.f ? 4u : (v.y < 0.f ? 8u : 0u)) |
+             (v.z > 0.f ? 16u : (v.z < 0.f ? 32u : 0u)) | (v.w > 0.f ? 64u : (v.w < 0.f ? 128u : 0u));
+    }
+    return a;
+  }
   __device__ __forceinline__ Col col(int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& aux,
                                              const Col&) const {
     if (col >= kp) return;
     const size_t off = (size_t)row * kp + col;
     struct { float4 x, d, v; } a;
-    a.x = *reinterpret_cast<const float4*>(xp + off);
-    a.d = *reinterpret_cast<const float4*>(dp + off);
-    a.v = *reinterpret_cast<const float4*>(vp + off);
+    a.x = __ldg(reinterpret_cast<const float4*>(xp + off));
+    a.d = aux.d;
+    {
+      const uint32_t c = aux.vs;
+      a.v = make_float4((c & 1u) ? 1.f : ((c & 2u) ? -1.f : 0.f), (c & 4u) ? 1.f : ((c & 8u) ? -1.f : 0.f),
+                        (c & 16u) ? 1.f : ((c & 32u) ? -1.f : 0.f),
+                        (c & 64u) ? 1.f : ((c & 128u) ? -1.f : 0.f));
+    }
     const float4 x4 = a.x;
     float4 d4 = a.d;
     float4 v4 = a.v;

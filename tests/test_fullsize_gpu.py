@@ -219,3 +219,50 @@ def test_config4_apgd_l2_vitl14(ref, mode):
     assert racc_ours == racc_ref
     assert float((out - r).norm() / (r - x).norm().clamp_min(1e-12)) <= LIMITS4[mode][1]
     assert float((l_ours - l_ref).abs().max()) <= 0.02 * float(l_ref.abs().max())
+
+
+def test_outer_step_param_grads_vitl14(ref):
+    """The outer FARE step at full size (row a12, train/adversarial_training_clip.py:340-362):
+    every parameter gradient of `rvlm_vit_train_grads` (bf16 operands, the engine the trainer
+    uses) against autograd through the fp32 oracle on the same adversarial batch."""
+    from robustvlm_b200.engine import FMT_BF16, LossSpec, VitEngine
+    o1, m1 = ref["o1"], ref["m1"]
+    x_adv = ref["pgd_fare"]
+    params = dict(o1.named_parameters())
+    for p in params.values():
+        p.requires_grad_(True)
+    try:
+        loss = oa.compute_loss("l2", m1(x_adv, output_normalize=False), None, ref["e_orig_diff"],
+                               100.0, None, "mean")
+        grads_ref = dict(zip(params, torch.autograd.grad(loss, list(params.values()))))
+    finally:
+        for p in params.values():
+            p.requires_grad_(False)
+    _MODELS.clear()
+    torch.cuda.empty_cache()
+    eng = VitEngine(o1.state_dict(), fmt_fwd=FMT_BF16, fmt_bwd=FMT_BF16)
+    grads = {k: torch.full_like(v, float("nan"), device="cuda") for k, v in o1.state_dict().items()}
+    spec = LossSpec("l2", False, emb_orig=ref["e_orig_diff"].cuda())
+    loss_b, emb = eng.train_grads(x_adv.cuda(), spec, grads, 1.0 / B)
+    torch.cuda.synchronize()
+    loss_rel = abs(float(loss_b.mean()) - float(loss)) / abs(float(loss))
+    worst, worst_ratio = ("", 1.0), 0.0
+    num = den_a = den_b = 0.0
+    for k, r in grads_ref.items():
+        g = grads[k].cpu().double().flatten()
+        rr = r.double().flatten()
+        assert torch.isfinite(g).all(), k
+        cos = float(torch.nn.functional.cosine_similarity(g, rr, dim=0))
+        if cos < worst[1]:
+            worst = (k, cos)
+        worst_ratio = max(worst_ratio, abs(float(g.norm() / rr.norm().clamp_min(1e-30)) - 1.0))
+        num += float(g @ rr)
+        den_a += float(g @ g)
+        den_b += float(rr @ rr)
+    cos_all = num / (den_a * den_b) ** 0.5
+    with torch.no_grad():
+        e_ref = m1(x_adv, output_normalize=False)
+    emb_rel = float((emb.cpu() - e_ref).norm() / e_ref.norm())
+    _log("fullsize_outer_step", loss_rel_err=loss_rel, cos_all=cos_all, worst_key=worst[0],
+         worst_cos=worst[1], worst_norm_ratio_err=worst_ratio, emb_rel_err_bf16=emb_rel)
+    assert loss_rel <= 2e-2 and cos_all >= 0.999 and worst[1] >= 0.99

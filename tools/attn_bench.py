@@ -77,6 +77,27 @@ def main():
     us3, g3 = bwd("rvlm_attn_bwd_lse", "0")
     res.update(bwd4_us=us4, bwd3_us=us3, bwd4_vs_bwd3_rel=float((g4 - g3).norm() / g3.norm()),
                bwd4_tflops=10.0 * B * H * T * T * 64 / (us4 * 1e-6) / 1e12)
+    # split-operand forward (fp16 hi + lo, three MMAs per product) at the same shape
+    if args.fmt == 0:
+        x32 = torch.randn(B * T, 3 * W, device="cuda") * 1.5
+        qh = x32.half()
+        ql = (x32 - qh.float()).half()
+        oh, ol = torch.empty(B * T, W, device="cuda", dtype=torch.half), torch.empty(B * T, W, device="cuda", dtype=torch.half)
+        cs = lambda: nat.call("rvlm_attn_fwd_split", nat.ptr(qh), nat.ptr(ql), nat.ptr(oh), nat.ptr(ol),  # noqa: E731
+                              nat.ptr(lse), nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.stream_ptr())
+        for key, env in (("split_v2_us", "0"), ("split_v1_us", "1")):
+            os.environ["RVLM_ATTN_SPLIT1"] = env
+            for _ in range(2):
+                cs()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.reps):
+                cs()
+            b.record()
+            torch.cuda.synchronize()
+            res[key] = a.elapsed_time(b) * 1e3 / args.reps
+        os.environ.pop("RVLM_ATTN_SPLIT1", None)
     print(json.dumps(res), flush=True)
 
 

@@ -195,7 +195,7 @@ int rvlm_attn_bwd_lse(const void* qkv16, const void* o16, const void* do16, floa
                       void* stream);
 /* Split-operand forward (the attention part of RVLM_FMT_F16X2): q | k | v and o as fp16 hi + lo
  * pairs in separate buffers of the same layout; softmax(q k^T / 8) v with every product formed as
- * hi*hi + lo*hi + hi*lo.  o_lo and lse may be NULL.  T <= 272. */
+ * hi*hi + lo*hi + hi*lo.  o_lo and lse may be NULL.  T <= 257. */
 int rvlm_attn_fwd_split(const void* qkv_hi, const void* qkv_lo, void* o_hi, void* o_lo, float* lse,
                         int B, int T, int H, void* stream);
 /* Class-token row only (the last block of the tower needs nothing else):

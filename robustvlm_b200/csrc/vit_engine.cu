@@ -621,7 +621,7 @@ extern "C" int rvlm_vit_create(const rvlm_vit_config* cfg, const rvlm_vit_weight
   E->geom.image = cfg->image; E->geom.patch = cfg->patch; E->geom.grid = g;
   E->geom.np = E->np; E->geom.kp = E->kp;
   for (int c = 0; c < 3; ++c) { E->geom.mean[c] = cfg->mean[c]; E->geom.inv_std[c] = 1.f / cfg->std[c]; }
-  if (E->T > 272 || (E->kp & 3)) { delete E; return RVLM_ERR_UNSUPPORTED; }
+  if (E->T > 272 || (E->kp & 3) || (E->split && E->T > 257)) { delete E; return RVLM_ERR_UNSUPPORTED; }
   E->attn_simt = (cfg->flags & RVLM_VIT_ATTN_SIMT) ? 1 : 0;
   {
     const char* e = getenv("RVLM_CLS_LAST");

@@ -85,8 +85,7 @@ def main():
         oh, ol = torch.empty(B * T, W, device="cuda", dtype=torch.half), torch.empty(B * T, W, device="cuda", dtype=torch.half)
         cs = lambda: nat.call("rvlm_attn_fwd_split", nat.ptr(qh), nat.ptr(ql), nat.ptr(oh), nat.ptr(ol),  # noqa: E731
                               nat.ptr(lse), nat.c_int(B), nat.c_int(T), nat.c_int(H), nat.stream_ptr())
-        for key, env in (("split_v2_us", "0"), ("split_v1_us", "1")):
-            os.environ["RVLM_ATTN_SPLIT1"] = env
+        for key in ("split_us",):
             for _ in range(2):
                 cs()
             torch.cuda.synchronize()
@@ -97,7 +96,6 @@ def main():
             b.record()
             torch.cuda.synchronize()
             res[key] = a.elapsed_time(b) * 1e3 / args.reps
-        os.environ.pop("RVLM_ATTN_SPLIT1", None)
     print(json.dumps(res), flush=True)
 
 

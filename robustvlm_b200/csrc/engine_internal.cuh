@@ -213,6 +213,9 @@ struct EpiPatchPgdLinf {
 // ---- misc elementwise (convert.cu) ----------------------------------------
 // fmt 0 / 1 = fp16 / bf16; fmt 2 = the fp16 lo half of a split operand, fp16(v - float(fp16(v)))
 int launch_convert16(const float* src, uint16_t* dst, long long n, int fmt, cudaStream_t st);
+// dst = fmt_dst(src) for a 16-bit buffer in fmt_src (n % 8 == 0)
+int launch_recast16(const uint16_t* src, uint16_t* dst, long long n, int fmt_src, int fmt_dst,
+                    cudaStream_t st);
 // dst[c, r] (pitch ldd) = 16-bit(src[r, c]) for src [R, C] row-major
 int launch_transpose_convert16(const float* src, uint16_t* dst, int R, int C, int ldd, int fmt,
                                cudaStream_t st);

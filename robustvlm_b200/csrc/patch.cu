@@ -172,6 +172,33 @@ __global__ void transpose_convert16_kernel(const float* __restrict__ src,
   }
 }
 
+// 16-bit -> 16-bit format change (fp16 <-> bf16) of a contiguous buffer, 8 elements per thread:
+// the outer training step keeps a gradient-format copy of every forward GEMM operand for the
+// weight-gradient GEMMs when its forward runs in another format (fp16 forward, bf16 gradients)
+__global__ void recast16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                long long n8, int fmt_src, int fmt_dst) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = src[i];
+    const uint32_t* a = &u.x;
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack2(a[j], fmt_src);
+      o[j] = pack2(f.x, f.y, fmt_dst);
+    }
+    dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+int launch_recast16(const uint16_t* src, uint16_t* dst, long long n, int fmt_src, int fmt_dst,
+                    cudaStream_t st) {
+  if (n & 7) return RVLM_ERR_INVAL;
+  recast16_kernel<<<nblk(n >> 3, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                     reinterpret_cast<uint4*>(dst), n >> 3,
+                                                     fmt_src, fmt_dst);
+  return rc();
+}
+
 int launch_convert16(const float* src, uint16_t* dst, long long n, int fmt, cudaStream_t st) {
   convert16_kernel<<<nblk(n, 256), 256, 0, st>>>(src, dst, 1, (int)n, (int)n, fmt);
   return rc();

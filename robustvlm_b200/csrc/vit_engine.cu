@@ -105,7 +105,8 @@ struct Ws {
   // split forward: the fp16 lo halves of the transient forward operands
   uint16_t *a16lo, *y16lo, *act16lo, *qkvf16lo, *o16lo;
   // outer training step (stash == 2): per-layer GEMM inputs kept for the weight gradients
-  uint16_t *ty16, *tz16, *tact16;   // [L] x [M, W], [M, W], [M, F]
+  uint16_t *ty16, *tz16, *tact16;   // [L] x [M, W], [M, W], [M, F]   (gradient format)
+  uint16_t *to16, *ta16;            // mixed formats only: gradient-format copies of o [L][M, W] and the patch operand
   float *red;                        // column-reduction scratch
   float *t_xhat, *t_pooled, *t_dpooled, *t_demb;
   // backward
@@ -172,6 +173,10 @@ Ws carve(const Engine& E, uint8_t* base, int B, int stash) {
     w.ty16 = take<uint16_t>(p, used, L * M * W);
     w.tz16 = take<uint16_t>(p, used, L * M * W);
     w.tact16 = take<uint16_t>(p, used, L * M * F);
+    if (E.ff != E.cfg.fmt_bwd) {
+      w.to16 = take<uint16_t>(p, used, L * M * W);
+      w.ta16 = take<uint16_t>(p, used, R * E.kld);
+    }
     w.red = take<float>(p, used, (size_t)2 * TRAIN_RSPLIT * (3 * W > F ? 3 * W : F));
     w.t_xhat = take<float>(p, used, (size_t)B * W);
     w.t_pooled = take<float>(p, used, (size_t)B * W);
@@ -229,9 +234,14 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
     float* st1 = w.stats1 + s * (size_t)M * 2;
     float* st2 = w.stats2 + s * (size_t)M * 2;
     const bool train = w.stash == 2;
-    uint16_t* y1 = train ? w.ty16 + (size_t)l * MW : w.y16;
-    uint16_t* z1 = train ? w.tz16 + (size_t)l * MW : w.y16;
-    uint16_t* act = train ? w.tact16 + (size_t)l * M * F : w.act16;
+    // outer training step: the GEMM inputs are kept for the weight gradients, in the GRADIENT
+    // format (one MMA = one format).  Same formats: the kept copy is the operand itself; mixed
+    // (fp16 forward for a <= 1e-3 embedding, bf16 gradients): the forward runs on the transient
+    // forward-format buffers and a recast copy is kept.
+    const bool mixed = train && ff != E.cfg.fmt_bwd;
+    uint16_t* y1 = (train && !mixed) ? w.ty16 + (size_t)l * MW : w.y16;
+    uint16_t* z1 = (train && !mixed) ? w.tz16 + (size_t)l * MW : w.y16;
+    uint16_t* act = (train && !mixed) ? w.tact16 + (size_t)l * M * F : w.act16;
     uint16_t* y1lo = sp ? w.y16lo : nullptr;
     uint16_t* qf = w.qkvf16;   // q|k|v the forward attention reads
     RV(ln_fwd_strided(x_in, 0, Lw.ln1_g, Lw.ln1_b, y1, nullptr, 0, st1, M, W, ff, st, y1lo));
@@ -243,6 +253,7 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
                          sp ? w.qkvf16lo : nullptr};
       RV((launch_gemm_fwd(y1, y1lo, W, Lw.wqkv, Lw.wqkv_lo, W, M, 3 * W, W, ff, epi, st)));
     }
+    if (mixed) RV(launch_recast16(y1, w.ty16 + (size_t)l * MW, (long long)MW, ff, E.cfg.fmt_bwd, st));
     if (l == E.L - 1 && E.cls_last && !train) {
       // ---- last block, class-token rows only (row pitch T*W inside the [B*T, W] streams; the
       // per-row operands of the MLP live compactly in the first B rows of their buffers)
@@ -275,6 +286,7 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       EpiStore32 epi{xm, W, Lw.bo, x_in, W};
       RV((launch_gemm_fwd(o, sp ? w.o16lo : nullptr, W, Lw.wo, Lw.wo_lo, W, M, W, W, ff, epi, st)));
     }
+    if (mixed) RV(launch_recast16(o, w.to16 + (size_t)l * MW, (long long)MW, ff, E.cfg.fmt_bwd, st));
     uint16_t* z1lo = sp ? w.y16lo : nullptr;
     RV(ln_fwd_strided(xm, 0, Lw.ln2_g, Lw.ln2_b, z1, nullptr, 0, st2, M, W, ff, st, z1lo));
     {
@@ -285,6 +297,10 @@ int run_forward(const Engine& E, const Ws& w, int B, cudaStream_t st) {
       EpiStore32 epi{x_out, W, Lw.bpr, xm, W};
       RV((launch_gemm_fwd(act, sp ? w.act16lo : nullptr, F, Lw.wpr, Lw.wpr_lo, F, M, W, F, ff, epi,
                           st)));
+    }
+    if (mixed) {
+      RV(launch_recast16(z1, w.tz16 + (size_t)l * MW, (long long)MW, ff, E.cfg.fmt_bwd, st));
+      RV(launch_recast16(act, w.tact16 + (size_t)l * M * F, (long long)M * F, ff, E.cfg.fmt_bwd, st));
     }
   }
   return 0;
@@ -472,7 +488,7 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
     RV(launch_ln_param_grads(w.dz32, xm, st2, M, W, w.red, g->ln_2_weight[l], g->ln_2_bias[l], st));
     RV(rvlm_layernorm_bwd(w.dz32, xm, st2, Lw.ln2_g, w.dx32, w.dx32, w.dx16, M, W, fg, 0, stv));
     // attn.out_proj: xm = x + o W_o^T + b_o ; dY = dx (now the gradient w.r.t. xm)
-    RV(wgrad(w.dx16, W, o, W, M, fg, g->attn_out_proj_weight[l], st));
+    RV(wgrad(w.dx16, W, ff != fg ? w.to16 + (size_t)l * MW : o, W, M, fg, g->attn_out_proj_weight[l], st));
     RV(launch_colsum16(w.dx16, M, W, fg, w.red, g->attn_out_proj_bias[l], st));
     {
       EpiStore16 epi{w.do16, W, nullptr, fg};
@@ -508,7 +524,8 @@ int run_backward_train(const Engine& E, const Ws& w, int B, const rvlm_vit_grads
                              cudaMemcpyDeviceToDevice, st)));
   {
     EpiWgradPatch epi{g->conv1_weight, E.kp};
-    RV((launch_gemm16<128, true, true>(w.dtok16, W, w.a16, E.kld, W, E.kp32, R, fg, epi, st)));
+    RV((launch_gemm16<128, true, true>(w.dtok16, W, ff != fg ? w.ta16 : w.a16, E.kld, W, E.kp32, R, fg,
+                                       epi, st)));
   }
   if (events) RV(cuda_rc(cudaEventRecord((cudaEvent_t)events[E.L], st)));
   return 0;
@@ -776,11 +793,13 @@ extern "C" int rvlm_vit_train_grads_ev(rvlm_vit_handle h, void* workspace, size_
   if (events && n_events != reinterpret_cast<Engine*>(h)->L + 1) return RVLM_ERR_INVAL;
   if (loss->mode != 1 && loss->mode != 2) return RVLM_ERR_INVAL;
   const Engine& E = *reinterpret_cast<Engine*>(h);
-  if (E.split || E.cfg.fmt_fwd != E.cfg.fmt_bwd) return RVLM_ERR_UNSUPPORTED;  // wgrad: one operand format
+  if (E.split) return RVLM_ERR_UNSUPPORTED;   // (mixed fp16 / bf16 formats keep recast copies for the wgrads)
   Ws w = carve(E, reinterpret_cast<uint8_t*>(workspace), B, 2);
   if (w.total > workspace_bytes) return RVLM_ERR_NOMEM;
   cudaStream_t st = (cudaStream_t)stream;
   RV(prep_state(E, w, B, x, nullptr, false, st));
+  if (E.ff != E.cfg.fmt_bwd)   // gradient-format copy of the patch operand for the conv1 weight gradient
+    RV(launch_patch_operand(w.xp, nullptr, w.ta16, E.kld, (long long)B * E.np, E.geom, E.cfg.fmt_bwd, st));
   RV(run_forward(E, w, B, st));
   RV(run_head(E, w, B, loss, 0, emb_out, nullptr, true, st, loss_scale));
   if (loss_out)

@@ -8,9 +8,10 @@
 
 The model's fp32 master parameters, their gradients and the AdamW moments live in flat
 buffers, so the step needs ONE all-reduce (NCCL over NVLink; parallel.allreduce_mean_) and
-ONE fused AdamW launch.  The attack runs on an fp16-forward / bf16-backward engine, the
-outer forward/backward on a bf16 engine (weight-gradient GEMMs need a single operand
-format); both read the same master parameters.
+ONE fused AdamW launch.  The attack runs on the fp16 / fp16 engine, the outer forward / backward
+on an fp16-forward / bf16-gradient engine (the weight-gradient GEMMs contract a forward
+activation with a gradient in ONE format: recast copies of the GEMM inputs are kept for them);
+both read the same master parameters.
 """
 from __future__ import annotations
 
@@ -21,7 +22,7 @@ import torch
 from . import _native as nat
 from . import attacks, checkpoint, parallel
 from ._native import c_double, c_int, c_int64
-from .engine import FMT_BF16, LossSpec, VitEngine
+from .engine import FMT_BF16, FMT_F16, LossSpec, VitEngine
 from .model import ClipVisionModel, ComputeLossWrapper, VisionTransformer, compute_acc
 
 
@@ -51,7 +52,7 @@ class AdversarialTrainer:
                  warmup=1400, loss="l2", loss_clean="none", clean_weight=0.0, trades=False,
                  inner_loss="l2", norm="linf", eps=4 / 255, stepsize=1 / 255, iterations=10,
                  attack="pgd", output_normalize=False, text_embedding=None, logit_scale=100.0,
-                 start_step=0):
+                 start_step=0, train_precision="mixed"):
         vt = model.model
         assert isinstance(vt, VisionTransformer)
         if opt not in ("adamw", "sgd"):
@@ -90,8 +91,14 @@ class AdversarialTrainer:
         self.step_total = start_step                                                    # :219
         self.opt_steps = 0                       # optimizer.step() calls (AdamW bias correction)
         mean, std = model.engine().cfg.mean, model.engine().cfg.std
+        # outer forward / backward: "mixed" = fp16 forward operands (embedding within 1e-3 of fp32,
+        # as the attack path) + bf16 gradient operands, with gradient-format copies of the GEMM
+        # inputs kept for the weight-gradient GEMMs; "bf16" = bf16 everywhere (round 1)
+        if train_precision not in ("mixed", "bf16"):
+            raise ValueError(f"train_precision {train_precision} not supported")
         self.train_engine = VitEngine(vt.state_dict(), mean=tuple(mean), std=tuple(std),
-                                      fmt_fwd=FMT_BF16, fmt_bwd=FMT_BF16, device=self.dev)
+                                      fmt_fwd=FMT_F16 if train_precision == "mixed" else FMT_BF16,
+                                      fmt_bwd=FMT_BF16, device=self.dev)
         self._bucketed = None            # parallel.BucketedAllReduce, built on first use
 
     # -- optimizer state / checkpoints (reference formats, checkpoint.py) ---------------

@@ -20,9 +20,12 @@ def _log(name, **kw):
     print(name, kw)
 
 
+@pytest.mark.parametrize("fmt_fwd", [0, 1], ids=["mixed_f16_fwd", "bf16_fwd"])
 @pytest.mark.parametrize("loss", ["l2", "ce"])
 @pytest.mark.parametrize("name", ["tiny-32", "tiny-14"])
-def test_param_grads_match_autograd(name, loss):
+def test_param_grads_match_autograd(name, loss, fmt_fwd):
+    """every parameter gradient of the outer step vs autograd through the oracle, for both outer
+    engines: fp16 forward + bf16 gradients (the trainer's default) and bf16 / bf16"""
     from robustvlm_b200.engine import FMT_BF16, LossSpec, VitEngine
     B = 4
     o = ovit.build(name, seed=1)
@@ -39,7 +42,7 @@ def test_param_grads_match_autograd(name, loss):
     lval = oa.compute_loss(loss, model(x, output_normalize=normalize), y, e_orig, 100.0, text, "mean")
     ref = dict(zip([n for n, _ in o.named_parameters()],
                    torch.autograd.grad(lval, list(o.parameters()))))
-    eng = VitEngine(o.state_dict(), fmt_fwd=FMT_BF16, fmt_bwd=FMT_BF16)
+    eng = VitEngine(o.state_dict(), fmt_fwd=fmt_fwd, fmt_bwd=FMT_BF16)
     grads = {k: torch.full_like(v, float("nan"), device="cuda") for k, v in o.state_dict().items()}
     spec = LossSpec(loss, normalize, emb_orig=e_orig.cuda(), text=text.cuda(), targets=y.cuda())
     loss_b, _ = eng.train_grads(x.cuda(), spec, grads, 1.0 / B)
@@ -58,7 +61,7 @@ def test_param_grads_match_autograd(name, loss):
         worst_ratio = max(worst_ratio, abs(ratio - 1.0))
         assert float(cos) > 0.99996, (k, float(cos))         # measured worst 0.99998
         assert 0.98 < ratio < 1.02, (k, ratio)
-    _log("param_grads", model=name, loss=loss, worst_key=worst[0], worst_cos=worst[1],
+    _log("param_grads", model=name, loss=loss, fmt_fwd=fmt_fwd, worst_key=worst[0], worst_cos=worst[1],
          worst_norm_ratio_err=worst_ratio, loss_rel_err=loss_rel)
 
 

@@ -313,7 +313,7 @@ int rvlm_vit_backward_input(rvlm_vit_handle h, void* workspace, size_t workspace
                             void* stream);
 /* Per-sample loss, pred flag, embedding / logits, and d(sum_b loss_b)/d(x+delta) as
  * grad_out[B,3,H,W] (true scale; with fp16 gradient operands each sample's gradient is carried
- * at unit max-abs internally and rescaled on output).  Outputs other than grad_out may be NULL. */
+ * at a fixed max-abs internally and rescaled on output).  Outputs other than grad_out may be NULL. */
 int rvlm_vit_loss_grad(rvlm_vit_handle h, void* workspace, size_t workspace_bytes, const float* x,
                        const float* delta, int B, const rvlm_loss_config* loss, float* grad_out,
                        float* loss_out, int* pred_out, float* emb_out, float* logits_out,

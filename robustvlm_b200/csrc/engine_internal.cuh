@@ -29,7 +29,7 @@ struct HeadArgs {
   uint16_t* dx16;         // [B*T, W]    (may be null)
   int fmt_g;
   float grad_scale;       // multiplies d loss_b / d emb
-  int grad_unit;          // 1: rescale each sample's CLS-row gradient to unit max-abs
+  int grad_unit;          // 1: rescale each sample's CLS-row gradient to max-abs 64 (fp16 range)
   float* unit_out;        // [B] the factor applied (1 when grad_unit == 0); may be null
   // outer training step only (may be null): per-sample vectors for the head's parameter grads
   float* t_xhat;          // [B, W] normalised CLS row

@@ -334,7 +334,7 @@ int run_head(const Engine& E, const Ws& w, int B, const rvlm_loss_config* lc, in
   A.pred = w.pred;
   A.fmt_g = E.cfg.fmt_bwd;
   A.grad_scale = grad_scale;
-  // fp16 gradient operands: every sample's gradient is rescaled to unit max-abs at the head (range);
+  // fp16 gradient operands: every sample's gradient is rescaled to max-abs 64 at the head (range);
   // consumers that need the true scale divide by w.gunit again (launch_unpatchify)
   A.grad_unit = (E.cfg.fmt_bwd == RVLM_FMT_F16 && w.stash != 2) ? 1 : 0;
   A.unit_out = w.gunit;

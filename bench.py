@@ -248,7 +248,7 @@ def run_reference(args):
 def gemm_traffic():
     """Measured DRAM bytes per GEMM launch (mean over the four forward GEMM variants of one
     block) from the committed ncu --set full capture; None when the summary is absent."""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     try:
         d = json.load(open(p))
         return d["mean_per_launch"], d["mean_algorithmic_per_launch"]
@@ -496,9 +496,9 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                          "traffic": gemm_traffic()[0],
                          "traffic_algorithmic": gemm_traffic()[1],
-                         "traffic_source": "profiles/r01_gemm_traffic.json (ncu --set full dram "
-                                           "bytes per launch, mean of the 4 forward GEMM variants; "
-                                           "a profiler cannot run inside the timed bench)",
+                         "traffic_source": "profiles/r02_gemm_traffic.json (ncu dram bytes per launch of "
+                                           "this round's kernels, mean of the 4 forward GEMMs of a "
+                                           "block; a profiler cannot run inside the timed bench)",
                          "peak_source": f"{which} bf16_tflops_sustained",
                          "kernel": "gemm16_2cta_kernel (tcgen05 cta_group::2, all epilogue variants)",
                          "launches": gemm_n,

@@ -125,8 +125,10 @@ def apgd(model, x, norm, eps, n_iter=10, use_rs=False, mask=None, alpha=None, n_
     x_adv_old = x_adv.clone()
     for i in range(n_iter):
         a = 0.75 if i > 0 else 1.0
+        x_dtype = x_adv.dtype
         x_adv, x_adv_old = _apgd_step(norm, x, x_adv.detach(), x_adv_old, grad, step_size, eps, a,
                                       _l2_unit, scale_then_divide=True)
+        x_adv = x_adv.to(dtype=x_dtype) + 0.0          # :289 (fp16 inputs: the iterate stays fp16)
         loss_indiv, g_new = fwd_bwd(x_adv, need_grad=i < n_iter - 1)                     # :293-297
         loss_indiv = loss_indiv.reshape(bs)
         if g_new is not None:

@@ -141,9 +141,11 @@ def apgd_schedule(n_iter):
 
 
 def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_last_grad,
-               schedule=None):
+               schedule=None, round_to=None):
     """fwd_bwd(x_adv, need_grad) -> (loss_indiv[B] f32, pred[B] int32, grad | None).
     `schedule` overrides (k0, n_iter_min, size_decr) (vlm_eval/attacks/apgd.py:194-198).
+    `round_to`: the iterate is rounded to this dtype after every step, as the reference's
+    `x_adv = x_adv_1.to(dtype=x_adv.dtype)` does for fp16 inputs (vlm_eval/attacks/apgd.py:289).
     Returns (x_best, acc(bool), loss_best, x_best_adv)."""
     B, n, dev = x.shape[0], _flat_n(x), x.device
     x_adv = x_start.clamp(0.0, 1.0).contiguous()
@@ -172,6 +174,8 @@ def _apgd_core(fwd_bwd, x, x_start, norm, eps, n_iter, alpha, thr_decr, skip_las
             nat.call("rvlm_apgd_step_l2", nat.ptr(x_adv), nat.ptr(x_adv_old), nat.ptr(x),
                      nat.ptr(grad), nat.ptr(step_size), c_int(B), c_int64(n), c_float(eps),
                      c_float(a), nat.ptr(ws), nat.stream_ptr())
+        if round_to is not None:
+            x_adv.copy_(x_adv.to(round_to))
         need_grad = not (skip_last_grad and i == n_iter - 1)
         loss, pred, g_new = fwd_bwd(x_adv, need_grad)
         if g_new is not None:

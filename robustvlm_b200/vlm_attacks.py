@@ -10,8 +10,12 @@ between two model evaluations -- mask, NaN scrub, sign / ell_2 normalisation, mo
 projection, image clamp, APGD proposal, best-point / step-size bookkeeping and restarts -- runs
 in the C-ABI kernels (`rvlm_pgd_update_*_masked`, `rvlm_mul_f32`, `rvlm_apgd_step_*`,
 `rvlm_apgd_bookkeep`) with no host read of a device value inside the loop.  The arithmetic is
-fp32 (the reference computes in the model's cast dtype, apgd.py:289); inputs of other dtypes
-are converted and the result is returned in the input dtype.  There is no CPU path.
+fp32.  For fp16 / bf16 inputs the reference keeps the iterate in the input dtype
+(`x_adv = x_adv_1.to(dtype=x_adv.dtype)`, apgd.py:289) with fp32 arithmetic inside a step (the
+fp32 step size promotes every expression): here the step kernels run in fp32 on the widened
+values and the iterate is rounded to the input dtype after every step, which reproduces that
+sequence except for `grad2 = x_adv - x_adv_old` (:205), which the reference rounds to the input
+dtype (at most one ulp of it).  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -135,7 +139,7 @@ def apgd(model, x, norm, eps, n_iter=10, use_rs=False, mask=None, alpha=None, n_
 
     x_best, _, loss_best, x_best_adv = _apgd_core(
         fwd_bwd, xf, x_adv, norm, eps, n_iter, alpha, 0.75, skip_last_grad=True,
-        schedule=(k0, k_min, k_decr))
+        schedule=(k0, k_min, k_decr), round_to=None if dt == torch.float32 else dt)
     return x_best.to(dt), loss_best, x_best_adv.to(dt)
 
 

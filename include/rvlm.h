@@ -92,12 +92,14 @@ int rvlm_gemm16_out32(const void* A, int lda, const void* B, int ldb, float* C, 
 int rvlm_gemm16_split_out32(const void* A_hi, const void* A_lo, int lda, const void* B_hi,
                             const void* B_lo, int ldb, float* C, int ldc, const float* bias,
                             const float* resid, int ldr, int M, int N, int K, void* stream);
-/* H = A*B^T + bias (pre-activation, may be NULL), Act = QuickGELU(H); both 16-bit [M,N] pitch ld */
-int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* H, void* Act, int ld,
+/* h = A*B^T + bias; Act = QuickGELU(h), G = QuickGELU'(h) (may be NULL; what the dgrad below
+ * multiplies by -- the pre-activation itself is never stored); both 16-bit [M,N] pitch ld */
+int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* G, void* Act, int ld,
                      const float* bias, int M, int N, int K, int fmt, void* stream);
-/* out = (A*B^T) .* QuickGELU'(H) ; 16-bit [M,N] pitch ld; H in fmt_h, A/B/out in fmt */
-int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int ldb, void* out, const void* H,
-                         int ld, int M, int N, int K, int fmt, int fmt_h, void* stream);
+/* out = (A*B^T) .* G ; 16-bit [M,N] pitch ld; G (as written by rvlm_gemm16_gelu) in fmt_g,
+ * A/B/out in fmt */
+int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int ldb, void* out, const void* G,
+                         int ld, int M, int N, int K, int fmt, int fmt_g, void* stream);
 
 /* ------------------------------------------------------------------------ *
  * 2. Perturbation updates.  Tensors are contiguous fp32 [B, n] (n % 4 == 0).

@@ -623,7 +623,8 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
   uint64_t* bar_trow = bars + 9;      // 512 arrivals: peeled row done with K / V
   uint64_t* bar_kdone = bars + 10;    // last tensor-core read of K / V of this item retired
   uint64_t* bar_dk = bars + 11;       // dK MMAs of a tile retired (Q_i / dS no longer read)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_dv = bars + 12;       // dV MMAs of a tile retired (P no longer read: dS may overwrite it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -639,6 +640,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
     mbar_init(bar_trow, 512);
     mbar_init(bar_kdone, 1);
     mbar_init(bar_dk, 1);
+    mbar_init(bar_dv, 1);
     fence_barrier_init();
   }
   if (warp == AT4_CTRL_WARP) {
@@ -698,8 +700,19 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                      make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
           umma_commit(bar_s);
           mbar_wait(bar_p, (2 * g) & 1, 174);        // P written, S consumed
-          if (j == 0 && it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 171);   // dK / dV drained
           tc_fence_after();
+          // dP first: it is what the workers wait for.  The dV MMAs, which read P from shared
+          // memory, run under the workers' dS arithmetic; the workers keep dS in registers and
+          // store it over P only once bar_dv says the tensor core is through with P.
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                // dP = dO_i V^T into the (consumed) S region
+            umma_f16(tmem + TR, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(va + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_dp);
+          if (j == 0 && it > 0) {                    // dK / dV accumulators of the last item drained
+            mbar_wait(bar_kv_free, (it - 1) & 1, 171);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj)             // dV_jj += P^T dO_i
 #pragma unroll
@@ -707,11 +720,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
               umma_f16(tmem + TDV + jj * 64,
                        make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
                        make_smem_desc_sw128(t1 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)                // dP = dO_i V^T into the (consumed) S region
-            umma_f16(tmem + TR, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
-                     make_smem_desc_sw128(va + k * 32, 16, 1024), idS, k > 0);
-          umma_commit(bar_dp);
+          umma_commit(bar_dv);
           mbar_wait(bar_p, (2 * g + 1) & 1, 175);    // dS written over P
           tc_fence_after();
           issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
@@ -867,24 +876,22 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             tmem_ld_wait();
             if (q + 1 < 4) tmem_ld16(tcol + (q + 1) * 16, v[(q + 1) & 1]);
 #pragma unroll
-            for (int q8 = 0; q8 < 2; ++q8) {
-              float d[8];
-#pragma unroll
-              for (int u = 0; u < 8; u += 2) {
-                const int i = q8 * 8 + u;
-                const float2 pp = unpackc<FMT>(pk[q * 8 + i / 2]);
-                d[u] = pp.x * fmaf(__uint_as_float(v[q & 1][i]), 0.125f, nDsc);
-                d[u + 1] = pp.y * fmaf(__uint_as_float(v[q & 1][i + 1]), 0.125f, nDsc);
-              }
-              *reinterpret_cast<uint4*>(prow + ((((uint32_t)(q * 2 + q8)) << 4) ^ rx)) =
-                  make_uint4(packc<FMT>(d[0], d[1]), packc<FMT>(d[2], d[3]),
-                             packc<FMT>(d[4], d[5]), packc<FMT>(d[6], d[7]));
+            for (int i = 0; i < 16; i += 2) {        // dS replaces P in the same registers
+              const float2 pp = unpackc<FMT>(pk[q * 8 + i / 2]);
+              pk[q * 8 + i / 2] =
+                  packc<FMT>(pp.x * fmaf(__uint_as_float(v[q & 1][i]), 0.125f, nDsc),
+                             pp.y * fmaf(__uint_as_float(v[q & 1][i + 1]), 0.125f, nDsc));
             }
           }
           if (TAIL && cq == 3) {
             s_tt[r] = p_t;
             s_tt[128 + r] = p_t * (b_t - Dr) * 0.125f;
           }
+          mbar_wait(bar_dv, g & 1, 186);   // the dV MMAs have read P: dS may take its place
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8)
+            *reinterpret_cast<uint4*>(prow + (((uint32_t)c8 << 4) ^ rx)) =
+                make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
         }
         if (TAIL) {
           // peeled KEY row (kv = 256): dv_256 += sum_q p_t[q] dO_q ; dk_256 += sum_q ds_t[q] Q_q
@@ -1098,7 +1105,7 @@ struct AttnFwd3Params {
   float* lse_out;
 };
 
-template <int FMT>
+template <int FMT, bool ONE>
 __global__ void __launch_bounds__(AT3_THREADS, 2)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 128
                  const __grid_constant__ CUtensorMap tmFull,   // qkv, box 64 x 256
@@ -1208,10 +1215,14 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         umma_commit(bar_pfree);
         mbar_wait(bar_p1, ph, 136);                                  // P[:, 128:256) written
         tc_fence_after();
+        // ONE: the second half has its own accumulator O1 in columns [64, 128) -- the S columns
+        // [0, 128) were consumed before bar_p0 -- and the epilogue combines the two
 #pragma unroll
         for (int s = 0; s < 8; ++s)
-          umma_f16(tmem, make_smem_desc_sw128(ca + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
-                   make_smem_desc_sw128(va + (8 + s) * 2048, 8192, 1024), idO, 1);
+          umma_f16(tmem + (ONE ? 64u : 0u),
+                   make_smem_desc_sw128(ca + (s >> 2) * 16384 + (s & 3) * 32, 16, 1024),
+                   make_smem_desc_sw128(va + (8 + s) * 2048, 8192, 1024), idO,
+                   ONE ? (s > 0 ? 1u : 0u) : 1u);
         umma_commit(bar_o);
         mbar_wait(bar_o, ph, 138);                                   // V and P consumed
         if (more) {
@@ -1359,6 +1370,109 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       }
       mbar_wait(bar_s, ph, 140);
       tc_fence_after();
+      uint8_t* prow = s_c + r * 128;
+      const uint32_t rx = (uint32_t)(r & 7) << 4;
+      const size_t grow = (size_t)b * T + row;
+      if constexpr (ONE) {
+        // ---- ONE sweep over S (TMEM reads are the floor of this kernel: 64 B / clk / SM, and the
+        // max pass + exp pass + O read of the two-sweep variant are 4608 cycles per tile).  Each
+        // 128-column half of the row is pulled into registers once; its own maximum normalises
+        // its probabilities (all <= 1 in the 16-bit P tile), its P V product accumulates in its
+        // own TMEM accumulator (O0 in columns [0, 64), O1 in [64, 128)), and the epilogue joins
+        // the halves:  O = (O0 2^(m0 - m) + O1 2^(m1 - m)) / (l0 2^(m0 - m) + l1 2^(m1 - m)).
+        // No second read of S, no rescaling of an accumulator in TMEM: 3072 cycles per tile.
+        float mc0 = 0.f, mc1 = 0.f, l0 = 0.f, l1 = 0.f, p_t = 0.f;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t tb = ts + half * 128;
+          uint32_t v0[32], v1[32], v2[32], v3[32];
+          tmem_ld32(tb, v0);
+          tmem_ld32(tb + 32, v1);
+          tmem_ld32(tb + 64, v2);
+          tmem_ld32(tb + 96, v3);
+          tmem_ld_wait();
+          if (half == 0 && more && r < 24 && (r < 16 || ntile == 1))   // next item's token-256 rows
+            pre = *reinterpret_cast<const uint4*>(tail_src(nitem / P.H, nitem % P.H));
+          float m0 = half == 0 ? s_t : -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            m0 = fmaxf(m0, __uint_as_float(v0[i]));
+            m1 = fmaxf(m1, __uint_as_float(v1[i]));
+            m2 = fmaxf(m2, __uint_as_float(v2[i]));
+            m3 = fmaxf(m3, __uint_as_float(v3[i]));
+          }
+          const float mc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c2;
+          if (half == 1) mbar_wait(bar_pfree, ph, 145);   // first-half PV MMAs done with the buffer
+          float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+          auto pexp32 = [&](const uint32_t (&v)[32], int blk) {   // blk: 32-column block 0..3
+#pragma unroll
+            for (int q8 = 0; q8 < 4; ++q8) {
+              float e[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                e[i] = fast_ex2(fmaf(__uint_as_float(v[q8 * 8 + i]), c2, -mc));
+              sum0 += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
+              const int cc = blk * 32 + q8 * 8;   // column within the 128-column half
+              *reinterpret_cast<uint4*>(prow + (cc >> 6) * 16384 +
+                                        (((uint32_t)((cc & 63) >> 3) << 4) ^ rx)) =
+                  make_uint4(packc<FMT>(e[0], e[1]), packc<FMT>(e[2], e[3]),
+                             packc<FMT>(e[4], e[5]), packc<FMT>(e[6], e[7]));
+            }
+          };
+          pexp32(v0, 0);
+          pexp32(v1, 1);
+          pexp32(v2, 2);
+          pexp32(v3, 3);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(half == 0 ? bar_p0 : bar_p1);
+          const float l = (sum0 + sum1) + (sum2 + sum3);
+          if (half == 0) {
+            mc0 = mc;
+            p_t = fast_ex2(fmaf(s_t, c2, -mc));
+            l0 = l + p_t;
+          } else {
+            mc1 = mc;
+            l1 = l;
+          }
+        }
+        const float mcf = fmaxf(mc0, mc1);
+        const float a0 = fast_ex2(mc0 - mcf), a1 = fast_ex2(mc1 - mcf);
+        const float rsum = fmaf(l0, a0, l1 * a1);
+        const float inv = 1.f / rsum;
+        const float w0 = a0 * inv, w1 = a1 * inv, wt = p_t * w0;
+        mbar_wait(bar_o, ph, 141);
+        tc_fence_after();
+        uint16_t* dst = P.o_out + grow * W + h * 64;
+#pragma unroll
+        for (int q16 = 0; q16 < 4; ++q16) {
+          uint32_t x[16], y[16];
+          tmem_ld16(ts + q16 * 16, x);
+          tmem_ld16(ts + 64 + q16 * 16, y);
+          tmem_ld_wait();
+          uint32_t pkd[8];
+#pragma unroll
+          for (int q8 = 0; q8 < 2; ++q8) {
+            const uint4 vu = *reinterpret_cast<const uint4*>(vt + q16 * 16 + q8 * 8);
+            const uint32_t* vaa = &vu.x;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 yv = unpackc<FMT>(vaa[i]);
+              const int c = q8 * 8 + 2 * i;
+              const float o0 = fmaf(__uint_as_float(x[c]), w0,
+                                    fmaf(__uint_as_float(y[c]), w1, wt * yv.x));
+              const float o1 = fmaf(__uint_as_float(x[c + 1]), w0,
+                                    fmaf(__uint_as_float(y[c + 1]), w1, wt * yv.y));
+              pkd[q8 * 4 + i] = packc<FMT>(o0, o1);
+            }
+          }
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + q16 * 16),
+                       "r"(pkd[0]), "r"(pkd[1]), "r"(pkd[2]), "r"(pkd[3]), "r"(pkd[4]), "r"(pkd[5]),
+                       "r"(pkd[6]), "r"(pkd[7])
+                       : "memory");
+        }
+        P.lse_out[((size_t)b * P.H + h) * T + row] = (mcf + log2f(rsum)) * 0.6931471805599453f;
+      } else {
       float mx;
       {
         float m0 = s_t, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -1389,8 +1503,6 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
       const float mc = mx * c2;
       const float p_t = fast_ex2(fmaf(s_t, c2, -mc));
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint8_t* prow = s_c + r * 128;
-      const uint32_t rx = (uint32_t)(r & 7) << 4;
       auto pexp = [&](const uint32_t (&v)[16], int q) {   // q: 16-column piece 0..7 of this half
         float e[16];
 #pragma unroll
@@ -1438,7 +1550,6 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
         tmem_ld32(ts + 32, v1);
         tmem_ld_wait();
         const float inv = 1.f / rsum;
-        const size_t grow = (size_t)b * T + row;
         uint4* dst = reinterpret_cast<uint4*>(P.o_out + grow * W + h * 64);
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) {
@@ -1462,6 +1573,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
           dst[q8] = u;
         }
         P.lse_out[((size_t)b * P.H + h) * T + row] = (mc + log2f(rsum)) * 0.6931471805599453f;
+      }
       }
       tc_fence_before();
       mbar_arrive(bar_ofree);
@@ -1512,16 +1624,22 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   if (T == 257 && use_fwd3) {   // one tile per CTA, two CTAs per SM
     AttnFwd3Params P3{B, H, H * 64, P.qkv, P.o_out, P.lse_out};
     const size_t smem3 = 3 * 32768 + 512 + 128 + 128 + 1024;
-    auto kern3 = fmt ? attn_fwd3_kernel<1> : attn_fwd3_kernel<0>;
-    static DeviceOnce set3[2];
-    if (!set3[fmt ? 1 : 0].done()) {
+    // one sweep over S (default) or the earlier max pass + exp pass (RVLM_ATTN_FWD_ONE=0; read
+    // per call: the tests cover both)
+    const char* env1 = getenv("RVLM_ATTN_FWD_ONE");
+    const bool one = !(env1 && env1[0] == '0');
+    auto kern3 = one ? (fmt ? attn_fwd3_kernel<1, true> : attn_fwd3_kernel<0, true>)
+                     : (fmt ? attn_fwd3_kernel<1, false> : attn_fwd3_kernel<0, false>);
+    static DeviceOnce set3[4];
+    const int ki = (fmt ? 1 : 0) + (one ? 2 : 0);
+    if (!set3[ki].done()) {
       cudaError_t e = cudaFuncSetAttribute(kern3, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem3);
       if (e == cudaSuccess)
         e = cudaFuncSetAttribute(kern3, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
       if (e != cudaSuccess) return -(int)e - 1000;
-      set3[fmt ? 1 : 0].mark();
+      set3[ki].mark();
     }
     int grid3 = 2 * sm_count();
     if (2 * B * H < grid3) grid3 = 2 * B * H;

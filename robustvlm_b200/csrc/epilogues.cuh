@@ -111,6 +111,9 @@ struct EpiStore32 {
     return resid ? *reinterpret_cast<const float4*>(resid + (size_t)row * ldr + col)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  __device__ __forceinline__ void prefetch(int row, int col, int ncols) const {
+    if (resid) prefetch_l2_span(resid + (size_t)row * ldr + col, ncols * 4);
+  }
   __device__ __forceinline__ Col col(int c) const { return load_bias(bias, c); }
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& r,
                                              const Col& b) const {
@@ -120,17 +123,16 @@ struct EpiStore32 {
 
 // QuickGELU (open_clip QuickGELU: x * sigmoid(1.702 x)), with
 // MUFU ex2 / rcp approximations (relative error ~1e-7, far below the 16-bit output).
-__device__ __forceinline__ float quick_gelu(float x) {
-  return x * fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x));  // 1.702 * log2(e)
-}
-__device__ __forceinline__ float quick_gelu_grad(float x) {
-  const float s = fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x));
-  return s * (1.f + 1.702f * x * (1.f - s));
+__device__ __forceinline__ float quick_sigmoid(float x) {
+  return fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x));  // 1.702 * log2(e)
 }
 
-// H16 = acc + bias (pre-activation, kept for the backward); A16 = quick_gelu(H)
+// A16 = quick_gelu(h), h = acc + bias; G16 = quick_gelu'(h), the only thing the backward needs of
+// the pre-activation: s = sigmoid(1.702 h) is at hand here, so the derivative costs three FMAs
+// in this epilogue and the dgrad epilogue (EpiGeluBwd) is left with one multiply -- no MUFU work
+// and no second evaluation of the sigmoid on the backward's critical path.
 struct EpiGelu {
-  uint16_t* H;  // may be null
+  uint16_t* G;  // may be null
   uint16_t* A;
   int ld;
   const float* bias;
@@ -143,9 +145,15 @@ struct EpiGelu {
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
                                              const Col& b) const {
     const float4 h = add4(acc, b);
-    const float4 a = make_float4(quick_gelu(h.x), quick_gelu(h.y), quick_gelu(h.z),
-                                 quick_gelu(h.w));
-    if (H) *reinterpret_cast<uint2*>(H + (size_t)row * ld + col) = pack4(h, fmt);
+    const float4 s = make_float4(quick_sigmoid(h.x), quick_sigmoid(h.y), quick_sigmoid(h.z),
+                                 quick_sigmoid(h.w));
+    const float4 a = make_float4(h.x * s.x, h.y * s.y, h.z * s.z, h.w * s.w);
+    if (G) {
+      // gelu'(h) = s (1 + 1.702 h (1 - s)) = s + 1.702 a (1 - s)
+      const float4 g = make_float4(fmaf(1.702f * a.x, 1.f - s.x, s.x), fmaf(1.702f * a.y, 1.f - s.y, s.y),
+                                   fmaf(1.702f * a.z, 1.f - s.z, s.z), fmaf(1.702f * a.w, 1.f - s.w, s.w));
+      *reinterpret_cast<uint2*>(G + (size_t)row * ld + col) = pack4(g, fmt);
+    }
     if (Alo) {
       uint2 hi, lo;
       split4(a, hi, lo);
@@ -157,24 +165,27 @@ struct EpiGelu {
   }
 };
 
-// out16 = acc * quick_gelu'(H16)   (dgrad through the MLP activation)
+// out16 = acc * G16, G = quick_gelu'(pre-activation) as stored by EpiGelu   (dgrad through the
+// MLP activation)
 struct EpiGeluBwd {
   uint16_t* out;
   int ld;
-  const uint16_t* H;
-  int fmt_h;
+  const uint16_t* G;
+  int fmt_g;
   int fmt_out;
   using Aux = uint2;
   using Col = NoAux;
   __device__ __forceinline__ Aux load(int row, int col) const {
-    return *reinterpret_cast<const uint2*>(H + (size_t)row * ld + col);
+    return *reinterpret_cast<const uint2*>(G + (size_t)row * ld + col);
+  }
+  __device__ __forceinline__ void prefetch(int row, int col, int ncols) const {
+    prefetch_l2_span(G + (size_t)row * ld + col, ncols * 2);
   }
   __device__ __forceinline__ Col col(int) const { return {}; }
-  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& hu,
+  __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& gu,
                                              const Col&) const {
-    const float4 h = unpack4(hu, fmt_h);
-    const float4 o = make_float4(acc.x * quick_gelu_grad(h.x), acc.y * quick_gelu_grad(h.y),
-                                 acc.z * quick_gelu_grad(h.z), acc.w * quick_gelu_grad(h.w));
+    const float4 g = unpack4(gu, fmt_g);
+    const float4 o = make_float4(acc.x * g.x, acc.y * g.y, acc.z * g.z, acc.w * g.w);
     *reinterpret_cast<uint2*>(out + (size_t)row * ld + col) = pack4(o, fmt_out);
   }
 };

@@ -57,68 +57,117 @@ struct GemmSmem {
 // guaranteed (N is required to be a multiple of 32 by the host wrappers).
 
 
+// Register budget of the roles (setmaxnreg, one warpgroup = 4 warps): the producer / MMA / TMEM
+// warps (warpgroup 0) hand registers to the two epilogue warpgroups, which then hold TWO chunks of
+// HBM operands (the fp32 residual rows) in flight without spilling.
+// 128 * 40 + 256 * 232 = 64512 <= 65536.
+constexpr int GEMM_REGS_CTRL = 40;
+constexpr int GEMM_REGS_EPI = 232;
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// Optional functor hook: prefetch(row, col, ncols) pulls the HBM operands of `ncols` columns of
+// one row into L2 (no registers held); functors without it are skipped.
+template <class E>
+__device__ __forceinline__ auto epi_prefetch(const E& e, int row, int col, int ncols, int)
+    -> decltype(e.prefetch(row, col, ncols), void()) {
+  e.prefetch(row, col, ncols);
+}
+template <class E>
+__device__ __forceinline__ void epi_prefetch(const E&, int, int, int, long) {}
+
 // Epilogue of one accumulator tile for one epilogue warp: drains this warp's 32 TMEM lanes x
 // (BN/2) columns in 32-column chunks.  Per chunk: tcgen05.ld -> registers -> XOR-swizzled
 // warp-private smem transpose -> each lane owns float4 pieces (4 consecutive columns of one
 // row, 8 lanes per row) -> Epi functor.  Latency is hidden inside the warp instead of across
-// warps (only two epilogue warps share an SM sub-partition): the HBM operands of the
-// epilogue and the per-column operand (bias) are requested first, the NEXT chunk's
-// tcgen05.ld is issued as soon as the registers are staged, and the eight transposed pieces
-// are read back in one batch before any math / store is issued.
+// warps (only two epilogue warps share an SM sub-partition):
+//   * the HBM operands of the epilogue (residual rows, stored GELU derivative ...) are requested
+//     BEFORE the wait on the accumulator -- the tile is known long before its MMAs retire: the
+//     whole warp tile as L2 prefetches (lane = row; under load an HBM access takes several
+//     thousand cycles, a chunk's work a few hundred), chunk 0 into registers; chunk c + 1 is
+//     then loaded (from L2) before chunk c is processed.  These loads used to be issued and
+//     consumed inside one chunk, four exposed HBM round trips per tile;
+//   * the NEXT chunk's tcgen05.ld is issued as soon as the registers are staged, and the eight
+//     transposed pieces are read back in one batch before any math / store is issued.
 template <int BN, bool GUARD, class Epi>
 __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, uint32_t taddr,
                                                     int row0, int n0, int half, int M, int N,
-                                                    int lane) {
+                                                    int lane, uint64_t* tfull, uint32_t tphase) {
   constexpr int NCH = BN / 64;
   const int rl = lane >> 3, c4 = lane & 7;
   const int cfirst = half * NCH;
   const int rem = N - (n0 + cfirst * 32);  // columns left for this half (N % 32 == 0)
   const int nch = rem <= 0 ? 0 : (rem >= NCH * 32 ? NCH : rem / 32);  // warp-uniform
+  typename Epi::Aux aux[2][8];
+  auto load_aux = [&](int cc, typename Epi::Aux (&a)[8]) {
+    const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + rl + 4 * i;
+      if (!GUARD || row < M) a[i] = epi.load(row, col);
+    }
+  };
+  if (nch > 0) {
+    if (!GUARD || row0 + lane < M) epi_prefetch(epi, row0 + lane, n0 + cfirst * 32, nch * 32, 0);
+    load_aux(0, aux[0]);
+  }
+  mbar_wait(tfull, tphase, 4);
+  tc_fence_after();
   if (nch == 0) return;
   uint32_t r[32];
   tmem_ld32(taddr + cfirst * 32, r);
-#pragma unroll 1
-  for (int cc = 0; cc < nch; ++cc) {
-    const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
-    typename Epi::Aux aux[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + rl + 4 * i;
-      if (!GUARD || row < M) aux[i] = epi.load(row, col);
-    }
-    const typename Epi::Col ca = epi.col(col);
-    tmem_ld_wait();
-    // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
+  for (int cc = 0; cc < NCH; ++cc) {
+    if (cc < nch) {
+      const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
+      if (cc + 1 < NCH && cc + 1 < nch) load_aux(cc + 1, aux[(cc + 1) & 1]);
+      const typename Epi::Col ca = epi.col(col);
+      tmem_ld_wait();
+      // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-          make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-    __syncwarp();
-    if (cc + 1 < nch) tmem_ld32(taddr + (cfirst + cc + 1) * 32, r);
-    float4 v[8];
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      if (cc + 1 < NCH && cc + 1 < nch) tmem_ld32(taddr + (cfirst + cc + 1) * 32, r);
+      float4 v[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = rl + 4 * i;
-      v[i] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-    }
-    __syncwarp();
+      for (int i = 0; i < 8; ++i) {
+        const int rr = rl + 4 * i;
+        v[i] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+      }
+      __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + rl + 4 * i;
-      if (!GUARD || row < M) epi(row, col, v[i], aux[i], ca);
+      for (int i = 0; i < 8; ++i) {
+        const int row = row0 + rl + 4 * i;
+        if (!GUARD || row < M) epi(row, col, v[i], aux[cc & 1][i], ca);
+      }
     }
   }
 }
 
-// The row guard is hoisted to the warp's 32-row slab: full slabs (all but the last M tile)
-// run branch-free, so the eight pieces' dependent chains (MUFU, conversions, stores)
-// interleave instead of executing one piece at a time.
+// Waits for the accumulator (`tfull`, parity `tphase`) and drains it.  The row guard is hoisted to
+// the warp's 32-row slab: full slabs (all but the last M tile) run branch-free, so the eight
+// pieces' dependent chains (MUFU, conversions, stores) interleave instead of executing one piece
+// at a time.
 template <int BN, class Epi>
 __device__ __forceinline__ void epilogue_drain(const Epi& epi, float* stg, uint32_t taddr,
                                                int row0, int n0, int half, int M, int N,
-                                               int lane) {
-  if (row0 + 32 <= M) epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, half, M, N, lane);
-  else if (row0 < M) epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, half, M, N, lane);
+                                               int lane, uint64_t* tfull, uint32_t tphase) {
+  if (row0 + 32 <= M)
+    epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, half, M, N, lane, tfull, tphase);
+  else if (row0 < M)
+    epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, half, M, N, lane, tfull, tphase);
+  else {
+    mbar_wait(tfull, tphase, 4);
+    tc_fence_after();
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -175,6 +224,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  setmaxnreg_dec<GEMM_REGS_CTRL>();
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
@@ -236,8 +287,10 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       umma_commit(&tfull_bar[acc]);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================== epilogue =====================
+    setmaxnreg_inc<GEMM_REGS_EPI>();
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the accumulator columns
     float* stg = staging + (warp - 4) * 1024;
@@ -246,11 +299,10 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
       const int row0 = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane);
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane, &tfull_bar[acc],
+                         acc_phase);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -403,6 +455,8 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  setmaxnreg_dec<GEMM_REGS_CTRL>();
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
@@ -463,8 +517,10 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       umma_commit_2cta(&tfull_bar[acc]);
     }
-  } else if (warp >= 4) {
+  }
+  } else {
     // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
+    setmaxnreg_inc<GEMM_REGS_EPI>();
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     float* stg = staging + (warp - 4) * 1024;
@@ -473,11 +529,10 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
       const int row0 = m_blk * 256 + (int)rank * 128 + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane);
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane, &tfull_bar[acc],
+                         acc_phase);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[acc]);
       else mbar_arrive_cluster(&tempty_bar[acc], 0);

@@ -48,21 +48,21 @@ extern "C" int rvlm_gemm16_out32(const void* A, int lda, const void* B, int ldb,
   return dispatch(A, lda, B, ldb, M, N, K, fmt, flags, epi, (cudaStream_t)stream);
 }
 
-extern "C" int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* H, void* Act,
+extern "C" int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* G, void* Act,
                                 int ld, const float* bias, int M, int N, int K, int fmt,
                                 void* stream) {
-  if ((reinterpret_cast<uintptr_t>(Act) & 15) || (reinterpret_cast<uintptr_t>(H) & 15) || (ld & 7))
+  if ((reinterpret_cast<uintptr_t>(Act) & 15) || (reinterpret_cast<uintptr_t>(G) & 15) || (ld & 7))
     return RVLM_ERR_ALIGN;
-  EpiGelu epi{reinterpret_cast<uint16_t*>(H), reinterpret_cast<uint16_t*>(Act), ld, bias, fmt, nullptr};
+  EpiGelu epi{reinterpret_cast<uint16_t*>(G), reinterpret_cast<uint16_t*>(Act), ld, bias, fmt, nullptr};
   return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, (cudaStream_t)stream);
 }
 
 extern "C" int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int ldb, void* out,
-                                    const void* H, int ld, int M, int N, int K, int fmt, int fmt_h,
+                                    const void* G, int ld, int M, int N, int K, int fmt, int fmt_g,
                                     void* stream) {
-  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(H) & 15) || (ld & 7))
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(G) & 15) || (ld & 7))
     return RVLM_ERR_ALIGN;
-  EpiGeluBwd epi{reinterpret_cast<uint16_t*>(out), ld, reinterpret_cast<const uint16_t*>(H), fmt_h,
+  EpiGeluBwd epi{reinterpret_cast<uint16_t*>(out), ld, reinterpret_cast<const uint16_t*>(G), fmt_g,
                  fmt};
   return launch_gemm16<256, false, false>(A, lda, B, ldb, M, N, K, fmt, epi, (cudaStream_t)stream);
 }

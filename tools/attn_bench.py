@@ -46,7 +46,8 @@ def main():
     q2, k2, v2 = qkv[-T:].float().view(1, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     s2 = (q2 @ k2.transpose(-1, -2)) * 0.125
     o_ref2 = (s2.softmax(-1) @ v2).permute(0, 2, 1, 3).reshape(T, W)
-    res = {"fwd3": os.environ.get("RVLM_ATTN_FWD3", "0"), "B": B, "us": us,
+    res = {"fwd3": os.environ.get("RVLM_ATTN_FWD3", "1"),
+           "fwd_one_sweep": os.environ.get("RVLM_ATTN_FWD_ONE", "1"), "B": B, "us": us,
            "tflops": 4.0 * B * H * T * T * 64 / (us * 1e-6) / 1e12,
            "err_o": float((o[: nb * T].float() - o_ref).abs().max()),
            "err_o_last": float((o[-T:].float() - o_ref2).abs().max()),

@@ -443,7 +443,16 @@ def run_ours(args):
             tms, tfl, nl = c_double(), c_double(), c_longlong()
             nat.check(nat.lib().rvlm_profile_gemm_collect(byref(tms), byref(tfl), byref(nl)))
             nat.lib().rvlm_profile_gemm(0)
-            prof = (tms.value, tfl.value, nl.value)
+            import ctypes
+            import json as _json
+            need = nat.lib().rvlm_profile_breakdown(None, 0)
+            buf = ctypes.create_string_buffer(int(need) + 8)
+            nat.lib().rvlm_profile_breakdown(buf, len(buf))
+            try:
+                bd = _json.loads(buf.value.decode())
+            except ValueError:
+                bd = {}
+            prof = (tms.value, tfl.value, nl.value, bd)
         if sampler:
             sampler.stop_flag = True
             sampler.join(timeout=2)
@@ -480,7 +489,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         peak_tf, _, which = read_peaks()
-        gemm_ms, gemm_fl, gemm_n = prof
+        gemm_ms, gemm_fl, gemm_n, breakdown = prof
         achieved = gemm_fl / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         algo_tf = (FWD_GF[args.model] + BWD_GF[args.model]) * ITERS * B * args.steps / 1e3
         line = {
@@ -505,6 +514,9 @@ def run_ours(args):
                          "gemm_ms_per_step": gemm_ms / args.steps,
                          "gemm_share_of_step": gemm_ms / ms if ms else None,
                          "whole_step_algorithmic_tflops": algo_tf / (ms / 1e3)},
+            # CUDA-event time of the bracketed kernels inside the timed steps (per step), by kernel /
+            # GEMM shape; "other" = everything not bracketed (head, class-token attention, layout)
+            "kernel_breakdown": kernel_breakdown(breakdown, ms, args.steps),
         }
     # ---- the other precision modes on the same workload (N = 1 only, bounded: 1 + 2 steps each)
     modes = {}
@@ -560,6 +572,21 @@ PRECISION_DTYPE = {
     "split": "f16 hi+lo fwd operands (3 MMAs per product, fp32-class) / f16 bwd operands, f32 accumulate",
     "bf16": "bf16 operands, f32 accumulate",
 }
+
+
+def kernel_breakdown(bd, ms_total, steps):
+    out, acc = {}, 0.0
+    for k, v in sorted(bd.items(), key=lambda kv: -kv[1]["ms"]):
+        per = v["ms"] / steps
+        acc += v["ms"]
+        out[k] = {"ms_per_step": round(per, 3), "launches_per_step": v["launches"] // steps,
+                  "us_per_launch": round(1e3 * v["ms"] / max(v["launches"], 1), 2),
+                  "share": round(v["ms"] / ms_total, 4) if ms_total else None}
+        if v["gflop"] > 0:
+            out[k]["tflops"] = round(v["gflop"] / v["ms"], 1)
+    out["other"] = {"ms_per_step": round((ms_total - acc) / steps, 3),
+                    "share": round(1 - acc / ms_total, 4) if ms_total else None}
+    return out
 
 
 def main():

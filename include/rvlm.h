@@ -60,6 +60,10 @@ long long rvlm_launch_count(void);
 void rvlm_launch_count_reset(void);
 int rvlm_profile_gemm(int enable);
 int rvlm_profile_gemm_collect(double* total_ms, double* total_flops, long long* launches);
+/* Per-kernel breakdown of the last collect(): the same mode also brackets the attention and
+ * LayerNorm launches; writes a JSON object {"<kernel>": {"ms", "launches", "gflop"}, ...} into
+ * `out` (truncated to `cap`) and returns the size needed. */
+int rvlm_profile_breakdown(char* out, int cap);
 
 /* ------------------------------------------------------------------------ *
  * 1. tcgen05 GEMM (the contraction under every nn.Linear / Conv2d-as-GEMM of

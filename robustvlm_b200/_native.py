@@ -12,7 +12,8 @@ import re
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p, c_size_t
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "librvlm_b200.so")
+# RVLM_LIB: development hook -- load an A/B build of the same library (csrc/Makefile OUTDIR=...)
+LIB_PATH = os.environ.get("RVLM_LIB") or os.path.join(_HERE, "_lib", "librvlm_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rvlm.h")
 
 _lib = None

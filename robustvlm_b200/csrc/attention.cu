@@ -560,7 +560,10 @@ static int launch_bwd3(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   }
   int grid = sm_count();
   if (P.B * P.H < grid) grid = P.B * P.H;
-  kern<<<grid, AT_THREADS, smem, st>>>(a, b, c, P);
+  {
+    KernelProfScope prof(st, "attn_bwd3", 10.0 * P.B * P.H * (double)P.T * P.T * 64);
+    kern<<<grid, AT_THREADS, smem, st>>>(a, b, c, P);
+  }
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
@@ -585,6 +588,11 @@ static int launch_bwd3(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
 //   * the peeled 257th query row needs no block reductions either (its lse is known).
 // TMEM, shared-memory tiles and the MMA sequence are those of version 3.
 // =====================================================================================
+// RVLM_BWD4_DP_FIRST (build-time, A/B): 1 = dP MMAs before the dV MMAs, dS held in registers
+// until bar_dv; 0 = dV first, one commit for both
+#ifndef RVLM_BWD4_DP_FIRST
+#define RVLM_BWD4_DP_FIRST 1
+#endif
 constexpr int AT4_THREADS = 544;   // 16 worker warps + 1 control warp
 constexpr int AT4_CTRL_WARP = 16;
 
@@ -699,6 +707,7 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             umma_f16(tmem + TR, make_smem_desc_sw128(t0 + k * 32, 16, 1024),
                      make_smem_desc_sw128(ka + k * 32, 16, 1024), idS, k > 0);
           umma_commit(bar_s);
+#if RVLM_BWD4_DP_FIRST
           mbar_wait(bar_p, (2 * g) & 1, 174);        // P written, S consumed
           tc_fence_after();
           // dP first: it is what the workers wait for.  The dV MMAs, which read P from shared
@@ -721,6 +730,23 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
                        make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
                        make_smem_desc_sw128(t1 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
           umma_commit(bar_dv);
+#else
+          mbar_wait(bar_p, (2 * g) & 1, 174);        // P written, S consumed
+          if (j == 0 && it > 0) mbar_wait(bar_kv_free, (it - 1) & 1, 171);   // dK / dV drained
+          tc_fence_after();
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj)             // dV_jj += P^T dO_i
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+              umma_f16(tmem + TDV + jj * 64,
+                       make_smem_desc_sw128(pa + jj * 32768 + s * 2048, 16384, 1024),
+                       make_smem_desc_sw128(t1 + s * 2048, 8192, 1024), idT, (j > 0 || s > 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)                // dP = dO_i V^T into the (consumed) S region
+            umma_f16(tmem + TR, make_smem_desc_sw128(t1 + k * 32, 16, 1024),
+                     make_smem_desc_sw128(va + k * 32, 16, 1024), idS, k > 0);
+          umma_commit(bar_dp);
+#endif
           mbar_wait(bar_p, (2 * g + 1) & 1, 175);    // dS written over P
           tc_fence_after();
           issue_mma2(tmem + TR, pa, ka, KVM, FMT, FMT);   // dQ_i = dS K  (acc in [0,64))
@@ -887,7 +913,9 @@ attn_bwd4_kernel(const __grid_constant__ CUtensorMap tmTile,   // qkv, box 64 x 
             s_tt[r] = p_t;
             s_tt[128 + r] = p_t * (b_t - Dr) * 0.125f;
           }
+#if RVLM_BWD4_DP_FIRST
           mbar_wait(bar_dv, g & 1, 186);   // the dV MMAs have read P: dS may take its place
+#endif
 #pragma unroll
           for (int c8 = 0; c8 < 8; ++c8)
             *reinterpret_cast<uint4*>(prow + (((uint32_t)c8 << 4) ^ rx)) =
@@ -1073,7 +1101,10 @@ static int launch_bwd4(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   }
   int grid = sm_count();
   if (P.B * P.H < grid) grid = P.B * P.H;
-  kern<<<grid, AT4_THREADS, smem, st>>>(a, b, c, P, lse_fwd);
+  {
+    KernelProfScope prof(st, "attn_bwd4", 10.0 * P.B * P.H * (double)P.T * P.T * 64);
+    kern<<<grid, AT4_THREADS, smem, st>>>(a, b, c, P, lse_fwd);
+  }
   count_launch(1);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -(int)e - 1000;
@@ -1643,7 +1674,10 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
     }
     int grid3 = 2 * sm_count();
     if (2 * B * H < grid3) grid3 = 2 * B * H;
-    kern3<<<grid3, AT3_THREADS, smem3, (cudaStream_t)stream>>>(tmTile, tmFull, P3);
+    {
+      KernelProfScope prof((cudaStream_t)stream, "attn_fwd3", 4.0 * B * H * (double)T * T * 64);
+      kern3<<<grid3, AT3_THREADS, smem3, (cudaStream_t)stream>>>(tmTile, tmFull, P3);
+    }
     count_launch(1);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -(int)e - 1000;

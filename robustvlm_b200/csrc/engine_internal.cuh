@@ -54,6 +54,7 @@ int launch_head_param_grads(const float* pooled, const float* demb, const float*
 
 // GEMM epilogue: conv1 weight gradient [W, kp] (the GEMM's N is kp rounded up to 32)
 struct EpiWgradPatch {
+  static constexpr const char* kTag = "gemm.wgrad_patch";
   float* G;
   int kp;
   struct Aux {};
@@ -88,6 +89,7 @@ int launch_unpatchify_add(const float* xp, const float* dp, float* img, int B, c
 
 // GEMM epilogue: patch-embedding forward.  Row r = b*np + p  ->  token row b*T + 1 + p.
 struct EpiPatchFwd {
+  static constexpr const char* kTag = "gemm.patch_fwd";
   float* tok;        // [B*T, W]
   const float* pos;  // [T, W]
   int np, T, W;
@@ -107,6 +109,7 @@ struct EpiPatchFwd {
 // GEMM epilogue: patch-embedding dgrad -> input gradient in patch-major layout,
 // G[r, k] = acc / std_c  (chain rule through Normalize, train/adversarial_training_clip.py:254)
 struct EpiPatchGrad {
+  static constexpr const char* kTag = "gemm.patch_grad";
   float* G;  // [rows, kp]
   int kp, pp;  // pp = patch*patch; kp % 4 == 0
   float inv_std[3];
@@ -128,6 +131,7 @@ struct EpiPatchGrad {
 // delta = clamp(x+delta,0,1)-x, and the next iteration's normalised 16-bit GEMM operand,
 // so no separate elementwise kernel runs per PGD step.  sign(acc / std) == sign(acc).
 struct EpiPatchPgdLinf {
+  static constexpr const char* kTag = "gemm.patch_pgd_linf";
   const float* xp;   // [rows, kp]
   float* dp;         // [rows, kp] delta (in place)
   float* vp;         // [rows, kp] velocity (in place)

@@ -54,6 +54,7 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
 struct NoAux {};
 
 struct EpiStore16 {
+  static constexpr const char* kTag = "gemm.store16";
   uint16_t* C;
   int ldc;
   const float* bias;  // may be null
@@ -73,6 +74,7 @@ struct EpiStore16 {
 // tcgen05.mma needs both operands in one format, and the backward's other operand is
 // a gradient.
 struct EpiStore16Dual {
+  static constexpr const char* kTag = "gemm.store16dual";
   uint16_t* C;
   uint16_t* C2;  // may be null
   int ldc;
@@ -100,6 +102,7 @@ struct EpiStore16Dual {
 
 // C32[row, col] = acc + bias[col] + resid[row, col]   (fp32 residual stream)
 struct EpiStore32 {
+  static constexpr const char* kTag = "gemm.store32";
   float* C;
   int ldc;
   const float* bias;   // may be null
@@ -127,11 +130,18 @@ __device__ __forceinline__ float quick_sigmoid(float x) {
   return fast_rcp(1.f + fast_ex2(-2.4554669595930157f * x));  // 1.702 * log2(e)
 }
 
+// RVLM_GELU_DERIV (build-time, A/B): 1 = the forward stores QuickGELU'(h); 0 = it stores h and the
+// dgrad epilogue evaluates the derivative (the earlier scheme)
+#ifndef RVLM_GELU_DERIV
+#define RVLM_GELU_DERIV 1
+#endif
+
 // A16 = quick_gelu(h), h = acc + bias; G16 = quick_gelu'(h), the only thing the backward needs of
 // the pre-activation: s = sigmoid(1.702 h) is at hand here, so the derivative costs three FMAs
 // in this epilogue and the dgrad epilogue (EpiGeluBwd) is left with one multiply -- no MUFU work
 // and no second evaluation of the sigmoid on the backward's critical path.
 struct EpiGelu {
+  static constexpr const char* kTag = "gemm.gelu";
   uint16_t* G;  // may be null
   uint16_t* A;
   int ld;
@@ -150,8 +160,12 @@ struct EpiGelu {
     const float4 a = make_float4(h.x * s.x, h.y * s.y, h.z * s.z, h.w * s.w);
     if (G) {
       // gelu'(h) = s (1 + 1.702 h (1 - s)) = s + 1.702 a (1 - s)
+#if !RVLM_GELU_DERIV
+      const float4 g = h;
+#else
       const float4 g = make_float4(fmaf(1.702f * a.x, 1.f - s.x, s.x), fmaf(1.702f * a.y, 1.f - s.y, s.y),
                                    fmaf(1.702f * a.z, 1.f - s.z, s.z), fmaf(1.702f * a.w, 1.f - s.w, s.w));
+#endif
       *reinterpret_cast<uint2*>(G + (size_t)row * ld + col) = pack4(g, fmt);
     }
     if (Alo) {
@@ -168,6 +182,7 @@ struct EpiGelu {
 // out16 = acc * G16, G = quick_gelu'(pre-activation) as stored by EpiGelu   (dgrad through the
 // MLP activation)
 struct EpiGeluBwd {
+  static constexpr const char* kTag = "gemm.gelu_bwd";
   uint16_t* out;
   int ld;
   const uint16_t* G;
@@ -184,7 +199,17 @@ struct EpiGeluBwd {
   __device__ __forceinline__ Col col(int) const { return {}; }
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& gu,
                                              const Col&) const {
+#if RVLM_GELU_DERIV
     const float4 g = unpack4(gu, fmt_g);
+#else
+    const float4 h = unpack4(gu, fmt_g);
+    const float4 sg = make_float4(quick_sigmoid(h.x), quick_sigmoid(h.y), quick_sigmoid(h.z),
+                                  quick_sigmoid(h.w));
+    const float4 g = make_float4(sg.x * (1.f + 1.702f * h.x * (1.f - sg.x)),
+                                 sg.y * (1.f + 1.702f * h.y * (1.f - sg.y)),
+                                 sg.z * (1.f + 1.702f * h.z * (1.f - sg.z)),
+                                 sg.w * (1.f + 1.702f * h.w * (1.f - sg.w)));
+#endif
     const float4 o = make_float4(acc.x * g.x, acc.y * g.y, acc.z * g.z, acc.w * g.w);
     *reinterpret_cast<uint2*>(out + (size_t)row * ld + col) = pack4(o, fmt_out);
   }

@@ -61,15 +61,33 @@ struct GemmSmem {
 // warps (warpgroup 0) hand registers to the two epilogue warpgroups, which then hold TWO chunks of
 // HBM operands (the fp32 residual rows) in flight without spilling.
 // 128 * 40 + 256 * 232 = 64512 <= 65536.
+// build-time switches of the epilogue pipeline (defaults = the measured best; the others are kept
+// for A/B builds: make OUTDIR=../_lib/var_x EXTRA=-DRVLM_...=0)
+#ifndef RVLM_GEMM_SETMAXNREG
+#define RVLM_GEMM_SETMAXNREG 1
+#endif
+#ifndef RVLM_EPI_UNROLL
+#define RVLM_EPI_UNROLL 1
+#endif
+#ifndef RVLM_EPI_PF2
+#define RVLM_EPI_PF2 1
+#endif
+#ifndef RVLM_EPI_AHEAD
+#define RVLM_EPI_AHEAD 1
+#endif
 constexpr int GEMM_REGS_CTRL = 40;
 constexpr int GEMM_REGS_EPI = 232;
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
+#if RVLM_GEMM_SETMAXNREG
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
 }
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() {
+#if RVLM_GEMM_SETMAXNREG
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
 }
 
 // Optional functor hook: prefetch(row, col, ncols) pulls the HBM operands of `ncols` columns of
@@ -114,42 +132,63 @@ __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, 
     }
   };
   if (nch > 0) {
+#if RVLM_EPI_PF2
     if (!GUARD || row0 + lane < M) epi_prefetch(epi, row0 + lane, n0 + cfirst * 32, nch * 32, 0);
+#endif
+#if RVLM_EPI_AHEAD
     load_aux(0, aux[0]);
+#endif
   }
   mbar_wait(tfull, tphase, 4);
   tc_fence_after();
   if (nch == 0) return;
   uint32_t r[32];
   tmem_ld32(taddr + cfirst * 32, r);
+  // one 32-column chunk; `cur` holds its HBM operands, `nxt` receives those of the next chunk
+  auto step = [&](int cc, typename Epi::Aux (&cur)[8], typename Epi::Aux (&nxt)[8]) {
+    const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
+#if RVLM_EPI_AHEAD
+    if (cc + 1 < nch) load_aux(cc + 1, nxt);
+#else
+    load_aux(cc, cur);
+#endif
+    const typename Epi::Col ca = epi.col(col);
+    tmem_ld_wait();
+    // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
 #pragma unroll
-  for (int cc = 0; cc < NCH; ++cc) {
-    if (cc < nch) {
-      const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
-      if (cc + 1 < NCH && cc + 1 < nch) load_aux(cc + 1, aux[(cc + 1) & 1]);
-      const typename Epi::Col ca = epi.col(col);
-      tmem_ld_wait();
-      // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+          make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    __syncwarp();
+    if (cc + 1 < nch) tmem_ld32(taddr + (cfirst + cc + 1) * 32, r);
+    float4 v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-      __syncwarp();
-      if (cc + 1 < NCH && cc + 1 < nch) tmem_ld32(taddr + (cfirst + cc + 1) * 32, r);
-      float4 v[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = rl + 4 * i;
-        v[i] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = row0 + rl + 4 * i;
-        if (!GUARD || row < M) epi(row, col, v[i], aux[cc & 1][i], ca);
-      }
+    for (int i = 0; i < 8; ++i) {
+      const int rr = rl + 4 * i;
+      v[i] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = row0 + rl + 4 * i;
+      if (!GUARD || row < M) epi(row, col, v[i], cur[i], ca);
+    }
+  };
+#if RVLM_EPI_UNROLL
+#pragma unroll
+  for (int cc = 0; cc < NCH; ++cc)
+    if (cc < nch) step(cc, aux[cc & 1], aux[(cc + 1) & 1]);
+#elif RVLM_EPI_AHEAD
+  // rolled two chunks at a time (static operand buffers, a quarter of the unrolled code)
+#pragma unroll 1
+  for (int cc = 0; cc < nch; cc += 2) {
+    step(cc, aux[0], aux[1]);
+    if (cc + 1 < nch) step(cc + 1, aux[1], aux[0]);
   }
+#else
+#pragma unroll 1
+  for (int cc = 0; cc < nch; ++cc) step(cc, aux[0], aux[0]);
+#endif
 }
 
 // Waits for the accumulator (`tfull`, parity `tphase`) and drains it.  The row guard is hoisted to
@@ -576,9 +615,22 @@ struct GemmProfScope {
   int slot;
   // flops: algorithmic 2MNK of the product; mma_factor: tensor-pipe passes per product (3 for
   // split operands) -- reported separately so the roofline can state both
-  GemmProfScope(cudaStream_t s, double flops, double mma_factor = 1.0);
+  // tag: the kernel's name in the per-kernel breakdown (static string); is_gemm: counts towards
+  // the tcgen05 GEMM totals of rvlm_profile_gemm_collect
+  GemmProfScope(cudaStream_t s, double flops, double mma_factor = 1.0, const char* tag = "gemm",
+                bool is_gemm = true, int n = 0, int k = 0);
   ~GemmProfScope();
 };
+// a non-GEMM kernel launch in the same per-kernel breakdown (attention, LayerNorm ...)
+struct KernelProfScope : GemmProfScope {
+  KernelProfScope(cudaStream_t s, const char* tag, double flops = 0.0)
+      : GemmProfScope(s, flops, 1.0, tag, false, 0, 0) {}
+};
+// tag of an epilogue functor: its kTag member if it has one
+template <class E>
+constexpr auto epi_tag(int) -> decltype(E::kTag) { return E::kTag; }
+template <class E>
+constexpr const char* epi_tag(long) { return "gemm"; }
 
 // "Has this been done on the current device?" for the per-function cudaFuncSetAttribute
 // opt-ins: the attribute is per device, so the cache is too (a process may drive several GPUs).
@@ -636,7 +688,8 @@ int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   if (num_tiles < grid) grid = num_tiles;
   cudaError_t e;
   {
-    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K);
+    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K, 1.0, epi_tag<Epi>(0), true,
+                       N, K);
     kern<<<grid, GEMM_THREADS, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
     e = cudaGetLastError();
   }
@@ -681,7 +734,8 @@ int launch_gemm16_2cta(const void* A, int lda, const void* B, int ldb, int M, in
   if (2 * num_tiles < grid) grid = 2 * num_tiles;
   cudaError_t e;
   {
-    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K, SPLIT ? 3.0 : 1.0);
+    GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K, SPLIT ? 3.0 : 1.0,
+                       epi_tag<Epi>(0), true, N, K);
     kern<<<grid, GEMM_THREADS, S::kTotal, stream>>>(tmA, tmB, tmAlo, tmBlo, M, N, K, fmt, epi);
     e = cudaGetLastError();
   }

@@ -3,7 +3,11 @@
 // dlopen'ed on a machine with no GPU), SM count, error strings.
 #include "gemm.cuh"
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
 #include <vector>
 #include "../../include/rvlm.h"
 
@@ -54,12 +58,17 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-struct ProfRec { cudaEvent_t e0, e1; double flops, mma; };
+struct ProfRec { cudaEvent_t e0, e1; double flops, mma; const char* tag; bool gemm; int n, k; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
+static std::string g_prof_breakdown = "{}";   // per-kernel JSON of the last collect()
 
-GemmProfScope::GemmProfScope(cudaStream_t s, double flops, double mma_factor) : st(s), slot(-1) {
+bool kernel_prof_on() { return g_prof_on; }
+
+GemmProfScope::GemmProfScope(cudaStream_t s, double flops, double mma_factor, const char* tag,
+                             bool is_gemm, int n, int k)
+    : st(s), slot(-1) {
   if (!g_prof_on) return;
   if (g_prof_used == g_prof.size()) {
     ProfRec r{};
@@ -69,6 +78,10 @@ GemmProfScope::GemmProfScope(cudaStream_t s, double flops, double mma_factor) : 
   slot = (int)g_prof_used++;
   g_prof[slot].flops = flops;
   g_prof[slot].mma = flops * mma_factor;
+  g_prof[slot].tag = tag;
+  g_prof[slot].gemm = is_gemm;
+  g_prof[slot].n = n;
+  g_prof[slot].k = k;
   cudaEventRecord(g_prof[slot].e0, st);
 }
 GemmProfScope::~GemmProfScope() {
@@ -121,19 +134,54 @@ extern "C" int rvlm_profile_gemm(int enable) {
 
 extern "C" int rvlm_profile_gemm_collect(double* total_ms, double* total_flops,
                                          long long* launches) {
+  // totals over the tcgen05 GEMM launches only (the roofline's kernel); every bracketed kernel
+  // goes into the per-tag breakdown
   double ms = 0.0, fl = 0.0;
+  long long ng = 0;
+  struct Agg { double ms = 0.0, flops = 0.0; long long n = 0; };
+  std::map<std::string, Agg> agg;
   for (size_t i = 0; i < rvlm::g_prof_used; ++i) {
     cudaError_t e = cudaEventSynchronize(rvlm::g_prof[i].e1);
     if (e != cudaSuccess) return -(int)e - 1000;
     float t = 0.f;
     e = cudaEventElapsedTime(&t, rvlm::g_prof[i].e0, rvlm::g_prof[i].e1);
     if (e != cudaSuccess) return -(int)e - 1000;
-    ms += t;
-    fl += rvlm::g_prof[i].flops;
+    if (rvlm::g_prof[i].gemm) {
+      ms += t;
+      fl += rvlm::g_prof[i].flops;
+      ++ng;
+    }
+    std::string key = rvlm::g_prof[i].tag ? rvlm::g_prof[i].tag : "?";
+    if (rvlm::g_prof[i].gemm)   // one line per GEMM shape: epilogue / N / K
+      key += " N=" + std::to_string(rvlm::g_prof[i].n) + " K=" + std::to_string(rvlm::g_prof[i].k);
+    Agg& a = agg[key];
+    a.ms += t;
+    a.flops += rvlm::g_prof[i].flops;
+    ++a.n;
   }
+  std::string js = "{";
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s\"%s\": {\"ms\": %.4f, \"launches\": %lld, \"gflop\": %.3f}",
+             js.size() > 1 ? ", " : "", kv.first.c_str(), kv.second.ms, kv.second.n,
+             kv.second.flops * 1e-9);
+    js += buf;
+  }
+  js += "}";
+  rvlm::g_prof_breakdown = js;
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
-  if (launches) *launches = (long long)rvlm::g_prof_used;
+  if (launches) *launches = ng;
   rvlm::g_prof_used = 0;
   return 0;
+}
+
+extern "C" int rvlm_profile_breakdown(char* out, int cap) {
+  const std::string& js = rvlm::g_prof_breakdown;
+  if (out && cap > 0) {
+    const size_t n = js.size() < (size_t)cap - 1 ? js.size() : (size_t)cap - 1;
+    memcpy(out, js.data(), n);
+    out[n] = 0;
+  }
+  return (int)js.size() + 1;
 }

@@ -7,7 +7,7 @@
 // lane), two-pass mean/variance in fp32, 128-bit coalesced loads and stores.  The
 // forward emits the 16-bit GEMM operand directly; the backward fuses the residual
 // add and emits both the fp32 residual gradient and its 16-bit GEMM-operand copy.
-#include "ptx.cuh"
+#include "gemm.cuh"
 #include "../../include/rvlm.h"
 
 namespace rvlm {
@@ -178,6 +178,7 @@ int ln_fwd_strided(const float* x, long long ldx, const float* gamma, const floa
   uint16_t* ylo = reinterpret_cast<uint16_t*>(y16lo_);
   float2* s = reinterpret_cast<float2*>(stats);
   const LnStrides sd{ldx ? ldx : W, ldy ? ldy : W, 0, 0};
+  KernelProfScope prof(st, "ln_fwd");
   switch (W) {
     case 128: ln_fwd_kernel<1><<<grid, block, 0, st>>>(x, gamma, beta, y, ylo, y32, s, M, fmt, sd); break;
     case 256: ln_fwd_kernel<2><<<grid, block, 0, st>>>(x, gamma, beta, y, ylo, y32, s, M, fmt, sd); break;
@@ -200,6 +201,7 @@ int ln_bwd_strided_t(const void* dy, long long lddy, const float* x, long long l
   uint16_t* d16 = reinterpret_cast<uint16_t*>(dx16);
   const float2* s = reinterpret_cast<const float2*>(stats);
   const LnStrides sd{ldx ? ldx : W, ldo ? ldo : W, lddy ? lddy : W, ldres ? ldres : W};
+  KernelProfScope prof(st, "ln_bwd");
   switch (W) {
     case 128: ln_bwd_kernel<1, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T, sd); break;
     case 256: ln_bwd_kernel<2, DY16><<<grid, block, 0, st>>>(dy, x, s, gamma, dres, dx32, d16, M, fmt, drop_T, sd); break;

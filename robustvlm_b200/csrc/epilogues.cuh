@@ -50,6 +50,51 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
+// ---- direct (row-per-lane) epilogue pieces: 16 consecutive columns of one row -------------------
+// 256-bit global accesses: one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                 "=r"(v[7])
+               : "l"(p)
+               : "memory");
+}
+// the bias of 16 consecutive columns (the same addresses in every lane: broadcast loads)
+__device__ __forceinline__ void load_bias16(const float* bias, int col, float (&b)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = load_bias(bias, col + 4 * i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+}
+// acc + bias of 16 accumulator columns
+__device__ __forceinline__ void acc_bias16(const uint32_t (&r)[16], const float* bias, int col,
+                                           float (&v)[16]) {
+  float b[16];
+  load_bias16(bias, col, b);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + b[i];
+}
+__device__ __forceinline__ void pack16(const float (&v)[16], int fmt, uint32_t (&pk)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pk[i] = pack2(v[2 * i], v[2 * i + 1], fmt);
+}
+// fp16 hi + lo pairs of 16 values
+__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    hi[i] = pack2(v[2 * i], v[2 * i + 1], 0);
+    const float2 h = unpack2(hi[i], 0);
+    lo[i] = pack2(v[2 * i] - h.x, v[2 * i + 1] - h.y, 0);
+  }
+}
+struct NoAux16 {};
+
 // C16[row, col] = acc + bias[col]
 struct NoAux {};
 
@@ -66,6 +111,17 @@ struct EpiStore16 {
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
                                              const Col& b) const {
     *reinterpret_cast<uint2*>(C + (size_t)row * ldc + col) = pack4(add4(acc, b), fmt);
+  }
+  static constexpr bool kDirect = true;
+  using Aux16 = NoAux16;
+  __device__ __forceinline__ Aux16 load16(int, int) const { return {}; }
+  __device__ __forceinline__ void direct(int row, int col, const uint32_t (&r)[16],
+                                         const Aux16&) const {
+    float v[16];
+    acc_bias16(r, bias, col, v);
+    uint32_t pk[8];
+    pack16(v, fmt, pk);
+    st_global_v8(C + (size_t)row * ldc + col, pk);
   }
 };
 
@@ -98,6 +154,29 @@ struct EpiStore16Dual {
     }
     if (C2) *reinterpret_cast<uint2*>(C2 + (size_t)row * ldc + col) = pack4(v, fmt2);
   }
+  static constexpr bool kDirect = true;
+  using Aux16 = NoAux16;
+  __device__ __forceinline__ Aux16 load16(int, int) const { return {}; }
+  __device__ __forceinline__ void direct(int row, int col, const uint32_t (&r)[16],
+                                         const Aux16&) const {
+    float v[16];
+    acc_bias16(r, bias, col, v);
+    uint32_t pk[8];
+    const size_t off = (size_t)row * ldc + col;
+    if (Clo) {
+      uint32_t lo[8];
+      split16(v, pk, lo);
+      st_global_v8(C + off, pk);
+      st_global_v8(Clo + off, lo);
+    } else {
+      pack16(v, fmt, pk);
+      st_global_v8(C + off, pk);
+    }
+    if (C2) {
+      pack16(v, fmt2, pk);
+      st_global_v8(C2 + off, pk);
+    }
+  }
 };
 
 // C32[row, col] = acc + bias[col] + resid[row, col]   (fp32 residual stream)
@@ -114,13 +193,39 @@ struct EpiStore32 {
     return resid ? *reinterpret_cast<const float4*>(resid + (size_t)row * ldr + col)
                  : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  __device__ __forceinline__ void prefetch(int row, int col, int ncols) const {
-    if (resid) prefetch_l2_span(resid + (size_t)row * ldr + col, ncols * 4);
-  }
+
   __device__ __forceinline__ Col col(int c) const { return load_bias(bias, c); }
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& r,
                                              const Col& b) const {
     *reinterpret_cast<float4*>(C + (size_t)row * ldc + col) = add4(add4(acc, b), r);
+  }
+  static constexpr bool kDirect = true;
+  struct Aux16 { uint32_t a[8], b[8]; };
+  __device__ __forceinline__ Aux16 load16(int row, int col) const {
+    Aux16 x;
+    if (resid) {
+      const float* p = resid + (size_t)row * ldr + col;
+      ld_global_v8(p, x.a);
+      ld_global_v8(p + 8, x.b);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x.a[i] = x.b[i] = 0u;
+    }
+    return x;
+  }
+  __device__ __forceinline__ void direct(int row, int col, const uint32_t (&r)[16],
+                                         const Aux16& x) const {
+    float v[16];
+    acc_bias16(r, bias, col, v);
+    uint32_t o0[8], o1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o0[i] = __float_as_uint(v[i] + __uint_as_float(x.a[i]));
+      o1[i] = __float_as_uint(v[8 + i] + __uint_as_float(x.b[i]));
+    }
+    float* p = C + (size_t)row * ldc + col;
+    st_global_v8(p, o0);
+    st_global_v8(p + 8, o1);
   }
 };
 
@@ -177,6 +282,45 @@ struct EpiGelu {
       *reinterpret_cast<uint2*>(A + (size_t)row * ld + col) = pack4(a, fmt);
     }
   }
+  static constexpr bool kDirect = true;
+  using Aux16 = NoAux16;
+  __device__ __forceinline__ Aux16 load16(int, int) const { return {}; }
+  __device__ __forceinline__ void direct(int row, int col, const uint32_t (&r)[16],
+                                         const Aux16&) const {
+    float h[16], a[16];
+    acc_bias16(r, bias, col, h);
+    uint32_t pk[8];
+    const size_t off = (size_t)row * ld + col;
+#if RVLM_GELU_DERIV
+    float g[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float s = quick_sigmoid(h[i]);
+      a[i] = h[i] * s;
+      g[i] = fmaf(1.702f * a[i], 1.f - s, s);
+    }
+    if (G) {
+      pack16(g, fmt, pk);
+      st_global_v8(G + off, pk);
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = h[i] * quick_sigmoid(h[i]);
+    if (G) {
+      pack16(h, fmt, pk);
+      st_global_v8(G + off, pk);
+    }
+#endif
+    if (Alo) {
+      uint32_t lo[8];
+      split16(a, pk, lo);
+      st_global_v8(A + off, pk);
+      st_global_v8(Alo + off, lo);
+    } else {
+      pack16(a, fmt, pk);
+      st_global_v8(A + off, pk);
+    }
+  }
 };
 
 // out16 = acc * G16, G = quick_gelu'(pre-activation) as stored by EpiGelu   (dgrad through the
@@ -193,9 +337,7 @@ struct EpiGeluBwd {
   __device__ __forceinline__ Aux load(int row, int col) const {
     return *reinterpret_cast<const uint2*>(G + (size_t)row * ld + col);
   }
-  __device__ __forceinline__ void prefetch(int row, int col, int ncols) const {
-    prefetch_l2_span(G + (size_t)row * ld + col, ncols * 2);
-  }
+
   __device__ __forceinline__ Col col(int) const { return {}; }
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux& gu,
                                              const Col&) const {
@@ -212,6 +354,33 @@ struct EpiGeluBwd {
 #endif
     const float4 o = make_float4(acc.x * g.x, acc.y * g.y, acc.z * g.z, acc.w * g.w);
     *reinterpret_cast<uint2*>(out + (size_t)row * ld + col) = pack4(o, fmt_out);
+  }
+  static constexpr bool kDirect = true;
+  struct Aux16 { uint32_t g[8]; };
+  __device__ __forceinline__ Aux16 load16(int row, int col) const {
+    Aux16 x;
+    ld_global_v8(G + (size_t)row * ld + col, x.g);
+    return x;
+  }
+  __device__ __forceinline__ void direct(int row, int col, const uint32_t (&r)[16],
+                                         const Aux16& x) const {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 t = unpack2(x.g[i], fmt_g);
+#if RVLM_GELU_DERIV
+      const float g0 = t.x, g1 = t.y;
+#else
+      const float s0 = quick_sigmoid(t.x), s1 = quick_sigmoid(t.y);
+      const float g0 = s0 * (1.f + 1.702f * t.x * (1.f - s0));
+      const float g1 = s1 * (1.f + 1.702f * t.y * (1.f - s1));
+#endif
+      v[2 * i] = __uint_as_float(r[2 * i]) * g0;
+      v[2 * i + 1] = __uint_as_float(r[2 * i + 1]) * g1;
+    }
+    uint32_t pk[8];
+    pack16(v, fmt_out, pk);
+    st_global_v8(out + (size_t)row * ld + col, pk);
   }
 };
 

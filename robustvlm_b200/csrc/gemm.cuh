@@ -64,13 +64,13 @@ struct GemmSmem {
 // build-time switches of the epilogue pipeline (defaults = the measured best; the others are kept
 // for A/B builds: make OUTDIR=../_lib/var_x EXTRA=-DRVLM_...=0)
 #ifndef RVLM_GEMM_SETMAXNREG
-#define RVLM_GEMM_SETMAXNREG 1
+#define RVLM_GEMM_SETMAXNREG 0
 #endif
 #ifndef RVLM_EPI_UNROLL
 #define RVLM_EPI_UNROLL 1
 #endif
-#ifndef RVLM_EPI_PF2
-#define RVLM_EPI_PF2 1
+#ifndef RVLM_EPI_DIRECT
+#define RVLM_EPI_DIRECT 1
 #endif
 #ifndef RVLM_EPI_AHEAD
 #define RVLM_EPI_AHEAD 1
@@ -90,15 +90,11 @@ __device__ __forceinline__ void setmaxnreg_dec() {
 #endif
 }
 
-// Optional functor hook: prefetch(row, col, ncols) pulls the HBM operands of `ncols` columns of
-// one row into L2 (no registers held); functors without it are skipped.
+// does the functor offer the direct (row-per-lane, no shared-memory staging) interface?
 template <class E>
-__device__ __forceinline__ auto epi_prefetch(const E& e, int row, int col, int ncols, int)
-    -> decltype(e.prefetch(row, col, ncols), void()) {
-  e.prefetch(row, col, ncols);
-}
+constexpr auto epi_is_direct(int) -> decltype(E::kDirect) { return E::kDirect && RVLM_EPI_DIRECT; }
 template <class E>
-__device__ __forceinline__ void epi_prefetch(const E&, int, int, int, long) {}
+constexpr bool epi_is_direct(long) { return false; }
 
 // Epilogue of one accumulator tile for one epilogue warp: drains this warp's 32 TMEM lanes x
 // (BN/2) columns in 32-column chunks.  Per chunk: tcgen05.ld -> registers -> XOR-swizzled
@@ -132,9 +128,6 @@ __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, 
     }
   };
   if (nch > 0) {
-#if RVLM_EPI_PF2
-    if (!GUARD || row0 + lane < M) epi_prefetch(epi, row0 + lane, n0 + cfirst * 32, nch * 32, 0);
-#endif
 #if RVLM_EPI_AHEAD
     load_aux(0, aux[0]);
 #endif
@@ -191,6 +184,43 @@ __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, 
 #endif
 }
 
+// Direct epilogue: lane = row, no shared-memory staging.  The transposing variant above moves
+// every accumulator element through shared memory twice (8 STS.128 + 8 LDS.128 per chunk, 256 KB
+// per CTA and tile) while the mainloop's TMA fills and tcgen05 operand reads already take the
+// shared-memory port at full rate for a K = 1024 tile (2 x 512 KB per 8192 cycles = 128 B / clk);
+// with 256-bit global accesses a lane stores its OWN row's 16 consecutive columns as one or two
+// full 32-byte sectors per instruction instead.  Functor interface: Aux16 load16(row, col) (HBM
+// operands of 16 columns, requested one piece ahead), direct(row, col, r, aux) for 16 accumulator
+// columns r[0 .. 16).
+template <int BN, bool GUARD, class Epi>
+__device__ __forceinline__ void epilogue_drain_direct(const Epi& epi, uint32_t taddr, int row0,
+                                                      int n0, int half, int M, int N, int lane,
+                                                      uint64_t* tfull, uint32_t tphase) {
+  constexpr int NP = BN / 32;              // 16-column pieces of this warp's half of the tile
+  const int c0 = n0 + half * (BN / 2);
+  const int rem = N - c0;                  // columns left for this half (N % 32 == 0)
+  const int np = rem <= 0 ? 0 : (rem >= BN / 2 ? NP : rem / 16);   // warp-uniform
+  const int row = row0 + lane;
+  const bool valid = !GUARD || row < M;
+  typename Epi::Aux16 aux[2];
+  if (np > 0 && valid) aux[0] = epi.load16(row, c0);
+  mbar_wait(tfull, tphase, 4);
+  tc_fence_after();
+  if (np == 0) return;
+  uint32_t r[2][16];
+  const uint32_t t0 = taddr + half * (BN / 2);
+  tmem_ld16(t0, r[0]);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    if (p < np) {
+      if (p + 1 < NP && p + 1 < np && valid) aux[(p + 1) & 1] = epi.load16(row, c0 + (p + 1) * 16);
+      tmem_ld_wait();
+      if (p + 1 < NP && p + 1 < np) tmem_ld16(t0 + (p + 1) * 16, r[(p + 1) & 1]);
+      if (valid) epi.direct(row, c0 + p * 16, r[p & 1], aux[p & 1]);
+    }
+  }
+}
+
 // Waits for the accumulator (`tfull`, parity `tphase`) and drains it.  The row guard is hoisted to
 // the warp's 32-row slab: full slabs (all but the last M tile) run branch-free, so the eight
 // pieces' dependent chains (MUFU, conversions, stores) interleave instead of executing one piece
@@ -199,7 +229,16 @@ template <int BN, class Epi>
 __device__ __forceinline__ void epilogue_drain(const Epi& epi, float* stg, uint32_t taddr,
                                                int row0, int n0, int half, int M, int N,
                                                int lane, uint64_t* tfull, uint32_t tphase) {
-  if (row0 + 32 <= M)
+  if constexpr (epi_is_direct<Epi>(0)) {
+    if (row0 + 32 <= M)
+      epilogue_drain_direct<BN, false>(epi, taddr, row0, n0, half, M, N, lane, tfull, tphase);
+    else if (row0 < M)
+      epilogue_drain_direct<BN, true>(epi, taddr, row0, n0, half, M, N, lane, tfull, tphase);
+    else {
+      mbar_wait(tfull, tphase, 4);
+      tc_fence_after();
+    }
+  } else if (row0 + 32 <= M)
     epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, half, M, N, lane, tfull, tphase);
   else if (row0 < M)
     epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, half, M, N, lane, tfull, tphase);

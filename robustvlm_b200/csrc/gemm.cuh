@@ -9,14 +9,14 @@
 // torch.nn.Linear; here they are TMA -> shared memory (128B swizzle) ->
 // tcgen05.mma -> TMEM -> fused epilogue.
 //
-// Roles (256 threads, 1 CTA / SM, persistent over output tiles):
+// Roles (GEMM_THREADS = 640, 1 CTA / SM, persistent over output tiles):
 //   warp 0 lane 0 : TMA producer   (kStages-deep smem ring, full/empty mbarriers)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma, double-buffered TMEM accumulator)
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue       (tcgen05.ld -> registers -> swizzled smem transpose ->
+//   warps 4..19   : epilogue       (tcgen05.ld -> registers -> swizzled smem transpose ->
 //                                   Epi functor on row-contiguous float4 pieces -> HBM);
-//                                   two warps per TMEM lane quarter, each takes half the
-//                                   accumulator columns
+//                                   four warps per TMEM lane quarter, each takes a quarter of
+//                                   the accumulator columns (GEMM_EPI_WARPS / 4 slices)
 //
 // Tile: BLOCK_M = 128 (UMMA M, one TMEM lane per row), BLOCK_N = BN (UMMA N),
 // BLOCK_K = 64 elements (= one 128-byte swizzle row).
@@ -30,10 +30,26 @@
 
 namespace rvlm {
 
+// Epilogue geometry (build-time, A/B: make OUTDIR=../_lib/var_x EXTRA="-DRVLM_EPI_WARPS=8
+// -DRVLM_EPI_GC=32").  The K = 1024 GEMMs of the tower are bound by their EPILOGUE: with 8 epilogue
+// warps (two per SM sub-partition) each warp issues one instruction every ~6 cycles on dependent
+// chains (measured: removing the MUFU work from the GELU dgrad epilogue took 14 % off that GEMM,
+// adding three FMAs per element to the GELU forward epilogue put 5 % on), so the epilogue runs on
+// 16 warps -- four per sub-partition, each draining 64 accumulator columns of its lane quarter in
+// 16-column granules (half the registers per warp: 640 threads leave 96 per thread).
+#ifndef RVLM_EPI_WARPS
+#define RVLM_EPI_WARPS 16
+#endif
+#ifndef RVLM_EPI_GC
+#define RVLM_EPI_GC 16
+#endif
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 384;
-constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_EPI_WARPS = RVLM_EPI_WARPS;        // 8 or 16
+constexpr int GEMM_EPI_GC = RVLM_EPI_GC;              // granule: 16 or 32 accumulator columns
+constexpr int GEMM_THREADS = 128 + GEMM_EPI_WARPS * 32;
+static_assert(GEMM_EPI_WARPS == 8 || GEMM_EPI_WARPS == 16, "epilogue warps: 8 or 16");
+static_assert(GEMM_EPI_GC == 16 || GEMM_EPI_GC == 32, "granule: 16 or 32 columns");
 
 template <int BN>
 struct GemmSmem {
@@ -42,7 +58,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * 32 * 4;  // per-warp transpose tiles
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_EPI_GC * 4;  // per-warp transpose tiles
   static constexpr int kTotal =
       kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /*align slack*/;
 };
@@ -57,195 +73,81 @@ struct GemmSmem {
 // guaranteed (N is required to be a multiple of 32 by the host wrappers).
 
 
-// Register budget of the roles (setmaxnreg, one warpgroup = 4 warps): the producer / MMA / TMEM
-// warps (warpgroup 0) hand registers to the two epilogue warpgroups, which then hold TWO chunks of
-// HBM operands (the fp32 residual rows) in flight without spilling.
-// 128 * 40 + 256 * 232 = 64512 <= 65536.
-// build-time switches of the epilogue pipeline (defaults = the measured best; the others are kept
-// for A/B builds: make OUTDIR=../_lib/var_x EXTRA=-DRVLM_...=0)
-#ifndef RVLM_GEMM_SETMAXNREG
-#define RVLM_GEMM_SETMAXNREG 0
-#endif
-#ifndef RVLM_EPI_UNROLL
-#define RVLM_EPI_UNROLL 1
-#endif
-#ifndef RVLM_EPI_DIRECT
-#define RVLM_EPI_DIRECT 1
-#endif
-#ifndef RVLM_EPI_AHEAD
-#define RVLM_EPI_AHEAD 1
-#endif
-constexpr int GEMM_REGS_CTRL = 40;
-constexpr int GEMM_REGS_EPI = 232;
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() {
-#if RVLM_GEMM_SETMAXNREG
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-#endif
-}
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() {
-#if RVLM_GEMM_SETMAXNREG
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-#endif
-}
-
-// does the functor offer the direct (row-per-lane, no shared-memory staging) interface?
-template <class E>
-constexpr auto epi_is_direct(int) -> decltype(E::kDirect) { return E::kDirect && RVLM_EPI_DIRECT; }
-template <class E>
-constexpr bool epi_is_direct(long) { return false; }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
 // Epilogue of one accumulator tile for one epilogue warp: drains this warp's 32 TMEM lanes x
-// (BN/2) columns in 32-column chunks.  Per chunk: tcgen05.ld -> registers -> XOR-swizzled
-// warp-private smem transpose -> each lane owns float4 pieces (4 consecutive columns of one
-// row, 8 lanes per row) -> Epi functor.  Latency is hidden inside the warp instead of across
-// warps (only two epilogue warps share an SM sub-partition):
-//   * the HBM operands of the epilogue (residual rows, stored GELU derivative ...) are requested
-//     BEFORE the wait on the accumulator -- the tile is known long before its MMAs retire: the
-//     whole warp tile as L2 prefetches (lane = row; under load an HBM access takes several
-//     thousand cycles, a chunk's work a few hundred), chunk 0 into registers; chunk c + 1 is
-//     then loaded (from L2) before chunk c is processed.  These loads used to be issued and
-//     consumed inside one chunk, four exposed HBM round trips per tile;
-//   * the NEXT chunk's tcgen05.ld is issued as soon as the registers are staged, and the eight
-//     transposed pieces are read back in one batch before any math / store is issued.
+// (BN / slices) columns in granules of GC columns (slices = epilogue warps per lane quarter).
+// Per granule: tcgen05.ld -> registers -> XOR-swizzled warp-private smem transpose -> each lane
+// owns float4 pieces (4 consecutive columns of one row; GC / 4 lanes per row, so a warp-wide
+// access covers whole sectors of 32 / (GC / 4) rows) -> Epi functor.  Latency is hidden inside the
+// warp as far as it goes: the HBM operands of the epilogue and the per-column operand (bias) are
+// requested first, the NEXT granule's tcgen05.ld is issued as soon as the registers are staged,
+// and the transposed pieces are read back in one batch before any math / store is issued.
 template <int BN, bool GUARD, class Epi>
 __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, uint32_t taddr,
-                                                    int row0, int n0, int half, int M, int N,
-                                                    int lane, uint64_t* tfull, uint32_t tphase) {
-  constexpr int NCH = BN / 64;
-  const int rl = lane >> 3, c4 = lane & 7;
-  const int cfirst = half * NCH;
-  const int rem = N - (n0 + cfirst * 32);  // columns left for this half (N % 32 == 0)
-  const int nch = rem <= 0 ? 0 : (rem >= NCH * 32 ? NCH : rem / 32);  // warp-uniform
-  typename Epi::Aux aux[2][8];
-  auto load_aux = [&](int cc, typename Epi::Aux (&a)[8]) {
-    const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
+                                                    int row0, int n0, int slice, int M, int N,
+                                                    int lane) {
+  constexpr int GC = GEMM_EPI_GC;
+  constexpr int SLICES = GEMM_EPI_WARPS / 4;
+  constexpr int NG = BN / SLICES / GC;       // granules per warp
+  constexpr int LPR = GC / 4;                // lanes per row after the transpose (4 or 8)
+  constexpr int RPP = 32 / LPR;              // rows per pass (8 or 4)
+  constexpr int NPASS = LPR;                 // passes over the 32 rows
+  static_assert(NG >= 1, "tile too narrow for this epilogue geometry");
+  const int rl = lane / LPR, c4 = lane % LPR;
+  // 16-byte groups XOR-swizzled by row so that both the row-wise writes and the piece-wise reads
+  // are bank-conflict free (row pitch 128 B: row & 7; row pitch 64 B: (row >> 1) & 3)
+  auto swz = [](int row) { return GC == 32 ? (row & 7) : ((row >> 1) & 3); };
+  const int cbase = slice * NG * GC;
+  const int rem = N - (n0 + cbase);          // columns left for this slice (N % 32 == 0)
+  const int ng = rem <= 0 ? 0 : (rem >= NG * GC ? NG : rem / GC);   // warp-uniform
+  if (ng == 0) return;
+  uint32_t r[GC];
+  auto ld = [&](int g) { tmem_ld_cols(taddr + cbase + g * GC, r); };
+  ld(0);
+#pragma unroll 1
+  for (int g = 0; g < ng; ++g) {
+    const int col = n0 + cbase + g * GC + 4 * c4;
+    typename Epi::Aux aux[NPASS];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + rl + 4 * i;
-      if (!GUARD || row < M) a[i] = epi.load(row, col);
+    for (int i = 0; i < NPASS; ++i) {
+      const int row = row0 + rl + RPP * i;
+      if (!GUARD || row < M) aux[i] = epi.load(row, col);
     }
-  };
-  if (nch > 0) {
-#if RVLM_EPI_AHEAD
-    load_aux(0, aux[0]);
-#endif
-  }
-  mbar_wait(tfull, tphase, 4);
-  tc_fence_after();
-  if (nch == 0) return;
-  uint32_t r[32];
-  tmem_ld32(taddr + cfirst * 32, r);
-  // one 32-column chunk; `cur` holds its HBM operands, `nxt` receives those of the next chunk
-  auto step = [&](int cc, typename Epi::Aux (&cur)[8], typename Epi::Aux (&nxt)[8]) {
-    const int col = n0 + (cfirst + cc) * 32 + 4 * c4;
-#if RVLM_EPI_AHEAD
-    if (cc + 1 < nch) load_aux(cc + 1, nxt);
-#else
-    load_aux(cc, cur);
-#endif
     const typename Epi::Col ca = epi.col(col);
     tmem_ld_wait();
-    // transpose: lane == row writes its 32 columns; 16-byte groups XOR-swizzled by row
+    // transpose: lane == row writes its GC columns
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+    for (int j = 0; j < LPR; ++j)
+      *reinterpret_cast<uint4*>(stg + lane * GC + ((j ^ swz(lane)) << 2)) =
           make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     __syncwarp();
-    if (cc + 1 < nch) tmem_ld32(taddr + (cfirst + cc + 1) * 32, r);
-    float4 v[8];
+    if (g + 1 < ng) ld(g + 1);
+    float4 v[NPASS];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int rr = rl + 4 * i;
-      v[i] = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4 ^ (rr & 7)) << 2));
+    for (int i = 0; i < NPASS; ++i) {
+      const int rr = rl + RPP * i;
+      v[i] = *reinterpret_cast<const float4*>(stg + rr * GC + ((c4 ^ swz(rr)) << 2));
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = row0 + rl + 4 * i;
-      if (!GUARD || row < M) epi(row, col, v[i], cur[i], ca);
-    }
-  };
-#if RVLM_EPI_UNROLL
-#pragma unroll
-  for (int cc = 0; cc < NCH; ++cc)
-    if (cc < nch) step(cc, aux[cc & 1], aux[(cc + 1) & 1]);
-#elif RVLM_EPI_AHEAD
-  // rolled two chunks at a time (static operand buffers, a quarter of the unrolled code)
-#pragma unroll 1
-  for (int cc = 0; cc < nch; cc += 2) {
-    step(cc, aux[0], aux[1]);
-    if (cc + 1 < nch) step(cc + 1, aux[1], aux[0]);
-  }
-#else
-#pragma unroll 1
-  for (int cc = 0; cc < nch; ++cc) step(cc, aux[0], aux[0]);
-#endif
-}
-
-// Direct epilogue: lane = row, no shared-memory staging.  The transposing variant above moves
-// every accumulator element through shared memory twice (8 STS.128 + 8 LDS.128 per chunk, 256 KB
-// per CTA and tile) while the mainloop's TMA fills and tcgen05 operand reads already take the
-// shared-memory port at full rate for a K = 1024 tile (2 x 512 KB per 8192 cycles = 128 B / clk);
-// with 256-bit global accesses a lane stores its OWN row's 16 consecutive columns as one or two
-// full 32-byte sectors per instruction instead.  Functor interface: Aux16 load16(row, col) (HBM
-// operands of 16 columns, requested one piece ahead), direct(row, col, r, aux) for 16 accumulator
-// columns r[0 .. 16).
-template <int BN, bool GUARD, class Epi>
-__device__ __forceinline__ void epilogue_drain_direct(const Epi& epi, uint32_t taddr, int row0,
-                                                      int n0, int half, int M, int N, int lane,
-                                                      uint64_t* tfull, uint32_t tphase) {
-  constexpr int NP = BN / 32;              // 16-column pieces of this warp's half of the tile
-  const int c0 = n0 + half * (BN / 2);
-  const int rem = N - c0;                  // columns left for this half (N % 32 == 0)
-  const int np = rem <= 0 ? 0 : (rem >= BN / 2 ? NP : rem / 16);   // warp-uniform
-  const int row = row0 + lane;
-  const bool valid = !GUARD || row < M;
-  typename Epi::Aux16 aux[2];
-  if (np > 0 && valid) aux[0] = epi.load16(row, c0);
-  mbar_wait(tfull, tphase, 4);
-  tc_fence_after();
-  if (np == 0) return;
-  uint32_t r[2][16];
-  const uint32_t t0 = taddr + half * (BN / 2);
-  tmem_ld16(t0, r[0]);
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    if (p < np) {
-      if (p + 1 < NP && p + 1 < np && valid) aux[(p + 1) & 1] = epi.load16(row, c0 + (p + 1) * 16);
-      tmem_ld_wait();
-      if (p + 1 < NP && p + 1 < np) tmem_ld16(t0 + (p + 1) * 16, r[(p + 1) & 1]);
-      if (valid) epi.direct(row, c0 + p * 16, r[p & 1], aux[p & 1]);
+    for (int i = 0; i < NPASS; ++i) {
+      const int row = row0 + rl + RPP * i;
+      if (!GUARD || row < M) epi(row, col, v[i], aux[i], ca);
     }
   }
 }
 
-// Waits for the accumulator (`tfull`, parity `tphase`) and drains it.  The row guard is hoisted to
-// the warp's 32-row slab: full slabs (all but the last M tile) run branch-free, so the eight
-// pieces' dependent chains (MUFU, conversions, stores) interleave instead of executing one piece
-// at a time.
+// The row guard is hoisted to the warp's 32-row slab: full slabs (all but the last M tile)
+// run branch-free, so the pieces' dependent chains (MUFU, conversions, stores) interleave
+// instead of executing one piece at a time.
 template <int BN, class Epi>
 __device__ __forceinline__ void epilogue_drain(const Epi& epi, float* stg, uint32_t taddr,
-                                               int row0, int n0, int half, int M, int N,
-                                               int lane, uint64_t* tfull, uint32_t tphase) {
-  if constexpr (epi_is_direct<Epi>(0)) {
-    if (row0 + 32 <= M)
-      epilogue_drain_direct<BN, false>(epi, taddr, row0, n0, half, M, N, lane, tfull, tphase);
-    else if (row0 < M)
-      epilogue_drain_direct<BN, true>(epi, taddr, row0, n0, half, M, N, lane, tfull, tphase);
-    else {
-      mbar_wait(tfull, tphase, 4);
-      tc_fence_after();
-    }
-  } else if (row0 + 32 <= M)
-    epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, half, M, N, lane, tfull, tphase);
-  else if (row0 < M)
-    epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, half, M, N, lane, tfull, tphase);
-  else {
-    mbar_wait(tfull, tphase, 4);
-    tc_fence_after();
-  }
+                                               int row0, int n0, int slice, int M, int N,
+                                               int lane) {
+  if (row0 + 32 <= M) epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, slice, M, N, lane);
+  else if (row0 < M) epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, slice, M, N, lane);
 }
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
@@ -302,8 +204,6 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-  setmaxnreg_dec<GEMM_REGS_CTRL>();
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
@@ -365,22 +265,21 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       umma_commit(&tfull_bar[acc]);
     }
-  }
-  } else {
+  } else if (warp >= 4) {
     // ===================== epilogue =====================
-    setmaxnreg_inc<GEMM_REGS_EPI>();
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int half = (warp - 4) >> 2;  // which half of the accumulator columns
-    float* stg = staging + (warp - 4) * 1024;
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int slice = (warp - 4) >> 2;  // which slice of the accumulator columns
+    float* stg = staging + (warp - 4) * 32 * GEMM_EPI_GC;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
       const int row0 = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane, &tfull_bar[acc],
-                         acc_phase);
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, slice, M, N, lane);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -464,7 +363,7 @@ struct Gemm2Smem {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;   // 128 x 64
   static constexpr int kBBytes = 128 * GEMM_BK * 2;       // half of the 256-row B tile
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
-  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * 32 * 4;
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_EPI_GC * 4;
   static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 256 + 1024;
 };
 
@@ -533,8 +432,6 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-  setmaxnreg_dec<GEMM_REGS_CTRL>();
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
@@ -595,22 +492,21 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       umma_commit_2cta(&tfull_bar[acc]);
     }
-  }
-  } else {
+  } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 TMEM lanes) =====================
-    setmaxnreg_inc<GEMM_REGS_EPI>();
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    float* stg = staging + (warp - 4) * 1024;
+    const int slice = (warp - 4) >> 2;
+    float* stg = staging + (warp - 4) * 32 * GEMM_EPI_GC;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
       const int row0 = m_blk * 256 + (int)rank * 128 + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, half, M, N, lane, &tfull_bar[acc],
-                         acc_phase);
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, slice, M, N, lane);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[acc]);
       else mbar_arrive_cluster(&tempty_bar[acc], 0);
@@ -655,7 +551,7 @@ struct GemmProfScope {
   // flops: algorithmic 2MNK of the product; mma_factor: tensor-pipe passes per product (3 for
   // split operands) -- reported separately so the roofline can state both
   // tag: the kernel's name in the per-kernel breakdown (static string); is_gemm: counts towards
-  // the tcgen05 GEMM totals of rvlm_profile_gemm_collect
+  // the tcgen05 GEMM totals of rvlm_profile_gemm_collect; n, k: the GEMM shape (breakdown key)
   GemmProfScope(cudaStream_t s, double flops, double mma_factor = 1.0, const char* tag = "gemm",
                 bool is_gemm = true, int n = 0, int k = 0);
   ~GemmProfScope();

@@ -72,9 +72,7 @@ int rvlm_profile_breakdown(char* out, int cap);
  *
  *    C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ resid[M,N])
  *    A, B: 16-bit (fmt), row-major, pitches lda/ldb in elements (16-byte
- *    aligned rows).  N must be a multiple of 32.  Outputs and the residual / stored-derivative
- *    inputs are accessed 256 bits at a time: base pointers and row pitches 32-byte aligned
- *    (RVLM_ERR_ALIGN otherwise).
+ *    aligned rows).  N must be a multiple of 32.
  *    flags: bit0 = B is given as [K,N] row-major (MN-major operand)
  *           bit1 = A is given as [K,M] row-major (MN-major operand)
  *           bit2 = 128-column tiles instead of 256

@@ -9,14 +9,14 @@
 // torch.nn.Linear; here they are TMA -> shared memory (128B swizzle) ->
 // tcgen05.mma -> TMEM -> fused epilogue.
 //
-// Roles (GEMM_THREADS = 640, 1 CTA / SM, persistent over output tiles):
+// Roles (GEMM_THREADS = 128 + 32 x epilogue warps, 1 CTA / SM, persistent over output tiles):
 //   warp 0 lane 0 : TMA producer   (kStages-deep smem ring, full/empty mbarriers)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma, double-buffered TMEM accumulator)
 //   warp 2        : TMEM allocator
-//   warps 4..19   : epilogue       (tcgen05.ld -> registers -> swizzled smem transpose ->
+//   warps 4..11   : epilogue       (tcgen05.ld -> registers -> swizzled smem transpose ->
 //                                   Epi functor on row-contiguous float4 pieces -> HBM);
-//                                   four warps per TMEM lane quarter, each takes a quarter of
-//                                   the accumulator columns (GEMM_EPI_WARPS / 4 slices)
+//                                   GEMM_EPI_WARPS / 4 warps per TMEM lane quarter, each takes
+//                                   one slice of the accumulator columns
 //
 // Tile: BLOCK_M = 128 (UMMA M, one TMEM lane per row), BLOCK_N = BN (UMMA N),
 // BLOCK_K = 64 elements (= one 128-byte swizzle row).
@@ -30,18 +30,16 @@
 
 namespace rvlm {
 
-// Epilogue geometry (build-time, A/B: make OUTDIR=../_lib/var_x EXTRA="-DRVLM_EPI_WARPS=8
-// -DRVLM_EPI_GC=32").  The K = 1024 GEMMs of the tower are bound by their EPILOGUE: with 8 epilogue
-// warps (two per SM sub-partition) each warp issues one instruction every ~6 cycles on dependent
-// chains (measured: removing the MUFU work from the GELU dgrad epilogue took 14 % off that GEMM,
-// adding three FMAs per element to the GELU forward epilogue put 5 % on), so the epilogue runs on
-// 16 warps -- four per sub-partition, each draining 64 accumulator columns of its lane quarter in
-// 16-column granules (half the registers per warp: 640 threads leave 96 per thread).
+// Epilogue geometry (build-time; A/B builds: make OUTDIR=../_lib/var_x EXTRA="-DRVLM_EPI_WARPS=16
+// -DRVLM_EPI_GC=16", tools/ab_variants.sh).  Measured in-step on B200 (config 2, ms per step of
+// the K = 1024 GEMMs gelu / gelu' / out-proj): 8 warps x 32-column granules 127.9 / 112.9 / 38.6;
+// 8 x 16: 135.9 / 135.1 / 44.0; 16 x 16: 128.0 / 136.4 / 46.6 -- the width of the row pieces a
+// warp-wide access covers matters more than the number of warps, so the default stays 8 x 32.
 #ifndef RVLM_EPI_WARPS
-#define RVLM_EPI_WARPS 16
+#define RVLM_EPI_WARPS 8
 #endif
 #ifndef RVLM_EPI_GC
-#define RVLM_EPI_GC 16
+#define RVLM_EPI_GC 32
 #endif
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;

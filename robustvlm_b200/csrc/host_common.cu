@@ -112,7 +112,7 @@ extern "C" const char* rvlm_strerror(int code) {
   switch (code) {
     case 0: return "ok";
     case RVLM_ERR_INVAL: return "invalid argument";
-    case RVLM_ERR_ALIGN: return "pointer or pitch not aligned (16 bytes for operands, 32 for GEMM outputs)";
+    case RVLM_ERR_ALIGN: return "pointer or pitch not 16-byte aligned";
     case RVLM_ERR_DRIVER: return "cuTensorMapEncodeTiled entry point unavailable";
     case RVLM_ERR_TMAP: return "tensor map encode failed";
     case RVLM_ERR_NOMEM: return "workspace too small";

@@ -218,16 +218,6 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ---- L2 prefetch (no destination register: the line is only pulled into L2) ------------
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-// the 128-byte lines of `bytes` bytes starting at p
-__device__ __forceinline__ void prefetch_l2_span(const void* p, int bytes) {
-  const char* c = reinterpret_cast<const char*>(p);
-  for (int o = 0; o < bytes; o += 128) prefetch_l2(c + o);
-}
-
 // ---------------------------------------------------------------------------
 // 16-bit conversions (runtime format: 0 = fp16, 1 = bf16)
 // ---------------------------------------------------------------------------

@@ -96,12 +96,13 @@ int rvlm_gemm16_out32(const void* A, int lda, const void* B, int ldb, float* C, 
 int rvlm_gemm16_split_out32(const void* A_hi, const void* A_lo, int lda, const void* B_hi,
                             const void* B_lo, int ldb, float* C, int ldc, const float* bias,
                             const float* resid, int ldr, int M, int N, int K, void* stream);
-/* h = A*B^T + bias; Act = QuickGELU(h), G = QuickGELU'(h) (may be NULL; what the dgrad below
- * multiplies by -- the pre-activation itself is never stored); both 16-bit [M,N] pitch ld */
+/* h = A*B^T + bias; Act = QuickGELU(h), G = QuickGELU'(h) - 1/2 (may be NULL; what the dgrad
+ * below multiplies by, offset so that the 16-bit value stays within +-0.6 -- the pre-activation
+ * itself is never stored); both 16-bit [M,N] pitch ld */
 int rvlm_gemm16_gelu(const void* A, int lda, const void* B, int ldb, void* G, void* Act, int ld,
                      const float* bias, int M, int N, int K, int fmt, void* stream);
-/* out = (A*B^T) .* G ; 16-bit [M,N] pitch ld; G (as written by rvlm_gemm16_gelu) in fmt_g,
- * A/B/out in fmt */
+/* out = (A*B^T) .* (G + 1/2) ; 16-bit [M,N] pitch ld; G (as written by rvlm_gemm16_gelu) in
+ * fmt_g, A/B/out in fmt */
 int rvlm_gemm16_gelu_bwd(const void* A, int lda, const void* B, int ldb, void* out, const void* G,
                          int ld, int M, int N, int K, int fmt, int fmt_g, void* stream);
 

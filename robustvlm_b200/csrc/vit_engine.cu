@@ -98,7 +98,7 @@ struct Ws {
   float *x32;     // [(L+1)] or [2] x [M, W]
   float *xm32;    // [L] or [1]
   float *stats1, *stats2;  // [L] x [M, 2]
-  // [L] or [1]; qkv16 is the backward's copy (fmt_bwd); h16 holds QuickGELU'(pre-activation), the
+  // [L] or [1]; qkv16 is the backward's copy (fmt_bwd); h16 holds QuickGELU'(pre-activation) - 1/2, the
   // factor the MLP dgrad multiplies by (the pre-activation itself is never stored)
   uint16_t *qkv16, *o16, *h16;
   uint16_t* qkvf16;             // [M, 3W] transient forward-format q|k|v

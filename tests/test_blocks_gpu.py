@@ -65,7 +65,7 @@ def test_gemm_fp32_residual_and_gelu():
     nat.call("rvlm_gemm16_out32", nat.ptr(A), nat.c_int(K), nat.ptr(B), nat.c_int(K), nat.ptr(C),
              nat.c_int(N), nat.ptr(bias), nat.ptr(resid), nat.c_int(N), nat.c_int(M), nat.c_int(N),
              nat.c_int(K), nat.c_int(0), nat.c_int(0), nat.stream_ptr())
-    Gh = torch.empty(M, N, device="cuda", dtype=torch.half)   # QuickGELU'(pre-activation)
+    Gh = torch.empty(M, N, device="cuda", dtype=torch.half)   # QuickGELU'(pre-activation) - 1/2
     Act = torch.empty(M, N, device="cuda", dtype=torch.half)
     nat.call("rvlm_gemm16_gelu", nat.ptr(A), nat.c_int(K), nat.ptr(B), nat.c_int(K), nat.ptr(Gh),
              nat.ptr(Act), nat.c_int(N), nat.ptr(bias), nat.c_int(M), nat.c_int(N), nat.c_int(K),
@@ -84,7 +84,7 @@ def test_gemm_fp32_residual_and_gelu():
     gel = ref * sg
     assert (Act.float() - gel).abs().max() < 2e-2
     gprime = sg * (1 + 1.702 * ref * (1 - sg))
-    assert (Gh.float() - gprime).abs().max() < 2e-3     # fp16 of a value in [-0.1, 1.1]
+    assert (Gh.float() + 0.5 - gprime).abs().max() < 1e-3     # fp16 of a value in [-0.6, 0.6]
     dref = (G.float() @ Bt.float().t()) * gprime
     assert (dH.float() - dref).abs().max() <= 2e-2 * dref.abs().max()
 

@@ -54,8 +54,9 @@ int rvlm_abi_version(void);
 const char* rvlm_strerror(int code);
 
 /* Accounting for the benchmark: number of kernels this library has launched, and an
- * optional mode that brackets every tcgen05 GEMM launch with CUDA events on its stream
- * (collect() synchronises and returns the summed device time and algorithmic FLOPs). */
+ * optional mode that brackets every tcgen05 GEMM launch (enable = 1) or every GEMM, attention and
+ * LayerNorm launch (enable = 2) with CUDA events on its stream (collect() synchronises and returns
+ * the summed device time and algorithmic FLOPs of the GEMM launches). */
 long long rvlm_launch_count(void);
 void rvlm_launch_count_reset(void);
 int rvlm_profile_gemm(int enable);

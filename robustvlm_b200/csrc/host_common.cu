@@ -59,17 +59,16 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 struct ProfRec { cudaEvent_t e0, e1; double flops, mma; const char* tag; bool gemm; int n, k; };
-static bool g_prof_on = false;
+static int g_prof_on = 0;   // 0 off, 1 tcgen05 GEMM launches, 2 every bracketed kernel
 static std::vector<ProfRec> g_prof;
 static size_t g_prof_used = 0;
 static std::string g_prof_breakdown = "{}";   // per-kernel JSON of the last collect()
 
-bool kernel_prof_on() { return g_prof_on; }
 
 GemmProfScope::GemmProfScope(cudaStream_t s, double flops, double mma_factor, const char* tag,
                              bool is_gemm, int n, int k)
     : st(s), slot(-1) {
-  if (!g_prof_on) return;
+  if (g_prof_on == 0 || (!is_gemm && g_prof_on < 2)) return;
   if (g_prof_used == g_prof.size()) {
     ProfRec r{};
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
@@ -127,7 +126,7 @@ extern "C" long long rvlm_launch_count(void) { return rvlm::g_launches.load(); }
 extern "C" void rvlm_launch_count_reset(void) { rvlm::g_launches.store(0); }
 
 extern "C" int rvlm_profile_gemm(int enable) {
-  rvlm::g_prof_on = enable != 0;
+  rvlm::g_prof_on = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   rvlm::g_prof_used = 0;
   return 0;
 }

@@ -120,9 +120,12 @@ struct EpiPatchGrad {
   __device__ __forceinline__ void operator()(int row, int col, const float4& acc, const Aux&,
                                              const Col&) const {
     if (col >= kp) return;
+    // one channel per piece (patch * patch and col are multiples of 4); no run-time indexing of
+    // the functor's arrays
+    const int ch = col / pp;
+    const float is = ch == 0 ? inv_std[0] : (ch == 1 ? inv_std[1] : inv_std[2]);
     *reinterpret_cast<float4*>(G + (size_t)row * kp + col) =
-        make_float4(acc.x * inv_std[(col + 0) / pp], acc.y * inv_std[(col + 1) / pp],
-                    acc.z * inv_std[(col + 2) / pp], acc.w * inv_std[(col + 3) / pp]);
+        make_float4(acc.x * is, acc.y * is, acc.z * is, acc.w * is);
   }
 };
 
@@ -132,6 +135,7 @@ struct EpiPatchGrad {
 // so no separate elementwise kernel runs per PGD step.  sign(acc / std) == sign(acc).
 struct EpiPatchPgdLinf {
   static constexpr const char* kTag = "gemm.patch_pgd_linf";
+  static constexpr int kPiecesPerBatch = 4;   // 13 live registers per piece on top of the accumulator
   const float* xp;   // [rows, kp]
   float* dp;         // [rows, kp] delta (in place)
   float* vp;         // [rows, kp] velocity (in place)
@@ -146,19 +150,21 @@ struct EpiPatchPgdLinf {
   // (profiles/r02_kernels_ncu.txt) against 86 us for the plain patch dgrad; x is read-only (ld.nc)
   // (inside rvlm_pgd_run the velocity is 0 at the start and sign(...) afterwards, i.e. always in
   // {-1, 0, +1}: it is carried through the Aux registers as four 2-bit codes)
-  struct Aux { float4 d; uint32_t vs; };
+  // (x too: read inside operator() its eight loads per granule sat behind the early-exit branch,
+  // one exposed round trip per piece)
+  struct Aux { float4 d, x; uint32_t vs; };
   struct Col {};
   __device__ __forceinline__ Aux load(int row, int col) const {
+    // unconditional loads (pad columns read the row's last valid piece; operator() ignores them):
+    // a conditionally initialised Aux array ends up in local memory, and every load is then
+    // followed by a store that waits for it
+    const size_t off = (size_t)row * kp + (col < kp ? col : kp - 4);
     Aux a;
-    a.d = make_float4(0.f, 0.f, 0.f, 0.f);
-    a.vs = 0u;
-    if (col < kp) {
-      const size_t off = (size_t)row * kp + col;
-      a.d = *reinterpret_cast<const float4*>(dp + off);
-      const float4 v = *reinterpret_cast<const float4*>(vp + off);
-      a.vs = (v.x > 0.f ? 1u : (v.x < 0.f ? 2u : 0u)) | (v.y > 0.f ? 4u : (v.y < 0.f ? 8u : 0u)) |
-             (v.z > 0.f ? 16u : (v.z < 0.f ? 32u : 0u)) | (v.w > 0.f ? 64u : (v.w < 0.f ? 128u : 0u));
-    }
+    a.d = *reinterpret_cast<const float4*>(dp + off);
+    a.x = __ldg(reinterpret_cast<const float4*>(xp + off));
+    const float4 v = *reinterpret_cast<const float4*>(vp + off);
+    a.vs = (v.x > 0.f ? 1u : (v.x < 0.f ? 2u : 0u)) | (v.y > 0.f ? 4u : (v.y < 0.f ? 8u : 0u)) |
+           (v.z > 0.f ? 16u : (v.z < 0.f ? 32u : 0u)) | (v.w > 0.f ? 64u : (v.w < 0.f ? 128u : 0u));
     return a;
   }
   __device__ __forceinline__ Col col(int) const { return {}; }
@@ -167,7 +173,7 @@ struct EpiPatchPgdLinf {
     if (col >= kp) return;
     const size_t off = (size_t)row * kp + col;
     struct { float4 x, d, v; } a;
-    a.x = __ldg(reinterpret_cast<const float4*>(xp + off));
+    a.x = aux.x;
     a.d = aux.d;
     {
       const uint32_t c = aux.vs;
@@ -183,6 +189,11 @@ struct EpiPatchPgdLinf {
     float* dd = &d4.x;
     float* vv = &v4.x;
     float nx[4];
+    // the channel of all four columns (patch * patch is a multiple of 4, col too); selected
+    // without indexing the functor's arrays at run time -- that would copy it to local memory
+    const int ch = col / pp;
+    const float mean_c = ch == 0 ? mean[0] : (ch == 1 ? mean[1] : mean[2]);
+    const float istd_c = ch == 0 ? inv_std[0] : (ch == 1 ? inv_std[1] : inv_std[2]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float g = gg[i];
@@ -195,8 +206,7 @@ struct EpiPatchPgdLinf {
       const float xa = fminf(fmaxf(__fadd_rn(xx[i], dn), 0.f), 1.f);
       dd[i] = __fsub_rn(xa, xx[i]);
       vv[i] = vn;
-      const int c = (col + i) / pp;
-      nx[i] = (__fadd_rn(xx[i], dd[i]) - mean[c]) * inv_std[c];
+      nx[i] = (__fadd_rn(xx[i], dd[i]) - mean_c) * istd_c;
     }
     *reinterpret_cast<float4*>(dp + off) = d4;
     *reinterpret_cast<float4*>(vp + off) = v4;

@@ -71,6 +71,12 @@ struct GemmSmem {
 // guaranteed (N is required to be a multiple of 32 by the host wrappers).
 
 
+// pieces per batch of an epilogue functor: its kPiecesPerBatch member if it has one, else "all"
+template <class E>
+constexpr auto epi_batch(int) -> decltype(E::kPiecesPerBatch) { return E::kPiecesPerBatch; }
+template <class E>
+constexpr int epi_batch(long) { return 1 << 20; }
+
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
 
@@ -104,15 +110,22 @@ __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, 
   uint32_t r[GC];
   auto ld = [&](int g) { tmem_ld_cols(taddr + cbase + g * GC, r); };
   ld(0);
+  // pieces handled per batch: all of a granule's, unless the functor asks for fewer (a functor
+  // with many live registers per piece, Epi::kPiecesPerBatch)
+  constexpr int NB = epi_batch<Epi>(0) < NPASS ? epi_batch<Epi>(0) : NPASS;
+  static_assert(NPASS % NB == 0, "pieces per batch must divide the passes");
 #pragma unroll 1
   for (int g = 0; g < ng; ++g) {
     const int col = n0 + cbase + g * GC + 4 * c4;
-    typename Epi::Aux aux[NPASS];
+    typename Epi::Aux aux[NB];
+    auto load_aux = [&](int b0) {
 #pragma unroll
-    for (int i = 0; i < NPASS; ++i) {
-      const int row = row0 + rl + RPP * i;
-      if (!GUARD || row < M) aux[i] = epi.load(row, col);
-    }
+      for (int i = 0; i < NB; ++i) {
+        const int row = row0 + rl + RPP * (b0 + i);
+        if (!GUARD || row < M) aux[i] = epi.load(row, col);
+      }
+    };
+    load_aux(0);
     const typename Epi::Col ca = epi.col(col);
     tmem_ld_wait();
     // transpose: lane == row writes its GC columns
@@ -122,17 +135,21 @@ __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, 
           make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
     __syncwarp();
     if (g + 1 < ng) ld(g + 1);
-    float4 v[NPASS];
 #pragma unroll
-    for (int i = 0; i < NPASS; ++i) {
-      const int rr = rl + RPP * i;
-      v[i] = *reinterpret_cast<const float4*>(stg + rr * GC + ((c4 ^ swz(rr)) << 2));
-    }
-    __syncwarp();
+    for (int b0 = 0; b0 < NPASS; b0 += NB) {
+      if (b0 > 0) load_aux(b0);
+      float4 v[NB];
 #pragma unroll
-    for (int i = 0; i < NPASS; ++i) {
-      const int row = row0 + rl + RPP * i;
-      if (!GUARD || row < M) epi(row, col, v[i], aux[i], ca);
+      for (int i = 0; i < NB; ++i) {
+        const int rr = rl + RPP * (b0 + i);
+        v[i] = *reinterpret_cast<const float4*>(stg + rr * GC + ((c4 ^ swz(rr)) << 2));
+      }
+      if (b0 + NB >= NPASS) __syncwarp();   // staging tile free for the next granule
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int row = row0 + rl + RPP * (b0 + i);
+        if (!GUARD || row < M) epi(row, col, v[i], aux[i], ca);
+      }
     }
   }
 }

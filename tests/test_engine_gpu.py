@@ -222,3 +222,36 @@ def test_fp16_operands_survive_outlier_channels(mode):
          act_scale=float(e_ref.abs().max()))
     assert rel_err(emb, e_ref) < 1e-3
     assert cos > 0.999 and mis_big < 5e-3 and ratio < 2e-2
+
+
+def test_profile_breakdown_covers_the_step():
+    """rvlm_profile_gemm(2) brackets every GEMM / attention / LayerNorm launch with CUDA events;
+    rvlm_profile_breakdown returns them by kernel and GEMM shape (bench.py's kernel_breakdown),
+    and the GEMM totals of rvlm_profile_gemm_collect count the tcgen05 GEMM launches only."""
+    import ctypes
+
+    from robustvlm_b200 import _native as nat
+    from robustvlm_b200.engine import NORM_LINF, LossSpec
+    eng, model = make_engine("tiny-14", seed=1)
+    x, d0 = synth_batch(3, seed=0)
+    with torch.no_grad():
+        e_orig = model(x, output_normalize=False) + 0.1
+    spec = LossSpec("l2", False, emb_orig=e_orig.cuda())
+    run = lambda: eng.pgd_run(x.cuda(), spec, norm=NORM_LINF, eps=4 / 255, stepsize=1 / 255,  # noqa: E731
+                              iterations=2, maximize=True, delta0=d0.cuda())
+    ref = run()
+    nat.lib().rvlm_profile_gemm(2)
+    out = run()
+    tms, tfl, nl = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    nat.check(nat.lib().rvlm_profile_gemm_collect(ctypes.byref(tms), ctypes.byref(tfl), ctypes.byref(nl)))
+    nat.lib().rvlm_profile_gemm(0)
+    need = nat.lib().rvlm_profile_breakdown(None, 0)
+    buf = ctypes.create_string_buffer(int(need) + 8)
+    nat.lib().rvlm_profile_breakdown(buf, len(buf))
+    bd = json.loads(buf.value.decode())
+    assert torch.equal(out, ref)                       # bracketing does not change the results
+    gemm = {k: v for k, v in bd.items() if k.startswith("gemm.")}
+    assert sum(v["launches"] for v in gemm.values()) == nl.value > 0
+    assert abs(sum(v["ms"] for v in gemm.values()) - tms.value) < 1e-3 * max(tms.value, 1e-3) + 1e-3
+    assert any(k.startswith("gemm.patch_pgd_linf") for k in bd) and "ln_fwd" in bd and "ln_bwd" in bd
+    assert all(v["ms"] > 0 for v in bd.values()) and tfl.value > 0

@@ -50,6 +50,44 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
   return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
 }
 
+// ---- TMA-store epilogue pieces (lane = accumulator row) -----------------------------------------
+// The 16-bit outputs of a 32-column chunk go through a per-warp staging tile [32 rows x 64 bytes]
+// in the 64B-swizzled layout of make_tmap_2d_store16 and leave with ONE cp.async.bulk.tensor store
+// per output, issued by lane 0: no read-back from shared memory, no per-lane global stores or
+// address arithmetic, rows past M clipped by the tensor map.
+int make_tmap_2d_store16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                         uint64_t ld);
+bool epi_tma_enabled();   // RVLM_EPI_TMA (default on)
+
+constexpr int EPI_TMA_TILE_BYTES = 32 * 64;
+
+// the bias of a chunk's 32 columns (the same addresses in every lane: broadcast loads)
+__device__ __forceinline__ void load_bias32(const float* bias, int col, float (&b)[32]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 t = load_bias(bias, col + 4 * i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+}
+// lane's row of a staging tile: 32 packed 16-bit values = four 16-byte groups, group index XORed
+// with bits 7-8 of the byte address (CU_TENSOR_MAP_SWIZZLE_64B)
+__device__ __forceinline__ void sts_row64(uint8_t* tile, int lane, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(tile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+// the staging tiles of this warp are free again (the previous chunk's stores have read them)
+__device__ __forceinline__ void tma_stage_acquire(int lane) {
+  if (lane == 0) tma_store_wait_read0();
+  __syncwarp();
+}
+// every lane's writes to the staging tiles become visible to the async proxy; then lane 0 may issue
+__device__ __forceinline__ void tma_stage_publish() {
+  fence_proxy_async_smem();
+  __syncwarp();
+}
+
 // C16[row, col] = acc + bias[col]
 struct NoAux {};
 
@@ -59,6 +97,31 @@ struct EpiStore16 {
   int ldc;
   const float* bias;  // may be null
   int fmt;
+  // TMA-store path (filled by prepare() on the host, just before the launch)
+  int tma = 0;
+  CUtensorMap tmC;
+  int prepare(int M, int N) {
+    tma = epi_tma_enabled() && make_tmap_2d_store16(&tmC, C, M, N, ldc) == 0;
+    return 0;
+  }
+  __device__ __forceinline__ bool tma_on() const { return tma != 0; }
+  __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
+                                            uint8_t* stg) const {
+    float b[32];
+    load_bias32(bias, col, b);
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      pk[i] = pack2(__uint_as_float(r[2 * i]) + b[2 * i], __uint_as_float(r[2 * i + 1]) + b[2 * i + 1],
+                    fmt);
+    tma_stage_acquire(lane);
+    sts_row64(stg, lane, pk);
+    tma_stage_publish();
+    if (lane == 0) {
+      tma_store_2d(&tmC, stg, col, row0);
+      tma_store_commit();
+    }
+  }
   using Aux = NoAux;
   using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
@@ -81,6 +144,47 @@ struct EpiStore16Dual {
   const float* bias;
   int fmt, fmt2;
   uint16_t* Clo;  // may be null: fp16 lo half of C (split-operand forward; fmt == 0)
+  // TMA-store path: one or two outputs (C, and C2 or Clo); three (split + second format) fall back
+  int tma = 0;
+  CUtensorMap tmC, tmX;
+  int prepare(int M, int N) {
+    tma = 0;
+    if (!epi_tma_enabled() || (C2 && Clo)) return 0;
+    if (make_tmap_2d_store16(&tmC, C, M, N, ldc)) return 0;
+    uint16_t* x = C2 ? C2 : Clo;
+    if (x && make_tmap_2d_store16(&tmX, x, M, N, ldc)) return 0;
+    tma = 1;
+    return 0;
+  }
+  __device__ __forceinline__ bool tma_on() const { return tma != 0; }
+  __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
+                                            uint8_t* stg) const {
+    float v[32];
+    load_bias32(bias, col, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+    uint32_t pk[16], px[16];
+    const bool second = C2 || Clo;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      pk[i] = pack2(v[2 * i], v[2 * i + 1], Clo ? 0 : fmt);
+      if (Clo) {
+        const float2 h = unpack2(pk[i], 0);
+        px[i] = pack2(v[2 * i] - h.x, v[2 * i + 1] - h.y, 0);
+      } else {
+        px[i] = pack2(v[2 * i], v[2 * i + 1], fmt2);
+      }
+    }
+    tma_stage_acquire(lane);
+    sts_row64(stg, lane, pk);
+    if (second) sts_row64(stg + EPI_TMA_TILE_BYTES, lane, px);
+    tma_stage_publish();
+    if (lane == 0) {
+      tma_store_2d(&tmC, stg, col, row0);
+      if (second) tma_store_2d(&tmX, stg + EPI_TMA_TILE_BYTES, col, row0);
+      tma_store_commit();
+    }
+  }
   using Aux = NoAux;
   using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }
@@ -140,6 +244,43 @@ struct EpiGelu {
   const float* bias;
   int fmt;
   uint16_t* Alo;  // may be null: fp16 lo half of A (split-operand forward; fmt == 0)
+  // TMA-store path: A and (if kept) G; the split forward's third output falls back
+  int tma = 0;
+  CUtensorMap tmA, tmG;
+  int prepare(int M, int N) {
+    tma = 0;
+    if (!epi_tma_enabled() || Alo) return 0;
+    if (make_tmap_2d_store16(&tmA, A, M, N, ld)) return 0;
+    if (G && make_tmap_2d_store16(&tmG, G, M, N, ld)) return 0;
+    tma = 1;
+    return 0;
+  }
+  __device__ __forceinline__ bool tma_on() const { return tma != 0; }
+  __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
+                                            uint8_t* stg) const {
+    float h[32];
+    load_bias32(bias, col, h);
+    uint32_t pa[16], pg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float h0 = h[2 * i] + __uint_as_float(r[2 * i]);
+      const float h1 = h[2 * i + 1] + __uint_as_float(r[2 * i + 1]);
+      const float s0 = quick_sigmoid(h0), s1 = quick_sigmoid(h1);
+      const float a0 = h0 * s0, a1 = h1 * s1;
+      pa[i] = pack2(a0, a1, fmt);
+      pg[i] = pack2(fmaf(1.702f * a0, 1.f - s0, s0 - 0.5f), fmaf(1.702f * a1, 1.f - s1, s1 - 0.5f),
+                    fmt);
+    }
+    tma_stage_acquire(lane);
+    sts_row64(stg, lane, pa);
+    if (G) sts_row64(stg + EPI_TMA_TILE_BYTES, lane, pg);
+    tma_stage_publish();
+    if (lane == 0) {
+      tma_store_2d(&tmA, stg, col, row0);
+      if (G) tma_store_2d(&tmG, stg + EPI_TMA_TILE_BYTES, col, row0);
+      tma_store_commit();
+    }
+  }
   using Aux = NoAux;
   using Col = float4;
   __device__ __forceinline__ Aux load(int, int) const { return {}; }

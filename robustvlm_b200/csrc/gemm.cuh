@@ -154,6 +154,42 @@ __device__ __forceinline__ void epilogue_drain_impl(const Epi& epi, float* stg, 
   }
 }
 
+// does the functor offer the TMA-store path (tma_on / tma_chunk / prepare)?
+template <class E>
+constexpr auto epi_has_tma(int) -> decltype(&E::tma_on, true) { return true; }
+template <class E>
+constexpr bool epi_has_tma(long) { return false; }
+template <class E>
+auto epi_prepare(E& e, int M, int N, int) -> decltype(e.prepare(M, N), void()) { e.prepare(M, N); }
+template <class E>
+void epi_prepare(E&, int, int, long) {}
+
+// TMA-store epilogue of one accumulator tile for one epilogue warp: lane = accumulator row, the
+// warp's columns in 32-column chunks; the functor converts a chunk in registers, writes its
+// row into the warp's staging tile(s) and lane 0 hands them to the TMA (Epi::tma_chunk).  The next
+// chunk's tcgen05.ld is in flight while the current one is processed.
+template <int BN, class Epi>
+__device__ __forceinline__ void epilogue_drain_tma(const Epi& epi, uint8_t* stg, uint32_t taddr,
+                                                   int row0, int n0, int slice, int M, int N,
+                                                   int lane) {
+  constexpr int SLICES = GEMM_EPI_WARPS / 4;
+  constexpr int NCH = BN / SLICES / 32;
+  const int cbase = slice * NCH * 32;
+  const int rem = N - (n0 + cbase);          // columns left for this slice (N % 32 == 0)
+  const int nch = rem <= 0 ? 0 : (rem >= NCH * 32 ? NCH : rem / 32);   // warp-uniform
+  if (nch == 0 || row0 >= M) return;
+  uint32_t r[2][32];
+  tmem_ld32(taddr + cbase, r[0]);
+#pragma unroll
+  for (int cc = 0; cc < NCH; ++cc) {
+    if (cc < nch) {
+      tmem_ld_wait();
+      if (cc + 1 < NCH && cc + 1 < nch) tmem_ld32(taddr + cbase + (cc + 1) * 32, r[(cc + 1) & 1]);
+      epi.tma_chunk(row0, lane, n0 + cbase + cc * 32, r[cc & 1], stg);
+    }
+  }
+}
+
 // The row guard is hoisted to the warp's 32-row slab: full slabs (all but the last M tile)
 // run branch-free, so the pieces' dependent chains (MUFU, conversions, stores) interleave
 // instead of executing one piece at a time.
@@ -161,14 +197,28 @@ template <int BN, class Epi>
 __device__ __forceinline__ void epilogue_drain(const Epi& epi, float* stg, uint32_t taddr,
                                                int row0, int n0, int slice, int M, int N,
                                                int lane) {
+  if constexpr (epi_has_tma<Epi>(0) && GEMM_EPI_GC == 32) {
+    if (epi.tma_on()) {   // (grid-uniform)
+      epilogue_drain_tma<BN>(epi, reinterpret_cast<uint8_t*>(stg), taddr, row0, n0, slice, M, N, lane);
+      return;
+    }
+  }
   if (row0 + 32 <= M) epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, slice, M, N, lane);
   else if (row0 < M) epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, slice, M, N, lane);
+}
+// before an epilogue warp leaves the kernel: its outstanding TMA stores are complete
+template <class Epi>
+__device__ __forceinline__ void epilogue_finish(const Epi& epi, int lane) {
+  if constexpr (epi_has_tma<Epi>(0)) {
+    if (epi.tma_on() && lane == 0) tma_store_wait0();
+    __syncwarp();
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              int M, int N, int K, int fmt, Epi epi) {
+              int M, int N, int K, int fmt, const __grid_constant__ Epi epi) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -298,6 +348,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
+    epilogue_finish(epi, lane);
   }
 
   tc_fence_before();
@@ -387,7 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmAlo,
                    const __grid_constant__ CUtensorMap tmBlo, int M, int N, int K, int fmt,
-                   Epi epi) {
+                   const __grid_constant__ Epi epi) {
   using S = Gemm2Smem<SPLIT>;
   constexpr int kStages = S::kStages;
   constexpr int BN = 256;
@@ -526,6 +577,7 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (leader) mbar_arrive(&tempty_bar[acc]);
       else mbar_arrive_cluster(&tempty_bar[acc], 0);
     }
+    epilogue_finish(epi, lane);
   }
 
   tc_fence_before();
@@ -638,9 +690,11 @@ int launch_gemm16(const void* A, int lda, const void* B, int ldb, int M, int N, 
   if (num_tiles < grid) grid = num_tiles;
   cudaError_t e;
   {
+    Epi epi_k = epi;
+    epi_prepare(epi_k, M, N, 0);   // tensor maps of a TMA-store epilogue
     GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K, 1.0, epi_tag<Epi>(0), true,
                        N, K);
-    kern<<<grid, GEMM_THREADS, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi);
+    kern<<<grid, GEMM_THREADS, GemmSmem<BN>::kTotal, stream>>>(tmA, tmB, M, N, K, fmt, epi_k);
     e = cudaGetLastError();
   }
   count_launch();
@@ -684,9 +738,11 @@ int launch_gemm16_2cta(const void* A, int lda, const void* B, int ldb, int M, in
   if (2 * num_tiles < grid) grid = 2 * num_tiles;
   cudaError_t e;
   {
+    Epi epi_k = epi;
+    epi_prepare(epi_k, M, N, 0);   // tensor maps of a TMA-store epilogue
     GemmProfScope prof(stream, 2.0 * (double)M * (double)N * (double)K, SPLIT ? 3.0 : 1.0,
                        epi_tag<Epi>(0), true, N, K);
-    kern<<<grid, GEMM_THREADS, S::kTotal, stream>>>(tmA, tmB, tmAlo, tmBlo, M, N, K, fmt, epi);
+    kern<<<grid, GEMM_THREADS, S::kTotal, stream>>>(tmA, tmB, tmAlo, tmBlo, M, N, K, fmt, epi_k);
     e = cudaGetLastError();
   }
   count_launch();

@@ -55,6 +55,32 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   return r == CUDA_SUCCESS ? 0 : RVLM_ERR_TMAP;
 }
 
+// Tensor map for TMA STORES of a 16-bit [rows, cols] row-major output (pitch ld elements): box =
+// 32 rows x 32 columns (64-byte rows, 64B swizzle), the per-warp staging tile of the GEMM epilogue.
+int make_tmap_2d_store16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                         uint64_t ld) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return RVLM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || ((ld * 2) & 15) || (cols & 31)) return RVLM_ERR_ALIGN;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : RVLM_ERR_TMAP;
+}
+
+bool epi_tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RVLM_EPI_TMA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 

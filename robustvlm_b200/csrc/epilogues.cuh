@@ -57,7 +57,9 @@ __device__ __forceinline__ float4 add4(const float4& a, const float4& b) {
 // address arithmetic, rows past M clipped by the tensor map.
 int make_tmap_2d_store16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                          uint64_t ld);
-bool epi_tma_enabled();   // RVLM_EPI_TMA (default on)
+// RVLM_EPI_TMA: 0 = off, 1 (default) = the epilogues with two outputs or an input tile (where it
+// measured faster: fc + QuickGELU 127 -> 117 ms / step), 2 = every 16-bit-output epilogue
+int epi_tma_level();
 
 constexpr int EPI_TMA_TILE_BYTES = 32 * 64;
 
@@ -76,6 +78,14 @@ __device__ __forceinline__ void sts_row64(uint8_t* tile, int lane, const uint32_
   for (int j = 0; j < 4; ++j)
     *reinterpret_cast<uint4*>(tile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
         make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+}
+__device__ __forceinline__ void lds_row64(const uint8_t* tile, int lane, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 t =
+        *reinterpret_cast<const uint4*>(tile + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+    pk[4 * j] = t.x; pk[4 * j + 1] = t.y; pk[4 * j + 2] = t.z; pk[4 * j + 3] = t.w;
+  }
 }
 // the staging tiles of this warp are free again (the previous chunk's stores have read them)
 __device__ __forceinline__ void tma_stage_acquire(int lane) {
@@ -101,12 +111,13 @@ struct EpiStore16 {
   int tma = 0;
   CUtensorMap tmC;
   int prepare(int M, int N) {
-    tma = epi_tma_enabled() && make_tmap_2d_store16(&tmC, C, M, N, ldc) == 0;
+    // (single plain output: measured equal to the transposing epilogue -- only at level 2)
+    tma = epi_tma_level() >= 2 && make_tmap_2d_store16(&tmC, C, M, N, ldc) == 0;
     return 0;
   }
   __device__ __forceinline__ bool tma_on() const { return tma != 0; }
   __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
-                                            uint8_t* stg) const {
+                                            uint8_t* stg, TmaCtx&) const {
     float b[32];
     load_bias32(bias, col, b);
     uint32_t pk[16];
@@ -149,16 +160,16 @@ struct EpiStore16Dual {
   CUtensorMap tmC, tmX;
   int prepare(int M, int N) {
     tma = 0;
-    if (!epi_tma_enabled() || (C2 && Clo)) return 0;
-    if (make_tmap_2d_store16(&tmC, C, M, N, ldc)) return 0;
     uint16_t* x = C2 ? C2 : Clo;
+    if (epi_tma_level() < (x ? 1 : 2) || (C2 && Clo)) return 0;
+    if (make_tmap_2d_store16(&tmC, C, M, N, ldc)) return 0;
     if (x && make_tmap_2d_store16(&tmX, x, M, N, ldc)) return 0;
     tma = 1;
     return 0;
   }
   __device__ __forceinline__ bool tma_on() const { return tma != 0; }
   __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
-                                            uint8_t* stg) const {
+                                            uint8_t* stg, TmaCtx&) const {
     float v[32];
     load_bias32(bias, col, v);
 #pragma unroll
@@ -249,7 +260,7 @@ struct EpiGelu {
   CUtensorMap tmA, tmG;
   int prepare(int M, int N) {
     tma = 0;
-    if (!epi_tma_enabled() || Alo) return 0;
+    if (epi_tma_level() < 1 || Alo) return 0;
     if (make_tmap_2d_store16(&tmA, A, M, N, ld)) return 0;
     if (G && make_tmap_2d_store16(&tmG, G, M, N, ld)) return 0;
     tma = 1;
@@ -257,7 +268,7 @@ struct EpiGelu {
   }
   __device__ __forceinline__ bool tma_on() const { return tma != 0; }
   __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
-                                            uint8_t* stg) const {
+                                            uint8_t* stg, TmaCtx&) const {
     float h[32];
     load_bias32(bias, col, h);
     uint32_t pa[16], pg[16];
@@ -321,6 +332,50 @@ struct EpiGeluBwd {
   const uint16_t* G;
   int fmt_g;
   int fmt_out;
+  // TMA path: the G tile of a chunk is fetched into the warp's second staging tile by a TMA load
+  // (requested one chunk ahead, the first chunk of a tile before its MMAs retire), the output
+  // leaves by a TMA store
+  int tma = 0;
+  CUtensorMap tmO, tmG;
+  int prepare(int M, int N) {
+    tma = 0;
+    if (epi_tma_level() < 1) return 0;
+    if (make_tmap_2d_store16(&tmO, out, M, N, ld)) return 0;
+    if (make_tmap_2d_store16(&tmG, G, M, N, ld)) return 0;
+    tma = 1;
+    return 0;
+  }
+  __device__ __forceinline__ bool tma_on() const { return tma != 0; }
+  __device__ __forceinline__ void tma_request(int row0, int col, uint8_t* stg, TmaCtx& c) const {
+    mbar_arrive_expect_tx(c.bar, EPI_TMA_TILE_BYTES);
+    tma_load_2d(stg + EPI_TMA_TILE_BYTES, &tmG, c.bar, col, row0);
+  }
+  __device__ __forceinline__ void tma_prefetch(int row0, int lane, int col, uint8_t* stg,
+                                               TmaCtx& c) const {
+    if (lane == 0) tma_request(row0, col, stg, c);
+  }
+  __device__ __forceinline__ void tma_chunk(int row0, int lane, int col, const uint32_t (&r)[32],
+                                            uint8_t* stg, TmaCtx& c) const {
+    mbar_wait(c.bar, c.phase, 9);
+    c.phase ^= 1u;
+    uint32_t g[16], pk[16];
+    lds_row64(stg + EPI_TMA_TILE_BYTES, lane, g);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float2 t = unpack2(g[i], fmt_g);   // gelu' - 1/2
+      pk[i] = pack2(__uint_as_float(r[2 * i]) * (t.x + 0.5f),
+                    __uint_as_float(r[2 * i + 1]) * (t.y + 0.5f), fmt_out);
+    }
+    __syncwarp();   // every lane has consumed its row of the G tile: it may be overwritten
+    if (lane == 0 && c.next_col >= 0) tma_request(row0, c.next_col, stg, c);
+    tma_stage_acquire(lane);
+    sts_row64(stg, lane, pk);
+    tma_stage_publish();
+    if (lane == 0) {
+      tma_store_2d(&tmO, stg, col, row0);
+      tma_store_commit();
+    }
+  }
   using Aux = uint2;
   using Col = NoAux;
   __device__ __forceinline__ Aux load(int row, int col) const {

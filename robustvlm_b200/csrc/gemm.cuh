@@ -55,7 +55,7 @@ struct GemmSmem {
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarrierBytes = 256;
+  static constexpr int kBarrierBytes = 512;   // pipeline barriers + one mbarrier per epilogue warp
   static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_EPI_GC * 4;  // per-warp transpose tiles
   static constexpr int kTotal =
       kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /*align slack*/;
@@ -164,28 +164,48 @@ auto epi_prepare(E& e, int M, int N, int) -> decltype(e.prepare(M, N), void()) {
 template <class E>
 void epi_prepare(E&, int, int, long) {}
 
-// TMA-store epilogue of one accumulator tile for one epilogue warp: lane = accumulator row, the
+template <class E>
+__device__ __forceinline__ auto epi_tma_prefetch(const E& e, int row0, int lane, int col,
+                                                 uint8_t* stg, TmaCtx& c, int)
+    -> decltype(e.tma_prefetch(row0, lane, col, stg, c), void()) {
+  e.tma_prefetch(row0, lane, col, stg, c);
+}
+template <class E>
+__device__ __forceinline__ void epi_tma_prefetch(const E&, int, int, int, uint8_t*, TmaCtx&, long) {}
+
+// TMA epilogue of one accumulator tile for one epilogue warp: lane = accumulator row, the
 // warp's columns in 32-column chunks; the functor converts a chunk in registers, writes its
-// row into the warp's staging tile(s) and lane 0 hands them to the TMA (Epi::tma_chunk).  The next
-// chunk's tcgen05.ld is in flight while the current one is processed.
+// row into the warp's staging tile and lane 0 hands it to the TMA (Epi::tma_chunk).  The next
+// chunk's tcgen05.ld is in flight while the current one is processed; a functor with an input
+// tile has chunk 0's requested before the wait on the accumulator (tma_prefetch).
+template <int BN>
+struct TmaSlice {
+  static constexpr int SLICES = GEMM_EPI_WARPS / 4;
+  static constexpr int NCH = BN / SLICES / 32;
+  int cbase, nch;
+  __device__ __forceinline__ TmaSlice(int n0, int slice, int N) {
+    cbase = slice * NCH * 32;
+    const int rem = N - (n0 + cbase);          // columns left for this slice (N % 32 == 0)
+    nch = rem <= 0 ? 0 : (rem >= NCH * 32 ? NCH : rem / 32);   // warp-uniform
+  }
+};
 template <int BN, class Epi>
 __device__ __forceinline__ void epilogue_drain_tma(const Epi& epi, uint8_t* stg, uint32_t taddr,
                                                    int row0, int n0, int slice, int M, int N,
-                                                   int lane) {
-  constexpr int SLICES = GEMM_EPI_WARPS / 4;
-  constexpr int NCH = BN / SLICES / 32;
-  const int cbase = slice * NCH * 32;
-  const int rem = N - (n0 + cbase);          // columns left for this slice (N % 32 == 0)
-  const int nch = rem <= 0 ? 0 : (rem >= NCH * 32 ? NCH : rem / 32);   // warp-uniform
-  if (nch == 0 || row0 >= M) return;
+                                                   int lane, TmaCtx& ctx) {
+  const TmaSlice<BN> sl(n0, slice, N);
+  constexpr int NCH = TmaSlice<BN>::NCH;
+  if (sl.nch == 0 || row0 >= M) return;
   uint32_t r[2][32];
-  tmem_ld32(taddr + cbase, r[0]);
+  tmem_ld32(taddr + sl.cbase, r[0]);
 #pragma unroll
   for (int cc = 0; cc < NCH; ++cc) {
-    if (cc < nch) {
+    if (cc < sl.nch) {
       tmem_ld_wait();
-      if (cc + 1 < NCH && cc + 1 < nch) tmem_ld32(taddr + cbase + (cc + 1) * 32, r[(cc + 1) & 1]);
-      epi.tma_chunk(row0, lane, n0 + cbase + cc * 32, r[cc & 1], stg);
+      const bool more = cc + 1 < NCH && cc + 1 < sl.nch;
+      if (more) tmem_ld32(taddr + sl.cbase + (cc + 1) * 32, r[(cc + 1) & 1]);
+      ctx.next_col = more ? n0 + sl.cbase + (cc + 1) * 32 : -1;
+      epi.tma_chunk(row0, lane, n0 + sl.cbase + cc * 32, r[cc & 1], stg, ctx);
     }
   }
 }
@@ -196,13 +216,21 @@ __device__ __forceinline__ void epilogue_drain_tma(const Epi& epi, uint8_t* stg,
 template <int BN, class Epi>
 __device__ __forceinline__ void epilogue_drain(const Epi& epi, float* stg, uint32_t taddr,
                                                int row0, int n0, int slice, int M, int N,
-                                               int lane) {
+                                               int lane, uint64_t* tfull, uint32_t tphase,
+                                               TmaCtx& ctx) {
   if constexpr (epi_has_tma<Epi>(0) && GEMM_EPI_GC == 32) {
     if (epi.tma_on()) {   // (grid-uniform)
-      epilogue_drain_tma<BN>(epi, reinterpret_cast<uint8_t*>(stg), taddr, row0, n0, slice, M, N, lane);
+      uint8_t* st8 = reinterpret_cast<uint8_t*>(stg);
+      const TmaSlice<BN> sl(n0, slice, N);
+      if (sl.nch > 0 && row0 < M) epi_tma_prefetch(epi, row0, lane, n0 + sl.cbase, st8, ctx, 0);
+      mbar_wait(tfull, tphase, 4);
+      tc_fence_after();
+      epilogue_drain_tma<BN>(epi, st8, taddr, row0, n0, slice, M, N, lane, ctx);
       return;
     }
   }
+  mbar_wait(tfull, tphase, 4);
+  tc_fence_after();
   if (row0 + 32 <= M) epilogue_drain_impl<BN, false>(epi, stg, taddr, row0, n0, slice, M, N, lane);
   else if (row0 < M) epilogue_drain_impl<BN, true>(epi, stg, taddr, row0, n0, slice, M, N, lane);
 }
@@ -258,6 +286,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * 32);
     }
+    for (int i = 0; i < GEMM_EPI_WARPS; ++i) mbar_init(&bars[32 + i], 1);   // epilogue input tiles
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -335,16 +364,16 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;             // TMEM lane quarter this warp may access
     const int slice = (warp - 4) >> 2;  // which slice of the accumulator columns
     float* stg = staging + (warp - 4) * 32 * GEMM_EPI_GC;
+    TmaCtx tctx{&bars[32 + (warp - 4)], 0u, -1};
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
       const int row0 = m_blk * GEMM_BM + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, slice, M, N, lane);
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, slice, M, N, lane, &tfull_bar[acc],
+                         acc_phase, tctx);
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
@@ -430,7 +459,7 @@ struct Gemm2Smem {
   static constexpr int kBBytes = 128 * GEMM_BK * 2;       // half of the 256-row B tile
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_EPI_GC * 4;
-  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 256 + 1024;
+  static constexpr int kTotal = kStages * kStageBytes + kStagingBytes + 512 + 1024;
 };
 
 template <class Epi, bool SPLIT>
@@ -484,6 +513,7 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS * 32);
     }
+    for (int i = 0; i < GEMM_EPI_WARPS; ++i) mbar_init(&bars[32 + i], 1);   // epilogue input tiles
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -563,16 +593,16 @@ gemm16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int q = warp & 3;
     const int slice = (warp - 4) >> 2;
     float* stg = staging + (warp - 4) * 32 * GEMM_EPI_GC;
+    TmaCtx tctx{&bars[32 + (warp - 4)], 0u, -1};
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tfull_bar[acc], acc_phase, 4);
-      tc_fence_after();
       const int row0 = m_blk * 256 + (int)rank * 128 + q * 32;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BN;
-      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, slice, M, N, lane);
+      epilogue_drain<BN>(epi, stg, taddr, row0, n_blk * BN, slice, M, N, lane, &tfull_bar[acc],
+                         acc_phase, tctx);
       tc_fence_before();
       if (leader) mbar_arrive(&tempty_bar[acc]);
       else mbar_arrive_cluster(&tempty_bar[acc], 0);

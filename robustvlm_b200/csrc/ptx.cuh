@@ -139,6 +139,15 @@ __device__ __forceinline__ void tma_store_wait0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// per-warp state of a TMA epilogue with an INPUT tile (the stored GELU derivative): the warp's
+// mbarrier for the tile's arrival, its phase, and the column of the next chunk of the same
+// accumulator tile (-1: none -- the next tile's first chunk is requested by tma_prefetch)
+struct TmaCtx {
+  uint64_t* bar;
+  uint32_t phase;
+  int next_col;
+};
+
 // ---------------------------------------------------------------------------
 // tcgen05: TMEM allocation
 // ---------------------------------------------------------------------------

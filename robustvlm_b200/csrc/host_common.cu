@@ -72,13 +72,9 @@ int make_tmap_2d_store16(CUtensorMap* out, const void* base, uint64_t rows, uint
   return r == CUDA_SUCCESS ? 0 : RVLM_ERR_TMAP;
 }
 
-int epi_tma_level() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("RVLM_EPI_TMA");
-    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
-  }
-  return v;
+int epi_tma_level() {   // (read per call: the tests cover every level)
+  const char* e = getenv("RVLM_EPI_TMA");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
 }
 
 static std::atomic<long long> g_launches{0};

@@ -32,8 +32,10 @@ def _dt(fmt):
     (256, 256, 64, 0, 8), (512, 512, 1024, 0, 8), (1000, 768, 1024, 1, 8), (4112, 3072, 1024, 0, 8),
     (300, 96, 192, 1, 8),
 ])
-def test_gemm16(M, N, K, fmt, flags):
+@pytest.mark.parametrize("tma", ["2", "0"])   # TMA-store epilogue / transposing epilogue
+def test_gemm16(M, N, K, fmt, flags, tma, monkeypatch):
     nat = _nat()
+    monkeypatch.setenv("RVLM_EPI_TMA", tma)
     torch.manual_seed(M + N + K)
     A = torch.randn(M, K, device="cuda").to(_dt(fmt))
     B = torch.randn(N, K, device="cuda").to(_dt(fmt))
@@ -48,12 +50,14 @@ def test_gemm16(M, N, K, fmt, flags):
     torch.cuda.synchronize()
     tol = (2e-2 if fmt else 3e-3)
     err = (C.float() - ref).abs().max().item()
-    _log("gemm16", M=M, N=N, K=K, fmt=fmt, flags=flags, err=err)
+    _log("gemm16", M=M, N=N, K=K, fmt=fmt, flags=flags, tma=tma, err=err)
     assert err <= tol * ref.abs().max().item()
 
 
-def test_gemm_fp32_residual_and_gelu():
+@pytest.mark.parametrize("tma", ["2", "1", "0"])
+def test_gemm_fp32_residual_and_gelu(tma, monkeypatch):
     nat = _nat()
+    monkeypatch.setenv("RVLM_EPI_TMA", tma)
     torch.manual_seed(0)
     M, N, K = 700, 512, 256
     A = (torch.randn(M, K, device="cuda") * 0.5).half()

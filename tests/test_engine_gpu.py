@@ -255,3 +255,24 @@ def test_profile_breakdown_covers_the_step():
     assert abs(sum(v["ms"] for v in gemm.values()) - tms.value) < 1e-3 * max(tms.value, 1e-3) + 1e-3
     assert any(k.startswith("gemm.patch_pgd_linf") for k in bd) and "ln_fwd" in bd and "ln_bwd" in bd
     assert all(v["ms"] > 0 for v in bd.values()) and tfl.value > 0
+
+
+def test_tma_epilogue_equals_transposing_epilogue(monkeypatch):
+    """RVLM_EPI_TMA selects how the 16-bit GEMM outputs leave the SM (staging tile + TMA store, the
+    stored GELU derivative by TMA load) -- the arithmetic is the same: embeddings and gradients of
+    the two paths agree to rounding."""
+    from robustvlm_b200.engine import LossSpec
+    x, d0 = synth_batch(3, seed=2)
+    res = {}
+    for lvl in ("2", "0"):
+        monkeypatch.setenv("RVLM_EPI_TMA", lvl)
+        eng, model = make_engine("tiny-14", seed=1)
+        with torch.no_grad():
+            e_orig = model(x, output_normalize=False) + 0.1
+        emb = eng.forward(x.cuda(), d0.cuda(), output_normalize=False)
+        out = eng.loss_grad(x.cuda(), LossSpec("l2", False, emb_orig=e_orig.cuda()), delta=d0.cuda())
+        res[lvl] = (emb.cpu(), out["grad"].cpu())
+    e_rel = rel_err(res["2"][0], res["0"][0])
+    g_rel = rel_err(res["2"][1], res["0"][1])
+    _log("tma_vs_transposing_epilogue", emb_rel=e_rel, grad_rel=g_rel)
+    assert e_rel < 1e-6 and g_rel < 1e-5

@@ -29,6 +29,7 @@ timeout -s KILL 600 ncu --profile-from-start off --metrics gpu__time_duration.su
   --log-file /tmp/${TAG}_launches.csv python tools/profile_kernels.py --step > gpurun_out/${TAG}_launches.log 2>&1
 python tools/ncu_summary.py launches /tmp/${TAG}_launches.csv > gpurun_out/${TAG}_launches.txt 2>&1
 head -14 gpurun_out/${TAG}_launches.txt
+[ "${RVLM_NCU_FULL:-1}" = 1 ] || exit 0
 echo "== ncu --set full: attention forward / backward"
 for k in attn_fwd3 attn_bwd4; do
   timeout -s KILL 400 ncu --set full --import-source on --clock-control none -k regex:$k -c 1 -f \

@@ -1650,9 +1650,7 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   if (rc) return rc;
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
-  const char* env3 = getenv("RVLM_ATTN_FWD3");   // default on; RVLM_ATTN_FWD3=0 selects fwd2
-  const bool use_fwd3 = !(env3 && env3[0] == '0');   // (read per call: the tests toggle it)
-  if (T == 257 && use_fwd3) {   // one tile per CTA, two CTAs per SM
+  if (T == 257) {   // ViT-L/14: one tile per CTA, two CTAs per SM (the generic kernel serves T <= 256)
     AttnFwd3Params P3{B, H, H * 64, P.qkv, P.o_out, P.lse_out};
     const size_t smem3 = 3 * 32768 + 512 + 128 + 128 + 1024;
     // one sweep over S (default) or the earlier max pass + exp pass (RVLM_ATTN_FWD_ONE=0; read
@@ -1732,11 +1730,9 @@ extern "C" int rvlm_attn_bwd(const void* qkv16, const void* o16, const void* do1
   if (fmt_qkv != fmt_g) return RVLM_ERR_UNSUPPORTED;
   if (!lse_tmp) return RVLM_ERR_INVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  // the fused dQ / dK / dV kernel (version 3: statistics recomputed) for T in {256, 257};
-  // RVLM_ATTN_BWD3=0 selects the generic dQ + dK/dV kernel pair (read per call: the tests cover both)
-  const char* e3 = getenv("RVLM_ATTN_BWD3");
-  const int use_v3 = (e3 && e3[0] == '0') ? 0 : 1;
-  if (use_v3 && (T == 257 || T == 256)) {
+  // the fused dQ / dK / dV kernel (version 3: statistics recomputed) for T in {256, 257}; other
+  // token counts: the generic dQ + dK/dV kernel pair
+  if (T == 257 || T == 256) {
     AttnBwd2Params P{};
     P.B = B; P.T = T; P.H = H; P.W = H * 64;
     P.tm = 256; P.kvm = 256; P.nblk = 4; P.ntile = 2;

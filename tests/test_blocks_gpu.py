@@ -150,26 +150,23 @@ def _attn_ref(qkv, B, T, H):
     return o, torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("impl", ["simt", "tc", "tc3", "tc_fwd2", "tc_fwd_two_sweep"])
+@pytest.mark.parametrize("impl", ["simt", "tc", "tc3", "tc_fwd_two_sweep"])
 @pytest.mark.parametrize("B,T,H", [(2, 50, 2), (3, 257, 4), (1, 257, 16), (2, 256, 4), (40, 257, 8),
                                    (37, 257, 16)])
 def test_attention_fwd_bwd(impl, B, T, H, monkeypatch):
     nat = _nat()
-    # forward: T = 257 runs attn_fwd3 (one tile per CTA, two CTAs per SM) unless RVLM_ATTN_FWD3=0
-    # (one sweep over S by default; RVLM_ATTN_FWD_ONE=0: the max pass + exp pass variant)
-    monkeypatch.setenv("RVLM_ATTN_FWD3", "0" if impl == "tc_fwd2" else "1")
+    # forward: T = 257 runs attn_fwd3 (one tile per CTA, two CTAs per SM; one sweep over S by
+    # default, RVLM_ATTN_FWD_ONE=0: the max pass + exp pass variant), other T the generic kernel
     monkeypatch.setenv("RVLM_ATTN_FWD_ONE", "0" if impl == "tc_fwd_two_sweep" else "1")
-    if impl in ("tc_fwd2", "tc_fwd_two_sweep"):
-        if T != 257:
-            pytest.skip("fwd2 is already the forward for T != 257")
-        impl = "tc"
-    if impl == "tc3":   # the fused dQ/dK/dV backward kernel (T in {256, 257})
-        if T < 256:
-            pytest.skip("fused backward covers T in {256, 257}")
-        monkeypatch.setenv("RVLM_ATTN_BWD3", "1")
-        impl = "tc"
-    else:
-        monkeypatch.setenv("RVLM_ATTN_BWD3", "0")
+    if impl == "tc_fwd_two_sweep" and T != 257:
+        pytest.skip("attn_fwd3 serves T = 257 only")
+    # backward: T in {256, 257} runs the fused dQ / dK / dV kernel ("tc3"), other token counts the
+    # generic dQ + dK/dV pair ("tc")
+    if impl == "tc" and T >= 256:
+        pytest.skip("T in {256, 257}: covered by tc3")
+    if impl == "tc3" and T < 256:
+        pytest.skip("fused backward serves T in {256, 257}")
+    impl = "simt" if impl == "simt" else "tc"
     torch.manual_seed(B * T + H)
     W = H * 64
     qkv = (torch.randn(B * T, 3 * W, device="cuda") * 1.5).half()
@@ -209,7 +206,6 @@ def test_attention_fwd_uneven_halves(one, monkeypatch):
     the epilogue: rows whose two halves (and the peeled 257th key) differ by many e-folds in
     either direction must come out like the fp32 reference."""
     nat = _nat()
-    monkeypatch.setenv("RVLM_ATTN_FWD3", "1")
     monkeypatch.setenv("RVLM_ATTN_FWD_ONE", one)
     B, T, H = 6, 257, 4
     W = H * 64

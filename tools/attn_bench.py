@@ -1,6 +1,6 @@
 """Time rvlm_attn_fwd (and optionally bwd) alone at the ViT-L/14 bench shape (B = 256, T = 257,
 H = 16) with CUDA events; checks the forward against a plain fp32 PyTorch reference on a slice.
-RVLM_ATTN_FWD3=1 selects the one-tile-per-CTA / two-CTAs-per-SM forward."""
+RVLM_ATTN_FWD_ONE=0 selects the two-sweep variant of the forward."""
 import argparse
 import json
 import os
@@ -46,8 +46,7 @@ def main():
     q2, k2, v2 = qkv[-T:].float().view(1, T, 3, H, 64).permute(2, 0, 3, 1, 4)
     s2 = (q2 @ k2.transpose(-1, -2)) * 0.125
     o_ref2 = (s2.softmax(-1) @ v2).permute(0, 2, 1, 3).reshape(T, W)
-    res = {"fwd3": os.environ.get("RVLM_ATTN_FWD3", "1"),
-           "fwd_one_sweep": os.environ.get("RVLM_ATTN_FWD_ONE", "1"), "B": B, "us": us,
+    res = {"fwd_one_sweep": os.environ.get("RVLM_ATTN_FWD_ONE", "1"), "B": B, "us": us,
            "tflops": 4.0 * B * H * T * T * 64 / (us * 1e-6) / 1e12,
            "err_o": float((o[: nb * T].float() - o_ref).abs().max()),
            "err_o_last": float((o[-T:].float() - o_ref2).abs().max()),

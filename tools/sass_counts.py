@@ -35,14 +35,14 @@ def main():
                 if k != "total" and (op == k or op.startswith(k + ".") or (k == "UTCHMMA.2CTA" and op.startswith("UTCHMMA.2CTA"))):
                     cur[k] += 1
     print(f"# {lib}: arch {sorted(arch)}; SASS instruction counts per kernel (static)")
-    print(" ".join(f"{k:>9}" for k in ["UTCHMMA", "(.2CTA)", "LDTM", "STTM", "UTMALDG", "MUFU.EX2", "REDG", "HMMA", "total"]) + "  kernel")
+    print(" ".join(f"{k:>9}" for k in ["UTCHMMA", "(.2CTA)", "LDTM", "STTM", "UTMALDG", "UTMASTG", "MUFU.EX2", "REDG", "HMMA", "total"]) + "  kernel")
     tot = collections.Counter()
     for name, c in counts.items():
         tot.update(c)
         if c["total"] < 50:
             continue
-        print(" ".join(f"{c[k]:9d}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "MUFU.EX2", "REDG", "HMMA", "total"]) + "  " + name[:120])
-    print(" ".join(f"{tot[k]:9d}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "MUFU.EX2", "REDG", "HMMA", "total"]) + "  TOTAL")
+        print(" ".join(f"{c[k]:9d}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "MUFU.EX2", "REDG", "HMMA", "total"]) + "  " + name[:120])
+    print(" ".join(f"{tot[k]:9d}" for k in ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "MUFU.EX2", "REDG", "HMMA", "total"]) + "  TOTAL")
 
 
 if __name__ == "__main__":

@@ -419,7 +419,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, profile=False, sample=True):
+    def timed(fn, steps, profile=False, sample=True, finish=None):
         barrier()
         sampler = ClockSampler(local) if (rank == 0 and sample) else None
         if sampler:
@@ -431,6 +431,8 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if finish:
+            finish()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -482,9 +484,71 @@ def run_ours(args):
     # one more step with EVERY kernel bracketed (the events between back-to-back short kernels cost
     # ~1 % of the step, so this pass is not the one `value` is taken from)
     ms_bd, _, prof_bd, _ = timed(step_resident, 1, profile=2, sample=False)
-    for _ in range(min(args.warmup, 1)):
-        step_e2e()
-    ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+    class E2EPipeline:
+        """The end-to-end step as a data loader would drive it: every step's inputs come from
+        pinned host memory and its result goes back to pinned host memory INSIDE the timed region,
+        on a second stream, so that the copies of step i + 1 / step i - 1 run under the compute of
+        step i (double-buffered device inputs; the public call attacks.pgd is unchanged)."""
+
+        def __init__(self):
+            self.cs = torch.cuda.Stream(device=dev)
+            self.xd = [torch.empty_like(x), torch.empty_like(x)]
+            self.dd = [torch.empty_like(d0), torch.empty_like(d0)]
+            self.ev_in = [torch.cuda.Event(), torch.cuda.Event()]
+            self.ev_cmp = [torch.cuda.Event(), torch.cuda.Event()]
+            self.reset()
+
+        def reset(self):
+            torch.cuda.synchronize()
+            self.i, self.primed = 0, False
+
+        def _h2d(self, b):
+            with torch.cuda.stream(self.cs):
+                self.xd[b].copy_(x_h, non_blocking=True)
+                self.dd[b].copy_(d0_h, non_blocking=True)
+                self.ev_in[b].record(self.cs)
+
+        def step(self):
+            main = torch.cuda.current_stream()
+            b = self.i & 1
+            if not self.primed:                  # the first step's inputs: nothing to hide under
+                self.cs.wait_stream(main)
+                self._h2d(b)
+                self.primed = True
+            main.wait_event(self.ev_in[b])
+            adv = attacks.pgd(m, wrap, self.xd[b], None, "linf", EPS, ITERS, STEPSIZE, False,
+                              perturbation=self.dd[b], mode="max", chunk=chunk)
+            self.ev_cmp[b].record(main)
+            if self.i > 0:                       # the other buffer was read by step i - 1
+                self.cs.wait_event(self.ev_cmp[b ^ 1])
+            self._h2d(b ^ 1)                     # next step's inputs, under this step's compute
+            self.cs.wait_event(self.ev_cmp[b])   # this step's result, under the next step's compute
+            with torch.cuda.stream(self.cs):
+                out_h.copy_(adv, non_blocking=True)
+            adv.record_stream(self.cs)
+            self.i += 1
+            return adv
+
+        def finish(self):
+            torch.cuda.current_stream().wait_stream(self.cs)
+
+    e2e_how = "copies overlapped with the neighbouring steps' compute on a second stream"
+    try:
+        pipe = E2EPipeline()
+        for _ in range(min(args.warmup, 1)):
+            pipe.step()
+        pipe.finish()
+        pipe.reset()
+        ms_e2e, _, _, _ = timed(pipe.step, args.steps, finish=pipe.finish)
+        torch.cuda.synchronize()
+        e2e_ok = bool(torch.equal(out_h, step_resident().cpu()))   # same inputs, deterministic path
+        del pipe
+    except Exception as exc:  # noqa: BLE001 -- fall back to the plain sequence, say so
+        e2e_how = f"sequential (pipelined path failed: {type(exc).__name__})"
+        for _ in range(min(args.warmup, 1)):
+            step_e2e()
+        ms_e2e, _, _, _ = timed(step_e2e, args.steps)
+        e2e_ok = None
 
     n_img = B * world * args.steps
     value = n_img / (ms / 1e3)
@@ -503,7 +567,8 @@ def run_ours(args):
             "dtype": PRECISION_DTYPE[args.precision],
             "data": "synthetic", "config": workload_config(args, B),
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(2 * x_h.numel() * 4),
-                    "d2h_bytes_per_step": int(x_h.numel() * 4)},
+                    "d2h_bytes_per_step": int(x_h.numel() * 4), "copies": e2e_how,
+                    "result_equals_resident_run": e2e_ok},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,

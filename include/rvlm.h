@@ -184,7 +184,9 @@ int rvlm_layernorm_bwd16(const void* dy16, const float* x, const float* stats, c
 /* Multi-head attention core, head dim 64, no mask: softmax(q k^T / 8) v.
  *   qkv16 [B*T, 3W] (q | k | v per token; head h at columns 64h..64h+63), W = 64 H
  *   o16 [B*T, W]; lse [B, H, T] (log-sum-exp of the scaled scores)
- * tcgen05 kernels (production) and CUDA-core kernels (on-device checker). */
+ * tcgen05 kernels (production) and CUDA-core kernels (on-device checker).  The T = 256 / 257
+ * kernels write rows 256 bits at a time: o16 (forward) and dqkv16 (rvlm_attn_bwd_lse) must be
+ * 32-byte aligned (RVLM_ERR_ALIGN otherwise). */
 int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, int T, int H, int fmt,
                   void* stream);
 /* Backward: qkv16 is the backward's copy of q|k|v in fmt_qkv, do16 the output gradient and

@@ -1651,6 +1651,7 @@ extern "C" int rvlm_attn_fwd(const void* qkv16, void* o16, float* lse, int B, in
   rc = make_tmap_3d(&tmFull, qkv16, W3, T, B, W3, (uint64_t)T * W3, 64, P.kvm);
   if (rc) return rc;
   if (T == 257) {   // ViT-L/14: one tile per CTA, two CTAs per SM (the generic kernel serves T <= 256)
+    if (reinterpret_cast<uintptr_t>(o16) & 31) return RVLM_ERR_ALIGN;   // 256-bit row stores
     AttnFwd3Params P3{B, H, H * 64, P.qkv, P.o_out, P.lse_out};
     const size_t smem3 = 3 * 32768 + 512 + 128 + 128 + 1024;
     // one sweep over S (default) or the earlier max pass + exp pass (RVLM_ATTN_FWD_ONE=0; read
@@ -1699,6 +1700,7 @@ extern "C" int rvlm_attn_bwd_lse(const void* qkv16, const void* o16, const void*
   const bool use_v4 = !(e4 && e4[0] == '0');   // (read per call: the tests cover both)
   if (!use_v4 || (T != 257 && T != 256))
     return rvlm_attn_bwd(qkv16, o16, do16, lse, dqkv16, B, T, H, fmt_qkv, fmt_o, fmt_g, stream);
+  if (reinterpret_cast<uintptr_t>(dqkv16) & 31) return RVLM_ERR_ALIGN;   // 256-bit row stores
   AttnBwd2Params P{};
   P.B = B; P.T = T; P.H = H; P.W = H * 64;
   P.tm = 256; P.kvm = 256; P.nblk = 4; P.ntile = 2;

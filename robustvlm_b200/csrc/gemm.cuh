@@ -13,10 +13,13 @@
 //   warp 0 lane 0 : TMA producer   (kStages-deep smem ring, full/empty mbarriers)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma, double-buffered TMEM accumulator)
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue       (tcgen05.ld -> registers -> swizzled smem transpose ->
-//                                   Epi functor on row-contiguous float4 pieces -> HBM);
-//                                   GEMM_EPI_WARPS / 4 warps per TMEM lane quarter, each takes
-//                                   one slice of the accumulator columns
+//   warps 4..11   : epilogue; GEMM_EPI_WARPS / 4 warps per TMEM lane quarter, each takes one
+//                   slice of the accumulator columns.  Two paths:
+//                   TMA (16-bit outputs): tcgen05.ld -> registers (lane = row) -> Epi math ->
+//                     64B-swizzled per-warp staging tile -> cp.async.bulk.tensor store per
+//                     output and 32-column chunk (an input tile arrives by TMA load);
+//                   transposing (fp32 outputs, patch epilogues): tcgen05.ld -> registers ->
+//                     swizzled smem transpose -> Epi functor on row-contiguous float4 pieces
 //
 // Tile: BLOCK_M = 128 (UMMA M, one TMEM lane per row), BLOCK_N = BN (UMMA N),
 // BLOCK_K = 64 elements (= one 128-byte swizzle row).
@@ -56,7 +59,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 512;   // pipeline barriers + one mbarrier per epilogue warp
-  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_EPI_GC * 4;  // per-warp transpose tiles
+  // per-warp staging: transpose tile of the classic epilogue = two 2 KB TMA tiles of the TMA one
+  static constexpr int kStagingBytes = GEMM_EPI_WARPS * 32 * GEMM_EPI_GC * 4;
   static constexpr int kTotal =
       kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024 /*align slack*/;
 };

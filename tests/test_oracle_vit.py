@@ -9,7 +9,8 @@ from oracle import vit
 transformers = pytest.importorskip("transformers")
 
 
-@pytest.mark.parametrize("name", ["tiny-32", "tiny-14"])
+# (ViT-L-14 / ViT-B-32: the full-size towers of BASELINE.json's configs, one image on the CPU)
+@pytest.mark.parametrize("name", ["tiny-32", "tiny-14", "ViT-B-32", "ViT-L-14"])
 def test_restated_vit_matches_hf(name):
     from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection
     cfg = vit.CONFIGS[name]
@@ -24,11 +25,18 @@ def test_restated_vit_matches_hf(name):
     assert not [k for k in missing if "position_ids" not in k], missing
     assert not unexpected, unexpected
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(2, 3, cfg.image_size, cfg.image_size, generator=g)
+    x = torch.randn(2 if name.startswith("tiny") else 1, 3, cfg.image_size, cfg.image_size,
+                    generator=g)
     with torch.no_grad():
         a = m(x)
         b = hf(pixel_values=x).image_embeds
     assert float((a - b).norm() / b.norm()) < 1e-5
+    # the input gradient too (what the attack path differentiates): the same scalar of the embedding
+    w = torch.randn(cfg.out_dim, generator=g)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (ga,) = torch.autograd.grad((m(xa) * w).sum(), xa)
+    (gb,) = torch.autograd.grad((hf(pixel_values=xb).image_embeds * w).sum(), xb)
+    assert float((ga - gb).norm() / gb.norm()) < 1e-4
 
 
 def test_param_counts_match_reference_checkpoints():
